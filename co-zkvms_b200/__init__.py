@@ -1,0 +1,324 @@
+"""co-zkvms_b200 - B200-native engine for the party-local BN254 G1 MSM of ChainSafe/co-zkvms.
+
+This package is a thin ctypes binding of libcozk_msm.so (C ABI: include/cozk_msm.h; CUDA sources: csrc/).
+The directory name carries a hyphen, so import it with importlib:
+
+    cozk = importlib.import_module("co-zkvms_b200")
+
+There is no CPU path: loading fails loudly when the library has not been built, and `Context()` fails when
+no B200 is visible.  The oracle under oracle/ is never imported from here.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libcozk_msm.so")
+SOURCES = ["msm.cu", "aux.cu", "pst13.cu"]
+HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+MONT, CANON = 0, 1
+OK, ERR_INVALID_ARG, ERR_KEY_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_BAD_HANDLE = 0, -1, -2, -3, -4, -5
+DIST = {"uniform": 0, "const": 1, "wminus": 2, "dup": 3, "small16": 4, "zero_half": 5}
+
+# every symbol include/cozk_msm.h and csrc/pst13.hpp declare (checked by tests/test_abi.py without a GPU)
+ABI_SYMBOLS = [
+    "cozk_init", "cozk_destroy", "cozk_device_count", "cozk_srs_register", "cozk_srs_release", "cozk_srs_len",
+    "cozk_msm_batch", "cozk_msm_batch_device", "cozk_g1_sum", "cozk_set_option", "cozk_last_stats", "cozk_last_error",
+    "cozk_dev_alloc", "cozk_dev_free", "cozk_dev_upload", "cozk_dev_download", "cozk_host_alloc_pinned",
+    "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_testgen_bases", "cozk_testgen_scalars",
+    "cozk_srs_register_device", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench",
+    "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_open",
+    "cozk_pst13_combine_commitment_shares",
+]
+
+
+class CozkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cozk error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(force=False, verbose=False):
+    """Compile libcozk_msm.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", "cozk_msm.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libcozk_msm.so is not built (run __graft_entry__.build()); there is no fallback path")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, u64, ci, cu, cd = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint,
+                               ctypes.POINTER(ctypes.c_double))
+    pp = ctypes.POINTER(vp)
+    L.cozk_init.argtypes = [pp, ctypes.POINTER(ci), ci]
+    L.cozk_destroy.argtypes = [vp]
+    L.cozk_destroy.restype = None
+    L.cozk_device_count.argtypes = [vp]
+    L.cozk_srs_register.argtypes = [vp, vp, sz, sz, vp, ctypes.POINTER(u64)]
+    L.cozk_srs_register_device.argtypes = [vp, ci, vp, sz, ctypes.POINTER(u64)]
+    L.cozk_srs_release.argtypes = [vp, u64]
+    L.cozk_srs_len.argtypes = [vp, u64, ctypes.POINTER(sz)]
+    L.cozk_msm_batch.argtypes = [vp, u64, sz, sz, pp, sz, sz, ci, cu, vp]
+    L.cozk_msm_batch_device.argtypes = [vp, ci, u64, sz, sz, pp, sz, sz, ci, cu, vp]
+    L.cozk_g1_sum.argtypes = [vp, sz, vp]
+    L.cozk_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
+    L.cozk_last_stats.argtypes = [vp, cd]
+    L.cozk_last_error.restype = ctypes.c_char_p
+    L.cozk_dev_alloc.argtypes = [vp, ci, sz, pp]
+    L.cozk_dev_free.argtypes = [vp, ci, vp]
+    L.cozk_dev_upload.argtypes = [vp, ci, vp, vp, sz]
+    L.cozk_dev_download.argtypes = [vp, ci, vp, vp, sz]
+    L.cozk_host_alloc_pinned.argtypes = [sz, pp]
+    L.cozk_host_free_pinned.argtypes = [vp]
+    L.cozk_dev_flush_l2.argtypes = [vp, ci]
+    L.cozk_testgen_bases.argtypes = [vp, ci, u64, sz, sz, vp]
+    L.cozk_testgen_scalars.argtypes = [vp, ci, ci, u64, sz, sz, sz, ci, vp, sz]
+    L.cozk_test_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.cozk_test_g1_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.cozk_microbench.argtypes = [vp, ci, ci, ci, ci, ci, cd, cd]
+    L.cozk_pst13_commit.argtypes = [vp, u64, vp, sz, sz, ci, cu, vp]
+    L.cozk_pst13_batch_commit.argtypes = [vp, u64, pp, sz, sz, sz, ci, ctypes.POINTER(cu), vp]
+    L.cozk_pst13_batch_commit_rep3.argtypes = [vp, u64, pp, ctypes.POINTER(ctypes.c_uint8), sz, sz, ci, ctypes.POINTER(cu), ci, vp,
+                                               ctypes.POINTER(ctypes.c_uint8)]
+    L.cozk_pst13_open.argtypes = [vp, ctypes.POINTER(u64), sz, vp, sz, vp, ci, vp, vp]
+    L.cozk_pst13_combine_commitment_shares.argtypes = [vp, sz, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise CozkError(rc, lib().cozk_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(a)
+
+
+class DeviceBuffer:
+    """A raw device allocation owned by a Context."""
+
+    def __init__(self, ctx, nbytes, device=0):
+        self.ctx, self.nbytes, self.device = ctx, nbytes, device
+        p = ctypes.c_void_p()
+        _check(lib().cozk_dev_alloc(ctx.handle, device, nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        _check(lib().cozk_dev_upload(self.ctx.handle, self.device, ctypes.c_void_p(self.ptr + offset), _ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, nbytes=None, offset=0):
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = np.empty(nbytes, dtype=np.uint8)
+        _check(lib().cozk_dev_download(self.ctx.handle, self.device, _ptr(out), ctypes.c_void_p(self.ptr + offset), nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().cozk_dev_free(self.ctx.handle, self.device, ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        p = ctypes.c_void_p()
+        _check(lib().cozk_host_alloc_pinned(nbytes, ctypes.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().cozk_host_free_pinned(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class Context:
+    """Owns the devices of one process (cozk_ctx).  devices: list of CUDA device ids, default [0]."""
+
+    def __init__(self, devices=None):
+        L = lib()
+        h = ctypes.c_void_p()
+        if devices is None:
+            rc = L.cozk_init(ctypes.byref(h), None, 1)
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = L.cozk_init(ctypes.byref(h), arr, len(devices))
+        _check(rc)
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            lib().cozk_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def device_count(self):
+        return lib().cozk_device_count(self.handle)
+
+    # ---- SRS
+    def srs_register(self, bases, infinity=None, stride=None):
+        """bases: uint8 array (n, stride>=64), each row x||y Fq Montgomery (arkworks in-memory limbs)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        n = bases.shape[0]
+        stride = bases.shape[1] if stride is None else stride
+        inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
+        h = ctypes.c_uint64()
+        _check(lib().cozk_srs_register(self.handle, _ptr(bases), n, stride, _ptr(inf), ctypes.byref(h)))
+        return h.value
+
+    def srs_register_device(self, dbuf, n, device=0):
+        h = ctypes.c_uint64()
+        _check(lib().cozk_srs_register_device(self.handle, device, ctypes.c_void_p(dbuf.ptr), n, ctypes.byref(h)))
+        return h.value
+
+    def srs_release(self, srs):
+        _check(lib().cozk_srs_release(self.handle, srs))
+
+    def srs_len(self, srs):
+        n = ctypes.c_size_t()
+        _check(lib().cozk_srs_len(self.handle, srs, ctypes.byref(n)))
+        return n.value
+
+    # ---- MSM
+    def msm_batch(self, srs, scalars, n=None, base_offset=0, stride=32, form=MONT, max_num_bits=0):
+        """scalars: list of uint8 arrays (each at least (n-1)*stride+32 bytes) or a 2-D/3-D array (k, n, stride).
+        Returns (k, 72) uint8 wire points."""
+        if isinstance(scalars, np.ndarray) and scalars.ndim == 3:
+            vecs = [scalars[j] for j in range(scalars.shape[0])]
+        elif isinstance(scalars, np.ndarray) and scalars.ndim == 2:
+            vecs = [scalars]
+        else:
+            vecs = list(scalars)
+        vecs = [np.ascontiguousarray(v, dtype=np.uint8) for v in vecs]
+        k = len(vecs)
+        if n is None:
+            n = vecs[0].size // stride if k else 0
+        ptrs = (ctypes.c_void_p * max(k, 1))(*[v.ctypes.data for v in vecs])
+        out = np.zeros((k, 72), dtype=np.uint8)
+        _check(lib().cozk_msm_batch(self.handle, srs, base_offset, n, ptrs, k, stride, form, max_num_bits, _ptr(out)))
+        return out
+
+    def msm_batch_ptrs(self, srs, ptr_list, n, base_offset=0, stride=32, form=MONT, max_num_bits=0, device=None, out=None):
+        """Raw-pointer variant: host pointers (device=None) or device pointers on context device `device`."""
+        k = len(ptr_list)
+        ptrs = (ctypes.c_void_p * max(k, 1))(*ptr_list)
+        out = np.zeros((k, 72), dtype=np.uint8) if out is None else out
+        if device is None:
+            _check(lib().cozk_msm_batch(self.handle, srs, base_offset, n, ptrs, k, stride, form, max_num_bits, _ptr(out)))
+        else:
+            _check(lib().cozk_msm_batch_device(self.handle, device, srs, base_offset, n, ptrs, k, stride, form,
+                                               max_num_bits, _ptr(out)))
+        return out
+
+    def set_option(self, name, value):
+        _check(lib().cozk_set_option(self.handle, name.encode(), int(value)))
+
+    def last_stats(self):
+        s = (ctypes.c_double * 12)()
+        _check(lib().cozk_last_stats(self.handle, s))
+        keys = ["h2d_ms", "decompose_ms", "sort_ms", "accumulate_ms", "reduce_ms", "finish_ms", "total_ms", "launches",
+                "window", "windows", "field_mults", "pairs"]
+        return dict(zip(keys, list(s)))
+
+    # ---- memory / generators / test kernels
+    def alloc(self, nbytes, device=0):
+        return DeviceBuffer(self, nbytes, device)
+
+    def flush_l2(self, device=0):
+        _check(lib().cozk_dev_flush_l2(self.handle, device))
+
+    def testgen_bases(self, seed, n, start=0, device=0):
+        buf = self.alloc(max(n, 1) * 64, device)
+        _check(lib().cozk_testgen_bases(self.handle, device, seed, start, n, ctypes.c_void_p(buf.ptr)))
+        return buf
+
+    def testgen_scalars(self, dist, seed, n, form=MONT, stride=32, start=0, total_n=None, device=0):
+        buf = self.alloc(max(n, 1) * stride, device)
+        _check(lib().cozk_testgen_scalars(self.handle, device, DIST[dist], seed, start, n,
+                                          n if total_n is None else total_n, form, ctypes.c_void_p(buf.ptr), stride))
+        return buf
+
+    def field_op(self, op, a, b=None, device=0):
+        ops = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "fr_from_mont": 5}
+        a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+        n = a.shape[0]
+        da = self.alloc(a.nbytes, device).upload(a)
+        db = self.alloc(a.nbytes, device).upload(np.ascontiguousarray(b, dtype=np.uint8)) if b is not None else None
+        do = self.alloc(a.nbytes, device)
+        try:
+            _check(lib().cozk_test_field_op(self.handle, device, ops[op], ctypes.c_void_p(da.ptr),
+                                            ctypes.c_void_p(db.ptr) if db else None, ctypes.c_void_p(do.ptr), n))
+            return do.download().reshape(n, 32)
+        finally:
+            for x in (da, db, do):
+                if x:
+                    x.free()
+
+    def g1_op(self, op, a, b=None, device=0):
+        ops = {"add": 0, "madd": 1, "dbl": 2}
+        a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 72)
+        n = a.shape[0]
+        da = self.alloc(a.nbytes, device).upload(a)
+        db = self.alloc(a.nbytes, device).upload(np.ascontiguousarray(b, dtype=np.uint8)) if b is not None else None
+        do = self.alloc(a.nbytes, device)
+        try:
+            _check(lib().cozk_test_g1_op(self.handle, device, ops[op], ctypes.c_void_p(da.ptr),
+                                         ctypes.c_void_p(db.ptr) if db else None, ctypes.c_void_p(do.ptr), n))
+            return do.download().reshape(n, 72)
+        finally:
+            for x in (da, db, do):
+                if x:
+                    x.free()
+
+    def microbench(self, which, blocks, threads, iters, device=0):
+        names = {"imad": 0, "fq_mul": 1, "fq_sqr": 2, "madd": 3}
+        ms, ops = ctypes.c_double(), ctypes.c_double()
+        _check(lib().cozk_microbench(self.handle, device, names[which], blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops)))
+        return ms.value, ops.value
+
+
+def g1_sum(points72):
+    """Host-side sum of 72-byte wire points (combine_comm / combine_commitment_shares semantics)."""
+    pts = np.ascontiguousarray(points72, dtype=np.uint8).reshape(-1, 72)
+    out = np.zeros(72, dtype=np.uint8)
+    _check(lib().cozk_g1_sum(_ptr(pts), pts.shape[0], _ptr(out)))
+    return out
+
+
+from . import pst13  # noqa: E402  (host-side mirror of the reference's PST13 / MultilinearPC interface)

@@ -1,0 +1,88 @@
+// Internal definitions shared by the translation units of libcozk_msm.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cozk_msm.h"
+#include "curve.cuh"
+
+namespace cozk {
+
+void set_error(const std::string& msg);
+
+#define COZK_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cozk::set_error(buf__);                                                                  \
+            return COZK_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+// grow-only device scratch buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return COZK_OK;
+        if (p) COZK_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        COZK_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return COZK_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Device {
+    int id = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::mutex mu;  // one MSM at a time per device
+    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, pk[2], pp[2], rs[2], rw[2], out, flush;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t copy_done[2] = {};
+    double stats[12] = {};
+    ~Device();
+};
+
+struct SrsEntry {
+    size_t n = 0;
+    std::vector<affine*> d_bases;    // per device
+    std::vector<uint8_t*> d_inf;     // per device, may be null
+};
+
+}  // namespace cozk
+
+struct cozk_ctx;
+namespace cozk {
+// The one entry every public MSM call funnels into (msm.cu).  only_device < 0: use all devices of the context.
+int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offset, size_t n, const void* const* host_scalars,
+                 const void* const* dev_scalars, size_t k, size_t stride, int form, unsigned max_bits, void* out);
+}  // namespace cozk
+
+struct cozk_ctx {
+    std::vector<std::unique_ptr<cozk::Device>> devs;
+    std::mutex mu;  // guards the SRS table and options
+    std::map<uint64_t, cozk::SrsEntry> srs;
+    uint64_t next_handle = 1;
+    long opt_window = 0;             // 0 = choose per call
+    long opt_group_pairs = 1L << 27; // (key, val) pairs per vector group
+};

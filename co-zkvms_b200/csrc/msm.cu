@@ -1,0 +1,572 @@
+// libcozk_msm.so - the engine behind include/cozk_msm.h: kernels (thin __global__ wrappers around the thread bodies
+// of msm_kernels.cuh), the per-device pipeline driver, multi-device sharding and the C ABI.
+//
+// Reference boundary this replaces: jolt_core::msm::{msm_field_elements, batch_msm} as called from
+// co-jolt/src/poly/commitment/pst13.rs:286, :319, :461 and ark_ec::VariableBaseMSM::msm_bigint as called from
+// co-noir-spartan/co-spartan/src/worker.rs:585, :804.  No CPU MSM path exists in this library.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "engine.hpp"
+#include "msm_kernels.cuh"
+#include "msm_plan.hpp"
+
+namespace cozk {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+Device::~Device() {
+    cudaSetDevice(id);
+    DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
+                      &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : copy_done) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) k_decompose(DecomposeArgs A) {
+    decompose_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+template <int L, bool LEVEL1>
+__global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
+    accumulate_body<L, LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+__global__ void __launch_bounds__(128, 3) k_reduce(ReduceArgs A) {
+    reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+__global__ void __launch_bounds__(32) k_finish(FinishArgs A) {
+    finish_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+
+static inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------------ one group on one device
+// Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
+static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
+                     const uint8_t* const* d_vec_ptrs, size_t vector_stride, size_t stride, int form, double* launches) {
+    cudaStream_t st = D.stream;
+    int rc;
+    if ((rc = D.keys_a.ensure(P.m * 4))) return rc;
+    if ((rc = D.vals_a.ensure(P.m * 4))) return rc;
+    if ((rc = D.keys_b.ensure(P.m * 4))) return rc;
+    if ((rc = D.vals_b.ensure(P.m * 4))) return rc;
+    if ((rc = D.buckets.ensure(P.total_buckets * sizeof(xyzz)))) return rc;
+    if ((rc = D.out.ensure((size_t)P.g * 72 + 256))) return rc;
+
+    COZK_CUDA(cudaEventRecord(D.ev[1], st));
+    // 1 decompose
+    DecomposeArgs DA{d_scalars, d_vec_ptrs, vector_stride, stride, form, P.n, P.g, P.c, P.W, d_inf,
+                     D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>()};
+    k_decompose<<<grid_for((size_t)P.g * P.n, 256), 256, 0, st>>>(DA);
+    *launches += 1;
+    COZK_CUDA(cudaGetLastError());
+    COZK_CUDA(cudaEventRecord(D.ev[2], st));
+
+    // 2 sort (key, val) pairs by key
+    if (P.m > (size_t)0x7FFFFFFF) {
+        set_error("internal: group too large for the sort");
+        return COZK_ERR_INVALID_ARG;
+    }
+    size_t tmp_bytes = 0;
+    COZK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>(),
+                                              D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>(), (int)P.m, 0,
+                                              (int)P.sort_bits, st));
+    if ((rc = D.sort_tmp.ensure(tmp_bytes))) return rc;
+    COZK_CUDA(cub::DeviceRadixSort::SortPairs(D.sort_tmp.p, tmp_bytes, D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>(),
+                                              D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>(), (int)P.m, 0,
+                                              (int)P.sort_bits, st));
+    COZK_CUDA(cudaEventRecord(D.ev[3], st));
+
+    // 3 accumulate, level by level
+    COZK_CUDA(cudaMemsetAsync(D.buckets.p, 0, P.total_buckets * sizeof(xyzz), st));
+    for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
+        size_t m = P.acc_entries[lvl];
+        size_t T = (m + ACC_L - 1) / ACC_L;
+        DevBuf& pk_out = D.pk[lvl & 1];
+        DevBuf& pp_out = D.pp[lvl & 1];
+        if ((rc = pk_out.ensure(2 * T * 4))) return rc;
+        if ((rc = pp_out.ensure(2 * T * sizeof(xyzz)))) return rc;
+        AccumulateArgs A{m,
+                         lvl == 0 ? D.keys_b.as<uint32_t>() : D.pk[(lvl - 1) & 1].as<uint32_t>(),
+                         D.vals_b.as<uint32_t>(),
+                         d_bases,
+                         lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
+                         D.buckets.as<xyzz>(),
+                         pk_out.as<uint32_t>(),
+                         pp_out.as<xyzz>()};
+        if (lvl == 0) k_accumulate<ACC_L, true><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+    }
+    COZK_CUDA(cudaEventRecord(D.ev[4], st));
+
+    // 4 bucket reduce tree
+    size_t windows = (size_t)P.g * P.W;
+    for (size_t lvl = 0; lvl < P.red.size(); ++lvl) {
+        const ReduceLevel& R = P.red[lvl];
+        size_t threads = windows * (R.n_in / R.l);
+        DevBuf& s_out = D.rs[lvl & 1];
+        DevBuf& w_out = D.rw[lvl & 1];
+        if ((rc = s_out.ensure(threads * sizeof(xyzz)))) return rc;
+        if ((rc = w_out.ensure(threads * sizeof(xyzz)))) return rc;
+        ReduceArgs A{lvl == 0 ? D.buckets.as<xyzz>() : D.rs[(lvl - 1) & 1].as<xyzz>(),
+                     lvl == 0 ? nullptr : D.rw[(lvl - 1) & 1].as<xyzz>(),
+                     s_out.as<xyzz>(),
+                     w_out.as<xyzz>(),
+                     R.n_in,
+                     R.l,
+                     R.log_len,
+                     threads};
+        k_reduce<<<grid_for(threads, 128), 128, 0, st>>>(A);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+    }
+    COZK_CUDA(cudaEventRecord(D.ev[5], st));
+
+    // 5 finish
+    size_t last = (P.red.size() - 1) & 1;
+    FinishArgs F{D.rs[last].as<xyzz>(), D.rw[last].as<xyzz>(), P.g, P.W, P.c, D.out.as<uint8_t>(), nullptr};
+    k_finish<<<grid_for(P.g, 32), 32, 0, st>>>(F);
+    *launches += 1;
+    COZK_CUDA(cudaGetLastError());
+    return COZK_OK;
+}
+
+static void add_stage_times(Device& D) {
+    float ms;
+    for (int s = 1; s <= 5; ++s) {
+        if (cudaEventElapsedTime(&ms, D.ev[s], D.ev[s + 1]) == cudaSuccess) D.stats[s] += ms;
+    }
+}
+
+// host-side sum of wire points (used to combine point-range shards): out = sum of count 72-byte points
+static void host_sum(const uint8_t* pts, size_t count, uint8_t* out) {
+    xyzz acc = xyzz_identity();
+    for (size_t i = 0; i < count; ++i) acc = xyzz_add(acc, xyzz_from_wire(pts + 72 * i));
+    xyzz_to_wire(acc, out);
+}
+
+constexpr size_t MAX_POINTS_PER_PASS = (size_t)1 << 26;
+
+// All k vectors over bases [offset, offset+n) on ONE device.  host_scalars xor dev_scalars.
+static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t offset, size_t n,
+                         const void* const* host_scalars, const void* const* dev_scalars, size_t k, size_t stride, int form,
+                         unsigned max_bits, uint8_t* out) {
+    Device& D = *ctx->devs[dev_index];
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    for (double& s : D.stats) s = 0;
+    double launches = 0;
+    uint32_t bits = (max_bits == 0 || max_bits > 254) ? 254 : max_bits;
+    const size_t max_buckets = (size_t)1 << 25;  // 4 GiB of XYZZ buckets per group
+    size_t passes = (n + MAX_POINTS_PER_PASS - 1) / MAX_POINTS_PER_PASS;
+    std::vector<uint8_t> partial(passes > 1 ? passes * k * 72 : 0);
+    COZK_CUDA(cudaEventRecord(D.ev[0], D.stream));
+    double plan_mults = 0, plan_pairs = 0;
+    uint32_t last_c = 0, last_W = 0;
+
+    for (size_t pass = 0; pass < passes; ++pass) {
+        size_t lo = pass * MAX_POINTS_PER_PASS;
+        size_t pn = std::min(MAX_POINTS_PER_PASS, n - lo);
+        const affine* d_bases = S.d_bases[dev_index] + offset + lo;
+        const uint8_t* d_inf = S.d_inf[dev_index] ? S.d_inf[dev_index] + offset + lo : nullptr;
+        uint8_t* pass_out = passes > 1 ? partial.data() + pass * k * 72 : out;
+
+        // vectors per group: bounded by the pair budget
+        MsmPlan probe = make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window);
+        size_t per_vec = probe.m;
+        size_t gmax = std::max<size_t>(1, (size_t)ctx->opt_group_pairs / std::max<size_t>(per_vec, 1));
+        gmax = std::min<size_t>(gmax, 4096);
+        size_t vstride = ((pn - 1) * stride + 32 + 255) & ~(size_t)255;
+
+        size_t ngroups = (k + gmax - 1) / gmax;
+        // stage group 0's scalars, then overlap the copy of group i+1 with the compute of group i
+        auto stage = [&](size_t gi) -> int {
+            size_t v0 = gi * gmax, g = std::min(gmax, k - v0);
+            int slot = (int)(gi & 1);
+            if (host_scalars) {
+                int rc = D.scalars[slot].ensure(g * vstride);
+                if (rc) return rc;
+                for (size_t v = 0; v < g; ++v) {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(host_scalars[v0 + v]) + lo * stride;
+                    COZK_CUDA(cudaMemcpyAsync(D.scalars[slot].as<uint8_t>() + v * vstride, src, (pn - 1) * stride + 32,
+                                              cudaMemcpyHostToDevice, D.copy_stream));
+                }
+            } else {
+                int rc = D.vec_ptrs.ensure(2 * 4096 * sizeof(void*));
+                if (rc) return rc;
+                std::vector<const uint8_t*> ptrs(g);
+                for (size_t v = 0; v < g; ++v) ptrs[v] = reinterpret_cast<const uint8_t*>(dev_scalars[v0 + v]) + lo * stride;
+                COZK_CUDA(cudaMemcpyAsync(D.vec_ptrs.as<const uint8_t*>() + slot * 4096, ptrs.data(), g * sizeof(void*),
+                                          cudaMemcpyHostToDevice, D.copy_stream));
+                COZK_CUDA(cudaStreamSynchronize(D.copy_stream));  // ptrs goes out of scope
+            }
+            COZK_CUDA(cudaEventRecord(D.copy_done[slot], D.copy_stream));
+            return COZK_OK;
+        };
+        int rc = stage(0);
+        if (rc) return rc;
+        for (size_t gi = 0; gi < ngroups; ++gi) {
+            size_t v0 = gi * gmax, g = std::min(gmax, k - v0);
+            int slot = (int)(gi & 1);
+            MsmPlan P = make_plan(pn, (uint32_t)g, bits, max_buckets, (uint32_t)ctx->opt_window);
+            plan_mults += P.field_mults();
+            plan_pairs += (double)P.m;
+            last_c = P.c;
+            last_W = P.W;
+            COZK_CUDA(cudaStreamWaitEvent(D.stream, D.copy_done[slot], 0));
+            if (gi + 1 < ngroups) {
+                // the other staging slot was last read by group gi-1, which has been synchronised below
+                if ((rc = stage(gi + 1))) return rc;
+            }
+            rc = run_group(D, P, d_bases, d_inf, host_scalars ? D.scalars[slot].as<uint8_t>() : nullptr,
+                           host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096, vstride, stride, form,
+                           &launches);
+            if (rc) return rc;
+            COZK_CUDA(cudaMemcpyAsync(pass_out + v0 * 72, D.out.p, g * 72, cudaMemcpyDeviceToHost, D.stream));
+            COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
+            COZK_CUDA(cudaStreamSynchronize(D.stream));
+            add_stage_times(D);
+        }
+    }
+    COZK_CUDA(cudaEventRecord(D.ev[7], D.stream));
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    float total_ms = 0;
+    cudaEventElapsedTime(&total_ms, D.ev[0], D.ev[7]);
+    D.stats[6] = total_ms;
+    D.stats[0] = std::max(0.0, total_ms - (D.stats[1] + D.stats[2] + D.stats[3] + D.stats[4] + D.stats[5]));
+    D.stats[7] = launches;
+    D.stats[8] = last_c;
+    D.stats[9] = last_W;
+    D.stats[10] = plan_mults;
+    D.stats[11] = plan_pairs;
+    if (passes > 1) {
+        std::vector<uint8_t> col(passes * 72);
+        for (size_t v = 0; v < k; ++v) {
+            for (size_t p = 0; p < passes; ++p) memcpy(col.data() + 72 * p, partial.data() + (p * k + v) * 72, 72);
+            host_sum(col.data(), passes, out + 72 * v);
+        }
+    }
+    return COZK_OK;
+}
+
+int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offset, size_t n,
+                        const void* const* host_scalars, const void* const* dev_scalars, size_t k, size_t stride, int form,
+                        unsigned max_bits, void* out) {
+    if (!ctx || !out || k == 0 || (!host_scalars && !dev_scalars)) {
+        set_error("null pointer or k == 0");
+        return COZK_ERR_INVALID_ARG;
+    }
+    if ((form != COZK_MONT && form != COZK_CANON) || stride < 32 || (stride & 15)) {
+        set_error("bad scalar form or stride (stride must be >= 32 and a multiple of 16)");
+        return COZK_ERR_INVALID_ARG;
+    }
+    const void* const* sc = host_scalars ? host_scalars : dev_scalars;
+    for (size_t j = 0; j < k; ++j) {
+        if (!sc[j] && n) {
+            set_error("null scalar vector");
+            return COZK_ERR_INVALID_ARG;
+        }
+        if (dev_scalars && ((uintptr_t)sc[j] & 15)) {
+            set_error("device scalar vectors must be 16-byte aligned");
+            return COZK_ERR_INVALID_ARG;
+        }
+    }
+    SrsEntry S;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->srs.find(srs);
+        if (it == ctx->srs.end()) {
+            set_error("unknown SRS handle");
+            return COZK_ERR_BAD_HANDLE;
+        }
+        S = it->second;
+    }
+    if (base_offset > S.n || n > S.n - base_offset) {
+        set_error("Key length error: base_offset + n exceeds the registered SRS");
+        return COZK_ERR_KEY_LENGTH;
+    }
+    uint8_t* o = reinterpret_cast<uint8_t*>(out);
+    if (n == 0) {
+        for (size_t j = 0; j < k; ++j) {
+            memset(o + 72 * j, 0, 72);
+            o[72 * j + 64] = 1;
+        }
+        return COZK_OK;
+    }
+    int nd = (int)ctx->devs.size();
+    if (only_device >= 0 || nd == 1) {
+        int d = only_device >= 0 ? only_device : 0;
+        if (d >= nd) {
+            set_error("device index out of range");
+            return COZK_ERR_INVALID_ARG;
+        }
+        return run_on_device(ctx, d, S, base_offset, n, host_scalars, dev_scalars, k, stride, form, max_bits, o);
+    }
+    // several devices: shard by vector when there are enough of them, else by point range; combine on the host
+    std::vector<int> rcs(nd, COZK_OK);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    if (k >= (size_t)nd) {
+        for (int d = 0; d < nd; ++d) {
+            size_t v0 = k * d / nd, v1 = k * (d + 1) / nd;
+            th.emplace_back([&, d, v0, v1] {
+                rcs[d] = run_on_device(ctx, d, S, base_offset, n, host_scalars + v0, nullptr, v1 - v0, stride, form, max_bits,
+                                       o + 72 * v0);
+                if (rcs[d]) errs[d] = g_error;
+            });
+        }
+        for (auto& t : th) t.join();
+    } else {
+        std::vector<uint8_t> partial((size_t)nd * k * 72);
+        std::vector<std::vector<const void*>> ptrs(nd, std::vector<const void*>(k));
+        std::vector<size_t> los(nd + 1);
+        for (int d = 0; d <= nd; ++d) los[d] = n * (size_t)d / nd;
+        for (int d = 0; d < nd; ++d) {
+            for (size_t j = 0; j < k; ++j) ptrs[d][j] = reinterpret_cast<const uint8_t*>(host_scalars[j]) + los[d] * stride;
+            th.emplace_back([&, d] {
+                size_t cnt = los[d + 1] - los[d];
+                if (cnt == 0) {
+                    for (size_t j = 0; j < k; ++j) {
+                        memset(&partial[((size_t)d * k + j) * 72], 0, 72);
+                        partial[((size_t)d * k + j) * 72 + 64] = 1;
+                    }
+                    return;
+                }
+                rcs[d] = run_on_device(ctx, d, S, base_offset + los[d], cnt, ptrs[d].data(), nullptr, k, stride, form, max_bits,
+                                       &partial[(size_t)d * k * 72]);
+                if (rcs[d]) errs[d] = g_error;
+            });
+        }
+        for (auto& t : th) t.join();
+        std::vector<uint8_t> col((size_t)nd * 72);
+        for (size_t j = 0; j < k; ++j) {
+            for (int d = 0; d < nd; ++d) memcpy(&col[72 * d], &partial[((size_t)d * k + j) * 72], 72);
+            host_sum(col.data(), nd, o + 72 * j);
+        }
+    }
+    for (int d = 0; d < nd; ++d) {
+        if (rcs[d]) {
+            set_error(errs[d]);
+            return rcs[d];
+        }
+    }
+    return COZK_OK;
+}
+
+}  // namespace cozk
+
+using namespace cozk;
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* cozk_last_error(void) { return g_error.c_str(); }
+
+int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) {
+        set_error("null out pointer");
+        return COZK_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+        return COZK_ERR_NO_DEVICE;
+    }
+    if (n_devices <= 0) n_devices = 1;
+    std::unique_ptr<cozk_ctx> ctx(new cozk_ctx);
+    for (int i = 0; i < n_devices; ++i) {
+        int id = device_ids ? device_ids[i] : i;
+        if (id < 0 || id >= count) {
+            set_error("device id out of range");
+            return COZK_ERR_NO_DEVICE;
+        }
+        std::unique_ptr<Device> D(new Device);
+        D->id = id;
+        COZK_CUDA(cudaSetDevice(id));
+        cudaDeviceProp prop;
+        COZK_CUDA(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) {
+            set_error("this library is built for sm_100a (B200) only");
+            return COZK_ERR_NO_DEVICE;
+        }
+        D->sm_count = prop.multiProcessorCount;
+        COZK_CUDA(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
+        COZK_CUDA(cudaStreamCreateWithFlags(&D->copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : D->ev) COZK_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : D->copy_done) COZK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->devs.push_back(std::move(D));
+    }
+    *out = ctx.release();
+    return COZK_OK;
+}
+
+void cozk_destroy(cozk_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& kv : ctx->srs) {
+        for (size_t d = 0; d < kv.second.d_bases.size(); ++d) {
+            cudaSetDevice(ctx->devs[d]->id);
+            if (kv.second.d_bases[d]) cudaFree(kv.second.d_bases[d]);
+            if (kv.second.d_inf[d]) cudaFree(kv.second.d_inf[d]);
+        }
+    }
+    delete ctx;
+}
+
+int cozk_device_count(const cozk_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out) {
+    if (!ctx || !out || (!bases && n) || stride_bytes < 64) {
+        set_error("null pointer or stride < 64");
+        return COZK_ERR_INVALID_ARG;
+    }
+    SrsEntry S;
+    S.n = n;
+    bool any_inf = false;
+    if (infinity)
+        for (size_t i = 0; i < n && !any_inf; ++i) any_inf = infinity[i] != 0;
+    for (auto& D : ctx->devs) {
+        COZK_CUDA(cudaSetDevice(D->id));
+        affine* d = nullptr;
+        uint8_t* di = nullptr;
+        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(affine)));
+        if (stride_bytes == 64) {
+            COZK_CUDA(cudaMemcpy(d, bases, n * 64, cudaMemcpyHostToDevice));
+        } else {
+            COZK_CUDA(cudaMemcpy2D(d, 64, bases, stride_bytes, 64, n, cudaMemcpyHostToDevice));
+        }
+        if (any_inf) {
+            COZK_CUDA(cudaMalloc(&di, n));
+            COZK_CUDA(cudaMemcpy(di, infinity, n, cudaMemcpyHostToDevice));
+        }
+        S.d_bases.push_back(d);
+        S.d_inf.push_back(di);
+    }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    *out = ctx->next_handle++;
+    ctx->srs[*out] = S;
+    return COZK_OK;
+}
+
+int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_bases64, size_t n, cozk_srs* out) {
+    if (!ctx || !out || (!d_bases64 && n) || device_index < 0 || device_index >= (int)ctx->devs.size()) {
+        set_error("bad argument");
+        return COZK_ERR_INVALID_ARG;
+    }
+    SrsEntry S;
+    S.n = n;
+    for (size_t di = 0; di < ctx->devs.size(); ++di) {
+        Device& D = *ctx->devs[di];
+        COZK_CUDA(cudaSetDevice(D.id));
+        affine* d = nullptr;
+        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(affine)));
+        COZK_CUDA(cudaMemcpyPeer(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine)));
+        S.d_bases.push_back(d);
+        S.d_inf.push_back(nullptr);
+    }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    *out = ctx->next_handle++;
+    ctx->srs[*out] = S;
+    return COZK_OK;
+}
+
+int cozk_srs_release(cozk_ctx* ctx, cozk_srs srs) {
+    if (!ctx) return COZK_ERR_INVALID_ARG;
+    SrsEntry S;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->srs.find(srs);
+        if (it == ctx->srs.end()) {
+            set_error("unknown SRS handle");
+            return COZK_ERR_BAD_HANDLE;
+        }
+        S = it->second;
+        ctx->srs.erase(it);
+    }
+    for (size_t d = 0; d < S.d_bases.size(); ++d) {
+        std::lock_guard<std::mutex> lock(ctx->devs[d]->mu);
+        cudaSetDevice(ctx->devs[d]->id);
+        if (S.d_bases[d]) cudaFree(S.d_bases[d]);
+        if (S.d_inf[d]) cudaFree(S.d_inf[d]);
+    }
+    return COZK_OK;
+}
+
+int cozk_srs_len(cozk_ctx* ctx, cozk_srs srs, size_t* out_n) {
+    if (!ctx || !out_n) return COZK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->srs.find(srs);
+    if (it == ctx->srs.end()) {
+        set_error("unknown SRS handle");
+        return COZK_ERR_BAD_HANDLE;
+    }
+    *out_n = it->second.n;
+    return COZK_OK;
+}
+
+int cozk_msm_batch(cozk_ctx* ctx, cozk_srs srs, size_t base_offset, size_t n, const void* const* scalars, size_t k,
+                   size_t stride_bytes, int form, unsigned max_num_bits, void* out) {
+    if (!scalars) {
+        set_error("null scalars");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return msm_dispatch(ctx, -1, srs, base_offset, n, scalars, nullptr, k, stride_bytes, form, max_num_bits, out);
+}
+
+int cozk_msm_batch_device(cozk_ctx* ctx, int device_index, cozk_srs srs, size_t base_offset, size_t n,
+                          const void* const* d_scalars, size_t k, size_t stride_bytes, int form, unsigned max_num_bits,
+                          void* out) {
+    if (!d_scalars || device_index < 0) {
+        set_error("null scalars or negative device index");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return msm_dispatch(ctx, device_index, srs, base_offset, n, nullptr, d_scalars, k, stride_bytes, form, max_num_bits, out);
+}
+
+int cozk_g1_sum(const void* points72, size_t count, void* out72) {
+    if ((!points72 && count) || !out72) {
+        set_error("null pointer");
+        return COZK_ERR_INVALID_ARG;
+    }
+    host_sum(reinterpret_cast<const uint8_t*>(points72), count, reinterpret_cast<uint8_t*>(out72));
+    return COZK_OK;
+}
+
+int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
+    if (!ctx || !name) return COZK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!strcmp(name, "window")) {
+        if (value != 0 && (value < (long)C_MIN || value > (long)C_MAX)) {
+            set_error("window out of range");
+            return COZK_ERR_INVALID_ARG;
+        }
+        ctx->opt_window = value;
+    } else if (!strcmp(name, "group_pairs")) {
+        if (value < 1) return COZK_ERR_INVALID_ARG;
+        ctx->opt_group_pairs = value;
+    } else {
+        set_error("unknown option");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return COZK_OK;
+}
+
+int cozk_last_stats(cozk_ctx* ctx, double* out12) {
+    if (!ctx || !out12) return COZK_ERR_INVALID_ARG;
+    Device& D = *ctx->devs[0];
+    std::lock_guard<std::mutex> lock(D.mu);
+    for (int i = 0; i < 12; ++i) out12[i] = D.stats[i];
+    return COZK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// Thread bodies of the MSM pipeline.  Every body is a pure function of its thread index (no shared memory, no
+// warp intrinsics), so the same source runs as a CUDA thread (msm.cu wraps each body in a __global__ kernel) and,
+// for logic tests without a GPU, as a loop iteration in tests/emul/ (host build; never shipped in the library).
+//
+// Pipeline for a group of g scalar vectors of n points against one base range (what one `batch_msm` call of the
+// reference, co-jolt/src/poly/commitment/pst13.rs:319-323, asks for):
+//   1 decompose     scalar -> W signed c-bit digits -> (key, val) pairs.  key = (vector*W + window)*B + |digit|-1,
+//                   B = 2^(c-1); val = point index | sign << 31.  Zero digits get the sentinel key.
+//   2 sort          pairs by key (cub radix sort in msm.cu) -> every bucket is one contiguous run.
+//   3 accumulate    load-balanced segmented sum: thread t owns pairs [t*L, (t+1)*L), whatever buckets they belong to.
+//                   Runs that lie inside one chunk are written straight to their bucket; the (at most two) runs that
+//                   cross a chunk edge are written as partial sums and summed by the same body one level up, until
+//                   one thread sees a whole level.  Work per thread is constant for ANY scalar distribution - the
+//                   co-jolt party shares are constant vectors (one bucket per window holds all n points).
+//   4 bucket reduce sum_b (b+1) * bucket[b] per window by a radix-l tree of (S, W) pairs:
+//                   S = sum of children, W = sum_s W_s + len * sum_s s * S_s   (len = indices a child spans).
+//   5 finish        Horner over the windows (c doublings each), one inversion, affine wire point.
+#pragma once
+#include <cstddef>
+
+#include "curve.cuh"
+
+namespace cozk {
+
+constexpr uint32_t KEY_SENTINEL = 0xFFFFFFFFu;  // zero digit / unused partial slot
+constexpr uint32_t KEY_FILL = 0x80000000u;      // partial slot that only keeps a run contiguous (identity point)
+constexpr uint32_t KEY_MASK = 0x7FFFFFFFu;
+constexpr uint32_t VAL_NEG = 0x80000000u;
+
+constexpr int SCALAR_MONT = 0;   // Fr Montgomery (what msm_field_elements gets)
+constexpr int SCALAR_CANON = 1;  // BigInt<4> (what msm_bigint gets)
+
+COZK_HD fq load_fq(const void* p) {
+    fq r;
+#if defined(__CUDA_ARCH__)
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#else
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    for (int i = 0; i < 8; ++i) r.v[i] = q[i];
+#endif
+    return r;
+}
+COZK_HD void store_fq(void* p, const fq& a) {
+#if defined(__CUDA_ARCH__)
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+#else
+    uint32_t* q = reinterpret_cast<uint32_t*>(p);
+    for (int i = 0; i < 8; ++i) q[i] = a.v[i];
+#endif
+}
+COZK_HD affine load_affine(const affine* p) {
+    affine r;
+    r.x = load_fq(&p->x);
+    r.y = load_fq(&p->y);
+    return r;
+}
+COZK_HD xyzz load_xyzz(const xyzz* p) {
+    xyzz r;
+    r.X = load_fq(&p->X);
+    r.Y = load_fq(&p->Y);
+    r.ZZ = load_fq(&p->ZZ);
+    r.ZZZ = load_fq(&p->ZZZ);
+    return r;
+}
+COZK_HD void store_xyzz(xyzz* p, const xyzz& a) {
+    store_fq(&p->X, a.X);
+    store_fq(&p->Y, a.Y);
+    store_fq(&p->ZZ, a.ZZ);
+    store_fq(&p->ZZZ, a.ZZZ);
+}
+
+// ------------------------------------------------------------------------------------------------ 1 decompose
+struct DecomposeArgs {
+    const uint8_t* scalars;    // device copy; vector v starts at scalars + v*vector_stride, element i at + i*stride
+    const uint8_t* const* vec_ptrs;  // if non-null: vector v starts at vec_ptrs[v] instead (device-resident shares)
+    size_t vector_stride;      // bytes between vectors
+    size_t stride;             // bytes between elements (32 dense, 64 Rep3 AoS share a)
+    int form;                  // SCALAR_MONT / SCALAR_CANON
+    size_t n;                  // points per vector
+    uint32_t g;                // vectors in this group
+    uint32_t c;                // window bits
+    uint32_t W;                // windows
+    const uint8_t* infinity;   // optional per-base flag (already offset to this base range), or null
+    uint32_t* keys;            // [g*W*n]
+    uint32_t* vals;            // [g*W*n]
+};
+
+// bits [off, off+c) of a 256-bit little-endian integer, c <= 24
+COZK_HD uint32_t extract_bits(const fr& s, uint32_t off, uint32_t c) {
+    uint32_t limb = off >> 5, sh = off & 31;
+    uint64_t lo = s.v[limb];
+    uint64_t hi = (limb + 1 < 8) ? s.v[limb + 1] : 0;
+    uint64_t x = (lo | (hi << 32)) >> sh;
+    return (uint32_t)x & ((1u << c) - 1u);
+}
+
+// thread tid = v*n + i
+COZK_HD void decompose_body(size_t tid, const DecomposeArgs& A) {
+    if (tid >= (size_t)A.g * A.n) return;
+    uint32_t v = (uint32_t)(tid / A.n);
+    size_t i = tid - (size_t)v * A.n;
+    const uint8_t* vec = A.vec_ptrs ? A.vec_ptrs[v] : A.scalars + (size_t)v * A.vector_stride;
+    fr s = load_fq(vec + i * A.stride);
+    if (A.form == SCALAR_MONT) s = fr_from_mont(s); else s = fr_reduce_canon(s);
+    bool skip = A.infinity && A.infinity[i];
+    const uint32_t B = 1u << (A.c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < A.W; ++w) {
+        uint32_t d = extract_bits(s, w * A.c, A.c) + carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (d > B) {  // digit in [-B+1, B]; the top window never carries because W*c >= bits + 1
+            d = (1u << A.c) - d;
+            neg = VAL_NEG;
+            carry = 1;
+        }
+        size_t o = ((size_t)v * A.W + w) * A.n + i;
+        bool zero = (d == 0) || skip;
+        A.keys[o] = zero ? KEY_SENTINEL : ((v * A.W + w) * B + d - 1);
+        A.vals[o] = zero ? 0u : ((uint32_t)i | neg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 3 accumulate
+// One body for all levels.  LEVEL1: entries are (key, val) pairs pointing into the base table (mixed additions);
+// otherwise entries are (key, xyzz partial sum) produced by the level below (full additions).
+struct AccumulateArgs {
+    size_t m;                 // number of entries at this level
+    const uint32_t* keys;     // [m] sorted (level 1) / partial keys of the level below
+    const uint32_t* vals;     // level 1 only
+    const affine* bases;      // level 1 only, already offset to the base range
+    const xyzz* pts_in;       // levels >= 2
+    xyzz* buckets;            // [g*W*B]
+    uint32_t* pkeys;          // [2*T] partial keys out, T = ceil(m/L)
+    xyzz* ppts;               // [2*T] partial sums out
+};
+
+template <int L, bool LEVEL1>
+COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
+    size_t start = t * (size_t)L;
+    if (start >= A.m) return;
+    size_t end = start + L < A.m ? start + L : A.m;
+    uint32_t cur = A.keys[start] & KEY_MASK;  // sentinel -> KEY_MASK, never a real key
+    bool left_open = start > 0 && cur != KEY_MASK && (A.keys[start - 1] & KEY_MASK) == cur;
+    bool first_run = true;
+    uint32_t key0 = KEY_SENTINEL, key1 = KEY_SENTINEL;
+    xyzz acc = xyzz_identity();
+    for (size_t i = start; i < end; ++i) {
+        uint32_t raw = A.keys[i];
+        uint32_t k = raw & KEY_MASK;
+        if (k != cur) {
+            // the run `cur` ends inside this chunk: it is closed on the right
+            if (cur != KEY_MASK) {
+                if (first_run && left_open) {
+                    key0 = cur;
+                    store_xyzz(&A.ppts[2 * t], acc);
+                } else {
+                    store_xyzz(&A.buckets[cur], acc);
+                }
+            }
+            acc = xyzz_identity();
+            cur = k;
+            first_run = false;
+        }
+        if (k == KEY_MASK) continue;
+        if (LEVEL1) {
+            uint32_t val = A.vals[i];
+            affine p = load_affine(&A.bases[val & ~VAL_NEG]);
+            p.y = fq_cneg(p.y, (val & VAL_NEG) != 0);
+            acc = xyzz_madd(acc, p);
+        } else {
+            if (raw & KEY_FILL) continue;
+            acc = xyzz_add(acc, load_xyzz(&A.pts_in[i]));
+        }
+    }
+    bool right_open = end < A.m && cur != KEY_MASK && (A.keys[end] & KEY_MASK) == cur;
+    if (cur != KEY_MASK) {
+        bool lo = first_run && left_open;
+        if (!lo && !right_open) {
+            store_xyzz(&A.buckets[cur], acc);
+        } else if (first_run) {
+            // the whole chunk is one run, open on at least one side: sum in slot 0, a filler keeps the run contiguous
+            key0 = cur;
+            store_xyzz(&A.ppts[2 * t], acc);
+            key1 = cur | KEY_FILL;
+        } else {
+            key1 = cur;
+            store_xyzz(&A.ppts[2 * t + 1], acc);
+        }
+    }
+    A.pkeys[2 * t] = key0;
+    A.pkeys[2 * t + 1] = key1;
+}
+
+// ------------------------------------------------------------------------------------------------ 4 bucket reduce
+struct ReduceArgs {
+    const xyzz* s_in;   // [windows * n_in]
+    const xyzz* w_in;   // same shape, or null at the first level (all W = 0)
+    xyzz* s_out;        // [windows * n_in / l]
+    xyzz* w_out;
+    uint32_t n_in;      // children per window
+    uint32_t l;         // children per thread (power of two dividing n_in)
+    uint32_t log_len;   // log2 of the number of bucket indices one child spans
+    size_t threads;     // windows * n_in / l
+};
+
+COZK_HD void reduce_body(size_t tid, const ReduceArgs& A) {
+    if (tid >= A.threads) return;
+    size_t base = tid * A.l;  // windows are contiguous and n_in % l == 0, so groups never straddle windows
+    xyzz run = xyzz_identity(), acc = xyzz_identity();
+    for (uint32_t s = A.l - 1; s >= 1; --s) {
+        run = xyzz_add(run, load_xyzz(&A.s_in[base + s]));
+        acc = xyzz_add(acc, run);  // ends as sum_s s * S_s
+    }
+    run = xyzz_add(run, load_xyzz(&A.s_in[base]));
+    for (uint32_t k = 0; k < A.log_len; ++k) acc = xyzz_dbl(acc);
+    if (A.w_in) {
+        for (uint32_t s = 0; s < A.l; ++s) acc = xyzz_add(acc, load_xyzz(&A.w_in[base + s]));
+    }
+    store_xyzz(&A.s_out[tid], run);
+    store_xyzz(&A.w_out[tid], acc);
+}
+
+// ------------------------------------------------------------------------------------------------ 5 finish
+struct FinishArgs {
+    const xyzz* s;    // [g*W] per-window sum of buckets
+    const xyzz* w;    // [g*W] per-window sum_b b * bucket[b]   (0-based b; the bucket value is b+1)
+    uint32_t g, W, c;
+    uint8_t* out;     // [g] 72-byte wire points (device memory)
+    xyzz* out_xyzz;   // [g] optional un-normalised sums (for the multi-GPU combine), or null
+};
+
+COZK_HD void finish_body(size_t v, const FinishArgs& A) {
+    if (v >= A.g) return;
+    xyzz acc = xyzz_identity();
+    for (uint32_t w = A.W; w-- > 0;) {
+        for (uint32_t k = 0; k < A.c; ++k) acc = xyzz_dbl(acc);
+        size_t o = (size_t)v * A.W + w;
+        acc = xyzz_add(acc, xyzz_add(load_xyzz(&A.s[o]), load_xyzz(&A.w[o])));
+    }
+    if (A.out_xyzz) store_xyzz(&A.out_xyzz[v], acc);
+    xyzz_to_wire(acc, A.out + 72 * v);
+}
+
+}  // namespace cozk

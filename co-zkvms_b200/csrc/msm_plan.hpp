@@ -1,0 +1,95 @@
+// Host-side plan of one MSM group: window size, window count, chunk length and the level structure of the two
+// multi-level stages.  Pure C++ (no CUDA), shared by the engine (msm.cu) and the logic tests (tests/emul/).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace cozk {
+
+constexpr int ACC_L = 32;          // entries per thread in the accumulate stage (all levels)
+constexpr uint32_t REDUCE_L = 16;  // children per thread in the bucket-reduce tree
+constexpr uint32_t C_MIN = 2, C_MAX = 22;
+
+struct ReduceLevel {
+    uint32_t n_in, l, log_len;
+};
+
+struct MsmPlan {
+    size_t n = 0;        // points per vector
+    uint32_t g = 0;      // vectors in the group
+    uint32_t bits = 254; // significant scalar bits
+    uint32_t c = 0, W = 0, B = 0;
+    size_t m = 0;                    // g*W*n pairs
+    size_t total_buckets = 0;        // g*W*B
+    uint32_t sort_bits = 0;          // radix-sort key bits (covers the sentinel)
+    std::vector<size_t> acc_entries; // entries per accumulate level (level 1 first)
+    std::vector<ReduceLevel> red;    // bucket-reduce tree levels
+
+    // field multiplications this plan performs (for the roofline's "actual" figure): 10 per mixed add, 14 per full add
+    double field_mults() const {
+        double pairs = (double)m;
+        double mul = 10.0 * pairs;
+        for (size_t k = 1; k < acc_entries.size(); ++k) mul += 14.0 * 0.5 * (double)acc_entries[k];
+        double nb = (double)total_buckets;
+        mul += 14.0 * 2.0 * nb;
+        for (size_t k = 1; k < red.size(); ++k) mul += 14.0 * 3.0 * (double)g * W * red[k].n_in;
+        mul += (double)g * W * (9.0 * c + 28.0);
+        return mul;
+    }
+};
+
+inline uint32_t windows_for(uint32_t bits, uint32_t c) { return (bits + 1 + c - 1) / c; }
+
+// cost model in field multiplications: per window n mixed adds (+ the partial-merge overhead) and ~31 per bucket
+inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_buckets) {
+    uint32_t best = C_MIN;
+    double best_cost = 1e300;
+    for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
+        uint32_t W = windows_for(bits, c);
+        double B = (double)(1u << (c - 1));
+        if ((double)g * W * B > (double)max_buckets) break;
+        if ((double)g * W * B >= 2147483647.0) break;
+        double cost = (double)W * (11.0 * (double)n + 31.0 * B) + 400.0 * (double)(c > 4 ? (c - 1 + 3) / 4 : 1);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0) {
+    MsmPlan p;
+    p.n = n;
+    p.g = g;
+    p.bits = bits == 0 || bits > 254 ? 254 : bits;
+    p.c = force_c ? force_c : choose_window(n, g, p.bits, max_buckets);
+    p.W = windows_for(p.bits, p.c);
+    p.B = 1u << (p.c - 1);
+    p.m = (size_t)g * p.W * n;
+    p.total_buckets = (size_t)g * p.W * p.B;
+    uint32_t sb = 1;
+    while (((uint64_t)1 << sb) <= (uint64_t)p.total_buckets) ++sb;  // 2^sb > max key, so the sentinel sorts last
+    p.sort_bits = sb > 32 ? 32 : sb;
+    size_t e = p.m;
+    p.acc_entries.push_back(e);
+    while (e > (size_t)ACC_L) {
+        size_t t = (e + ACC_L - 1) / ACC_L;
+        e = 2 * t;
+        p.acc_entries.push_back(e);
+    }
+    uint32_t n_in = p.B, log_len = 0;
+    while (n_in > 1) {
+        uint32_t l = n_in < REDUCE_L ? n_in : REDUCE_L;
+        p.red.push_back({n_in, l, log_len});
+        uint32_t ll = 0;
+        while ((1u << ll) < l) ++ll;
+        log_len += ll;
+        n_in /= l;
+    }
+    if (p.red.empty()) p.red.push_back({1, 1, 0});  // B == 1: one pass that just copies S and sets W = 0
+    return p;
+}
+
+}  // namespace cozk

@@ -1,0 +1,125 @@
+/* cozk_msm.h - C ABI of the B200-native BN254 G1 multi-scalar-multiplication engine.
+ *
+ * Drop-in boundary for the party-local MSM of ChainSafe/co-zkvms (all paths relative to the reference tree):
+ *
+ *   replaces  jolt_core::msm::VariableBaseMSM::msm_field_elements(bases, gpu_bases=None, scalars, max_num_bits, use_icicle)
+ *               call sites  co-jolt/src/poly/commitment/pst13.rs:286-292 (PST13::commit)
+ *                           co-jolt/src/poly/commitment/pst13.rs:461-467 (open(), one MSM per variable)
+ *             jolt_core::msm::VariableBaseMSM::batch_msm(bases, gpu_bases=None, polys)
+ *               call site   co-jolt/src/poly/commitment/pst13.rs:319-323 (PST13::batch_commit)
+ *             ark_ec::VariableBaseMSM::msm_bigint(bases, bigints)
+ *               call sites  co-noir-spartan/co-spartan/src/worker.rs:804 (distributed_open)
+ *                           inside MultilinearPC::commit, co-noir-spartan/co-spartan/src/worker.rs:585
+ *   and the device-resident SRS the reference sketches but leaves commented out
+ *               co-jolt/src/poly/commitment/pst13.rs:52-61, :235, :249 (`gpu_g1`).
+ *
+ * Data formats are the reference's in-memory images (arkworks 0.5):
+ *   field element   4 x u64 little-endian limbs, Montgomery form (R = 2^256)            32 B
+ *   base point      x || y, Fq Montgomery; `stride_bytes` lets a caller pass ark_ec's 72-byte
+ *                   Affine{x, y, infinity} array without repacking; infinity flags optional
+ *   scalar          Fr Montgomery (COZK_MONT: what msm_field_elements receives) or canonical
+ *                   integer (COZK_CANON: the BigInt<4> msm_bigint receives); element i of a vector
+ *                   lives at ptr + i*stride_bytes: 32 = dense Vec<Fr>, 64 = the `a` half of
+ *                   Rep3PrimeFieldShare{a, b} (mpc-types/src/protocols/rep3/arithmetic/types.rs:22-29),
+ *                   which removes copy_share_a (co-jolt/src/poly/dense_mlpoly.rs:102-110)
+ *   result          72 B: x[32] || y[32] (Fq Montgomery, AFFINE, fully reduced) || infinity u8 || pad[7]
+ *                   - affine because every caller normalises at once (pst13.rs:294, :328, :469; worker.rs:804),
+ *                   so the bytes are independent of window size, scheduling and GPU count.
+ *
+ * Conventions: the caller owns every host buffer and the engine keeps no host pointer after a call returns
+ * (the SRS is copied at registration).  Every function returns COZK_OK or a negative error code and never
+ * unwinds; cozk_last_error() gives the message for the calling thread.  All entry points are thread-safe; calls
+ * on one device serialise.  There is no CPU fallback: without a usable CUDA device cozk_init fails.
+ */
+#ifndef COZK_MSM_H
+#define COZK_MSM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COZK_OK 0
+#define COZK_ERR_INVALID_ARG (-1)    /* null pointer, k == 0, bad stride / form */
+#define COZK_ERR_KEY_LENGTH (-2)     /* base_offset + n exceeds the registered SRS: the reference's
+                                        ProofVerifyError::KeyLengthError / panic!("Key length error"), pst13.rs:311-316 */
+#define COZK_ERR_CUDA (-3)           /* a CUDA call failed; see cozk_last_error */
+#define COZK_ERR_NO_DEVICE (-4)      /* no usable CUDA device */
+#define COZK_ERR_BAD_HANDLE (-5)     /* unknown SRS handle */
+
+#define COZK_MONT 0
+#define COZK_CANON 1
+
+typedef struct cozk_ctx cozk_ctx; /* owns devices, streams, scratch */
+typedef uint64_t cozk_srs;        /* handle to device-resident bases */
+
+/* device_ids == NULL: use devices 0 .. n_devices-1 (n_devices == 0: device 0 only). */
+int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices);
+void cozk_destroy(cozk_ctx* ctx);
+int cozk_device_count(const cozk_ctx* ctx);
+
+/* Upload n bases (replicated on every device of the context).  bases: point i at bases + i*stride_bytes,
+ * stride_bytes >= 64.  infinity: n flags (non-zero = point at infinity, contributes nothing) or NULL. */
+int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out);
+int cozk_srs_release(cozk_ctx* ctx, cozk_srs srs);
+int cozk_srs_len(cozk_ctx* ctx, cozk_srs srs, size_t* out_n);
+
+/* k MSMs over the same base range [base_offset, base_offset + n) of one SRS:
+ *     out[j] = sum_i scalars[j][i] * bases[base_offset + i]          j = 0 .. k-1
+ * scalars: k host pointers.  max_num_bits mirrors the reference's `max_num_bits: Option<usize>`: 0 = unknown
+ * (254); a smaller value promises every scalar < 2^max_num_bits and lets the engine drop high windows.
+ * n == 0 gives k identities.  With several devices, k >= n_devices shards by vector, otherwise by point range
+ * (the reference's split_ck + combine_comm scheme: co-noir-spartan/co-spartan/src/utils.rs:38-83,
+ * snarks-core/src/poly/commitment.rs:56-63); partial sums are added on the host. */
+int cozk_msm_batch(cozk_ctx* ctx, cozk_srs srs, size_t base_offset, size_t n, const void* const* scalars, size_t k,
+                   size_t stride_bytes, int form, unsigned max_num_bits, void* out);
+
+/* Same, with the k scalar vectors already in device memory of device `device_index` of the context
+ * (kernel-only timing; device-resident shares kept across commit and open). */
+int cozk_msm_batch_device(cozk_ctx* ctx, int device_index, cozk_srs srs, size_t base_offset, size_t n,
+                          const void* const* d_scalars, size_t k, size_t stride_bytes, int form, unsigned max_num_bits,
+                          void* out);
+
+/* Host-side group helpers the shims need (sum of chunk commitments = combine_comm; sum of party shares =
+ * PST13::combine_commitment_shares, pst13.rs:72-108).  Points are 72-byte results. */
+int cozk_g1_sum(const void* points72, size_t count, void* out72);
+
+/* Tuning / introspection. */
+int cozk_set_option(cozk_ctx* ctx, const char* name, long value); /* "window" (0 = auto), "group_pairs" */
+/* Timings (ms, CUDA events) of the stages of the last cozk_msm_batch* call on device 0 of the context:
+ * [0] h2d  [1] decompose  [2] sort  [3] accumulate  [4] bucket-reduce  [5] finish+d2h  [6] total  [7] kernels launched
+ * [8] window bits c  [9] windows W  [10] field mults (plan)  [11] pairs m */
+int cozk_last_stats(cozk_ctx* ctx, double* out12);
+const char* cozk_last_error(void);
+
+/* ---- plain device-memory helpers so that callers (and the tests / bench) need no other CUDA binding */
+int cozk_dev_alloc(cozk_ctx* ctx, int device_index, size_t bytes, void** out);
+int cozk_dev_free(cozk_ctx* ctx, int device_index, void* ptr);
+int cozk_dev_upload(cozk_ctx* ctx, int device_index, void* dst, const void* src, size_t bytes);
+int cozk_dev_download(cozk_ctx* ctx, int device_index, void* dst, const void* src, size_t bytes);
+int cozk_host_alloc_pinned(size_t bytes, void** out);
+int cozk_host_free_pinned(void* ptr);
+int cozk_dev_flush_l2(cozk_ctx* ctx, int device_index); /* writes a 256 MiB scratch buffer */
+
+/* ---- synthetic inputs, generated on the device (bit-identical to oracle/bn254.c) */
+int cozk_testgen_bases(cozk_ctx* ctx, int device_index, uint64_t seed, size_t start, size_t n, void* d_out64);
+int cozk_testgen_scalars(cozk_ctx* ctx, int device_index, int dist, uint64_t seed, size_t start, size_t n, size_t total_n,
+                         int form, void* d_out, size_t stride_bytes);
+/* register bases that already live on device `device_index` (copied device-to-device; other devices get a peer copy) */
+int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_bases64, size_t n, cozk_srs* out);
+
+/* ---- element-wise kernels exposed for parity tests and roofline microbenchmarks (device pointers) */
+/* op: 0 fq_mul 1 fq_add 2 fq_sub 3 fq_sqr 4 fq_inv 5 fr_from_mont; arrays of n 32-byte elements */
+int cozk_test_field_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
+/* op: 0 xyzz_add 1 xyzz_madd 2 xyzz_dbl on arrays of n 72-byte wire points */
+int cozk_test_g1_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
+/* which: 0 = independent IMAD.WIDE chains (pipe peak), 1 = dependent fq_mul chains, 2 = fq_sqr chains, 3 = xyzz_madd chain.
+ * Runs `iters` operations per thread on blocks x threads; returns elapsed ms and the operation count. */
+int cozk_microbench(cozk_ctx* ctx, int device_index, int which, int blocks, int threads, int iters, double* out_ms,
+                    double* out_ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

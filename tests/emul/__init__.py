@@ -1,0 +1,64 @@
+"""Host emulation of the kernel thread bodies (test harness only; see emul.cpp)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "..", "..", "co-zkvms_b200", "csrc")
+LIB = os.path.join(HERE, "_build", "libemul.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [os.path.join(HERE, "emul.cpp")] + [os.path.join(CSRC, f) for f in
+                                                   ("field.cuh", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp")]
+        if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+            os.makedirs(os.path.dirname(LIB), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB,
+                                   os.path.join(HERE, "emul.cpp")])
+        L = ctypes.CDLL(LIB)
+        vp, sz, u32, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+        L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp]
+        L.emul_field_op.argtypes = [ci, vp, vp, vp, sz]
+        L.emul_g1_op.argtypes = [ci, vp, vp, vp, sz]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None):
+    """scalars: (g*n, stride) uint8 laid out vector after vector."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+    n = bases.shape[0]
+    out = np.zeros((g, 72), np.uint8)
+    st = np.zeros(4, np.uint32)
+    inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
+    rc = lib().emul_msm(_p(bases), n, _p(scalars), n * stride, stride, form, g, bits, c, _p(inf), _p(out), _p(st))
+    assert rc == 0, rc
+    return out, st
+
+
+def field_op(op, a, b=None):
+    ops = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "fr_from_mont": 5}
+    a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+    bb = np.ascontiguousarray(b, dtype=np.uint8) if b is not None else None
+    out = np.zeros_like(a)
+    lib().emul_field_op(ops[op], _p(a), _p(bb), _p(out), a.shape[0])
+    return out
+
+
+def g1_op(op, a, b=None):
+    ops = {"add": 0, "madd": 1, "dbl": 2}
+    a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 72)
+    bb = np.ascontiguousarray(b, dtype=np.uint8) if b is not None else None
+    out = np.zeros_like(a)
+    lib().emul_g1_op(ops[op], _p(a), _p(bb), _p(out), a.shape[0])
+    return out

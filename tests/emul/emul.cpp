@@ -1,0 +1,123 @@
+// Host emulation of the MSM pipeline - TEST HARNESS, never part of the shipped library.
+//
+// Compiles the very thread bodies the CUDA kernels wrap (co-zkvms_b200/csrc/msm_kernels.cuh) with g++ and runs each
+// "launch" as a sequential loop over thread indices, with std::sort standing in for the device radix sort.  It lets
+// the no-GPU test tier check the pipeline logic (digit recoding, segmented accumulation with open/closed runs,
+// the (S, W) reduce tree, Horner, exceptional group-law cases) against the oracle before any GPU time is spent.
+// Field arithmetic here is the portable host body of field.cuh; the PTX carry chains are checked separately by
+// tools/gen_field_ptx.py's interpreter and, on the GPU, by tests/test_gpu_field.py.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../co-zkvms_b200/csrc/msm_kernels.cuh"
+#include "../../co-zkvms_b200/csrc/msm_plan.hpp"
+
+using namespace cozk;
+
+extern "C" {
+
+// bases: n x 64 B; scalars: g vectors, vector v at scalars + v*vector_stride, element i at + i*stride; out: g x 72 B
+int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vector_stride, size_t stride, int form,
+             uint32_t g, uint32_t max_bits, uint32_t force_c, const uint8_t* infinity, uint8_t* out, uint32_t* stats) {
+    if (n == 0) {
+        for (uint32_t v = 0; v < g; ++v) {
+            memset(out + 72 * v, 0, 72);
+            out[72 * v + 64] = 1;
+        }
+        return 0;
+    }
+    MsmPlan P = make_plan(n, g, max_bits, (size_t)1 << 24, force_c);
+    std::vector<uint32_t> keys(P.m), vals(P.m);
+    DecomposeArgs D{scalars, nullptr, vector_stride, stride, form, n, g, P.c, P.W, infinity, keys.data(), vals.data()};
+    for (size_t t = 0; t < (size_t)g * n; ++t) decompose_body(t, D);
+
+    std::vector<size_t> order(P.m);
+    std::iota(order.begin(), order.end(), (size_t)0);
+    uint32_t mask = P.sort_bits >= 32 ? 0xFFFFFFFFu : ((1u << P.sort_bits) - 1u);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return (keys[a] & mask) < (keys[b] & mask); });
+    std::vector<uint32_t> sk(P.m), sv(P.m);
+    for (size_t i = 0; i < P.m; ++i) {
+        sk[i] = keys[order[i]];
+        sv[i] = vals[order[i]];
+    }
+
+    std::vector<xyzz> buckets(P.total_buckets);
+    memset(buckets.data(), 0, buckets.size() * sizeof(xyzz));
+    std::vector<uint32_t> pk_in, pk_out;
+    std::vector<xyzz> pp_in, pp_out;
+    for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
+        size_t m = P.acc_entries[lvl];
+        size_t T = (m + ACC_L - 1) / ACC_L;
+        pk_out.assign(2 * T, 0xDEADBEEFu);
+        pp_out.assign(2 * T, xyzz_identity());
+        AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), reinterpret_cast<const affine*>(bases),
+                         pp_in.data(), buckets.data(), pk_out.data(), pp_out.data()};
+        for (size_t t = 0; t < T; ++t) {
+            if (lvl == 0) accumulate_body<ACC_L, true>(t, A); else accumulate_body<ACC_L, false>(t, A);
+        }
+        pk_in.swap(pk_out);
+        pp_in.swap(pp_out);
+    }
+    // the top level must not leave any open run
+    for (uint32_t k : pk_in) if (k != KEY_SENTINEL) return 2;
+
+    std::vector<xyzz> s_in, w_in, s_out, w_out;
+    size_t windows = (size_t)g * P.W;
+    for (size_t lvl = 0; lvl < P.red.size(); ++lvl) {
+        const ReduceLevel& R = P.red[lvl];
+        size_t threads = windows * (R.n_in / R.l);
+        s_out.assign(threads, xyzz_identity());
+        w_out.assign(threads, xyzz_identity());
+        ReduceArgs A{lvl == 0 ? buckets.data() : s_in.data(), lvl == 0 ? nullptr : w_in.data(), s_out.data(), w_out.data(),
+                     R.n_in, R.l, R.log_len, threads};
+        for (size_t t = 0; t < threads; ++t) reduce_body(t, A);
+        s_in.swap(s_out);
+        w_in.swap(w_out);
+    }
+    FinishArgs F{s_in.data(), w_in.data(), g, P.W, P.c, out, nullptr};
+    for (size_t v = 0; v < g; ++v) finish_body(v, F);
+    if (stats) {
+        stats[0] = P.c;
+        stats[1] = P.W;
+        stats[2] = (uint32_t)P.acc_entries.size();
+        stats[3] = (uint32_t)P.red.size();
+    }
+    return 0;
+}
+
+// element-wise checks of the portable field / curve bodies (op: 0 fq_mul 1 fq_add 2 fq_sub 3 fq_sqr 4 fq_inv 5 fr_from_mont)
+void emul_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        fq x = load_fq(a + 32 * i), y = b ? load_fq(b + 32 * i) : fq_zero(), r;
+        switch (op) {
+            case 0: r = fq_mul(x, y); break;
+            case 1: r = fq_add(x, y); break;
+            case 2: r = fq_sub(x, y); break;
+            case 3: r = fq_sqr(x); break;
+            case 4: r = fq_inv(x); break;
+            default: r = fr_from_mont(x); break;
+        }
+        store_fq(out + 32 * i, r);
+    }
+}
+
+// op: 0 xyzz_add 1 xyzz_madd (b finite) 2 xyzz_dbl; inputs/outputs are 72-byte wire points
+void emul_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        xyzz pa = xyzz_from_wire(a + 72 * i), r;
+        if (op == 0) {
+            r = xyzz_add(pa, xyzz_from_wire(b + 72 * i));
+        } else if (op == 1) {
+            affine q;
+            q.x = load_fq(b + 72 * i);
+            q.y = load_fq(b + 72 * i + 32);
+            r = xyzz_madd(pa, q);
+        } else {
+            r = xyzz_dbl(pa);
+        }
+        xyzz_to_wire(r, out + 72 * i);
+    }
+}
+}

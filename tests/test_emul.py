@@ -1,0 +1,101 @@
+"""CPU tier: the kernel thread bodies (co-zkvms_b200/csrc/msm_kernels.cuh), compiled for the host and run as
+sequential loops, against the oracle.  This checks the pipeline LOGIC without a GPU; the PTX field arithmetic is
+checked by test_field_ptx.py and, on the device, by the gpu tier."""
+import numpy as np
+import pytest
+
+from oracle import pyref
+from tests import emul
+from tests import helpers as H
+
+
+def test_field_bodies(orc):
+    rng = np.random.default_rng(1)
+    vals = [0, 1, H.P - 1, H.P - 2, (1 << 253)] + [int.from_bytes(rng.bytes(32), "little") % H.P for _ in range(40)]
+    a = np.stack([H.le32(v) for v in vals])
+    b = np.roll(a, 3, axis=0)
+    for op in ("mul", "add", "sub"):
+        want = orc.field_op("fq", op, a.view(np.uint64), b.view(np.uint64)).view(np.uint8)
+        assert (emul.field_op(op, a, b) == want).all(), op
+    assert (emul.field_op("sqr", a) == orc.field_op("fq", "sqr", a.view(np.uint64)).view(np.uint8)).all()
+    assert (emul.field_op("inv", a) == orc.field_op("fq", "inv", a.view(np.uint64)).view(np.uint8)).all()
+    ar = np.stack([H.le32(v % H.R) for v in vals])
+    assert (emul.field_op("fr_from_mont", ar) == orc.field_op("fr", "from_mont", ar.view(np.uint64)).view(np.uint8)).all()
+
+
+def test_group_law_bodies(orc):
+    g = H.golden()
+    for case in g["adds"]:
+        a, b = H.point_wire(H.parse_point(case["a"])), H.point_wire(H.parse_point(case["b"]))
+        want = H.point_wire(H.parse_point(case["sum"]))
+        assert (emul.g1_op("add", a, b)[0] == want).all(), case
+        if case["b"] is not None:
+            assert (emul.g1_op("madd", a, b)[0] == want).all(), case
+    pts = np.zeros((16, 72), np.uint8)
+    pts[:, :64] = orc.gen_bases(2, 16)
+    assert (emul.g1_op("dbl", pts) == orc.g1_op("dbl", pts)).all()
+    assert (emul.g1_op("add", pts, np.roll(pts, 1, axis=0)) == orc.g1_op("add", pts, np.roll(pts, 1, axis=0))).all()
+
+
+def test_msm_golden():
+    for case in H.golden()["msm"]:
+        if case["n"] > 300:
+            continue
+        pts, sc = H.golden_msm_inputs(case)
+        want = H.point_wire(H.parse_point(case["result"]))
+        for form in (0, 1):
+            got, _ = emul.msm(H.bases_wire(pts), H.scalars_wire(sc, form), form=form)
+            assert (got[0] == want).all(), (case["n"], case["dist"], form)
+
+
+@pytest.mark.parametrize("dist", pyref.DISTS)
+def test_msm_all_windows(orc, dist):
+    """Every window size exercises a different level structure of the accumulate / reduce trees."""
+    n = 200
+    bases = orc.gen_bases(1, n)
+    sc = orc.gen_scalars(dist, 5, n)
+    want = orc.msm(bases, sc)
+    for c in (2, 3, 4, 6, 9, 12, 14):
+        got, st = emul.msm(bases, sc, c=c)
+        assert (got[0] == want).all(), (dist, c, st)
+
+
+def test_msm_batch_strides_bits_infinity(orc):
+    n, g = 150, 3
+    bases = orc.gen_bases(7, n)
+    vecs = [orc.gen_scalars(d, 20 + i, n, stride=64) for i, d in enumerate(("uniform", "const", "wminus"))]
+    got, _ = emul.msm(bases, np.concatenate(vecs), g=g, stride=64)
+    for j in range(g):
+        assert (got[j] == orc.msm(bases, vecs[j])).all(), j
+    # max_num_bits hint drops high windows; result unchanged
+    small = orc.gen_scalars("small16", 3, n)
+    got, st = emul.msm(bases, small, bits=16)
+    assert st[1] <= 3 and (got[0] == orc.msm(bases, small)).all()
+    # points at infinity contribute nothing
+    inf = np.zeros(n, np.uint8)
+    inf[::3] = 1
+    u = orc.gen_scalars("uniform", 4, n)
+    masked = u.copy()
+    masked[::3] = 0
+    got, _ = emul.msm(bases, u, infinity=inf)
+    assert (got[0] == orc.msm(bases, masked)).all()
+
+
+def test_degenerate_many_levels(orc):
+    """All points in one bucket per window (co-jolt party 0/1 shares): the open-run / partial-merge path, 3 levels deep."""
+    n = 1100
+    bases = orc.gen_bases(1, n)
+    sc = orc.gen_scalars("const", 8, n)
+    got, st = emul.msm(bases, sc, c=8)
+    assert st[2] >= 4
+    assert (got[0] == orc.msm(bases, sc)).all()
+    # duplicated bases with equal scalars force P + P inside a bucket
+    dup = bases.copy()
+    dup[1::2] = dup[0::2]
+    got, _ = emul.msm(dup, sc, c=5)
+    assert (got[0] == orc.msm(dup, sc)).all()
+    # P + (-P): bucket collapses to the identity
+    neg = np.tile(H.le32(H.R - 1), (n, 1))
+    neg[0::2] = H.le32(1)
+    got, _ = emul.msm(dup, neg, form=1, c=4)
+    assert got[0][64] == 1

@@ -1,0 +1,191 @@
+"""GPU tier: the MSM through the C ABI (cozk_msm_batch*), bit-exact against the oracle and the golden fixtures."""
+import numpy as np
+import pytest
+
+from oracle import pyref
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_vectors(ctx):
+    for case in H.golden()["msm"]:
+        pts, sc = H.golden_msm_inputs(case)
+        want = H.point_wire(H.parse_point(case["result"]))
+        srs = ctx.srs_register(H.bases_wire(pts))
+        for form in (0, 1):
+            got = ctx.msm_batch(srs, H.scalars_wire(sc, form), form=form)
+            assert (got[0] == want).all(), (case["n"], case["dist"], form)
+        ctx.srs_release(srs)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 33, 100, 1000, 4097, 1 << 14])
+def test_sizes_and_distributions(ctx, orc, n):
+    bases = orc.gen_bases(1, n)
+    srs = ctx.srs_register(bases)
+    for dist in pyref.DISTS:
+        sc = orc.gen_scalars(dist, 3, n)
+        got = ctx.msm_batch(srs, sc)
+        assert (got[0] == orc.msm(bases, sc)).all(), (n, dist)
+    ctx.srs_release(srs)
+
+
+def test_every_window_size(ctx, orc):
+    n = 3000
+    bases = orc.gen_bases(2, n)
+    srs = ctx.srs_register(bases)
+    u = orc.gen_scalars("uniform", 4, n)
+    c0 = orc.gen_scalars("const", 4, n)
+    wu, wc = orc.msm(bases, u), orc.msm(bases, c0)
+    try:
+        for c in range(2, 23):
+            ctx.set_option("window", c)
+            assert (ctx.msm_batch(srs, u)[0] == wu).all(), c
+            assert (ctx.msm_batch(srs, c0)[0] == wc).all(), c
+    finally:
+        ctx.set_option("window", 0)
+    ctx.srs_release(srs)
+
+
+def test_2pow18_all_party_distributions(ctx, orc):
+    """The three co-jolt party share shapes and the co-spartan one at 2^18."""
+    n = 1 << 18
+    bases = orc.gen_bases(1, n)
+    srs = ctx.srs_register(bases)
+    for dist in ("uniform", "const", "wminus", "dup"):
+        sc = orc.gen_scalars(dist, 2, n)
+        assert (ctx.msm_batch(srs, sc)[0] == orc.msm(bases, sc)).all(), dist
+    ctx.srs_release(srs)
+
+
+def test_batch_strides_forms_prefix_offset(ctx, orc):
+    n_srs, n = 5000, 2048
+    bases = orc.gen_bases(3, n_srs)
+    srs = ctx.srs_register(bases)
+    assert ctx.srs_len(srs) == n_srs
+    # a batch of vectors against the prefix bases[..n] (pst13.rs:319-323), Rep3 AoS stride
+    dists = ["uniform", "const", "wminus", "dup", "zero_half", "small16", "uniform"]
+    vecs = [orc.gen_scalars(d, 30 + i, n, stride=64) for i, d in enumerate(dists)]
+    got = ctx.msm_batch(srs, vecs, n=n, stride=64)
+    for j, v in enumerate(vecs):
+        assert (got[j] == orc.msm(bases[:n], v)).all(), j
+    # canonical form, a split_ck-style slice in the middle of the SRS (co-spartan/src/utils.rs:38-83)
+    can = orc.gen_scalars("uniform", 8, n, form=1)
+    got = ctx.msm_batch(srs, can, n=n, base_offset=1500, form=1)
+    assert (got[0] == orc.msm(bases[1500:1500 + n], can, form=1)).all()
+    # small groups: force several vector groups through the double-buffered staging
+    ctx.set_option("group_pairs", 40000)
+    try:
+        got = ctx.msm_batch(srs, vecs, n=n, stride=64)
+        for j, v in enumerate(vecs):
+            assert (got[j] == orc.msm(bases[:n], v)).all(), j
+    finally:
+        ctx.set_option("group_pairs", 1 << 27)
+    # max_num_bits hint (public u16 polynomials)
+    small = orc.gen_scalars("small16", 5, n)
+    assert (ctx.msm_batch(srs, small, n=n, max_num_bits=16)[0] == orc.msm(bases[:n], small)).all()
+    flags = np.zeros((n, 32), np.uint8)
+    flags[::3, 0] = 1
+    assert (ctx.msm_batch(srs, flags, n=n, form=1, max_num_bits=1)[0] == orc.msm(bases[:n], flags, form=1)).all()
+    ctx.srs_release(srs)
+
+
+def test_edge_cases_and_errors(cozk, ctx, orc):
+    n = 64
+    bases = orc.gen_bases(4, n)
+    srs = ctx.srs_register(bases)
+    sc = orc.gen_scalars("uniform", 1, n)
+    # empty input and all-zero scalars give the identity
+    assert ctx.msm_batch(srs, [sc], n=0)[0][64] == 1
+    assert ctx.msm_batch(srs, np.zeros((n, 32), np.uint8))[0][64] == 1
+    # canonical scalars >= r are integers, i.e. reduced mod r
+    big = np.full((n, 32), 0xFF, np.uint8)
+    red = np.tile(H.le32(((1 << 256) - 1) % H.R), (n, 1))
+    assert (ctx.msm_batch(srs, big, form=1)[0] == orc.msm(bases, red, form=1)).all()
+    # key length error (pst13.rs:311-316), bad handle, bad stride
+    with pytest.raises(cozk.CozkError) as e:
+        ctx.msm_batch(srs, np.zeros((n + 1, 32), np.uint8))
+    assert e.value.code == cozk.ERR_KEY_LENGTH
+    with pytest.raises(cozk.CozkError) as e:
+        ctx.msm_batch(srs, sc, n=8, base_offset=n - 4)
+    assert e.value.code == cozk.ERR_KEY_LENGTH
+    with pytest.raises(cozk.CozkError) as e:
+        ctx.msm_batch(srs + 1000, sc)
+    assert e.value.code == cozk.ERR_BAD_HANDLE
+    with pytest.raises(cozk.CozkError) as e:
+        ctx.msm_batch(srs, sc, n=4, stride=24)
+    assert e.value.code == cozk.ERR_INVALID_ARG
+    ctx.srs_release(srs)
+    # infinity flags and the 72-byte arkworks Affine stride
+    b72 = np.zeros((n, 72), np.uint8)
+    b72[:, :64] = bases
+    inf = np.zeros(n, np.uint8)
+    inf[5::9] = 1
+    srs = ctx.srs_register(b72, infinity=inf)
+    masked = sc.copy()
+    masked[5::9] = 0
+    assert (ctx.msm_batch(srs, sc)[0] == orc.msm(bases, masked)).all()
+    ctx.srs_release(srs)
+    # duplicated bases: P + P inside a bucket; opposite scalars: P + (-P)
+    dup = bases.copy()
+    dup[1::2] = dup[0::2]
+    srs = ctx.srs_register(dup)
+    c0 = orc.gen_scalars("const", 2, n)
+    assert (ctx.msm_batch(srs, c0)[0] == orc.msm(dup, c0)).all()
+    pm = np.tile(H.le32(H.R - 1), (n, 1))
+    pm[0::2] = H.le32(1)
+    assert ctx.msm_batch(srs, pm, form=1)[0][64] == 1
+    ctx.srs_release(srs)
+
+
+def test_device_resident_scalars(ctx, orc):
+    n = 1 << 15
+    dbases = ctx.testgen_bases(1, n)
+    srs = ctx.srs_register_device(dbases, n)
+    ds = [ctx.testgen_scalars(d, 6, n, stride=64) for d in ("uniform", "const")]
+    got = ctx.msm_batch_ptrs(srs, [d.ptr for d in ds], n, stride=64, device=0)
+    bases = orc.gen_bases(1, n)
+    for j, d in enumerate(("uniform", "const")):
+        assert (got[j] == orc.msm(bases, orc.gen_scalars(d, 6, n))).all(), d
+    st = ctx.last_stats()
+    assert st["launches"] >= 5 and st["pairs"] > 0
+    for d in ds:
+        d.free()
+    dbases.free()
+    ctx.srs_release(srs)
+
+
+def test_properties_at_2pow22(ctx):
+    """Size-independent checks at a size the oracle is not run at: split = sum of parts, linearity in the scalars,
+    constant vector = c * sum(P_i), all computed on the device and compared bit for bit."""
+    import importlib
+    cozk = importlib.import_module("co-zkvms_b200")
+    n = 1 << 22
+    dbases = ctx.testgen_bases(1, n)
+    srs = ctx.srs_register_device(dbases, n)
+    s = ctx.testgen_scalars("uniform", 2, n, form=1)
+    full = ctx.msm_batch_ptrs(srs, [s.ptr], n, form=1, device=0)[0]
+    # split at an odd boundary
+    cut = 1234567
+    a = ctx.msm_batch_ptrs(srs, [s.ptr], cut, form=1, device=0)[0]
+    b = ctx.msm_batch_ptrs(srs, [s.ptr + 32 * cut], n - cut, base_offset=cut, form=1, device=0)[0]
+    assert (cozk.g1_sum(np.stack([a, b])) == full).all()
+    # different window sizes give the same point
+    ctx.set_option("window", 13)
+    try:
+        assert (ctx.msm_batch_ptrs(srs, [s.ptr], n, form=1, device=0)[0] == full).all()
+    finally:
+        ctx.set_option("window", 0)
+    # constant vector: MSM(c, P) = c * MSM(1, P); check through c = 2: MSM(2) = MSM(1) + MSM(1)
+    ones = np.zeros((n, 32), np.uint8)
+    ones[:, 0] = 1
+    twos = ones.copy()
+    twos[:, 0] = 2
+    d1 = ctx.alloc(n * 32).upload(ones)
+    d2 = ctx.alloc(n * 32).upload(twos)
+    p1 = ctx.msm_batch_ptrs(srs, [d1.ptr], n, form=1, device=0, max_num_bits=2)[0]
+    p2 = ctx.msm_batch_ptrs(srs, [d2.ptr], n, form=1, device=0)[0]
+    assert (cozk.g1_sum(np.stack([p1, p1])) == p2).all()
+    for d in (s, d1, d2, dbases):
+        d.free()
+    ctx.srs_release(srs)

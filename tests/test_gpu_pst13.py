@@ -1,0 +1,105 @@
+"""GPU tier: the reference-facing commitment-scheme operations (csrc/pst13.hpp).  test_combine_commitments follows
+the reference's own test, co-jolt/src/poly/commitment/pst13.rs:476-547 (linearity of commit under
+combine_commitments); the opening is checked against a direct restatement of open() (pst13.rs:428-474) on the oracle."""
+import numpy as np
+import pytest
+
+from oracle import pyref
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _levels(orc, nv, seed=1):
+    # any fixed G1 points exercise the same arithmetic as the eq-basis SRS
+    levels, start = [], 0
+    for i in range(nv):
+        n = 1 << (nv - i)
+        levels.append(orc.gen_bases(seed, n, start=start))
+        start += n
+    return levels
+
+
+def test_combine_commitments(cozk, ctx, orc):
+    pst = cozk.pst13
+    nv = 3
+    setup = pst.PST13Setup(ctx, _levels(orc, nv))
+    n = 1 << nv
+    polys = [[pyref.scalar_uniform(40 + j, i) for i in range(n)] for j in range(3)]
+    rho = pyref.scalar_uniform(99, 0)
+    comms = pst.batch_commit(setup, [H.scalars_wire(p) for p in polys])
+    assert all(c.nv == nv for c in comms)
+    # combine_commitments(commit(p_i), rho^i) == commit(sum rho^i p_i)
+    joint = [sum(pow(rho, j, H.R) * polys[j][i] for j in range(3)) % H.R for i in range(n)]
+    joint_c = pst.commit(setup, H.scalars_wire(joint))
+    acc = None
+    for j, c in enumerate(comms):
+        acc = pyref.add(acc, pyref.mul(pow(rho, j, H.R), orc.wire_to_point(c.g_product)))
+    assert orc.wire_to_point(joint_c.g_product) == acc
+    setup.release()
+
+
+def test_batch_commit_rep3_matches_reference_semantics(cozk, ctx, orc):
+    pst = cozk.pst13
+    nv = 10
+    n = 1 << nv
+    setup = pst.PST13Setup(ctx, [orc.gen_bases(1, n)])
+    bases = orc.gen_bases(1, n)
+    # three parties' share-a arrays, built the way generate_poly_shares_rep3 does (dense_mlpoly.rs:553-588):
+    # party 0: constant c0, party 1: constant c1, party 2: w - c0 - c1;  AoS {a, b} with b = the next party's a
+    w = [pyref.limb(7, i + 2, 0) & 0xFFFFFFFF for i in range(n)]
+    a_shares = [pyref.scalars("const", 7, n), [pyref.scalar_uniform(7, 1)] * n, pyref.scalars("wminus", 7, n)]
+    assert all((a_shares[0][i] + a_shares[1][i] + a_shares[2][i]) % H.R == w[i] for i in range(n))
+    public = [pyref.limb(8, i, 0) & 0xFFFF for i in range(n)]
+    results = []
+    for party in range(3):
+        aos = np.zeros((n, 64), np.uint8)
+        aos[:, :32] = H.scalars_wire(a_shares[party])
+        aos[:, 32:] = H.scalars_wire(a_shares[(party + 1) % 3])
+        out = pst.batch_commit_rep3(setup, [aos, H.scalars_wire(public)], [True, False], commit_to_public=(party == 0),
+                                    max_num_bits=[0, 16])
+        assert (out[0].g_product == orc.msm(bases, aos)).all()       # stride-64 read of share a
+        if party == 0:
+            assert (out[1].g_product == orc.msm(bases, H.scalars_wire(public))).all()
+        else:
+            assert out[1] is None                                     # MaybeShared::Public(None)
+        results.append(out[0])
+    # the coordinator's sum of the three shares commits to the witness itself
+    combined = pst.combine_commitment_shares(results)
+    assert (combined.g_product == orc.msm(bases, H.scalars_wire(w))).all()
+    # key length error
+    with pytest.raises(cozk.CozkError) as e:
+        pst.batch_commit(setup, [np.zeros((2 * n, 32), np.uint8)])
+    assert e.value.code == cozk.ERR_KEY_LENGTH
+    setup.release()
+
+
+def _open_reference(orc, levels, evals, point):
+    """open() restated on Python ints + the oracle MSM (pst13.rs:428-474)."""
+    nv = len(point)
+    r = list(evals)
+    proofs = []
+    for i in range(nv):
+        k = nv - i
+        t = point[i]
+        half = 1 << (k - 1)
+        q = [(r[2 * b + 1] - r[2 * b]) % H.R for b in range(half)]
+        r = [(r[2 * b] * (1 - t) + r[2 * b + 1] * t) % H.R for b in range(half)]
+        scalars = [q[x >> 1] for x in range(1 << k)]
+        proofs.append(orc.msm(levels[i], H.scalars_wire(scalars)))
+    return np.stack(proofs), r[0]
+
+
+@pytest.mark.parametrize("nv,stride", [(1, 32), (4, 32), (9, 64)])
+def test_open(cozk, ctx, orc, nv, stride):
+    pst = cozk.pst13
+    levels = _levels(orc, nv, seed=5)
+    setup = pst.PST13Setup(ctx, levels)
+    n = 1 << nv
+    evals = [pyref.scalar_uniform(60, i) for i in range(n)]
+    point = [pyref.scalar_uniform(61, i) for i in range(nv)]
+    proofs, ev = pst.open(setup, H.scalars_wire(evals, stride=stride), H.scalars_wire(point), stride=stride)
+    want_proofs, want_ev = _open_reference(orc, levels, evals, point)
+    assert (proofs == want_proofs).all()
+    assert pyref.from_mont(H.to_int(ev), H.R) == want_ev
+    setup.release()

@@ -1,0 +1,62 @@
+"""CPU tier: the N>1 path's host logic (shard ranges, gloo gather of partial sums, host-side combine) with
+world_size 2 on the gloo backend.  The per-rank partial sums come from the oracle here (no GPU); on the GPU box the
+same functions carry the engine's partial sums (bench.py --gpus N)."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_ranges_partition():
+    sh = importlib.import_module("co-zkvms_b200.sharding")
+    for n in (0, 1, 7, 1 << 20, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            rs = [sh.shard_range(n, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import orc
+    cozk = importlib.import_module("co-zkvms_b200")
+    sh = importlib.import_module("co-zkvms_b200.sharding")
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n, k = 3001, 2
+    bases = orc.gen_bases(1, n)
+    vecs = [orc.gen_scalars(d, 9, n) for d in ("uniform", "const")]
+    lo, hi = sh.shard_range(n, rank, world)
+    partial = np.stack([orc.msm(bases[lo:hi], v[lo:hi], threads=2) for v in vecs])
+    allp = sh.gather_partials(partial)
+    total = sh.combine(allp, cozk.g1_sum)
+    want = np.stack([orc.msm(bases, v, threads=2) for v in vecs])
+    q.put((rank, bool((total == want).all()), allp.shape))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_and_combine():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res), res
+    assert all(r[2] == (2, 2, 72) for r in res)

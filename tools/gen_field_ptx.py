@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""Generator (and checker) for the 8x32-bit-limb Montgomery field arithmetic used by the CUDA kernels.
+
+It emits co-zkvms_b200/csrc/field_ptx.inc: one inline-PTX block per operation (mul, sqr, add, sub for
+BN254 Fq; mul for Fr), so that the carry flag never lives across two asm statements.  The same instruction
+lists can be *interpreted* here in Python (a tiny PTX subset: mul/mad/madc/add/addc/sub/subc/selp on u32
+with one carry flag), which is how the generated code is verified against big-integer arithmetic without a
+GPU (tests/test_field_ptx.py).
+
+Montgomery product, operand scanning, one limb of b per row; the running total T is kept as TWO multi-limb
+numbers so that every 32x32->64 product lands on an aligned (lo, hi) register pair and each row is a plain
+carry chain of wide multiply-adds:
+    T = EV + OD * 2^32,   EV = sum ev[k] 2^(32k),   OD = sum od[k] 2^(32k)
+    row i:  EV += sum_{j even} a_j b_i 2^(32 j)          (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32[.X])
+            OD += sum_{j odd}  a_j b_i 2^(32 (j-1))
+            m   = ev[0] * n0 mod 2^32
+            EV += sum_{j even} m p_j 2^(32 j);  OD += sum_{j odd} m p_j 2^(32 (j-1))     -> ev[0] == 0
+            T  /= 2^32:   EV' = OD,  OD' = EV >> 64,  and the stray limb ev[1] (weight 2^0) is folded into
+                          ev'[0] at the start of the next row, its carry feeding the OD' chain (weight 2^32).
+ptxas fuses each (mad.lo.cc, madc.hi.cc) pair into one IMAD.WIDE.U32 with a carry predicate, so a product costs
+8 rows x (8 + 8 + 1) = 136 integer multiply-adds.  T < 2^288 throughout (254-bit modulus), hence ev needs 9
+limbs, od 8, and no chain ever carries out of its top limb.
+"""
+import argparse
+import os
+import random
+
+P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+M32 = 0xFFFFFFFF
+
+
+def limbs32(x, n=8):
+    return [(x >> (32 * k)) & M32 for k in range(n)]
+
+
+class Prog:
+    """A straight-line PTX program over named u32 registers."""
+
+    def __init__(self):
+        self.ins = []
+        self.tmp = 0
+
+    def new(self, prefix="t"):
+        self.tmp += 1
+        return "%s%d" % (prefix, self.tmp)
+
+    def emit(self, op, dst, *src):
+        self.ins.append((op, dst) + tuple(src))
+
+    # ---- interpreter
+    def run(self, env):
+        env = dict(env)
+        cf = 0
+
+        def val(x):
+            return x if isinstance(x, int) else env[x]
+
+        for ins in self.ins:
+            op, dst, src = ins[0], ins[1], [val(s) for s in ins[2:]]
+            if op == "mul.wide":  # dst = (lo, hi)
+                prod = src[0] * src[1]
+                env[dst[0]], env[dst[1]] = prod & M32, prod >> 32
+                continue
+            if op == "mov":
+                r = src[0]
+            elif op == "mul.lo":
+                r = (src[0] * src[1]) & M32
+            elif op == "mul.hi":
+                r = (src[0] * src[1]) >> 32
+            elif op in ("mad.lo", "mad.lo.cc", "madc.lo", "madc.lo.cc", "mad.hi", "mad.hi.cc", "madc.hi", "madc.hi.cc"):
+                prod = src[0] * src[1]
+                part = (prod & M32) if ".lo" in op else (prod >> 32)
+                s = part + src[2] + (cf if op.startswith("madc") else 0)
+                r = s & M32
+                if op.endswith(".cc"):
+                    cf = s >> 32
+            elif op in ("add", "add.cc", "addc", "addc.cc"):
+                s = src[0] + src[1] + (cf if op.startswith("addc") else 0)
+                r = s & M32
+                if op.endswith(".cc"):
+                    cf = s >> 32
+            elif op in ("sub", "sub.cc", "subc", "subc.cc"):
+                s = src[0] - src[1] - (cf if op.startswith("subc") else 0)
+                r = s & M32
+                if op.endswith(".cc"):
+                    cf = 1 if s < 0 else 0
+            elif op == "selp.ne0":  # dst = (src[2] != 0) ? src[0] : src[1]
+                r = src[0] if src[2] != 0 else src[1]
+            elif op == "and":
+                r = src[0] & src[1]
+            else:
+                raise ValueError(op)
+            env[dst] = r
+        return env
+
+    # ---- PTX text
+    def ptx(self, names):
+        """names: register -> operand placeholder ('%0'...) for inputs/outputs; everything else becomes a local .reg."""
+        local = []
+        seen = set()
+        for ins in self.ins:
+            flat = []
+            for x in ins[1:]:
+                flat.extend(x if isinstance(x, tuple) else [x])
+            for x in flat:
+                if isinstance(x, str) and x not in names and x not in seen:
+                    seen.add(x)
+                    local.append(x)
+        lines = ["{"]
+        for i in range(0, len(local), 8):
+            lines.append(".reg .u32 " + ", ".join(local[i:i + 8]) + ";")
+        if any(ins[0] == "mul.wide" for ins in self.ins):
+            lines.append(".reg .u64 wd;")
+        need_pred = any(ins[0] == "selp.ne0" for ins in self.ins)
+        if need_pred:
+            lines.append(".reg .pred pq;")
+        pred_set_for = None
+
+        def o(x):
+            if isinstance(x, int):
+                return "0x%08x" % x
+            return names.get(x, x)
+
+        for ins in self.ins:
+            op, dst, src = ins[0], ins[1], ins[2:]
+            if op == "mul.wide":
+                lines.append("mul.wide.u32 wd, %s, %s;" % (o(src[0]), o(src[1])))
+                lines.append("mov.b64 {%s, %s}, wd;" % (o(dst[0]), o(dst[1])))
+            elif op == "selp.ne0":
+                if pred_set_for != src[2]:
+                    lines.append("setp.ne.u32 pq, %s, 0;" % o(src[2]))
+                    pred_set_for = src[2]
+                lines.append("selp.u32 %s, %s, %s, pq;" % (o(dst), o(src[0]), o(src[1])))
+            elif op == "mov":
+                lines.append("mov.u32 %s, %s;" % (o(dst), o(src[0])))
+            elif op == "and":
+                lines.append("and.b32 %s, %s, %s;" % (o(dst), o(src[0]), o(src[1])))
+            else:
+                lines.append("%s.u32 %s, %s;" % (op, o(dst), ", ".join(o(s) for s in src)))
+        lines.append("}")
+        return lines
+
+
+def cond_sub(pg, t, mod, out):
+    """out = t - mod if t >= mod else t   (t: 8 register names)"""
+    ml = limbs32(mod)
+    s = [pg.new("s") for _ in range(8)]
+    for k in range(8):
+        pg.emit("sub.cc" if k == 0 else "subc.cc", s[k], t[k], ml[k])
+    brw = pg.new("w")
+    pg.emit("subc", brw, 0, 0)  # 0xffffffff when t < mod
+    for k in range(8):
+        pg.emit("selp.ne0", out[k], t[k], s[k], brw)
+
+
+def gen_mul(mod, square=False):
+    """r = a*b/2^256 mod `mod`, fully reduced.  Inputs a0..a7, b0..b7 (b = a for square), outputs r0..r7."""
+    pg = Prog()
+    a = ["a%d" % k for k in range(8)]
+    b = a if square else ["b%d" % k for k in range(8)]
+    ml = limbs32(mod)
+    n0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    ev = [pg.new("e") for _ in range(9)]
+    od = [pg.new("o") for _ in range(8)]
+    stray = None
+    for i in range(8):
+        bi = b[i]
+        if i == 0:
+            for k in range(4):
+                pg.emit("mul.wide", (ev[2 * k], ev[2 * k + 1]), a[2 * k], bi)
+                pg.emit("mul.wide", (od[2 * k], od[2 * k + 1]), a[2 * k + 1], bi)
+            pg.emit("mov", ev[8], 0)
+        else:
+            # fold the stray limb (weight 2^0); its carry has weight 2^32 = od[0]
+            pg.emit("add.cc", ev[0], ev[0], stray)
+            for k in range(4):
+                pg.emit("madc.lo.cc", od[2 * k], a[2 * k + 1], bi, od[2 * k])
+                # the top pair never carries out (T < 2^288); keep .cc so that ptxas still fuses it into IMAD.WIDE
+                pg.emit("madc.hi.cc", od[2 * k + 1], a[2 * k + 1], bi, od[2 * k + 1])
+            for k in range(4):
+                pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", ev[2 * k], a[2 * k], bi, ev[2 * k])
+                pg.emit("madc.hi.cc", ev[2 * k + 1], a[2 * k], bi, ev[2 * k + 1])
+            pg.emit("addc", ev[8], ev[8], 0)
+        m = pg.new("m")
+        pg.emit("mul.lo", m, ev[0], n0)
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", ev[2 * k], m, ml[2 * k], ev[2 * k])
+            pg.emit("madc.hi.cc", ev[2 * k + 1], m, ml[2 * k], ev[2 * k + 1])
+        pg.emit("addc", ev[8], ev[8], 0)
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", od[2 * k], m, ml[2 * k + 1], od[2 * k])
+            pg.emit("madc.hi.cc", od[2 * k + 1], m, ml[2 * k + 1], od[2 * k + 1])
+        # T /= 2^32: ev[0] is zero now; ev[1] becomes the stray limb; EV' = OD; OD' = ev[2..8] ++ [0]
+        stray = ev[1]
+        new_od = ev[2:9]
+        z = pg.new("z")
+        pg.emit("mov", z, 0)
+        new_od = new_od + [z]
+        z8 = pg.new("z")
+        pg.emit("mov", z8, 0)
+        ev, od = od + [z8], new_od
+    # result = stray + EV + OD*2^32  as one 8-limb addition: (stray, od[0..6]) + ev[0..7]; od[7] and ev[8] are zero
+    lo = [stray] + od[0:7]
+    t = [pg.new("r") for _ in range(8)]
+    for k in range(8):
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), t[k], ev[k], lo[k])
+    cond_sub(pg, t, mod, ["r%d" % k for k in range(8)])
+    return pg
+
+
+def gen_add(mod):
+    pg = Prog()
+    t = [pg.new("t") for _ in range(8)]
+    for k in range(8):
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), t[k], "a%d" % k, "b%d" % k)
+    cond_sub(pg, t, mod, ["r%d" % k for k in range(8)])
+    return pg
+
+
+def gen_sub(mod):
+    pg = Prog()
+    ml = limbs32(mod)
+    t = [pg.new("t") for _ in range(8)]
+    for k in range(8):
+        pg.emit("sub.cc" if k == 0 else "subc.cc", t[k], "a%d" % k, "b%d" % k)
+    brw = pg.new("w")
+    pg.emit("subc", brw, 0, 0)
+    for k in range(8):
+        mk = pg.new("k")
+        pg.emit("and", mk, brw, ml[k])
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), "r%d" % k, t[k], mk)
+    return pg
+
+
+def run_binop(pg, x, y):
+    env = {}
+    for k in range(8):
+        env["a%d" % k] = (x >> (32 * k)) & M32
+        env["b%d" % k] = (y >> (32 * k)) & M32
+    out = pg.run(env)
+    return sum(out["r%d" % k] << (32 * k) for k in range(8))
+
+
+def self_check(trials=300, seed=1):
+    rnd = random.Random(seed)
+    Rinv = {m: pow(1 << 256, -1, m) for m in (P, R)}
+    for mod in (P, R):
+        pm, ps, pa, pb = gen_mul(mod), gen_mul(mod, True), gen_add(mod), gen_sub(mod)
+        edge = [0, 1, 2, mod - 1, mod - 2, (1 << 253), (1 << 254) % mod, M32, (1 << 224) - 1, mod >> 1]
+        vals = edge + [rnd.randrange(mod) for _ in range(trials)]
+        for i, x in enumerate(vals):
+            y = vals[(i * 7 + 3) % len(vals)]
+            assert run_binop(pm, x, y) == x * y * Rinv[mod] % mod, ("mul", hex(x), hex(y))
+            assert run_binop(ps, x, 0) == x * x * Rinv[mod] % mod, ("sqr", hex(x))
+            assert run_binop(pa, x, y) == (x + y) % mod, ("add", hex(x), hex(y))
+            assert run_binop(pb, x, y) == (x - y) % mod, ("sub", hex(x), hex(y))
+    return True
+
+
+def emit_fn(name, pg, nin):
+    names = {}
+    idx = 0
+    for k in range(8):
+        names["r%d" % k] = "%%%d" % idx
+        idx += 1
+    for k in range(8):
+        names["a%d" % k] = "%%%d" % idx
+        idx += 1
+    if nin == 2:
+        for k in range(8):
+            names["b%d" % k] = "%%%d" % idx
+            idx += 1
+    lines = pg.ptx(names)
+    body = "\n".join('        "%s\\n\\t"' % ln for ln in lines)
+    outs = ", ".join('"=r"(r[%d])' % k for k in range(8))
+    ins = ", ".join('"r"(a[%d])' % k for k in range(8))
+    if nin == 2:
+        ins += ", " + ", ".join('"r"(b[%d])' % k for k in range(8))
+    sig = "const uint32_t (&a)[8]" + (", const uint32_t (&b)[8]" if nin == 2 else "")
+    nmul = sum(1 for i in pg.ins if i[0].startswith(("mul", "mad")))
+    return ("// %d multiply(-add) PTX instructions; lo/hi pairs fuse into IMAD.WIDE.U32\n"
+            "__device__ __forceinline__ void %s(uint32_t (&r)[8], %s) {\n    asm(\n%s\n        : %s\n        : %s);\n}\n"
+            % (nmul, name, sig, body, outs, ins))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-o", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "co-zkvms_b200", "csrc", "field_ptx.inc"))
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    self_check(200 if not args.check else 2000)
+    parts = ["// GENERATED by tools/gen_field_ptx.py - do not edit.  8 x 32-bit limbs, little-endian, Montgomery R = 2^256.\n"
+             "// Every function returns a fully reduced value in [0, modulus).\n"]
+    parts.append(emit_fn("fq_mul_ptx", gen_mul(P), 2))
+    parts.append(emit_fn("fq_sqr_ptx", gen_mul(P, True), 1))
+    parts.append(emit_fn("fq_add_ptx", gen_add(P), 2))
+    parts.append(emit_fn("fq_sub_ptx", gen_sub(P), 2))
+    parts.append(emit_fn("fr_mul_ptx", gen_mul(R), 2))
+    parts.append(emit_fn("fr_add_ptx", gen_add(R), 2))
+    parts.append(emit_fn("fr_sub_ptx", gen_sub(R), 2))
+    with open(args.o, "w") as f:
+        f.write("\n".join(parts))
+    print("wrote", os.path.normpath(args.o))
+
+
+if __name__ == "__main__":
+    main()
