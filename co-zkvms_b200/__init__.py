@@ -307,7 +307,7 @@ class Context:
                     x.free()
 
     def microbench(self, which, blocks, threads, iters, device=0):
-        names = {"imad": 0, "fq_mul": 1, "fq_sqr": 2, "madd": 3}
+        names = {"imad": 0, "fq_mul": 1, "fq_sqr": 2, "madd": 3, "imad_cc": 4, "imad_lo": 5, "imad_hi": 6, "fq_mul4": 7}
         ms, ops = ctypes.c_double(), ctypes.c_double()
         _check(lib().cozk_microbench(self.handle, device, names[which], blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops)))
         return ms.value, ops.value

@@ -218,6 +218,73 @@ __global__ void __launch_bounds__(128, 4) k_bench_madd(int iters, const uint8_t*
     if (acc.X.v[0] == 0x12345u && acc.ZZ.v[7] == 0x7777u) store_xyzz(reinterpret_cast<xyzz*>(sink), acc);
 }
 
+// 4: the carry-chain form the field multiplication actually uses: rows of (mad.lo.cc, madc.hi.cc) pairs, which ptxas
+//    fuses into IMAD.WIDE.U32.X with a carry predicate in and out.  4 independent chains of 4 pairs per iteration.
+__global__ void k_bench_imad_cc(int iters, uint32_t* sink) {
+    uint32_t a0 = threadIdx.x * 2654435761u + 12345u, a1 = a0 ^ 0x55aa55aau, a2 = a0 * 3u + 1u, a3 = a0 * 7u + 5u;
+    uint32_t b = blockIdx.x * 40503u + 977u;
+    uint32_t e[4][9];
+    for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < 9; ++k) e[c][k] = a0 + 17u * k + c;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            asm volatile(
+                "mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+                "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+                "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+                "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+                "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+                "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+                "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+                "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+                "addc.u32 %8, %8, 0;\n\t"
+                : "+r"(e[c][0]), "+r"(e[c][1]), "+r"(e[c][2]), "+r"(e[c][3]), "+r"(e[c][4]), "+r"(e[c][5]), "+r"(e[c][6]),
+                  "+r"(e[c][7]), "+r"(e[c][8])
+                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b + c));
+        }
+    }
+    uint32_t s = 0;
+    for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < 9; ++k) s ^= e[c][k];
+    if (s == 0x1234567u) sink[0] = s;
+}
+// 5 / 6: 32-bit mad.lo / mad.hi, eight independent chains
+__global__ void k_bench_imad32(int hi, int iters, uint32_t* sink) {
+    uint32_t a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 977u;
+    uint32_t acc[8];
+    for (int k = 0; k < 8; ++k) acc[k] = a * (k + 3);
+    if (hi) {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b));
+        }
+    } else {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b));
+        }
+    }
+    uint32_t s = 0;
+    for (int k = 0; k < 8; ++k) s ^= acc[k];
+    if (s == 0x1234567u) sink[0] = s;
+}
+// 7: four independent field-multiplication chains per thread (more ILP than bench 1)
+__global__ void k_bench_fq4(int iters, const uint8_t* in, uint8_t* sink) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fq x0 = load_fq(in + 32 * (t & 1023)), x1 = load_fq(in + 32 * ((t + 7) & 1023));
+    fq x2 = load_fq(in + 32 * ((t + 13) & 1023)), x3 = load_fq(in + 32 * ((t + 29) & 1023));
+    fq y = load_fq(in + 32 * ((t + 3) & 1023));
+    for (int i = 0; i < iters; ++i) {
+        x0 = fq_mul(x0, y);
+        x1 = fq_mul(x1, y);
+        x2 = fq_mul(x2, y);
+        x3 = fq_mul(x3, y);
+    }
+    fq r = fq_add(fq_add(x0, x1), fq_add(x2, x3));
+    if (r.v[0] == 0x12345u && r.v[7] == 0x7777u) store_fq(sink, r);
+}
+
 static int get_device(cozk_ctx* ctx, int device_index, Device** out) {
     if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size()) {
         set_error("bad context or device index");
@@ -355,9 +422,18 @@ int cozk_microbench(cozk_ctx* ctx, int device_index, int which, int blocks, int 
         } else if (which == 1 || which == 2) {
             k_bench_fq<<<blocks, threads, 0, D->stream>>>(which, iters, buf, buf + 64 * 1024);
             ops = 2.0 * iters * (double)blocks * threads;
-        } else {
+        } else if (which == 3) {
             k_bench_madd<<<blocks, threads, 0, D->stream>>>(iters, buf, buf + 64 * 1024);
             ops = 2.0 * iters * (double)blocks * threads;
+        } else if (which == 4) {
+            k_bench_imad_cc<<<blocks, threads, 0, D->stream>>>(iters, reinterpret_cast<uint32_t*>(buf + 64 * 1024));
+            ops = 16.0 * iters * (double)blocks * threads;  // 4 chains x 4 wide multiply-adds
+        } else if (which == 5 || which == 6) {
+            k_bench_imad32<<<blocks, threads, 0, D->stream>>>(which == 6, iters, reinterpret_cast<uint32_t*>(buf + 64 * 1024));
+            ops = 8.0 * iters * (double)blocks * threads;
+        } else {
+            k_bench_fq4<<<blocks, threads, 0, D->stream>>>(iters, buf, buf + 64 * 1024);
+            ops = 4.0 * iters * (double)blocks * threads;
         }
         COZK_CUDA(cudaGetLastError());
         COZK_CUDA(cudaEventRecord(e1, D->stream));

@@ -60,6 +60,8 @@ struct Device {
     cudaEvent_t ev[8] = {};
     cudaEvent_t copy_done[2] = {};
     double stats[12] = {};
+    std::vector<xyzz> host_sums;  // per-window sums brought back for the host-side finish
+    bool finish_on_host = false;
     ~Device();
 };
 

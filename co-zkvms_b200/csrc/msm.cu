@@ -7,6 +7,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -38,8 +39,14 @@ template <int L, bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<L, LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
-__global__ void __launch_bounds__(128, 3) k_reduce(ReduceArgs A) {
-    reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+__global__ void __launch_bounds__(128, 3) k_group(GroupArgs A) {
+    group_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+__global__ void __launch_bounds__(128, 3) k_bitsum(BitsumArgs A) {
+    bitsum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+__global__ void __launch_bounds__(128, 3) k_plainsum(PlainSumArgs A) {
+    plainsum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
 __global__ void __launch_bounds__(32) k_finish(FinishArgs A) {
     finish_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
@@ -108,35 +115,49 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     }
     COZK_CUDA(cudaEventRecord(D.ev[4], st));
 
-    // 4 bucket reduce tree
+    // 4 bucket reduce: group running sums, then NS plain sums per window
     size_t windows = (size_t)P.g * P.W;
-    for (size_t lvl = 0; lvl < P.red.size(); ++lvl) {
-        const ReduceLevel& R = P.red[lvl];
-        size_t threads = windows * (R.n_in / R.l);
-        DevBuf& s_out = D.rs[lvl & 1];
-        DevBuf& w_out = D.rw[lvl & 1];
-        if ((rc = s_out.ensure(threads * sizeof(xyzz)))) return rc;
-        if ((rc = w_out.ensure(threads * sizeof(xyzz)))) return rc;
-        ReduceArgs A{lvl == 0 ? D.buckets.as<xyzz>() : D.rs[(lvl - 1) & 1].as<xyzz>(),
-                     lvl == 0 ? nullptr : D.rw[(lvl - 1) & 1].as<xyzz>(),
-                     s_out.as<xyzz>(),
-                     w_out.as<xyzz>(),
-                     R.n_in,
-                     R.l,
-                     R.log_len,
-                     threads};
-        k_reduce<<<grid_for(threads, 128), 128, 0, st>>>(A);
+    size_t groups = windows * P.G;
+    if ((rc = D.rs[0].ensure(groups * sizeof(xyzz)))) return rc;
+    if ((rc = D.rw[0].ensure(groups * sizeof(xyzz)))) return rc;
+    GroupArgs GA{D.buckets.as<xyzz>(), D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), P.group_l, groups};
+    k_group<<<grid_for(groups, 64), 64, 0, st>>>(GA);
+    *launches += 1;
+    COZK_CUDA(cudaGetLastError());
+    uint32_t chunks = P.G / P.bitsum_f;
+    size_t bthreads = windows * P.NS * chunks;
+    if ((rc = D.rs[1].ensure(bthreads * sizeof(xyzz)))) return rc;
+    if ((rc = D.rw[1].ensure((bthreads / 2 + 1) * sizeof(xyzz)))) return rc;
+    BitsumArgs BA{D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.G, P.NS, P.bitsum_f, chunks, bthreads};
+    k_bitsum<<<grid_for(bthreads, 64), 64, 0, st>>>(BA);
+    *launches += 1;
+    COZK_CUDA(cudaGetLastError());
+    xyzz* cur = D.rs[1].as<xyzz>();
+    xyzz* nxt = D.rw[1].as<xyzz>();
+    for (const SumLevel& L : P.sums) {
+        size_t threads = windows * P.NS * (L.n_in / L.f);
+        PlainSumArgs SA{cur, nxt, L.f, threads};
+        k_plainsum<<<grid_for(threads, 64), 64, 0, st>>>(SA);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
+        std::swap(cur, nxt);
     }
     COZK_CUDA(cudaEventRecord(D.ev[5], st));
 
-    // 5 finish
-    size_t last = (P.red.size() - 1) & 1;
-    FinishArgs F{D.rs[last].as<xyzz>(), D.rw[last].as<xyzz>(), P.g, P.W, P.c, D.out.as<uint8_t>(), nullptr};
-    k_finish<<<grid_for(P.g, 32), 32, 0, st>>>(F);
-    *launches += 1;
-    COZK_CUDA(cudaGetLastError());
+    // 5 finish: bit-position Horner + inversion.  Few vectors: on the host (a CPU core runs this serial chain an order
+    // of magnitude faster than one GPU thread); large batches: one GPU thread per vector, all in parallel.
+    size_t nsums = windows * P.NS;
+    if (P.g <= HOST_FINISH_MAX) {
+        D.host_sums.resize(nsums);
+        COZK_CUDA(cudaMemcpyAsync(D.host_sums.data(), cur, nsums * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+        D.finish_on_host = true;
+    } else {
+        FinishArgs F{cur, P.g, P.W, P.c, P.NS, P.log_l, D.out.as<uint8_t>()};
+        k_finish<<<grid_for(P.g, 32), 32, 0, st>>>(F);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+        D.finish_on_host = false;
+    }
     return COZK_OK;
 }
 
@@ -170,7 +191,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     size_t passes = (n + MAX_POINTS_PER_PASS - 1) / MAX_POINTS_PER_PASS;
     std::vector<uint8_t> partial(passes > 1 ? passes * k * 72 : 0);
     COZK_CUDA(cudaEventRecord(D.ev[0], D.stream));
-    double plan_mults = 0, plan_pairs = 0;
+    double plan_mults = 0, plan_pairs = 0, host_finish_ms = 0;
     uint32_t last_c = 0, last_W = 0;
 
     for (size_t pass = 0; pass < passes; ++pass) {
@@ -231,16 +252,25 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                            host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096, vstride, stride, form,
                            &launches);
             if (rc) return rc;
-            COZK_CUDA(cudaMemcpyAsync(pass_out + v0 * 72, D.out.p, g * 72, cudaMemcpyDeviceToHost, D.stream));
+            if (!D.finish_on_host)
+                COZK_CUDA(cudaMemcpyAsync(pass_out + v0 * 72, D.out.p, g * 72, cudaMemcpyDeviceToHost, D.stream));
             COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
             COZK_CUDA(cudaStreamSynchronize(D.stream));
             add_stage_times(D);
+            if (D.finish_on_host) {
+                auto h0 = std::chrono::steady_clock::now();
+                FinishArgs F{D.host_sums.data(), P.g, P.W, P.c, P.NS, P.log_l, pass_out + v0 * 72};
+                for (size_t v = 0; v < g; ++v) finish_body(v, F);
+                host_finish_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+            }
         }
     }
     COZK_CUDA(cudaEventRecord(D.ev[7], D.stream));
     COZK_CUDA(cudaStreamSynchronize(D.stream));
     float total_ms = 0;
     cudaEventElapsedTime(&total_ms, D.ev[0], D.ev[7]);
+    // ev[7] is recorded after the host-side finish, so total_ms (ev[0] -> ev[7]) already contains it
+    D.stats[5] += host_finish_ms;
     D.stats[6] = total_ms;
     D.stats[0] = std::max(0.0, total_ms - (D.stats[1] + D.stats[2] + D.stats[3] + D.stats[4] + D.stats[5]));
     D.stats[7] = launches;

@@ -12,9 +12,10 @@
 //                   cross a chunk edge are written as partial sums and summed by the same body one level up, until
 //                   one thread sees a whole level.  Work per thread is constant for ANY scalar distribution - the
 //                   co-jolt party shares are constant vectors (one bucket per window holds all n points).
-//   4 bucket reduce sum_b (b+1) * bucket[b] per window by a radix-l tree of (S, W) pairs:
-//                   S = sum of children, W = sum_s W_s + len * sum_s s * S_s   (len = indices a child spans).
-//   5 finish        Horner over the windows (c doublings each), one inversion, affine wire point.
+//   4 bucket reduce sum_b (b+1) * bucket[b] per window: group running sums over l buckets, then J + 2 plain "bit sums"
+//                   per window (no serial pass over the window, no doublings).
+//   5 finish        one Horner pass over the 254 bit positions, one inversion, affine wire point; on the host for
+//                   a few vectors, a GPU thread per vector for large batches.
 #pragma once
 #include <cstddef>
 
@@ -198,52 +199,100 @@ COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
 }
 
 // ------------------------------------------------------------------------------------------------ 4 bucket reduce
-struct ReduceArgs {
-    const xyzz* s_in;   // [windows * n_in]
-    const xyzz* w_in;   // same shape, or null at the first level (all W = 0)
-    xyzz* s_out;        // [windows * n_in / l]
+// Window value  V = sum_b (b+1) * bucket[b],  b in [0, B).  Two steps, both shallow (a single GPU thread needs about
+// 7 us per group addition, so depth - not work - is what this stage costs):
+//   4a group   threads own l consecutive buckets: S_g = sum, W_g = sum_s s * bucket[g*l + s]      (2l additions deep)
+//   4b bit sums  with b = g*l + s:  sum_b b * bucket[b] = sum_g W_g + l * sum_g g * S_g  and
+//              sum_g g * S_g = sum_j 2^j * T_j,  T_j = sum of the S_g whose index g has bit j set.
+//              So per window NS = J + 2 PLAIN sums (J = log2(B/l)): id 0 = sum W_g, id 1 = sum S_g, id 2+j = T_j,
+//              each a radix-f tree of additions; no doublings, no serial running sum across the window.
+//   V = sums[0] + sums[1] + l * sum_j 2^j * sums[2+j]  is folded into the bit-position Horner of stage 5.
+struct GroupArgs {
+    const xyzz* buckets;  // [windows * B]
+    xyzz* s_out;          // [windows * B / l]
     xyzz* w_out;
-    uint32_t n_in;      // children per window
-    uint32_t l;         // children per thread (power of two dividing n_in)
-    uint32_t log_len;   // log2 of the number of bucket indices one child spans
-    size_t threads;     // windows * n_in / l
+    uint32_t l;           // buckets per thread (power of two dividing B)
+    size_t threads;       // windows * B / l
 };
 
-COZK_HD void reduce_body(size_t tid, const ReduceArgs& A) {
+COZK_HD void group_body(size_t tid, const GroupArgs& A) {
     if (tid >= A.threads) return;
-    size_t base = tid * A.l;  // windows are contiguous and n_in % l == 0, so groups never straddle windows
+    size_t base = tid * A.l;  // windows are contiguous and B % l == 0, so groups never straddle windows
     xyzz run = xyzz_identity(), acc = xyzz_identity();
     for (uint32_t s = A.l - 1; s >= 1; --s) {
-        run = xyzz_add(run, load_xyzz(&A.s_in[base + s]));
-        acc = xyzz_add(acc, run);  // ends as sum_s s * S_s
+        run = xyzz_add(run, load_xyzz(&A.buckets[base + s]));
+        acc = xyzz_add(acc, run);  // ends as sum_s s * bucket[base + s]
     }
-    run = xyzz_add(run, load_xyzz(&A.s_in[base]));
-    for (uint32_t k = 0; k < A.log_len; ++k) acc = xyzz_dbl(acc);
-    if (A.w_in) {
-        for (uint32_t s = 0; s < A.l; ++s) acc = xyzz_add(acc, load_xyzz(&A.w_in[base + s]));
-    }
+    run = xyzz_add(run, load_xyzz(&A.buckets[base]));
     store_xyzz(&A.s_out[tid], run);
     store_xyzz(&A.w_out[tid], acc);
 }
 
+struct BitsumArgs {
+    const xyzz* s;     // [windows * G]
+    const xyzz* w;     // [windows * G]
+    xyzz* out;         // [windows * NS * chunks]
+    uint32_t G;        // groups per window
+    uint32_t NS;       // sums per window = log2(G) + 2
+    uint32_t f;        // groups per thread (power of two dividing G)
+    uint32_t chunks;   // G / f
+    size_t threads;    // windows * NS * chunks
+};
+
+// thread tid = (window * NS + id) * chunks + q  sums the f groups of chunk q that belong to sum `id`
+COZK_HD void bitsum_body(size_t tid, const BitsumArgs& A) {
+    if (tid >= A.threads) return;
+    uint32_t q = (uint32_t)(tid % A.chunks);
+    size_t rest = tid / A.chunks;
+    uint32_t id = (uint32_t)(rest % A.NS);
+    size_t win = rest / A.NS;
+    const xyzz* src = (id == 0 ? A.w : A.s) + win * A.G;
+    xyzz acc = xyzz_identity();
+    for (uint32_t e = 0; e < A.f; ++e) {
+        uint32_t g = q * A.f + e;
+        if (id >= 2 && !((g >> (id - 2)) & 1u)) continue;
+        acc = xyzz_add(acc, load_xyzz(&src[g]));
+    }
+    store_xyzz(&A.out[tid], acc);
+}
+
+struct PlainSumArgs {
+    const xyzz* in;   // contiguous arrays whose length is a multiple of f
+    xyzz* out;
+    uint32_t f;
+    size_t threads;
+};
+
+COZK_HD void plainsum_body(size_t tid, const PlainSumArgs& A) {
+    if (tid >= A.threads) return;
+    xyzz acc = load_xyzz(&A.in[tid * A.f]);
+    for (uint32_t e = 1; e < A.f; ++e) acc = xyzz_add(acc, load_xyzz(&A.in[tid * A.f + e]));
+    store_xyzz(&A.out[tid], acc);
+}
+
 // ------------------------------------------------------------------------------------------------ 5 finish
+// result = sum_w 2^(c*w) * V_w = sum over bit positions: position c*w carries sums[w][0] + sums[w][1], position
+// c*w + a + j (a = log2 l, j < J, a + J = c - 1) carries sums[w][2+j].  One Horner pass from the top bit down,
+// then one inversion.  The same body runs as a GPU thread per vector (large batches) or on the host (few vectors:
+// a CPU core runs this serial chain ~15x faster than a GPU thread).
 struct FinishArgs {
-    const xyzz* s;    // [g*W] per-window sum of buckets
-    const xyzz* w;    // [g*W] per-window sum_b b * bucket[b]   (0-based b; the bucket value is b+1)
-    uint32_t g, W, c;
-    uint8_t* out;     // [g] 72-byte wire points (device memory)
-    xyzz* out_xyzz;   // [g] optional un-normalised sums (for the multi-GPU combine), or null
+    const xyzz* sums;  // [g * W * NS]
+    uint32_t g, W, c, NS, log_l;
+    uint8_t* out;      // [g] 72-byte wire points
 };
 
 COZK_HD void finish_body(size_t v, const FinishArgs& A) {
     if (v >= A.g) return;
     xyzz acc = xyzz_identity();
+    const uint32_t J = A.NS - 2;
     for (uint32_t w = A.W; w-- > 0;) {
-        for (uint32_t k = 0; k < A.c; ++k) acc = xyzz_dbl(acc);
-        size_t o = (size_t)v * A.W + w;
-        acc = xyzz_add(acc, xyzz_add(load_xyzz(&A.s[o]), load_xyzz(&A.w[o])));
+        const xyzz* sw = A.sums + ((size_t)v * A.W + w) * A.NS;
+        for (uint32_t pos = A.c; pos-- > 0;) {
+            if (!xyzz_is_identity(acc)) acc = xyzz_dbl(acc);
+            if (pos >= A.log_l && pos - A.log_l < J) acc = xyzz_add(acc, load_xyzz(&sw[2 + pos - A.log_l]));
+            if (pos == 0) acc = xyzz_add(acc, xyzz_add(load_xyzz(&sw[0]), load_xyzz(&sw[1])));
+        }
     }
-    if (A.out_xyzz) store_xyzz(&A.out_xyzz[v], acc);
     xyzz_to_wire(acc, A.out + 72 * v);
 }
 

@@ -8,11 +8,13 @@
 namespace cozk {
 
 constexpr int ACC_L = 32;          // entries per thread in the accumulate stage (all levels)
-constexpr uint32_t REDUCE_L = 16;  // children per thread in the bucket-reduce tree
+constexpr uint32_t GROUP_L = 8;    // buckets per thread in the group step of the bucket reduce
+constexpr uint32_t SUM_F = 4;      // fan-in of the plain-sum trees of the bucket reduce
+constexpr uint32_t HOST_FINISH_MAX = 4;  // up to this many vectors the final Horner + inversion run on the host
 constexpr uint32_t C_MIN = 2, C_MAX = 22;
 
-struct ReduceLevel {
-    uint32_t n_in, l, log_len;
+struct SumLevel {
+    uint32_t n_in, f;  // per (window, sum id): n_in entries reduced f-fold
 };
 
 struct MsmPlan {
@@ -24,7 +26,10 @@ struct MsmPlan {
     size_t total_buckets = 0;        // g*W*B
     uint32_t sort_bits = 0;          // radix-sort key bits (covers the sentinel)
     std::vector<size_t> acc_entries; // entries per accumulate level (level 1 first)
-    std::vector<ReduceLevel> red;    // bucket-reduce tree levels
+    uint32_t group_l = 1, log_l = 0; // buckets per group, log2
+    uint32_t G = 1, NS = 2;          // groups per window, plain sums per window (log2 G + 2)
+    uint32_t bitsum_f = 1;           // fan-in of the first (masked) sum level
+    std::vector<SumLevel> sums;      // plain-sum levels after the masked one
 
     // field multiplications this plan performs (for the roofline's "actual" figure): 10 per mixed add, 14 per full add
     double field_mults() const {
@@ -32,9 +37,9 @@ struct MsmPlan {
         double mul = 10.0 * pairs;
         for (size_t k = 1; k < acc_entries.size(); ++k) mul += 14.0 * 0.5 * (double)acc_entries[k];
         double nb = (double)total_buckets;
-        mul += 14.0 * 2.0 * nb;
-        for (size_t k = 1; k < red.size(); ++k) mul += 14.0 * 3.0 * (double)g * W * red[k].n_in;
-        mul += (double)g * W * (9.0 * c + 28.0);
+        mul += 14.0 * 2.0 * nb;                                   // group step
+        mul += 14.0 * (double)g * W * G * (1.0 + NS / 2.0);       // masked sums + the trees above them
+        mul += (double)g * W * (9.0 * c + 14.0 * NS);             // bit-position Horner
         return mul;
     }
 };
@@ -79,16 +84,20 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
         e = 2 * t;
         p.acc_entries.push_back(e);
     }
-    uint32_t n_in = p.B, log_len = 0;
+    p.group_l = p.B < GROUP_L ? p.B : GROUP_L;
+    p.log_l = 0;
+    while ((1u << p.log_l) < p.group_l) ++p.log_l;
+    p.G = p.B / p.group_l;
+    uint32_t J = 0;
+    while ((1u << J) < p.G) ++J;
+    p.NS = J + 2;
+    p.bitsum_f = p.G < SUM_F ? p.G : SUM_F;
+    uint32_t n_in = p.G / p.bitsum_f;
     while (n_in > 1) {
-        uint32_t l = n_in < REDUCE_L ? n_in : REDUCE_L;
-        p.red.push_back({n_in, l, log_len});
-        uint32_t ll = 0;
-        while ((1u << ll) < l) ++ll;
-        log_len += ll;
-        n_in /= l;
+        uint32_t f = n_in < SUM_F ? n_in : SUM_F;
+        p.sums.push_back({n_in, f});
+        n_in /= f;
     }
-    if (p.red.empty()) p.red.push_back({1, 1, 0});  // B == 1: one pass that just copies S and sets W = 0
     return p;
 }
 

@@ -114,7 +114,8 @@ int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_base
 int cozk_test_field_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
 /* op: 0 xyzz_add 1 xyzz_madd 2 xyzz_dbl on arrays of n 72-byte wire points */
 int cozk_test_g1_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
-/* which: 0 = independent IMAD.WIDE chains (pipe peak), 1 = dependent fq_mul chains, 2 = fq_sqr chains, 3 = xyzz_madd chain.
+/* which: 0 = independent IMAD.WIDE chains (pipe peak), 1 = dependent fq_mul chains, 2 = fq_sqr chains, 3 = xyzz_madd chain,
+ * 4 = IMAD.WIDE carry chains (mad.lo.cc/madc.hi.cc rows), 5 = mad.lo.u32, 6 = mad.hi.u32, 7 = four fq_mul chains per thread.
  * Runs `iters` operations per thread on blocks x threads; returns elapsed ms and the operation count. */
 int cozk_microbench(cozk_ctx* ctx, int device_index, int which, int blocks, int threads, int iters, double* out_ms,
                     double* out_ops);

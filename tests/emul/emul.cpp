@@ -63,26 +63,28 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     // the top level must not leave any open run
     for (uint32_t k : pk_in) if (k != KEY_SENTINEL) return 2;
 
-    std::vector<xyzz> s_in, w_in, s_out, w_out;
     size_t windows = (size_t)g * P.W;
-    for (size_t lvl = 0; lvl < P.red.size(); ++lvl) {
-        const ReduceLevel& R = P.red[lvl];
-        size_t threads = windows * (R.n_in / R.l);
-        s_out.assign(threads, xyzz_identity());
-        w_out.assign(threads, xyzz_identity());
-        ReduceArgs A{lvl == 0 ? buckets.data() : s_in.data(), lvl == 0 ? nullptr : w_in.data(), s_out.data(), w_out.data(),
-                     R.n_in, R.l, R.log_len, threads};
-        for (size_t t = 0; t < threads; ++t) reduce_body(t, A);
-        s_in.swap(s_out);
-        w_in.swap(w_out);
+    std::vector<xyzz> gs(windows * P.G), gw(windows * P.G);
+    GroupArgs GA{buckets.data(), gs.data(), gw.data(), P.group_l, windows * P.G};
+    for (size_t t = 0; t < GA.threads; ++t) group_body(t, GA);
+    uint32_t chunks = P.G / P.bitsum_f;
+    std::vector<xyzz> cur(windows * P.NS * chunks), nxt;
+    BitsumArgs BA{gs.data(), gw.data(), cur.data(), P.G, P.NS, P.bitsum_f, chunks, windows * P.NS * chunks};
+    for (size_t t = 0; t < BA.threads; ++t) bitsum_body(t, BA);
+    for (const SumLevel& L : P.sums) {
+        size_t threads = windows * P.NS * (L.n_in / L.f);
+        nxt.assign(threads, xyzz_identity());
+        PlainSumArgs SA{cur.data(), nxt.data(), L.f, threads};
+        for (size_t t = 0; t < threads; ++t) plainsum_body(t, SA);
+        cur.swap(nxt);
     }
-    FinishArgs F{s_in.data(), w_in.data(), g, P.W, P.c, out, nullptr};
+    FinishArgs F{cur.data(), g, P.W, P.c, P.NS, P.log_l, out};
     for (size_t v = 0; v < g; ++v) finish_body(v, F);
     if (stats) {
         stats[0] = P.c;
         stats[1] = P.W;
         stats[2] = (uint32_t)P.acc_entries.size();
-        stats[3] = (uint32_t)P.red.size();
+        stats[3] = (uint32_t)P.sums.size();
     }
     return 0;
 }

@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""Size x distribution sweep of the single-GPU MSM (device-resident scalars), with stage breakdown.
+   python tools/sweep.py [--sizes 16,18,20,22,24] [--dists uniform,const,wminus] [--steps 3] [--batch 1]"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+cozk = importlib.import_module("co-zkvms_b200")
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--sizes", default="16,18,20,22,24")
+ap.add_argument("--dists", default="uniform,const,wminus")
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--window", type=int, default=0)
+ap.add_argument("--stride", type=int, default=32)
+args = ap.parse_args()
+
+ctx = cozk.Context()
+if args.window:
+    ctx.set_option("window", args.window)
+sizes = [int(x) for x in args.sizes.split(",")]
+nmax = 1 << max(sizes)
+dbases = ctx.testgen_bases(1, nmax)
+srs = ctx.srs_register_device(dbases, nmax)
+dbases.free()
+rows = []
+for dist in args.dists.split(","):
+    ds = [ctx.testgen_scalars(dist, 2 + j, nmax, stride=args.stride) for j in range(args.batch)]
+    for lg in sizes:
+        n = 1 << lg
+        out = np.zeros((args.batch, 72), np.uint8)
+        for _ in range(2):
+            ctx.msm_batch_ptrs(srs, [d.ptr for d in ds], n, stride=args.stride, device=0, out=out)
+        acc = {}
+        for _ in range(args.steps):
+            ctx.flush_l2()
+            ctx.msm_batch_ptrs(srs, [d.ptr for d in ds], n, stride=args.stride, device=0, out=out)
+            st = ctx.last_stats()
+            for k, v in st.items():
+                acc[k] = acc.get(k, 0.0) + v
+        st = {k: v / args.steps for k, v in acc.items()}
+        row = {"dist": dist, "log2n": lg, "batch": args.batch, "ms": st["total_ms"],
+               "Mpts_s": args.batch * n / st["total_ms"] / 1e3, "c": int(st["window"]), "W": int(st["windows"]),
+               "stages": {k: round(st[k], 3) for k in ("decompose_ms", "sort_ms", "accumulate_ms", "reduce_ms", "finish_ms", "h2d_ms")},
+               "x": bytes(out[0][:6]).hex()}
+        rows.append(row)
+        print("%-8s 2^%-2d k=%-3d c=%-2d W=%-2d %9.3f ms %8.1f Mpts/s  dec %.2f sort %.2f acc %.2f red %.2f fin %.2f other %.2f" % (
+            dist, lg, args.batch, row["c"], row["W"], row["ms"], row["Mpts_s"], st["decompose_ms"], st["sort_ms"],
+            st["accumulate_ms"], st["reduce_ms"], st["finish_ms"], st["h2d_ms"]), flush=True)
+    for d in ds:
+        d.free()
+print(json.dumps(rows))
