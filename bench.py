@@ -148,12 +148,16 @@ def main():
     pinned = cozk.PinnedBuffer(n * 32)
     pinned.array[:] = dscal.download()
 
-    # self-measured integer-multiply pipe peak (IMAD.WIDE.U32 lane-ops / s), 8 independent chains per thread
+    # self-measured integer-multiply pipe peak: the rate at which the chip retires 32x32->64-bit multiply-accumulates.
+    # Two estimates, the larger is the denominator: (a) carry-chained IMAD.WIDE.U32.X rows with loop-carried multipliers,
+    # (b) the field multiplication itself (136 such products each).  32-bit IMAD runs at twice that rate but a product
+    # needs two of them; IMAD.WIDE without carry (+ IADD3 pair) is slower (profiles/r1_microbench.md).
     sm = 148
-    ms, ops = ctx.microbench("imad", sm * 8, 256, 4096)
-    imad_peak = ops / (ms * 1e-3)
+    ms, ops = ctx.microbench("imad_cc", sm * 8, 256, 2048)
+    imad_cc_rate = ops / (ms * 1e-3)
     ms_f, ops_f = ctx.microbench("fq_mul", sm * 8, 256, 512)
     fqmul_rate = ops_f / (ms_f * 1e-3)
+    imad_peak = max(imad_cc_rate, fqmul_rate * LIMB_PRODUCTS_PER_MULT)
     ms_m, ops_m = ctx.microbench("madd", sm * 16, 128, 256)
     madd_rate = ops_m / (ms_m * 1e-3)
 
@@ -223,8 +227,10 @@ def main():
                 "roofline": {"bound": "imad", "kernel": "k_accumulate (bucket accumulation, all levels)",
                              "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "G limb-products/s (IMAD.WIDE.U32 lane-ops)",
                              "frac": achieved / imad_peak, "traffic": None,
-                             "peak_source": "self-measured in this run (8 independent mad.wide.u32 chains/thread); "
-                                            "MEASURED_PEAKS.json has no integer figure",
+                             "peak_source": "self-measured in this run: max(carry-chained IMAD.WIDE.U32.X microbenchmark, "
+                                            "fq_mul microbenchmark x 136); MEASURED_PEAKS.json has no integer figure; "
+                                            "nominal 148 SM x 32 lanes/clk x 1.965 GHz = 9309 G/s",
+                             "imad_cc_microbench_G_per_s": imad_cc_rate / 1e9,
                              "convention": "160 field mults/point x 136 limb products (SURVEY.md 8(d)); = 43,520 IMAD lo/hi slots",
                              "kernel_ms": acc_ms,
                              "pipeline_frac": limb_products / (ms_per_step * 1e-3) / imad_peak,

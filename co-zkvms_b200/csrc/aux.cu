@@ -165,16 +165,18 @@ __global__ void k_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out
 }
 
 // ------------------------------------------------------------------------------------------------ microbenchmarks
-// 0: eight independent chains of 64-bit multiply-accumulates per thread: the integer-multiply pipe at full ILP
+// 0: eight chains of 32 x 32 + 64 -> 64 multiply-accumulates per thread.  Each multiplicand is the low word of ANOTHER
+//    chain's accumulator, so no product is loop-invariant (ptxas otherwise hoists the multiply and the loop measures
+//    IADD3).  ptxas lowers mad.wide.u32 with a live addend to IMAD.WIDE.U32 R,a,b,RZ + a 3-input IADD3 / IADD3.X pair.
 __global__ void k_bench_imad(int iters, uint32_t* sink) {
     uint32_t a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 977u;
     uint64_t acc[8];
-    for (int k = 0; k < 8; ++k) acc[k] = (uint64_t)k * 0x9E3779B97F4A7C15ULL + a;
+    for (int k = 0; k < 8; ++k) acc[k] = (uint64_t)k * 0x9E3779B97F4A7C15ULL + a + b;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            // mad.wide.u32: 32 x 32 + 64 -> 64, compiles to one IMAD.WIDE.U32
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+            uint32_t mul = (uint32_t)acc[(k + 3) & 7];
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(mul), "r"(b));
         }
     }
     uint64_t s = 0;
@@ -219,7 +221,9 @@ __global__ void __launch_bounds__(128, 4) k_bench_madd(int iters, const uint8_t*
 }
 
 // 4: the carry-chain form the field multiplication actually uses: rows of (mad.lo.cc, madc.hi.cc) pairs, which ptxas
-//    fuses into IMAD.WIDE.U32.X with a carry predicate in and out.  4 independent chains of 4 pairs per iteration.
+//    fuses into IMAD.WIDE.U32.X with a carry predicate in and out.  4 chains of 4 pairs per iteration; the multiplier
+//    of each chain is a word of a neighbouring chain, so nothing is loop-invariant.  This is the roofline denominator:
+//    the highest rate at which the chip retires 32 x 32 -> 64-bit multiply-accumulates.
 __global__ void k_bench_imad_cc(int iters, uint32_t* sink) {
     uint32_t a0 = threadIdx.x * 2654435761u + 12345u, a1 = a0 ^ 0x55aa55aau, a2 = a0 * 3u + 1u, a3 = a0 * 7u + 5u;
     uint32_t b = blockIdx.x * 40503u + 977u;
@@ -241,7 +245,7 @@ __global__ void k_bench_imad_cc(int iters, uint32_t* sink) {
                 "addc.u32 %8, %8, 0;\n\t"
                 : "+r"(e[c][0]), "+r"(e[c][1]), "+r"(e[c][2]), "+r"(e[c][3]), "+r"(e[c][4]), "+r"(e[c][5]), "+r"(e[c][6]),
                   "+r"(e[c][7]), "+r"(e[c][8])
-                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b + c));
+                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(e[(c + 1) & 3][7] | 1u));
         }
     }
     uint32_t s = 0;
@@ -257,12 +261,12 @@ __global__ void k_bench_imad32(int hi, int iters, uint32_t* sink) {
     if (hi) {
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b));
+            for (int k = 0; k < 8; ++k) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(acc[(k + 3) & 7] | 0x80000001u), "r"(b));
         }
     } else {
         for (int i = 0; i < iters; ++i) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a + k), "r"(b));
+            for (int k = 0; k < 8; ++k) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(acc[(k + 3) & 7] | 1u), "r"(b));
         }
     }
     uint32_t s = 0;

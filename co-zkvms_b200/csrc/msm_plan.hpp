@@ -84,7 +84,10 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
         e = 2 * t;
         p.acc_entries.push_back(e);
     }
-    p.group_l = p.B < GROUP_L ? p.B : GROUP_L;
+    // few buckets: shallow groups (depth is what costs); millions of buckets: the stage is throughput bound and the
+    // NS masked sums per group dominate, so make groups larger
+    uint32_t gl = p.total_buckets <= ((size_t)1 << 20) ? GROUP_L : (p.total_buckets <= ((size_t)1 << 22) ? 2 * GROUP_L : 4 * GROUP_L);
+    p.group_l = p.B < gl ? p.B : gl;
     p.log_l = 0;
     while ((1u << p.log_l) < p.group_l) ++p.log_l;
     p.G = p.B / p.group_l;

@@ -47,7 +47,8 @@ def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None):
 
 
 def field_op(op, a, b=None):
-    ops = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "fr_from_mont": 5}
+    ops = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "fr_from_mont": 5,
+           "f29_mul": 10, "f29_add": 11, "f29_sub": 12, "f29_sqr": 13, "f29_inv": 14}
     a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
     bb = np.ascontiguousarray(b, dtype=np.uint8) if b is not None else None
     out = np.zeros_like(a)
@@ -56,7 +57,7 @@ def field_op(op, a, b=None):
 
 
 def g1_op(op, a, b=None):
-    ops = {"add": 0, "madd": 1, "dbl": 2}
+    ops = {"add": 0, "madd": 1, "dbl": 2, "f29_madd3": 3}
     a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 72)
     bb = np.ascontiguousarray(b, dtype=np.uint8) if b is not None else None
     out = np.zeros_like(a)

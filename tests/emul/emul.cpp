@@ -13,6 +13,7 @@
 
 #include "../../co-zkvms_b200/csrc/msm_kernels.cuh"
 #include "../../co-zkvms_b200/csrc/msm_plan.hpp"
+#include "../../experiments/radix29/curve29.cuh"
 
 using namespace cozk;
 
@@ -91,6 +92,25 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
 
 // element-wise checks of the portable field / curve bodies (op: 0 fq_mul 1 fq_add 2 fq_sub 3 fq_sqr 4 fq_inv 5 fr_from_mont)
 void emul_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    if (op >= 10) {
+        // 9 x 29-bit representation, entered and left through the arkworks wire form: 10 mul 11 add_mod 12 sub_mod 13 sqr 14 inv
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t wa[8], wb[8] = {0}, wr[8];
+            memcpy(wa, a + 32 * i, 32);
+            if (b) memcpy(wb, b + 32 * i, 32);
+            f29::fe x = f29::from_ark(wa), y = f29::from_ark(wb), r;
+            switch (op) {
+                case 10: r = f29::mul(x, y); break;
+                case 11: r = f29::add_mod(x, y); break;
+                case 12: r = f29::sub_mod(x, y); break;
+                case 13: r = f29::sqr(x); break;
+                default: r = f29::inv(x); break;
+            }
+            f29::to_ark(r, wr);
+            memcpy(out + 32 * i, wr, 32);
+        }
+        return;
+    }
     for (size_t i = 0; i < n; ++i) {
         fq x = load_fq(a + 32 * i), y = b ? load_fq(b + 32 * i) : fq_zero(), r;
         switch (op) {
@@ -107,6 +127,19 @@ void emul_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, siz
 
 // op: 0 xyzz_add 1 xyzz_madd (b finite) 2 xyzz_dbl; inputs/outputs are 72-byte wire points
 void emul_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    if (op == 3) {
+        // lazy mixed addition on the 29-bit field: ((a + b) + b) - b, which walks the lazy bounds through three calls
+        for (size_t i = 0; i < n; ++i) {
+            f29::xyzz29 acc = f29::from_wire29(a + 72 * i);
+            f29::xyzz29 q = f29::from_wire29(b + 72 * i);
+            f29::affine29 qa{q.X, q.Y}, qn{q.X, f29::sub<2>(f29::zero(), q.Y)};
+            acc = f29::madd_lazy(acc, qa);
+            acc = f29::madd_lazy(acc, qa);
+            acc = f29::madd_lazy(acc, qn);
+            f29::to_wire29(f29::normalize29(acc), out + 72 * i);
+        }
+        return;
+    }
     for (size_t i = 0; i < n; ++i) {
         xyzz pa = xyzz_from_wire(a + 72 * i), r;
         if (op == 0) {

@@ -99,3 +99,24 @@ def test_degenerate_many_levels(orc):
     neg[0::2] = H.le32(1)
     got, _ = emul.msm(dup, neg, form=1, c=4)
     assert got[0][64] == 1
+
+
+def test_radix29_experiment_is_correct(orc):
+    """experiments/radix29 (not in the product): 9 x 29-bit field and its lazy mixed addition, against the oracle."""
+    rng = np.random.default_rng(5)
+    vals = [0, 1, 2, H.P - 1, H.P - 2, 1 << 253, H.P >> 1, (1 << 29) - 1, 1 << 232]
+    vals += [int.from_bytes(rng.bytes(32), "little") % H.P for _ in range(200)]
+    a = np.stack([H.le32(v) for v in vals])
+    b = np.roll(a, 5, axis=0)
+    for op, o in (("f29_mul", "mul"), ("f29_add", "add"), ("f29_sub", "sub")):
+        assert (emul.field_op(op, a, b) == orc.field_op("fq", o, a.view(np.uint64), b.view(np.uint64)).view(np.uint8)).all(), op
+    assert (emul.field_op("f29_sqr", a) == orc.field_op("fq", "sqr", a.view(np.uint64)).view(np.uint8)).all()
+    assert (emul.field_op("f29_inv", a[:30]) == orc.field_op("fq", "inv", a[:30].view(np.uint64)).view(np.uint8)).all()
+    n = 120
+    pts = np.zeros((n, 72), np.uint8)
+    pts[:, :64] = orc.gen_bases(2, n)
+    other = np.roll(pts, 1, axis=0)
+    other[::7] = pts[::7]
+    other[3::11] = orc.g1_op("neg", pts[3::11])
+    pts[5::13] = H.point_wire(None)
+    assert (emul.g1_op("f29_madd3", pts, other) == orc.g1_op("add", pts, other)).all()
