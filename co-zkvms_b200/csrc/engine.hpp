@@ -86,5 +86,5 @@ struct cozk_ctx {
     std::map<uint64_t, cozk::SrsEntry> srs;
     uint64_t next_handle = 1;
     long opt_window = 0;             // 0 = choose per call
-    long opt_group_pairs = 1L << 27; // (key, val) pairs per vector group
+    long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
 };

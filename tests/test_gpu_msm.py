@@ -80,7 +80,7 @@ def test_batch_strides_forms_prefix_offset(ctx, orc):
         for j, v in enumerate(vecs):
             assert (got[j] == orc.msm(bases[:n], v)).all(), j
     finally:
-        ctx.set_option("group_pairs", 1 << 27)
+        ctx.set_option("group_pairs", 1 << 29)
     # max_num_bits hint (public u16 polynomials)
     small = orc.gen_scalars("small16", 5, n)
     assert (ctx.msm_batch(srs, small, n=n, max_num_bits=16)[0] == orc.msm(bases[:n], small)).all()
@@ -189,3 +189,28 @@ def test_properties_at_2pow22(ctx):
     for d in (s, d1, d2, dbases):
         d.free()
     ctx.srs_release(srs)
+
+
+def test_multi_device_context(cozk, orc):
+    """One process driving several GPUs (the Rust caller's shape): k >= devices shards by vector, otherwise by point
+    range with the partial sums added on the host (split_ck + combine_comm).  Skipped on a single-GPU box."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ndev = min(ndev, 8)
+    n = 1 << 15
+    bases = orc.gen_bases(1, n)
+    with cozk.Context(devices=list(range(ndev))) as mctx:
+        assert mctx.device_count == ndev
+        srs = mctx.srs_register(bases)
+        dists = ["uniform", "const", "wminus", "dup", "zero_half"] * 2
+        vecs = [orc.gen_scalars(d, 50 + i, n, stride=64) for i, d in enumerate(dists[: ndev + 1])]
+        got = mctx.msm_batch(srs, vecs, n=n, stride=64)            # by vector
+        for j, v in enumerate(vecs):
+            assert (got[j] == orc.msm(bases, v)).all(), j
+        one = mctx.msm_batch(srs, vecs[:1], n=n, stride=64)        # by point range
+        assert (one[0] == orc.msm(bases, vecs[0])).all()
+        odd = mctx.msm_batch(srs, vecs[:1], n=1001, base_offset=17, stride=64)
+        assert (odd[0] == orc.msm(bases[17:1018], vecs[0][:1001])).all()
+        mctx.srs_release(srs)

@@ -86,8 +86,10 @@ def main():
             bits = [0] * N_SHARED + PUBLIC_BITS[:n_pub]
             form_canon_pub = 1  # public coefficient polynomials are plain integers
             times = {}
-            # warm-up on a small batch (allocations, module load)
-            pst.batch_commit_rep3(setup, [shared[: 1 << 12]] * 2, [True, True], commit_to_public=False)
+            # untimed warm-up with the real shapes: the engine's scratch buffers grow to their final size here
+            pst.batch_commit_rep3(setup, polys[:N_SHARED], flags[:N_SHARED], commit_to_public=False)
+            if n_pub:
+                pst.batch_commit(setup, polys[N_SHARED:], stride=32, form=form_canon_pub, max_num_bits=bits[N_SHARED:])
 
             t0 = time.perf_counter()
             out = pst.batch_commit_rep3(setup, polys[:N_SHARED], flags[:N_SHARED], commit_to_public=False)

@@ -19,6 +19,8 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--window", type=int, default=0)
 ap.add_argument("--stride", type=int, default=32)
+ap.add_argument("--bits", type=int, default=0)
+ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
 
 ctx = cozk.Context()
@@ -32,15 +34,24 @@ dbases.free()
 rows = []
 for dist in args.dists.split(","):
     ds = [ctx.testgen_scalars(dist, 2 + j, nmax, stride=args.stride) for j in range(args.batch)]
+    if args.host:
+        pins = []
+        for d in ds:
+            pb = cozk.PinnedBuffer(nmax * args.stride)
+            pb.array[:] = d.download()
+            pins.append(pb)
     for lg in sizes:
         n = 1 << lg
         out = np.zeros((args.batch, 72), np.uint8)
+        ptrs = [pb.ptr for pb in pins] if args.host else [d.ptr for d in ds]
+        dev = None if args.host else 0
+        form = 1 if args.bits else 0
         for _ in range(2):
-            ctx.msm_batch_ptrs(srs, [d.ptr for d in ds], n, stride=args.stride, device=0, out=out)
+            ctx.msm_batch_ptrs(srs, ptrs, n, stride=args.stride, device=dev, out=out, max_num_bits=args.bits, form=form)
         acc = {}
         for _ in range(args.steps):
             ctx.flush_l2()
-            ctx.msm_batch_ptrs(srs, [d.ptr for d in ds], n, stride=args.stride, device=0, out=out)
+            ctx.msm_batch_ptrs(srs, ptrs, n, stride=args.stride, device=dev, out=out, max_num_bits=args.bits, form=form)
             st = ctx.last_stats()
             for k, v in st.items():
                 acc[k] = acc.get(k, 0.0) + v
