@@ -67,8 +67,10 @@ struct Device {
 
 struct SrsEntry {
     size_t n = 0;
-    std::vector<affine*> d_bases;    // per device
+    std::vector<affine*> d_bases;    // per device: table_W rows of n points, row w = 2^(table_c*w) * bases (row 0 = bases)
     std::vector<uint8_t*> d_inf;     // per device, may be null
+    uint32_t table_c = 0;            // window size the table rows were built for; 0 = no table
+    uint32_t table_W = 1;            // rows
 };
 
 }  // namespace cozk
@@ -87,4 +89,5 @@ struct cozk_ctx {
     uint64_t next_handle = 1;
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
+    long opt_table_max_bytes = 16L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table; 0 disables tables
 };

@@ -52,12 +52,17 @@ __global__ void __launch_bounds__(32) k_finish(FinishArgs A) {
     finish_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
 
+__global__ void __launch_bounds__(128) k_build_table(TableArgs A) {
+    table_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+
 static inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------------ one group on one device
 // Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
 static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
-                     const uint8_t* const* d_vec_ptrs, size_t vector_stride, size_t stride, int form, double* launches) {
+                     const uint8_t* const* d_vec_ptrs, size_t vector_stride, size_t stride, int form, size_t table_stride,
+                     size_t val_offset, double* launches) {
     cudaStream_t st = D.stream;
     int rc;
     if ((rc = D.keys_a.ensure(P.m * 4))) return rc;
@@ -70,7 +75,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     COZK_CUDA(cudaEventRecord(D.ev[1], st));
     // 1 decompose
     DecomposeArgs DA{d_scalars, d_vec_ptrs, vector_stride, stride, form, P.n, P.g, P.c, P.W, d_inf,
-                     D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>()};
+                     D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>(), P.Wb, table_stride, val_offset};
     k_decompose<<<grid_for((size_t)P.g * P.n, 256), 256, 0, st>>>(DA);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
@@ -116,7 +121,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     COZK_CUDA(cudaEventRecord(D.ev[4], st));
 
     // 4 bucket reduce: group running sums, then NS plain sums per window
-    size_t windows = (size_t)P.g * P.W;
+    size_t windows = (size_t)P.g * P.Wb;
     size_t groups = windows * P.G;
     if ((rc = D.rs[0].ensure(groups * sizeof(xyzz)))) return rc;
     if ((rc = D.rw[0].ensure(groups * sizeof(xyzz)))) return rc;
@@ -152,7 +157,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         COZK_CUDA(cudaMemcpyAsync(D.host_sums.data(), cur, nsums * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
         D.finish_on_host = true;
     } else {
-        FinishArgs F{cur, P.g, P.W, P.c, P.NS, P.log_l, D.out.as<uint8_t>()};
+        FinishArgs F{cur, P.g, P.Wb, P.c, P.NS, P.log_l, D.out.as<uint8_t>()};
         k_finish<<<grid_for(P.g, 32), 32, 0, st>>>(F);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
@@ -197,12 +202,22 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     for (size_t pass = 0; pass < passes; ++pass) {
         size_t lo = pass * MAX_POINTS_PER_PASS;
         size_t pn = std::min(MAX_POINTS_PER_PASS, n - lo);
-        const affine* d_bases = S.d_bases[dev_index] + offset + lo;
         const uint8_t* d_inf = S.d_inf[dev_index] ? S.d_inf[dev_index] + offset + lo : nullptr;
         uint8_t* pass_out = passes > 1 ? partial.data() + pass * k * 72 : out;
 
+        // With a precomputed table (2^(c*w) * P rows built at registration) all windows share one bucket set; use it
+        // when the cost model says so (a short prefix of a long SRS is cheaper with its own, smaller window).
+        uint32_t table_c = 0;
+        if (S.table_c && !ctx->opt_window) {
+            MsmPlan with_table = make_plan(pn, 1, bits, max_buckets, 0, S.table_c);
+            MsmPlan without = make_plan(pn, 1, bits, max_buckets, 0, 0);
+            if (with_table.W <= S.table_W && with_table.model_cost() <= without.model_cost()) table_c = S.table_c;
+        }
+        const affine* d_bases = table_c ? S.d_bases[dev_index] : S.d_bases[dev_index] + offset + lo;
+        const size_t table_stride = table_c ? S.n : 0, val_offset = table_c ? offset + lo : 0;
+
         // vectors per group: bounded by the pair budget
-        MsmPlan probe = make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window);
+        MsmPlan probe = make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, table_c);
         size_t per_vec = probe.m;
         size_t gmax = std::max<size_t>(1, (size_t)ctx->opt_group_pairs / std::max<size_t>(per_vec, 1));
         gmax = std::min<size_t>(gmax, 4096);
@@ -238,7 +253,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         for (size_t gi = 0; gi < ngroups; ++gi) {
             size_t v0 = gi * gmax, g = std::min(gmax, k - v0);
             int slot = (int)(gi & 1);
-            MsmPlan P = make_plan(pn, (uint32_t)g, bits, max_buckets, (uint32_t)ctx->opt_window);
+            MsmPlan P = make_plan(pn, (uint32_t)g, bits, max_buckets, (uint32_t)ctx->opt_window, table_c);
             plan_mults += P.field_mults();
             plan_pairs += (double)P.m;
             last_c = P.c;
@@ -250,7 +265,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             }
             rc = run_group(D, P, d_bases, d_inf, host_scalars ? D.scalars[slot].as<uint8_t>() : nullptr,
                            host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096, vstride, stride, form,
-                           &launches);
+                           table_stride, val_offset, &launches);
             if (rc) return rc;
             if (!D.finish_on_host)
                 COZK_CUDA(cudaMemcpyAsync(pass_out + v0 * 72, D.out.p, g * 72, cudaMemcpyDeviceToHost, D.stream));
@@ -259,7 +274,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             add_stage_times(D);
             if (D.finish_on_host) {
                 auto h0 = std::chrono::steady_clock::now();
-                FinishArgs F{D.host_sums.data(), P.g, P.W, P.c, P.NS, P.log_l, pass_out + v0 * 72};
+                FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out + v0 * 72};
                 for (size_t v = 0; v < g; ++v) finish_body(v, F);
                 host_finish_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
             }
@@ -455,6 +470,27 @@ void cozk_destroy(cozk_ctx* ctx) {
 
 int cozk_device_count(const cozk_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
+// rows of the precomputed table for an SRS of n points under the context's memory policy (1 = bases only)
+static void table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t* W) {
+    *c = 0;
+    *W = 1;
+    if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
+    uint32_t tc = choose_table_window(n);
+    uint32_t tw = windows_for(254, tc);
+    if ((double)tw * (double)n * sizeof(affine) > (double)ctx->opt_table_max_bytes) return;
+    if ((double)tw * (double)n >= 2147483648.0) return;  // table indices share 31 bits with the point index
+    *c = tc;
+    *W = tw;
+}
+static int build_table(Device& D, affine* d_table, size_t n, uint32_t c, uint32_t W) {
+    if (W <= 1 || n == 0) return COZK_OK;
+    TableArgs A{d_table, n, c, W};
+    k_build_table<<<grid_for(n, 128), 128, 0, D.stream>>>(A);
+    COZK_CUDA(cudaGetLastError());
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    return COZK_OK;
+}
+
 int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out) {
     if (!ctx || !out || (!bases && n) || stride_bytes < 64) {
         set_error("null pointer or stride < 64");
@@ -462,6 +498,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
     }
     SrsEntry S;
     S.n = n;
+    table_shape(ctx, n, &S.table_c, &S.table_W);
     bool any_inf = false;
     if (infinity)
         for (size_t i = 0; i < n && !any_inf; ++i) any_inf = infinity[i] != 0;
@@ -469,7 +506,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         COZK_CUDA(cudaSetDevice(D->id));
         affine* d = nullptr;
         uint8_t* di = nullptr;
-        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(affine)));
+        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine)));
         if (stride_bytes == 64) {
             COZK_CUDA(cudaMemcpy(d, bases, n * 64, cudaMemcpyHostToDevice));
         } else {
@@ -479,6 +516,8 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
             COZK_CUDA(cudaMalloc(&di, n));
             COZK_CUDA(cudaMemcpy(di, infinity, n, cudaMemcpyHostToDevice));
         }
+        int rc = build_table(*D, d, n, S.table_c, S.table_W);
+        if (rc) return rc;
         S.d_bases.push_back(d);
         S.d_inf.push_back(di);
     }
@@ -495,12 +534,15 @@ int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_base
     }
     SrsEntry S;
     S.n = n;
+    table_shape(ctx, n, &S.table_c, &S.table_W);
     for (size_t di = 0; di < ctx->devs.size(); ++di) {
         Device& D = *ctx->devs[di];
         COZK_CUDA(cudaSetDevice(D.id));
         affine* d = nullptr;
-        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(affine)));
+        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine)));
         COZK_CUDA(cudaMemcpyPeer(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine)));
+        int rc = build_table(D, d, n, S.table_c, S.table_W);
+        if (rc) return rc;
         S.d_bases.push_back(d);
         S.d_inf.push_back(nullptr);
     }
@@ -584,6 +626,10 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "group_pairs")) {
         if (value < 1) return COZK_ERR_INVALID_ARG;
         ctx->opt_group_pairs = value;
+    } else if (!strcmp(name, "table_max_mib")) {
+        // memory an SRS registered from now on may spend on its 2^(c*w) * P table; 0 = no tables
+        if (value < 0) return COZK_ERR_INVALID_ARG;
+        ctx->opt_table_max_bytes = value << 20;
     } else {
         set_error("unknown option");
         return COZK_ERR_INVALID_ARG;

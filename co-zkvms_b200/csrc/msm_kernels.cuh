@@ -89,6 +89,11 @@ struct DecomposeArgs {
     const uint8_t* infinity;   // optional per-base flag (already offset to this base range), or null
     uint32_t* keys;            // [g*W*n]
     uint32_t* vals;            // [g*W*n]
+    // Precomputed-table mode (table_stride != 0): the SRS holds 2^(c*w) * P_i at table[w*table_stride + i], so the
+    // digit of window w selects a point of table row w and ALL windows share one bucket set per vector.
+    uint32_t bucket_windows;   // W normally, 1 in table mode
+    size_t table_stride;       // points per table row (the registered SRS length), 0 = no table
+    size_t val_offset;         // base_offset of this call inside a table row (0 without table: bases are pre-offset)
 };
 
 // bits [off, off+c) of a 256-bit little-endian integer, c <= 24
@@ -122,8 +127,34 @@ COZK_HD void decompose_body(size_t tid, const DecomposeArgs& A) {
         }
         size_t o = ((size_t)v * A.W + w) * A.n + i;
         bool zero = (d == 0) || skip;
-        A.keys[o] = zero ? KEY_SENTINEL : ((v * A.W + w) * B + d - 1);
-        A.vals[o] = zero ? 0u : ((uint32_t)i | neg);
+        uint32_t bw = A.table_stride ? 0u : w;
+        A.keys[o] = zero ? KEY_SENTINEL : ((v * A.bucket_windows + bw) * B + d - 1);
+        A.vals[o] = zero ? 0u : ((uint32_t)((size_t)w * A.table_stride + A.val_offset + i) | neg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ SRS table (setup time)
+// table[w*n + i] = 2^(c*w) * P_i for w = 0 .. W-1, affine.  Built once when the SRS is registered (the reference builds
+// its SRS once in PST13::setup, outside prove time); thread i walks its point through the windows.
+struct TableArgs {
+    affine* table;   // [W*n], row 0 already holds the bases
+    size_t n;
+    uint32_t c, W;
+};
+
+COZK_HD void table_body(size_t i, const TableArgs& A) {
+    if (i >= A.n) return;
+    xyzz p = xyzz_from_affine(load_affine(&A.table[i]));
+    for (uint32_t w = 1; w < A.W; ++w) {
+        for (uint32_t k = 0; k < A.c; ++k) p = xyzz_dbl(p);
+        // back to affine (BN254 G1 has prime order: a finite point never doubles to the identity)
+        fq I = fq_inv(fq_mul(p.ZZ, p.ZZZ));
+        affine a;
+        a.x = fq_mul(p.X, fq_mul(I, p.ZZZ));
+        a.y = fq_mul(p.Y, fq_mul(I, p.ZZ));
+        store_fq(&A.table[(size_t)w * A.n + i].x, a.x);
+        store_fq(&A.table[(size_t)w * A.n + i].y, a.y);
+        p = xyzz_from_affine(a);
     }
 }
 

@@ -22,6 +22,7 @@ struct MsmPlan {
     uint32_t g = 0;      // vectors in the group
     uint32_t bits = 254; // significant scalar bits
     uint32_t c = 0, W = 0, B = 0;
+    uint32_t Wb = 0;                 // bucket sets per vector: W, or 1 when a precomputed 2^(c*w)*P table is used
     size_t m = 0;                    // g*W*n pairs
     size_t total_buckets = 0;        // g*W*B
     uint32_t sort_bits = 0;          // radix-sort key bits (covers the sentinel)
@@ -38,9 +39,13 @@ struct MsmPlan {
         for (size_t k = 1; k < acc_entries.size(); ++k) mul += 14.0 * 0.5 * (double)acc_entries[k];
         double nb = (double)total_buckets;
         mul += 14.0 * 2.0 * nb;                                   // group step
-        mul += 14.0 * (double)g * W * G * (1.0 + NS / 2.0);       // masked sums + the trees above them
-        mul += (double)g * W * (9.0 * c + 14.0 * NS);             // bit-position Horner
+        mul += 14.0 * (double)g * Wb * G * (1.0 + NS / 2.0);      // masked sums + the trees above them
+        mul += (double)g * Wb * (9.0 * c + 14.0 * NS);            // bit-position Horner
         return mul;
+    }
+    // the same figure from the cost model used to choose between plans (cheap, no level vectors needed)
+    double model_cost() const {
+        return 11.0 * (double)W * (double)n + 45.0 * (double)Wb * (double)B + 400.0 * (double)((c + 2) / 4);
     }
 };
 
@@ -55,7 +60,7 @@ inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_bu
         double B = (double)(1u << (c - 1));
         if ((double)g * W * B > (double)max_buckets) break;
         if ((double)g * W * B >= 2147483647.0) break;
-        double cost = (double)W * (11.0 * (double)n + 31.0 * B) + 400.0 * (double)(c > 4 ? (c - 1 + 3) / 4 : 1);
+        double cost = (double)W * (11.0 * (double)n + 45.0 * B) + 400.0 * (double)((c + 2) / 4);
         if (cost < best_cost) {
             best_cost = cost;
             best = c;
@@ -64,16 +69,32 @@ inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_bu
     return best;
 }
 
-inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0) {
+// window size for a registered SRS of n points whose windows all share one bucket set (precomputed table)
+inline uint32_t choose_table_window(size_t n) {
+    uint32_t best = C_MIN;
+    double best_cost = 1e300;
+    for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
+        double cost = 11.0 * (double)windows_for(254, c) * (double)n + 45.0 * (double)(1u << (c - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+// table_c != 0: use the SRS's precomputed table (window size fixed at registration, one bucket set per vector)
+inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0, uint32_t table_c = 0) {
     MsmPlan p;
     p.n = n;
     p.g = g;
     p.bits = bits == 0 || bits > 254 ? 254 : bits;
-    p.c = force_c ? force_c : choose_window(n, g, p.bits, max_buckets);
+    p.c = table_c ? table_c : (force_c ? force_c : choose_window(n, g, p.bits, max_buckets));
     p.W = windows_for(p.bits, p.c);
+    p.Wb = table_c ? 1 : p.W;
     p.B = 1u << (p.c - 1);
     p.m = (size_t)g * p.W * n;
-    p.total_buckets = (size_t)g * p.W * p.B;
+    p.total_buckets = (size_t)g * p.Wb * p.B;
     uint32_t sb = 1;
     while (((uint64_t)1 << sb) <= (uint64_t)p.total_buckets) ++sb;  // 2^sb > max key, so the sentinel sorts last
     p.sort_bits = sb > 32 ? 32 : sb;

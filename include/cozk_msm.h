@@ -86,7 +86,11 @@ int cozk_msm_batch_device(cozk_ctx* ctx, int device_index, cozk_srs srs, size_t 
 int cozk_g1_sum(const void* points72, size_t count, void* out72);
 
 /* Tuning / introspection. */
-int cozk_set_option(cozk_ctx* ctx, const char* name, long value); /* "window" (0 = auto), "group_pairs" */
+/* "window" (0 = auto; a forced window also bypasses the SRS table), "group_pairs", "table_max_mib": memory an SRS
+ * registered afterwards may spend on its precomputed table of 2^(c*w) * P rows (default 16384; 0 = none).  With a table
+ * all windows of a scalar share one bucket set, which removes the per-window bucket reduction and the 254 doublings of
+ * the final combine; the table is built once at registration, like the reference's SRS in PST13::setup. */
+int cozk_set_option(cozk_ctx* ctx, const char* name, long value);
 /* Timings (ms, CUDA events) of the stages of the last cozk_msm_batch* call on device 0 of the context:
  * [0] h2d  [1] decompose  [2] sort  [3] accumulate  [4] bucket-reduce  [5] finish+d2h  [6] total  [7] kernels launched
  * [8] window bits c  [9] windows W  [10] field mults (plan)  [11] pairs m */

@@ -21,7 +21,8 @@ extern "C" {
 
 // bases: n x 64 B; scalars: g vectors, vector v at scalars + v*vector_stride, element i at + i*stride; out: g x 72 B
 int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vector_stride, size_t stride, int form,
-             uint32_t g, uint32_t max_bits, uint32_t force_c, const uint8_t* infinity, uint8_t* out, uint32_t* stats) {
+             uint32_t g, uint32_t max_bits, uint32_t force_c, const uint8_t* infinity, uint8_t* out, uint32_t* stats,
+             uint32_t table_c, size_t srs_n, size_t base_offset) {
     if (n == 0) {
         for (uint32_t v = 0; v < g; ++v) {
             memset(out + 72 * v, 0, 72);
@@ -29,9 +30,21 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         }
         return 0;
     }
-    MsmPlan P = make_plan(n, g, max_bits, (size_t)1 << 24, force_c);
+    // table mode: `bases` holds the whole registered SRS (srs_n points); the call uses [base_offset, base_offset + n)
+    MsmPlan P = make_plan(n, g, max_bits, (size_t)1 << 24, force_c, table_c);
+    std::vector<affine> table;
+    const affine* base_ptr = reinterpret_cast<const affine*>(bases);
+    if (table_c) {
+        uint32_t rows = windows_for(254, table_c);
+        table.resize((size_t)rows * srs_n);
+        memcpy(table.data(), bases, srs_n * sizeof(affine));
+        TableArgs TA{table.data(), srs_n, table_c, rows};
+        for (size_t i = 0; i < srs_n; ++i) table_body(i, TA);
+        base_ptr = table.data();
+    }
     std::vector<uint32_t> keys(P.m), vals(P.m);
-    DecomposeArgs D{scalars, nullptr, vector_stride, stride, form, n, g, P.c, P.W, infinity, keys.data(), vals.data()};
+    DecomposeArgs D{scalars, nullptr, vector_stride, stride, form, n, g, P.c, P.W, infinity, keys.data(), vals.data(),
+                    P.Wb, table_c ? srs_n : 0, table_c ? base_offset : 0};
     for (size_t t = 0; t < (size_t)g * n; ++t) decompose_body(t, D);
 
     std::vector<size_t> order(P.m);
@@ -53,7 +66,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         size_t T = (m + ACC_L - 1) / ACC_L;
         pk_out.assign(2 * T, 0xDEADBEEFu);
         pp_out.assign(2 * T, xyzz_identity());
-        AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), reinterpret_cast<const affine*>(bases),
+        AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), base_ptr,
                          pp_in.data(), buckets.data(), pk_out.data(), pp_out.data()};
         for (size_t t = 0; t < T; ++t) {
             if (lvl == 0) accumulate_body<ACC_L, true>(t, A); else accumulate_body<ACC_L, false>(t, A);
@@ -64,7 +77,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     // the top level must not leave any open run
     for (uint32_t k : pk_in) if (k != KEY_SENTINEL) return 2;
 
-    size_t windows = (size_t)g * P.W;
+    size_t windows = (size_t)g * P.Wb;
     std::vector<xyzz> gs(windows * P.G), gw(windows * P.G);
     GroupArgs GA{buckets.data(), gs.data(), gw.data(), P.group_l, windows * P.G};
     for (size_t t = 0; t < GA.threads; ++t) group_body(t, GA);
@@ -79,7 +92,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         for (size_t t = 0; t < threads; ++t) plainsum_body(t, SA);
         cur.swap(nxt);
     }
-    FinishArgs F{cur.data(), g, P.W, P.c, P.NS, P.log_l, out};
+    FinishArgs F{cur.data(), g, P.Wb, P.c, P.NS, P.log_l, out};
     for (size_t v = 0; v < g; ++v) finish_body(v, F);
     if (stats) {
         stats[0] = P.c;

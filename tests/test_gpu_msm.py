@@ -214,3 +214,32 @@ def test_multi_device_context(cozk, orc):
         odd = mctx.msm_batch(srs, vecs[:1], n=1001, base_offset=17, stride=64)
         assert (odd[0] == orc.msm(bases[17:1018], vecs[0][:1001])).all()
         mctx.srs_release(srs)
+
+
+def test_precomputed_table_matches_plain_path(cozk, orc):
+    """An SRS registered with a 2^(c*w) * P table (default) and one without give the same bytes; prefix / offset calls
+    and batches included; the stats show which path ran."""
+    n = 1 << 14
+    bases = orc.gen_bases(6, n)
+    with cozk.Context() as c2:
+        with_table = c2.srs_register(bases)
+        c2.set_option("table_max_mib", 0)
+        plain = c2.srs_register(bases)
+        c2.set_option("table_max_mib", 16384)
+        vecs = [orc.gen_scalars(d, 70 + i, n, stride=64) for i, d in enumerate(("uniform", "const", "wminus", "dup"))]
+        a = c2.msm_batch(with_table, vecs, n=n, stride=64)
+        wa = c2.last_stats()["windows"]
+        b = c2.msm_batch(plain, vecs, n=n, stride=64)
+        wb = c2.last_stats()["windows"]
+        assert (a == b).all()
+        for j, v in enumerate(vecs):
+            assert (a[j] == orc.msm(bases, v)).all(), j
+        assert c2.last_stats()["window"] >= 2 and wa <= wb
+        # prefix and mid-SRS slice
+        for (off, m) in ((0, n // 2), (1000, 9000), (n - 40, 40)):
+            x = c2.msm_batch(with_table, [vecs[0]], n=m, base_offset=off, stride=64)
+            assert (x[0] == orc.msm(bases[off:off + m], vecs[0][:m])).all(), (off, m)
+        small = orc.gen_scalars("small16", 5, n)
+        assert (c2.msm_batch(with_table, small, max_num_bits=16)[0] == orc.msm(bases, small)).all()
+        c2.srs_release(with_table)
+        c2.srs_release(plain)
