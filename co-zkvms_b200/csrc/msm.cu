@@ -39,6 +39,9 @@ template <int L, bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<L, LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
+__global__ void __launch_bounds__(128, 3) k_boundary(BoundaryArgs A) {
+    boundary_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
 __global__ void __launch_bounds__(128, 3) k_group(GroupArgs A) {
     group_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
@@ -117,6 +120,12 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         else k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
+        if (lvl == 0 && T > 1) {
+            BoundaryArgs BA{T, pk_out.as<uint32_t>(), pp_out.as<xyzz>(), D.buckets.as<xyzz>()};
+            k_boundary<<<grid_for(T, 128), 128, 0, st>>>(BA);
+            *launches += 1;
+            COZK_CUDA(cudaGetLastError());
+        }
     }
     COZK_CUDA(cudaEventRecord(D.ev[4], st));
 

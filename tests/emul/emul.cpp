@@ -71,6 +71,10 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         for (size_t t = 0; t < T; ++t) {
             if (lvl == 0) accumulate_body<ACC_L, true>(t, A); else accumulate_body<ACC_L, false>(t, A);
         }
+        if (lvl == 0 && T > 1) {
+            BoundaryArgs BA{T, pk_out.data(), pp_out.data(), buckets.data()};
+            for (size_t t = 0; t < T; ++t) boundary_body(t, BA);
+        }
         pk_in.swap(pk_out);
         pp_in.swap(pp_out);
     }
