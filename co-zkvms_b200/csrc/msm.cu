@@ -484,7 +484,7 @@ static void table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t* W)
     *c = 0;
     *W = 1;
     if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
-    uint32_t tc = choose_table_window(n);
+    uint32_t tc = ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
     uint32_t tw = windows_for(254, tc);
     if ((double)tw * (double)n * sizeof(affine) > (double)ctx->opt_table_max_bytes) return;
     if ((double)tw * (double)n >= 2147483648.0) return;  // table indices share 31 bits with the point index
@@ -635,6 +635,10 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "group_pairs")) {
         if (value < 1) return COZK_ERR_INVALID_ARG;
         ctx->opt_group_pairs = value;
+    } else if (!strcmp(name, "table_window")) {
+        // window size of the tables of SRS registered from now on (0 = choose from the SRS length)
+        if (value != 0 && (value < (long)C_MIN || value > (long)C_MAX)) return COZK_ERR_INVALID_ARG;
+        ctx->opt_table_window = value;
     } else if (!strcmp(name, "table_max_mib")) {
         // memory an SRS registered from now on may spend on its 2^(c*w) * P table; 0 = no tables
         if (value < 0) return COZK_ERR_INVALID_ARG;

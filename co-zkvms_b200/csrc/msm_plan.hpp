@@ -51,18 +51,30 @@ struct MsmPlan {
 
 inline uint32_t windows_for(uint32_t bits, uint32_t c) { return (bits + 1 + c - 1) / c; }
 
-// cost model in field multiplications: per window n mixed adds (+ the partial-merge overhead) and ~31 per bucket
+// A window whose top digit has few bits concentrates all n points of that window in a handful of buckets: long runs
+// that every level of the segmented accumulation has to carry (serial latency).  Among plans within 3 % of the best
+// cost, take the one whose top window is fullest.
+inline uint32_t top_window_bits(uint32_t bits, uint32_t c) { return bits + 1 - (windows_for(bits, c) - 1) * c; }
+
+// cost model in field multiplications: per window n mixed adds (+ the partial-merge overhead) and ~45 per bucket
 inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_buckets) {
-    uint32_t best = C_MIN;
+    double cost[C_MAX + 1];
     double best_cost = 1e300;
     for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
+        cost[c] = 1e300;
         uint32_t W = windows_for(bits, c);
         double B = (double)(1u << (c - 1));
         if ((double)g * W * B > (double)max_buckets) break;
         if ((double)g * W * B >= 2147483647.0) break;
-        double cost = (double)W * (11.0 * (double)n + 45.0 * B) + 400.0 * (double)((c + 2) / 4);
-        if (cost < best_cost) {
-            best_cost = cost;
+        cost[c] = (double)W * (11.0 * (double)n + 45.0 * B) + 400.0 * (double)((c + 2) / 4);
+        if (cost[c] < best_cost) best_cost = cost[c];
+    }
+    uint32_t best = C_MIN, best_top = 0;
+    for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
+        if (cost[c] > best_cost * 1.03) continue;
+        uint32_t tb = top_window_bits(bits, c);
+        if (tb > best_top) {
+            best_top = tb;
             best = c;
         }
     }
@@ -71,12 +83,18 @@ inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_bu
 
 // window size for a registered SRS of n points whose windows all share one bucket set (precomputed table)
 inline uint32_t choose_table_window(size_t n) {
-    uint32_t best = C_MIN;
+    double cost[C_MAX + 1];
     double best_cost = 1e300;
     for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
-        double cost = 11.0 * (double)windows_for(254, c) * (double)n + 45.0 * (double)(1u << (c - 1));
-        if (cost < best_cost) {
-            best_cost = cost;
+        cost[c] = 11.0 * (double)windows_for(254, c) * (double)n + 45.0 * (double)(1u << (c - 1));
+        if (cost[c] < best_cost) best_cost = cost[c];
+    }
+    uint32_t best = C_MIN, best_top = 0;
+    for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
+        if (cost[c] > best_cost * 1.03) continue;
+        uint32_t tb = top_window_bits(254, c);
+        if (tb > best_top) {
+            best_top = tb;
             best = c;
         }
     }

@@ -20,12 +20,17 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--window", type=int, default=0)
 ap.add_argument("--stride", type=int, default=32)
 ap.add_argument("--bits", type=int, default=0)
+ap.add_argument("--table-window", type=int, default=-1, help="-1 auto, 0 no table, else forced table window")
 ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
 
 ctx = cozk.Context()
 if args.window:
     ctx.set_option("window", args.window)
+if args.table_window == 0:
+    ctx.set_option("table_max_mib", 0)
+elif args.table_window > 0:
+    ctx.set_option("table_window", args.table_window)
 sizes = [int(x) for x in args.sizes.split(",")]
 nmax = 1 << max(sizes)
 dbases = ctx.testgen_bases(1, nmax)
