@@ -39,17 +39,122 @@ template <int L, bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<L, LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
-__global__ void __launch_bounds__(128, 3) k_boundary(BoundaryArgs A) {
-    boundary_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
-}
 __global__ void __launch_bounds__(128, 3) k_group(GroupArgs A) {
     group_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
-__global__ void __launch_bounds__(128, 3) k_bitsum(BitsumArgs A) {
-    bitsum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+
+// ---- block-cooperative kernels for the shallow stages.  A single thread needs ~7 us per group addition, so the stages
+// that follow level 1 are bound by DEPTH: a block of ACC_TILE threads holds one partial sum per thread in shared memory
+// (structure of arrays: word k of thread t at w[k][t], conflict-free) and combines them in log2(ACC_TILE) steps.
+struct ShPoints {
+    uint32_t w[32][ACC_TILE];
+};
+__device__ __forceinline__ void sh_store(ShPoints& s, int t, const xyzz& p) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s.w[k][t] = p.X.v[k];
+        s.w[8 + k][t] = p.Y.v[k];
+        s.w[16 + k][t] = p.ZZ.v[k];
+        s.w[24 + k][t] = p.ZZZ.v[k];
+    }
 }
-__global__ void __launch_bounds__(128, 3) k_plainsum(PlainSumArgs A) {
-    plainsum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+__device__ __forceinline__ xyzz sh_load(const ShPoints& s, int t) {
+    xyzz p;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        p.X.v[k] = s.w[k][t];
+        p.Y.v[k] = s.w[8 + k][t];
+        p.ZZ.v[k] = s.w[16 + k][t];
+        p.ZZZ.v[k] = s.w[24 + k][t];
+    }
+    return p;
+}
+
+// Accumulate levels >= 2: block b owns partial slots [b*ACC_TILE, (b+1)*ACC_TILE).  Segmented inclusive scan by key
+// (keys are sorted, runs are contiguous), after which the last slot of every run holds the run's sum inside the tile.
+// Output contract = accumulate_body<ACC_TILE, false> run by ONE thread over the same tile (that body is the host
+// reference in tests/emul): closed runs go to their bucket, the at most two runs that cross the tile edge become the
+// two partial slots of this block.
+__global__ void __launch_bounds__(ACC_TILE) k_segscan(AccumulateArgs A) {
+    __shared__ ShPoints sp;
+    __shared__ uint32_t sk[ACC_TILE];
+    __shared__ uint32_t okey[2];
+    const int t = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * ACC_TILE;
+    const size_t i = base + t;
+    uint32_t raw = i < A.m ? A.keys[i] : KEY_SENTINEL;
+    const uint32_t k = raw & KEY_MASK;
+    xyzz p = (k != KEY_MASK && !(raw & KEY_FILL)) ? load_xyzz(&A.pts_in[i]) : xyzz_identity();
+    sk[t] = k;
+    sh_store(sp, t, p);
+    if (t < 2) okey[t] = KEY_SENTINEL;
+    __syncthreads();
+    for (int d = 1; d < ACC_TILE; d <<= 1) {
+        const bool take = t >= d && k != KEY_MASK && sk[t - d] == k;
+        xyzz q;
+        if (take) q = sh_load(sp, t - d);
+        __syncthreads();
+        if (take) {
+            p = xyzz_add(q, p);
+            sh_store(sp, t, p);
+        }
+        __syncthreads();
+    }
+    const bool run_end = t == ACC_TILE - 1 || sk[t + 1] != k;
+    if (k != KEY_MASK && run_end) {
+        const bool from_start = sk[0] == k;
+        const bool to_end = t == ACC_TILE - 1;
+        const bool left_open = from_start && base > 0 && (A.keys[base - 1] & KEY_MASK) == k;
+        const bool right_open = to_end && base + ACC_TILE < A.m && (A.keys[base + ACC_TILE] & KEY_MASK) == k;
+        if (!left_open && !right_open) {
+            store_xyzz(&A.buckets[k], p);
+        } else if (from_start) {
+            okey[0] = k;
+            store_xyzz(&A.ppts[2 * (size_t)blockIdx.x], p);
+            if (to_end) okey[1] = k | KEY_FILL;  // the whole tile is one run: the filler keeps it contiguous upstream
+        } else {
+            okey[1] = k;
+            store_xyzz(&A.ppts[2 * (size_t)blockIdx.x + 1], p);
+        }
+    }
+    __syncthreads();
+    if (t < 2) A.pkeys[2 * (size_t)blockIdx.x + t] = okey[t];
+}
+
+// Bucket-reduce sums: block (q, id, win) adds the groups of chunk q that belong to sum `id` of window `win`
+// (id 0: all W_g, id 1: all S_g, id 2+j: the S_g whose index has bit j set; plain = no masks, one source array).
+// Output contract = bitsum_body with f = chunk (masked) / plainsum_body with f = chunk (plain).
+struct TreeSumArgs {
+    const xyzz* s;
+    const xyzz* w;
+    xyzz* out;        // [(win*NS + id)*chunks + q]
+    uint32_t G;       // entries per (window[, id]) array
+    uint32_t NS;
+    uint32_t chunk;   // entries per block
+    uint32_t chunks;  // G / chunk
+    int masked;       // 1: sources are s / w with [win*G + e] and the bit masks; 0: source is s with [(win*NS + id)*G + e]
+};
+__global__ void __launch_bounds__(ACC_TILE) k_treesum(TreeSumArgs A) {
+    __shared__ ShPoints sp;
+    const int t = threadIdx.x;
+    const uint32_t q = blockIdx.x, id = blockIdx.y;
+    const size_t win = blockIdx.z;
+    const xyzz* src = A.masked ? ((id == 0 ? A.w : A.s) + win * A.G) : (A.s + (win * A.NS + id) * (size_t)A.G);
+    xyzz acc = xyzz_identity();
+    for (uint32_t e = q * A.chunk + t; e < (q + 1) * A.chunk; e += ACC_TILE) {
+        if (A.masked && id >= 2 && !((e >> (id - 2)) & 1u)) continue;
+        acc = xyzz_add(acc, load_xyzz(&src[e]));
+    }
+    sh_store(sp, t, acc);
+    __syncthreads();
+    for (int d = ACC_TILE / 2; d > 0; d >>= 1) {
+        if (t < d) {
+            acc = xyzz_add(acc, sh_load(sp, t + d));
+            sh_store(sp, t, acc);
+        }
+        __syncthreads();
+    }
+    if (t == 0) store_xyzz(&A.out[(win * A.NS + id) * (size_t)A.chunks + q], acc);
 }
 __global__ void __launch_bounds__(32) k_finish(FinishArgs A) {
     finish_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
@@ -103,7 +208,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     COZK_CUDA(cudaMemsetAsync(D.buckets.p, 0, P.total_buckets * sizeof(xyzz), st));
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
         size_t m = P.acc_entries[lvl];
-        size_t T = (m + ACC_L - 1) / ACC_L;
+        size_t T = lvl == 0 ? (m + ACC_L - 1) / ACC_L : (m + ACC_TILE - 1) / ACC_TILE;  // threads (level 1) / blocks
         DevBuf& pk_out = D.pk[lvl & 1];
         DevBuf& pp_out = D.pp[lvl & 1];
         if ((rc = pk_out.ensure(2 * T * 4))) return rc;
@@ -117,15 +222,9 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
                          pk_out.as<uint32_t>(),
                          pp_out.as<xyzz>()};
         if (lvl == 0) k_accumulate<ACC_L, true><<<grid_for(T, 128), 128, 0, st>>>(A);
-        else k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
-        if (lvl == 0 && T > 1) {
-            BoundaryArgs BA{T, pk_out.as<uint32_t>(), pp_out.as<xyzz>(), D.buckets.as<xyzz>()};
-            k_boundary<<<grid_for(T, 128), 128, 0, st>>>(BA);
-            *launches += 1;
-            COZK_CUDA(cudaGetLastError());
-        }
     }
     COZK_CUDA(cudaEventRecord(D.ev[4], st));
 
@@ -138,29 +237,25 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     k_group<<<grid_for(groups, 64), 64, 0, st>>>(GA);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
-    uint32_t chunks = P.G / P.bitsum_f;
-    size_t bthreads = windows * P.NS * chunks;
-    if ((rc = D.rs[1].ensure(bthreads * sizeof(xyzz)))) return rc;
-    if ((rc = D.rw[1].ensure((bthreads / 2 + 1) * sizeof(xyzz)))) return rc;
-    BitsumArgs BA{D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.G, P.NS, P.bitsum_f, chunks, bthreads};
-    k_bitsum<<<grid_for(bthreads, 64), 64, 0, st>>>(BA);
+    size_t nsums = windows * P.NS;
+    if ((rc = D.rs[1].ensure(nsums * P.sum_chunks * sizeof(xyzz)))) return rc;
+    if ((rc = D.rw[1].ensure(nsums * sizeof(xyzz)))) return rc;
+    TreeSumArgs TA{D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.G, P.NS, P.sum_chunk, P.sum_chunks, 1};
+    k_treesum<<<dim3(P.sum_chunks, P.NS, (unsigned)windows), ACC_TILE, 0, st>>>(TA);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
     xyzz* cur = D.rs[1].as<xyzz>();
-    xyzz* nxt = D.rw[1].as<xyzz>();
-    for (const SumLevel& L : P.sums) {
-        size_t threads = windows * P.NS * (L.n_in / L.f);
-        PlainSumArgs SA{cur, nxt, L.f, threads};
-        k_plainsum<<<grid_for(threads, 64), 64, 0, st>>>(SA);
+    if (P.sum_chunks > 1) {
+        TreeSumArgs TB{cur, nullptr, D.rw[1].as<xyzz>(), P.sum_chunks, P.NS, P.sum_chunks, 1, 0};
+        k_treesum<<<dim3(1, P.NS, (unsigned)windows), ACC_TILE, 0, st>>>(TB);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
-        std::swap(cur, nxt);
+        cur = D.rw[1].as<xyzz>();
     }
     COZK_CUDA(cudaEventRecord(D.ev[5], st));
 
     // 5 finish: bit-position Horner + inversion.  Few vectors: on the host (a CPU core runs this serial chain an order
     // of magnitude faster than one GPU thread); large batches: one GPU thread per vector, all in parallel.
-    size_t nsums = windows * P.NS;
     if (P.g <= HOST_FINISH_MAX) {
         D.host_sums.resize(nsums);
         COZK_CUDA(cudaMemcpyAsync(D.host_sums.data(), cur, nsums * sizeof(xyzz), cudaMemcpyDeviceToHost, st));

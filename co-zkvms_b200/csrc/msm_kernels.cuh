@@ -229,33 +229,6 @@ COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
     A.pkeys[2 * t + 1] = key1;
 }
 
-// ------------------------------------------------------------------------------------------------ 3b boundary merge
-// After level 1 most open runs span exactly two chunks (buckets hold about as many points as a chunk): the run is
-// then "tail of chunk t" + "head of chunk t+1", sitting in adjacent partial slots 2t+1 and 2t+2.  One thread per chunk
-// boundary finishes those with a single addition and retires both slots, so the generic levels above only see the
-// runs that cover whole chunks (long buckets, degenerate shares) and their per-level latency drops from ~16 serial
-// additions to one or two.
-struct BoundaryArgs {
-    size_t T;          // level-1 threads (chunks); partial arrays have 2*T slots
-    uint32_t* pkeys;   // [2*T], updated in place
-    const xyzz* ppts;  // [2*T]
-    xyzz* buckets;
-};
-
-COZK_HD void boundary_body(size_t t, const BoundaryArgs& A) {
-    if (t + 1 >= A.T) return;
-    uint32_t kt = A.pkeys[2 * t + 1];
-    if (kt == KEY_SENTINEL || (kt & KEY_FILL)) return;  // no tail, or chunk t is one whole run (generic path)
-    uint32_t kh = A.pkeys[2 * t + 2];
-    if (kh != kt) return;                                // (a head-or-whole slot never carries the fill flag)
-    // chunk t+1 must END the run: if it is a whole-chunk run its second slot is the filler of this key.  That slot may
-    // concurrently be retired by thread t+1, but only when it is a real tail, never when it is this filler.
-    if (A.pkeys[2 * t + 3] == (kt | KEY_FILL)) return;
-    store_xyzz(&A.buckets[kt], xyzz_add(load_xyzz(&A.ppts[2 * t + 1]), load_xyzz(&A.ppts[2 * t + 2])));
-    A.pkeys[2 * t + 1] = KEY_SENTINEL;
-    A.pkeys[2 * t + 2] = KEY_SENTINEL;
-}
-
 // ------------------------------------------------------------------------------------------------ 4 bucket reduce
 // Window value  V = sum_b (b+1) * bucket[b],  b in [0, B).  Two steps, both shallow (a single GPU thread needs about
 // 7 us per group addition, so depth - not work - is what this stage costs):

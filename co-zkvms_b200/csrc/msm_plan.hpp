@@ -7,15 +7,13 @@
 
 namespace cozk {
 
-constexpr int ACC_L = 32;          // entries per thread in the accumulate stage (all levels)
+constexpr int ACC_L = 32;          // pairs per thread at level 1 of the accumulate stage
+constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at levels >= 2 (block-cooperative segmented scan)
+constexpr uint32_t SUM_CHUNK = 1024;  // groups per thread block in the first level of the bucket-reduce sums
 constexpr uint32_t GROUP_L = 8;    // buckets per thread in the group step of the bucket reduce
-constexpr uint32_t SUM_F = 4;      // fan-in of the plain-sum trees of the bucket reduce
 constexpr uint32_t HOST_FINISH_MAX = 4;  // up to this many vectors the final Horner + inversion run on the host
 constexpr uint32_t C_MIN = 2, C_MAX = 22;
 
-struct SumLevel {
-    uint32_t n_in, f;  // per (window, sum id): n_in entries reduced f-fold
-};
 
 struct MsmPlan {
     size_t n = 0;        // points per vector
@@ -29,8 +27,8 @@ struct MsmPlan {
     std::vector<size_t> acc_entries; // entries per accumulate level (level 1 first)
     uint32_t group_l = 1, log_l = 0; // buckets per group, log2
     uint32_t G = 1, NS = 2;          // groups per window, plain sums per window (log2 G + 2)
-    uint32_t bitsum_f = 1;           // fan-in of the first (masked) sum level
-    std::vector<SumLevel> sums;      // plain-sum levels after the masked one
+    uint32_t sum_chunk = 1;          // groups summed per block in the masked level (min(G, SUM_CHUNK))
+    uint32_t sum_chunks = 1;         // G / sum_chunk partial sums per (window, id); > 1 needs the second, plain level
 
     // field multiplications this plan performs (for the roofline's "actual" figure): 10 per mixed add, 14 per full add
     double field_mults() const {
@@ -39,7 +37,7 @@ struct MsmPlan {
         for (size_t k = 1; k < acc_entries.size(); ++k) mul += 14.0 * 0.5 * (double)acc_entries[k];
         double nb = (double)total_buckets;
         mul += 14.0 * 2.0 * nb;                                   // group step
-        mul += 14.0 * (double)g * Wb * G * (1.0 + NS / 2.0);      // masked sums + the trees above them
+        mul += 14.0 * (double)g * Wb * G * (1.0 + NS / 2.0);      // masked sums + the tree above them
         mul += (double)g * Wb * (9.0 * c + 14.0 * NS);            // bit-position Horner
         return mul;
     }
@@ -118,8 +116,9 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     p.sort_bits = sb > 32 ? 32 : sb;
     size_t e = p.m;
     p.acc_entries.push_back(e);
-    while (e > (size_t)ACC_L) {
-        size_t t = (e + ACC_L - 1) / ACC_L;
+    // level 1: one thread per ACC_L pairs; levels >= 2: one block per ACC_TILE partial slots; each emits two slots.
+    // A level that ran as a single thread / block has seen everything: no open run is left.
+    for (size_t t = (e + ACC_L - 1) / ACC_L; t > 1; t = (e + ACC_TILE - 1) / ACC_TILE) {
         e = 2 * t;
         p.acc_entries.push_back(e);
     }
@@ -133,13 +132,8 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     uint32_t J = 0;
     while ((1u << J) < p.G) ++J;
     p.NS = J + 2;
-    p.bitsum_f = p.G < SUM_F ? p.G : SUM_F;
-    uint32_t n_in = p.G / p.bitsum_f;
-    while (n_in > 1) {
-        uint32_t f = n_in < SUM_F ? n_in : SUM_F;
-        p.sums.push_back({n_in, f});
-        n_in /= f;
-    }
+    p.sum_chunk = p.G < SUM_CHUNK ? p.G : SUM_CHUNK;
+    p.sum_chunks = p.G / p.sum_chunk;
     return p;
 }
 

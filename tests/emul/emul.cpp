@@ -63,36 +63,36 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     std::vector<xyzz> pp_in, pp_out;
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
         size_t m = P.acc_entries[lvl];
-        size_t T = (m + ACC_L - 1) / ACC_L;
+        size_t T = lvl == 0 ? (m + ACC_L - 1) / ACC_L : (m + ACC_TILE - 1) / ACC_TILE;
         pk_out.assign(2 * T, 0xDEADBEEFu);
         pp_out.assign(2 * T, xyzz_identity());
         AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), base_ptr,
                          pp_in.data(), buckets.data(), pk_out.data(), pp_out.data()};
         for (size_t t = 0; t < T; ++t) {
-            if (lvl == 0) accumulate_body<ACC_L, true>(t, A); else accumulate_body<ACC_L, false>(t, A);
-        }
-        if (lvl == 0 && T > 1) {
-            BoundaryArgs BA{T, pk_out.data(), pp_out.data(), buckets.data()};
-            for (size_t t = 0; t < T; ++t) boundary_body(t, BA);
+            // levels >= 2 run on the GPU as the block-cooperative k_segscan, whose output contract is this body with
+            // one "thread" per tile of ACC_TILE slots
+            if (lvl == 0) accumulate_body<ACC_L, true>(t, A); else accumulate_body<ACC_TILE, false>(t, A);
         }
         pk_in.swap(pk_out);
         pp_in.swap(pp_out);
     }
     // the top level must not leave any open run
-    for (uint32_t k : pk_in) if (k != KEY_SENTINEL) return 2;
+    if (P.acc_entries.size() > 1 || P.m > 0)
+        for (uint32_t k : pk_in) if (k != KEY_SENTINEL) return 2;
 
     size_t windows = (size_t)g * P.Wb;
     std::vector<xyzz> gs(windows * P.G), gw(windows * P.G);
     GroupArgs GA{buckets.data(), gs.data(), gw.data(), P.group_l, windows * P.G};
     for (size_t t = 0; t < GA.threads; ++t) group_body(t, GA);
-    uint32_t chunks = P.G / P.bitsum_f;
+    // on the GPU these two levels are k_treesum (masked, then plain); same output contract as the bodies below
+    uint32_t chunks = P.sum_chunks;
     std::vector<xyzz> cur(windows * P.NS * chunks), nxt;
-    BitsumArgs BA{gs.data(), gw.data(), cur.data(), P.G, P.NS, P.bitsum_f, chunks, windows * P.NS * chunks};
+    BitsumArgs BA{gs.data(), gw.data(), cur.data(), P.G, P.NS, P.sum_chunk, chunks, windows * P.NS * chunks};
     for (size_t t = 0; t < BA.threads; ++t) bitsum_body(t, BA);
-    for (const SumLevel& L : P.sums) {
-        size_t threads = windows * P.NS * (L.n_in / L.f);
+    if (chunks > 1) {
+        size_t threads = windows * P.NS;
         nxt.assign(threads, xyzz_identity());
-        PlainSumArgs SA{cur.data(), nxt.data(), L.f, threads};
+        PlainSumArgs SA{cur.data(), nxt.data(), chunks, threads};
         for (size_t t = 0; t < threads; ++t) plainsum_body(t, SA);
         cur.swap(nxt);
     }
@@ -102,7 +102,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         stats[0] = P.c;
         stats[1] = P.W;
         stats[2] = (uint32_t)P.acc_entries.size();
-        stats[3] = (uint32_t)P.sums.size();
+        stats[3] = P.sum_chunks;
     }
     return 0;
 }
