@@ -208,7 +208,8 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     COZK_CUDA(cudaMemsetAsync(D.buckets.p, 0, P.total_buckets * sizeof(xyzz), st));
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
         size_t m = P.acc_entries[lvl];
-        size_t T = lvl == 0 ? (m + ACC_L - 1) / ACC_L : (m + ACC_TILE - 1) / ACC_TILE;  // threads (level 1) / blocks
+        const int tile = P.acc_tile[lvl];
+        size_t T = (m + tile - 1) / tile;  // threads (serial body) or blocks (segmented scan)
         DevBuf& pk_out = D.pk[lvl & 1];
         DevBuf& pp_out = D.pp[lvl & 1];
         if ((rc = pk_out.ensure(2 * T * 4))) return rc;
@@ -222,6 +223,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
                          pk_out.as<uint32_t>(),
                          pp_out.as<xyzz>()};
         if (lvl == 0) k_accumulate<ACC_L, true><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else if (tile == ACC_L) k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
         else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
@@ -582,7 +584,7 @@ static void table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t* W)
     uint32_t tc = ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
     uint32_t tw = windows_for(254, tc);
     if ((double)tw * (double)n * sizeof(affine) > (double)ctx->opt_table_max_bytes) return;
-    if ((double)tw * (double)n >= 2147483648.0) return;  // table indices share 31 bits with the point index
+    if ((double)tw * (double)n >= 2147483647.0) return;  // table indices share 31 bits with the point index; all-ones is the skip mark
     *c = tc;
     *W = tw;
 }

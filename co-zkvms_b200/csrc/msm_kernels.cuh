@@ -5,7 +5,7 @@
 // Pipeline for a group of g scalar vectors of n points against one base range (what one `batch_msm` call of the
 // reference, co-jolt/src/poly/commitment/pst13.rs:319-323, asks for):
 //   1 decompose     scalar -> W signed c-bit digits -> (key, val) pairs.  key = (vector*W + window)*B + |digit|-1,
-//                   B = 2^(c-1); val = point index | sign << 31.  Zero digits get the sentinel key.
+//                   B = 2^(c-1); val = point index | sign << 31.  Zero digits keep a valid key and a skip mark in val.
 //   2 sort          pairs by key (cub radix sort in msm.cu) -> every bucket is one contiguous run.
 //   3 accumulate    load-balanced segmented sum: thread t owns pairs [t*L, (t+1)*L), whatever buckets they belong to.
 //                   Runs that lie inside one chunk are written straight to their bucket; the (at most two) runs that
@@ -27,6 +27,7 @@ constexpr uint32_t KEY_SENTINEL = 0xFFFFFFFFu;  // zero digit / unused partial s
 constexpr uint32_t KEY_FILL = 0x80000000u;      // partial slot that only keeps a run contiguous (identity point)
 constexpr uint32_t KEY_MASK = 0x7FFFFFFFu;
 constexpr uint32_t VAL_NEG = 0x80000000u;
+constexpr uint32_t VAL_SKIP = 0xFFFFFFFFu;      // zero digit: the pair stays in the list (bucket 0 of its window) but adds nothing
 
 constexpr int SCALAR_MONT = 0;   // Fr Montgomery (what msm_field_elements gets)
 constexpr int SCALAR_CANON = 1;  // BigInt<4> (what msm_bigint gets)
@@ -126,10 +127,12 @@ COZK_HD void decompose_body(size_t tid, const DecomposeArgs& A) {
             carry = 1;
         }
         size_t o = ((size_t)v * A.W + w) * A.n + i;
+        // A zero digit keeps a valid key (bucket 0 of its window) and is marked in val instead: the sort then needs no
+        // extra key bit for a sentinel, which saves a whole radix pass when the bucket index is a multiple of 8 bits.
         bool zero = (d == 0) || skip;
         uint32_t bw = A.table_stride ? 0u : w;
-        A.keys[o] = zero ? KEY_SENTINEL : ((v * A.bucket_windows + bw) * B + d - 1);
-        A.vals[o] = zero ? 0u : ((uint32_t)((size_t)w * A.table_stride + A.val_offset + i) | neg);
+        A.keys[o] = (v * A.bucket_windows + bw) * B + (zero ? 0u : d - 1);
+        A.vals[o] = zero ? VAL_SKIP : ((uint32_t)((size_t)w * A.table_stride + A.val_offset + i) | neg);
     }
 }
 
@@ -202,6 +205,7 @@ COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
         if (k == KEY_MASK) continue;
         if (LEVEL1) {
             uint32_t val = A.vals[i];
+            if (val == VAL_SKIP) continue;
             affine p = load_affine(&A.bases[val & ~VAL_NEG]);
             p.y = fq_cneg(p.y, (val & VAL_NEG) != 0);
             acc = xyzz_madd(acc, p);

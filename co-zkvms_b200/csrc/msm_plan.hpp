@@ -8,7 +8,8 @@
 namespace cozk {
 
 constexpr int ACC_L = 32;          // pairs per thread at level 1 of the accumulate stage
-constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at levels >= 2 (block-cooperative segmented scan)
+constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at small levels >= 2 (block-cooperative segmented scan)
+constexpr size_t ACC_SCAN_MAX = 65536;  // levels with more slots than this stay on the serial, work-efficient body
 constexpr uint32_t SUM_CHUNK = 1024;  // groups per thread block in the first level of the bucket-reduce sums
 constexpr uint32_t GROUP_L = 8;    // buckets per thread in the group step of the bucket reduce
 constexpr uint32_t HOST_FINISH_MAX = 4;  // up to this many vectors the final Horner + inversion run on the host
@@ -23,8 +24,9 @@ struct MsmPlan {
     uint32_t Wb = 0;                 // bucket sets per vector: W, or 1 when a precomputed 2^(c*w)*P table is used
     size_t m = 0;                    // g*W*n pairs
     size_t total_buckets = 0;        // g*W*B
-    uint32_t sort_bits = 0;          // radix-sort key bits (covers the sentinel)
+    uint32_t sort_bits = 0;          // radix-sort key bits
     std::vector<size_t> acc_entries; // entries per accumulate level (level 1 first)
+    std::vector<int> acc_tile;       // entries per thread (ACC_L: serial body) or per block (ACC_TILE: segmented scan)
     uint32_t group_l = 1, log_l = 0; // buckets per group, log2
     uint32_t G = 1, NS = 2;          // groups per window, plain sums per window (log2 G + 2)
     uint32_t sum_chunk = 1;          // groups summed per block in the masked level (min(G, SUM_CHUNK))
@@ -112,15 +114,21 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     p.m = (size_t)g * p.W * n;
     p.total_buckets = (size_t)g * p.Wb * p.B;
     uint32_t sb = 1;
-    while (((uint64_t)1 << sb) <= (uint64_t)p.total_buckets) ++sb;  // 2^sb > max key, so the sentinel sorts last
-    p.sort_bits = sb > 32 ? 32 : sb;
+    while (((uint64_t)1 << sb) < (uint64_t)p.total_buckets) ++sb;  // keys are < total_buckets (no sentinel at level 1)
+    p.sort_bits = sb;
     size_t e = p.m;
     p.acc_entries.push_back(e);
-    // level 1: one thread per ACC_L pairs; levels >= 2: one block per ACC_TILE partial slots; each emits two slots.
-    // A level that ran as a single thread / block has seen everything: no open run is left.
-    for (size_t t = (e + ACC_L - 1) / ACC_L; t > 1; t = (e + ACC_TILE - 1) / ACC_TILE) {
+    // Level 1: one thread per ACC_L pairs.  Levels >= 2 reduce the partial slots: big levels with the same serial body
+    // (one addition per live slot: work-efficient, 16 additions deep), small ones with the block-cooperative segmented
+    // scan (log2(ACC_TILE) additions deep, but up to that many additions per slot).  Every thread / block emits two
+    // slots; a level that ran as a single thread / block has seen everything and leaves no open run.
+    p.acc_tile.push_back(ACC_L);
+    for (size_t t = (e + ACC_L - 1) / ACC_L; t > 1;) {
         e = 2 * t;
+        int tile = e > ACC_SCAN_MAX ? ACC_L : ACC_TILE;
         p.acc_entries.push_back(e);
+        p.acc_tile.push_back(tile);
+        t = (e + tile - 1) / tile;
     }
     // few buckets: shallow groups (depth is what costs); millions of buckets: the stage is throughput bound and the
     // NS masked sums per group dominate, so make groups larger

@@ -63,7 +63,8 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     std::vector<xyzz> pp_in, pp_out;
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
         size_t m = P.acc_entries[lvl];
-        size_t T = lvl == 0 ? (m + ACC_L - 1) / ACC_L : (m + ACC_TILE - 1) / ACC_TILE;
+        const int tile = P.acc_tile[lvl];
+        size_t T = (m + tile - 1) / tile;
         pk_out.assign(2 * T, 0xDEADBEEFu);
         pp_out.assign(2 * T, xyzz_identity());
         AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), base_ptr,
@@ -71,7 +72,9 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         for (size_t t = 0; t < T; ++t) {
             // levels >= 2 run on the GPU as the block-cooperative k_segscan, whose output contract is this body with
             // one "thread" per tile of ACC_TILE slots
-            if (lvl == 0) accumulate_body<ACC_L, true>(t, A); else accumulate_body<ACC_TILE, false>(t, A);
+            if (lvl == 0) accumulate_body<ACC_L, true>(t, A);
+            else if (tile == ACC_L) accumulate_body<ACC_L, false>(t, A);
+            else accumulate_body<ACC_TILE, false>(t, A);
         }
         pk_in.swap(pk_out);
         pp_in.swap(pp_out);
