@@ -219,6 +219,12 @@ def main():
         limb_products = n * CANON_MULTS_PER_POINT * LIMB_PRODUCTS_PER_MULT
         achieved = limb_products / (acc_ms * 1e-3)
         plan_mults = st["field_mults"]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f)["k_accumulate<32,1>"].get("log2n=%d,dist=%s,window=%d" % (args.log2n, args.dist, int(st["window"])))
+        except Exception:
+            traffic = None
         line = {"metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery, IMAD.WIDE carry chains)", "data": "synthetic",
@@ -230,7 +236,9 @@ def main():
                                      "radix sort adds its own launches per step",
                 "roofline": {"bound": "imad", "kernel": "k_accumulate (bucket accumulation, all levels)",
                              "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "G limb-products/s (IMAD.WIDE.U32 lane-ops)",
-                             "frac": achieved / imad_peak, "traffic": None,
+                             "frac": achieved / imad_peak, "traffic": traffic,
+                             "traffic_note": "DRAM bytes per launch of k_accumulate<32,1> from the committed ncu --set full capture "
+                                             "(profiles/r1_accumulate_ncu.md); algorithmic bytes = pairs x 72",
                              "peak_source": "self-measured in this run: max(carry-chained IMAD.WIDE.U32.X microbenchmark, "
                                             "fq_mul microbenchmark x 136); MEASURED_PEAKS.json has no integer figure; "
                                             "nominal 148 SM x 32 lanes/clk x 1.965 GHz = 9309 G/s",
