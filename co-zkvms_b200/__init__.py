@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcozk_msm.so")
-SOURCES = ["msm.cu", "aux.cu", "pst13.cu"]
+SOURCES = ["msm.cu", "aux.cu", "pst13.cu", "fixed_base.cu"]
 HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -34,7 +34,8 @@ ABI_SYMBOLS = [
     "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_testgen_bases", "cozk_testgen_scalars",
     "cozk_srs_register_device", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench",
     "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_open",
-    "cozk_pst13_combine_commitment_shares",
+    "cozk_pst13_combine_commitment_shares", "cozk_pst13_coordinate_prove", "cozk_combine_comm",
+    "cozk_fixed_base_batch_mul",
 ]
 
 
@@ -102,6 +103,9 @@ def lib():
                                                ctypes.POINTER(ctypes.c_uint8)]
     L.cozk_pst13_open.argtypes = [vp, ctypes.POINTER(u64), sz, vp, sz, vp, ci, vp, vp]
     L.cozk_pst13_combine_commitment_shares.argtypes = [vp, sz, vp]
+    L.cozk_pst13_coordinate_prove.argtypes = [vp, sz, sz, vp]
+    L.cozk_combine_comm.argtypes = [vp, sz, vp]
+    L.cozk_fixed_base_batch_mul.argtypes = [vp, vp, vp, sz, sz, ci, vp, ctypes.POINTER(u64)]
     _lib = L
     return L
 
@@ -245,6 +249,17 @@ class Context:
             _check(lib().cozk_msm_batch_device(self.handle, device, srs, base_offset, n, ptrs, k, stride, form,
                                                max_num_bits, _ptr(out)))
         return out
+
+    def fixed_base_batch_mul(self, base72, scalars, stride=32, form=MONT, register=False):
+        """out[i] = scalars[i] * base (SRS generation, G1 half).  Returns (points (n, 72), srs handle or None)."""
+        base72 = np.ascontiguousarray(base72, dtype=np.uint8).reshape(72)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+        n = scalars.size // stride
+        out = np.zeros((n, 72), dtype=np.uint8)
+        h = ctypes.c_uint64()
+        _check(lib().cozk_fixed_base_batch_mul(self.handle, _ptr(base72), _ptr(scalars), n, stride, form, _ptr(out),
+                                               ctypes.byref(h) if register else None))
+        return out, (h.value if register else None)
 
     def set_option(self, name, value):
         _check(lib().cozk_set_option(self.handle, name.encode(), int(value)))

@@ -237,4 +237,38 @@ int cozk_pst13_combine_commitment_shares(const void* commitments, size_t count, 
     return COZK_OK;
 }
 
+int cozk_pst13_coordinate_prove(const void* proofs, size_t parties, size_t len, void* out_proofs) {
+    if (!proofs || !out_proofs || parties == 0) {
+        set_error("null pointer or no parties");
+        return COZK_ERR_INVALID_ARG;
+    }
+    const uint8_t* in = reinterpret_cast<const uint8_t*>(proofs);
+    uint8_t* out = reinterpret_cast<uint8_t*>(out_proofs);
+    std::vector<uint8_t> col(parties * 72);
+    for (size_t i = 0; i < len; ++i) {
+        for (size_t p = 0; p < parties; ++p) memcpy(&col[72 * p], in + (p * len + i) * 72, 72);
+        int rc = cozk_g1_sum(col.data(), parties, out + 72 * i);
+        if (rc) return rc;
+    }
+    return COZK_OK;
+}
+
+int cozk_combine_comm(const void* commitments, size_t count, void* out_commitment) {
+    unsigned lg = 0;
+    if (!commitments || !out_commitment || count == 0 || log2_exact(count, &lg)) {
+        set_error("null pointer, or the number of chunk commitments is not a power of two");
+        return COZK_ERR_INVALID_ARG;
+    }
+    const uint8_t* in = reinterpret_cast<const uint8_t*>(commitments);
+    uint64_t nv = 0;
+    memcpy(&nv, in, 8);
+    std::vector<uint8_t> pts(count * 72);
+    for (size_t i = 0; i < count; ++i) memcpy(&pts[72 * i], in + COZK_COMMITMENT_BYTES * i + 8, 72);
+    uint8_t sum[72];
+    int rc = cozk_g1_sum(pts.data(), count, sum);
+    if (rc) return rc;
+    write_commitment(reinterpret_cast<uint8_t*>(out_commitment), nv + lg, sum);
+    return COZK_OK;
+}
+
 }  // extern "C"

@@ -53,6 +53,14 @@ int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const v
 /* Coordinator side: sum of the parties' commitment shares; asserts equal nv (COZK_ERR_INVALID_ARG otherwise). */
 int cozk_pst13_combine_commitment_shares(const void* commitments, size_t count, void* out_commitment);
 
+/* Coordinator side of prove_rep3: PST13::coordinate_prove (pst13.rs:110-122) - element-wise a + b + c of the parties'
+ * proof vectors.  proofs: `parties` arrays of `len` wire points each, party-major; out: len wire points. */
+int cozk_pst13_coordinate_prove(const void* proofs, size_t parties, size_t len, void* out_proofs);
+
+/* combine_comm (snarks-core/src/poly/commitment.rs:56-63): sum of the workers' chunk commitments,
+ * nv = nv_0 + log2(count); count must be a power of two as `log_2()` assumes. */
+int cozk_combine_comm(const void* commitments, size_t count, void* out_commitment);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,3 +128,21 @@ def combine_commitment_shares(commitments):
     _check(_lib().cozk_pst13_combine_commitment_shares(raw.ctypes.data_as(ctypes.c_void_p), len(commitments),
                                                        out.ctypes.data_as(ctypes.c_void_p)))
     return PST13Commitment.from_bytes(out)
+
+
+def coordinate_prove(party_proofs):
+    """PST13::coordinate_prove (pst13.rs:110-122): element-wise sum of the parties' proof vectors."""
+    arr = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.uint8).reshape(-1, 72) for p in party_proofs]))
+    parties, length = arr.shape[0], arr.shape[1]
+    out = np.zeros((length, 72), dtype=np.uint8)
+    _check(_lib().cozk_pst13_coordinate_prove(arr.ctypes.data_as(ctypes.c_void_p), parties, length,
+                                              out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def combine_comm(commitments):
+    """combine_comm (snarks-core/src/poly/commitment.rs:56-63): sum of chunk commitments, nv += log2(#chunks)."""
+    raw = np.stack([c.to_bytes() for c in commitments])
+    out = np.zeros(COMMITMENT_BYTES, dtype=np.uint8)
+    _check(_lib().cozk_combine_comm(raw.ctypes.data_as(ctypes.c_void_p), len(commitments), out.ctypes.data_as(ctypes.c_void_p)))
+    return PST13Commitment.from_bytes(out)

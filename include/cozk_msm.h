@@ -85,6 +85,15 @@ int cozk_msm_batch_device(cozk_ctx* ctx, int device_index, cozk_srs srs, size_t 
  * PST13::combine_commitment_shares, pst13.rs:72-108).  Points are 72-byte results. */
 int cozk_g1_sum(const void* points72, size_t count, void* out72);
 
+/* Fixed-base batch multiplication, the G1 half of SRS generation:
+ *     out[i] = scalars[i] * base        i = 0 .. n-1, affine
+ * replaces `BatchMulPreprocessing::new(g, n).batch_mul(&pp_powers)` (co-noir-spartan/spartan/src/zk.rs:455-460) and the
+ * same step inside MultilinearPC::setup behind PST13::setup (co-jolt/src/poly/commitment/pst13.rs:49-62, :276-279).
+ * base72: a 72-byte wire point; scalars as in cozk_msm_batch (host pointer).  out_points72 (n x 72 B, may be NULL) gets
+ * the points; out_srs (may be NULL) registers them as a device-resident SRS in the same call. */
+int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, const void* scalars, size_t n, size_t stride_bytes,
+                              int form, void* out_points72, cozk_srs* out_srs);
+
 /* Tuning / introspection. */
 /* "window" (0 = auto; a forced window also bypasses the SRS table), "group_pairs", "table_max_mib": memory an SRS
  * registered afterwards may spend on its precomputed table of 2^(c*w) * P rows (default 16384; 0 = none).  With a table

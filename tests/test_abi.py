@@ -75,3 +75,22 @@ def test_combine_commitment_shares_host(cozk, orc):
     assert got.nv == 10 and (got.g_product == want).all()
     with pytest.raises(cozk.CozkError):
         pst.combine_commitment_shares([cs[0], pst.PST13Commitment(11, pts[1])])
+
+
+def test_coordinate_prove_and_combine_comm_host(cozk, orc):
+    pst = cozk.pst13
+    pts = np.zeros((12, 72), np.uint8)
+    pts[:, :64] = orc.gen_bases(8, 12)
+    parties = [pts[0:4], pts[4:8], pts[8:12]]
+    got = pst.coordinate_prove(parties)
+    for i in range(4):
+        want = orc.g1_op("add", orc.g1_op("add", pts[i][None], pts[4 + i][None]), pts[8 + i][None])[0]
+        assert (got[i] == want).all()
+    chunks = [pst.PST13Commitment(5, pts[i]) for i in range(4)]
+    c = pst.combine_comm(chunks)
+    want = pts[0]
+    for i in range(1, 4):
+        want = orc.g1_op("add", want[None], pts[i][None])[0]
+    assert c.nv == 7 and (c.g_product == want).all()
+    with pytest.raises(cozk.CozkError):
+        pst.combine_comm(chunks[:3])

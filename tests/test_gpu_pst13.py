@@ -103,3 +103,36 @@ def test_open(cozk, ctx, orc, nv, stride):
     assert (proofs == want_proofs).all()
     assert pyref.from_mont(H.to_int(ev), H.R) == want_ev
     setup.release()
+
+
+def test_fixed_base_batch_mul_srs_generation(cozk, ctx, orc):
+    """SRS generation, G1 half: out[i] = s_i * g against the oracle's double-and-add, including
+    s = 0, 1, r - 1 and a non-generator base; the registered handle commits like an uploaded SRS."""
+    n = 600
+    scal = [0, 1, 2, H.R - 1, H.R - 2, 255, 256, 1 << 200] + [pyref.scalar_uniform(77, i) for i in range(n - 8)]
+    for base_pt in (pyref.G1, pyref.base_point(3, 5)):
+        base = H.point_wire(base_pt)
+        for form in (0, 1):
+            pts, _ = ctx.fixed_base_batch_mul(base, H.scalars_wire(scal, form), form=form)
+            for i in (0, 1, 2, 3, 4, 5, 6, 7, 8, 99, n - 1):
+                want = orc.g1_mul(base, H.le32(scal[i]), form=orc.CANON)
+                assert (pts[i] == want).all(), (i, form)
+    # all points at once through linearity: sum_i s_i * g = (sum_i s_i) * g
+    base = H.point_wire(pyref.G1)
+    pts, srs = ctx.fixed_base_batch_mul(base, H.scalars_wire(scal), register=True)
+    total = cozk.g1_sum(pts)
+    assert (total == orc.g1_mul(base, H.le32(sum(scal) % H.R), form=orc.CANON)).all()
+    # the registered SRS (with its infinity flag for s = 0) commits like the same points uploaded by hand
+    assert ctx.srs_len(srs) == n
+    sc = orc.gen_scalars("uniform", 12, n)
+    manual = ctx.srs_register(pts, infinity=pts[:, 64].copy(), stride=72)
+    assert (ctx.msm_batch(srs, sc)[0] == ctx.msm_batch(manual, sc)[0]).all()
+    masked = sc.copy()
+    masked[0] = 0
+    bases = pts[:, :64].copy()
+    bases[0] = orc.gen_bases(1, 1)[0]
+    assert (ctx.msm_batch(srs, sc)[0] == orc.msm(bases, masked)).all()
+    ctx.srs_release(srs)
+    ctx.srs_release(manual)
+    ident, _ = ctx.fixed_base_batch_mul(H.point_wire(None), H.scalars_wire(scal[:5]))
+    assert (ident[:, 64] == 1).all()
