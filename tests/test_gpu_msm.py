@@ -243,3 +243,60 @@ def test_precomputed_table_matches_plain_path(cozk, orc):
         assert (c2.msm_batch(with_table, small, max_num_bits=16)[0] == orc.msm(bases, small)).all()
         c2.srs_release(with_table)
         c2.srs_release(plain)
+
+
+def test_randomised_shapes(ctx, orc):
+    """Seeded random shapes through the C ABI: n, base_offset, batch size, stride, form, distribution, bit hint."""
+    rng = np.random.default_rng(20261018)
+    n_srs = 6000
+    bases = orc.gen_bases(11, n_srs)
+    srs = ctx.srs_register(bases)
+    dists = list(pyref.DISTS)
+    for trial in range(24):
+        n = int(rng.integers(1, 3000))
+        off = int(rng.integers(0, n_srs - n + 1))
+        k = int(rng.integers(1, 6))
+        stride = int(rng.choice([32, 64, 48]))
+        form = int(rng.integers(0, 2))
+        vecs, want = [], []
+        for j in range(k):
+            d = dists[int(rng.integers(0, len(dists)))]
+            v = orc.gen_scalars(d, 1000 + 10 * trial + j, n, form=form, stride=stride)
+            vecs.append(v)
+            want.append(orc.msm(bases[off:off + n], v, form=form))
+        got = ctx.msm_batch(srs, vecs, n=n, base_offset=off, stride=stride, form=form)
+        for j in range(k):
+            assert (got[j] == want[j]).all(), (trial, n, off, k, stride, form, j)
+    ctx.srs_release(srs)
+
+
+def test_concurrent_callers(cozk, ctx, orc):
+    """Two host threads calling into one context at once (the reference runs two commits under rayon::join,
+    co-jolt/src/jolt/vm/jolt/witness.rs:350-365): calls serialise per device and both results are exact."""
+    import threading
+    n = 1 << 14
+    bases = orc.gen_bases(1, n)
+    srs = ctx.srs_register(bases)
+    vecs = [orc.gen_scalars(d, 90 + i, n) for i, d in enumerate(("uniform", "const", "wminus", "dup"))]
+    want = [orc.msm(bases, v) for v in vecs]
+    results, errors = {}, []
+
+    def worker(idx):
+        try:
+            for rep in range(6):
+                j = (idx + rep) % len(vecs)
+                out = ctx.msm_batch(srs, vecs[j])
+                if not (out[0] == want[j]).all():
+                    errors.append((idx, rep, j))
+            results[idx] = True
+        except Exception as e:  # noqa: BLE001
+            errors.append((idx, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert len(results) == 3
+    ctx.srs_release(srs)
