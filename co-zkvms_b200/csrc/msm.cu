@@ -137,8 +137,11 @@ struct TreeSumArgs {
 __global__ void __launch_bounds__(ACC_TILE) k_treesum(TreeSumArgs A) {
     __shared__ ShPoints sp;
     const int t = threadIdx.x;
-    const uint32_t q = blockIdx.x, id = blockIdx.y;
-    const size_t win = blockIdx.z;
+    // blockIdx.x = (win * NS + id) * chunks + q   (one-dimensional: windows can exceed the 65,535 limit of grid.y/z)
+    const uint32_t q = blockIdx.x % A.chunks;
+    const size_t rest = blockIdx.x / A.chunks;
+    const uint32_t id = (uint32_t)(rest % A.NS);
+    const size_t win = rest / A.NS;
     const xyzz* src = A.masked ? ((id == 0 ? A.w : A.s) + win * A.G) : (A.s + (win * A.NS + id) * (size_t)A.G);
     xyzz acc = xyzz_identity();
     for (uint32_t e = q * A.chunk + t; e < (q + 1) * A.chunk; e += ACC_TILE) {
@@ -243,13 +246,13 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     if ((rc = D.rs[1].ensure(nsums * P.sum_chunks * sizeof(xyzz)))) return rc;
     if ((rc = D.rw[1].ensure(nsums * sizeof(xyzz)))) return rc;
     TreeSumArgs TA{D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.G, P.NS, P.sum_chunk, P.sum_chunks, 1};
-    k_treesum<<<dim3(P.sum_chunks, P.NS, (unsigned)windows), ACC_TILE, 0, st>>>(TA);
+    k_treesum<<<(unsigned)(windows * P.NS * P.sum_chunks), ACC_TILE, 0, st>>>(TA);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
     xyzz* cur = D.rs[1].as<xyzz>();
     if (P.sum_chunks > 1) {
         TreeSumArgs TB{cur, nullptr, D.rw[1].as<xyzz>(), P.sum_chunks, P.NS, P.sum_chunks, 1, 0};
-        k_treesum<<<dim3(1, P.NS, (unsigned)windows), ACC_TILE, 0, st>>>(TB);
+        k_treesum<<<(unsigned)(windows * P.NS), ACC_TILE, 0, st>>>(TB);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
         cur = D.rw[1].as<xyzz>();

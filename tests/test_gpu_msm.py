@@ -300,3 +300,17 @@ def test_concurrent_callers(cozk, ctx, orc):
     assert not errors, errors
     assert len(results) == 3
     ctx.srs_release(srs)
+
+
+def test_large_batch_of_tiny_vectors(ctx, orc):
+    """1000 vectors of 8 points: tens of thousands of (vector, window) pairs in one group (the last PST13 opening levels
+    and small lookup tables produce such shapes)."""
+    n, k = 8, 1000
+    bases = orc.gen_bases(13, n)
+    srs = ctx.srs_register(bases)
+    vecs = [orc.gen_scalars("uniform" if j % 3 else "const", 2000 + j, n) for j in range(k)]
+    got = ctx.msm_batch(srs, vecs, n=n)
+    for j in range(0, k, 37):
+        assert (got[j] == orc.msm(bases, vecs[j])).all(), j
+    assert (got[k - 1] == orc.msm(bases, vecs[k - 1])).all()
+    ctx.srs_release(srs)
