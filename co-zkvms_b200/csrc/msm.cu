@@ -625,10 +625,18 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
             COZK_CUDA(cudaMalloc(&di, n));
             COZK_CUDA(cudaMemcpy(di, infinity, n, cudaMemcpyHostToDevice));
         }
-        int rc = build_table(*D, d, n, S.table_c, S.table_W);
-        if (rc) return rc;
         S.d_bases.push_back(d);
         S.d_inf.push_back(di);
+        int rc = build_table(*D, d, n, S.table_c, S.table_W);
+        if (rc) {
+            // nothing registered yet: give back what was allocated so far
+            for (size_t j = 0; j < S.d_bases.size(); ++j) {
+                cudaSetDevice(ctx->devs[j]->id);
+                cudaFree(S.d_bases[j]);
+                if (S.d_inf[j]) cudaFree(S.d_inf[j]);
+            }
+            return rc;
+        }
     }
     std::lock_guard<std::mutex> lock(ctx->mu);
     *out = ctx->next_handle++;
@@ -651,7 +659,14 @@ int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_base
         COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine)));
         COZK_CUDA(cudaMemcpyPeer(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine)));
         int rc = build_table(D, d, n, S.table_c, S.table_W);
-        if (rc) return rc;
+        if (rc) {
+            cudaFree(d);
+            for (size_t j = 0; j < S.d_bases.size(); ++j) {
+                cudaSetDevice(ctx->devs[j]->id);
+                cudaFree(S.d_bases[j]);
+            }
+            return rc;
+        }
         S.d_bases.push_back(d);
         S.d_inf.push_back(nullptr);
     }
