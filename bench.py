@@ -55,7 +55,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)  # an nvidia-smi query takes ~30-50 ms itself: about 15 samples per second
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
@@ -114,7 +114,8 @@ def main():
         v, ms, sample = cpu_reference_run(log2n, args.dist, args.steps, max(args.warmup, 1), cores)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u64 limbs (254-bit Montgomery)", "data": "synthetic", "config": config,
+                "dtype": "u64", "dtype_note": "254-bit Montgomery field elements on 4 x 64-bit limbs (mulx/adc)", "data": "synthetic",
+                "config": config,
                 "cpu_baseline": {"value": v, "unit": "Mpoints/s", "cores": cores, "kind": "port",
                                  "sample": sample + "; C restatement of the reference's CPU Pippenger (arkworks msm_bigint_wnaf "
                                            "shape); the Rust reference itself cannot be built here"},
@@ -227,7 +228,8 @@ def main():
             traffic = None
         line = {"metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u32 limbs (254-bit Montgomery, IMAD.WIDE carry chains)", "data": "synthetic",
+                "vs_baseline": None, "dtype": "u32", "dtype_note": "254-bit Montgomery field elements on 8 x 32-bit limbs, "
+                "IMAD.WIDE.U32 carry chains; bit-exact integer arithmetic", "data": "synthetic",
                 "config": config,
                 "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 72,
                         "ms_per_step": 1e3 * e2e_s / args.steps},

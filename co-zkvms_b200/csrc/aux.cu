@@ -226,10 +226,9 @@ __global__ void __launch_bounds__(128, 4) k_bench_madd(int iters, const uint8_t*
 //    the highest rate at which the chip retires 32 x 32 -> 64-bit multiply-accumulates.
 __global__ void k_bench_imad_cc(int iters, uint32_t* sink) {
     uint32_t a0 = threadIdx.x * 2654435761u + 12345u, a1 = a0 ^ 0x55aa55aau, a2 = a0 * 3u + 1u, a3 = a0 * 7u + 5u;
-    uint32_t b = blockIdx.x * 40503u + 977u;
     uint32_t e[4][9];
     for (int c = 0; c < 4; ++c)
-        for (int k = 0; k < 9; ++k) e[c][k] = a0 + 17u * k + c;
+        for (int k = 0; k < 9; ++k) e[c][k] = a0 + 17u * k + c + blockIdx.x * 40503u;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {

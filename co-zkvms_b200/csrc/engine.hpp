@@ -89,6 +89,8 @@ struct cozk_ctx {
     uint64_t next_handle = 1;
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
+    long opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never)
+    long opt_stream_chunks = 4;
     long opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     long opt_table_max_bytes = 16L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table; 0 disables tables
 };

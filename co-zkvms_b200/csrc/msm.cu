@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(ACC_TILE) k_segscan(AccumulateArgs A) {
         const bool left_open = from_start && base > 0 && (A.keys[base - 1] & KEY_MASK) == k;
         const bool right_open = to_end && base + ACC_TILE < A.m && (A.keys[base + ACC_TILE] & KEY_MASK) == k;
         if (!left_open && !right_open) {
-            store_xyzz(&A.buckets[k], p);
+            emit_bucket(A, k, p);
         } else if (from_start) {
             okey[0] = k;
             store_xyzz(&A.ppts[2 * (size_t)blockIdx.x], p);
@@ -173,9 +173,13 @@ static inline unsigned grid_for(size_t threads, unsigned block) { return (unsign
 // Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
 static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
                      const uint8_t* const* d_vec_ptrs, size_t vector_stride, size_t stride, int form, size_t table_stride,
-                     size_t val_offset, double* launches) {
+                     size_t val_offset, double* launches, int phases = 3, bool merge = false) {
+    // phases: bit 0 = decompose + sort + accumulate into the buckets, bit 1 = bucket reduce + finish.  A streamed MSM
+    // (one vector fed in point chunks while the next chunk is still on the PCIe bus) runs bit 0 once per chunk, with
+    // merge = true from the second chunk on, and bit 1 once at the end.
     cudaStream_t st = D.stream;
     int rc;
+    if (phases & 1) {
     if ((rc = D.keys_a.ensure(P.m * 4))) return rc;
     if ((rc = D.vals_a.ensure(P.m * 4))) return rc;
     if ((rc = D.keys_b.ensure(P.m * 4))) return rc;
@@ -208,7 +212,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     COZK_CUDA(cudaEventRecord(D.ev[3], st));
 
     // 3 accumulate, level by level
-    COZK_CUDA(cudaMemsetAsync(D.buckets.p, 0, P.total_buckets * sizeof(xyzz), st));
+    if (!merge) COZK_CUDA(cudaMemsetAsync(D.buckets.p, 0, P.total_buckets * sizeof(xyzz), st));
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
         size_t m = P.acc_entries[lvl];
         const int tile = P.acc_tile[lvl];
@@ -224,7 +228,8 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
                          lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
                          D.buckets.as<xyzz>(),
                          pk_out.as<uint32_t>(),
-                         pp_out.as<xyzz>()};
+                         pp_out.as<xyzz>(),
+                         merge ? 1 : 0};
         if (lvl == 0) k_accumulate<ACC_L, true><<<grid_for(T, 128), 128, 0, st>>>(A);
         else if (tile == ACC_L) k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
         else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
@@ -232,6 +237,8 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         COZK_CUDA(cudaGetLastError());
     }
     COZK_CUDA(cudaEventRecord(D.ev[4], st));
+    }  // phase bit 0
+    if (!(phases & 2)) return COZK_OK;
 
     // 4 bucket reduce: group running sums, then NS plain sums per window
     size_t windows = (size_t)P.g * P.Wb;
@@ -275,9 +282,9 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     return COZK_OK;
 }
 
-static void add_stage_times(Device& D) {
+static void add_stage_times(Device& D, int first = 1, int last = 5) {
     float ms;
-    for (int s = 1; s <= 5; ++s) {
+    for (int s = first; s <= last; ++s) {
         if (cudaEventElapsedTime(&ms, D.ev[s], D.ev[s + 1]) == cudaSuccess) D.stats[s] += ms;
     }
 }
@@ -324,6 +331,59 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         }
         const affine* d_bases = table_c ? S.d_bases[dev_index] : S.d_bases[dev_index] + offset + lo;
         const size_t table_stride = table_c ? S.n : 0, val_offset = table_c ? offset + lo : 0;
+
+        // One long vector from host memory: feed it in point chunks through ONE bucket set, so that the H2D copy of
+        // chunk i+1 overlaps decompose / sort / accumulate of chunk i; reduce and finish run once.
+        if (host_scalars && k == 1 && ctx->opt_stream_chunks > 1 && ctx->opt_stream_min_points > 0 &&
+            pn >= (size_t)ctx->opt_stream_min_points) {
+            const size_t C = (size_t)ctx->opt_stream_chunks;
+            const size_t cn_max = (((pn + C - 1) / C) + 31) & ~(size_t)31;
+            const size_t chunks = (pn + cn_max - 1) / cn_max;
+            const uint32_t cfix = table_c ? 0 : make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, 0).c;
+            const uint8_t* src0 = reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride;
+            auto stage_chunk = [&](size_t ci) -> int {
+                int slot = (int)(ci & 1);
+                size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
+                int rc = D.scalars[slot].ensure((cn_max - 1) * stride + 32 + 256);
+                if (rc) return rc;
+                COZK_CUDA(cudaMemcpyAsync(D.scalars[slot].p, src0 + clo * stride, (cn - 1) * stride + 32, cudaMemcpyHostToDevice,
+                                          D.copy_stream));
+                COZK_CUDA(cudaEventRecord(D.copy_done[slot], D.copy_stream));
+                return COZK_OK;
+            };
+            int rc = stage_chunk(0);
+            if (rc) return rc;
+            MsmPlan P;
+            for (size_t ci = 0; ci < chunks; ++ci) {
+                int slot = (int)(ci & 1);
+                size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
+                P = make_plan(cn, 1, bits, max_buckets, cfix ? cfix : (uint32_t)ctx->opt_window, table_c);
+                plan_mults += P.field_mults();
+                plan_pairs += (double)P.m;
+                last_c = P.c;
+                last_W = P.W;
+                COZK_CUDA(cudaStreamWaitEvent(D.stream, D.copy_done[slot], 0));
+                if (ci + 1 < chunks && (rc = stage_chunk(ci + 1))) return rc;  // the other slot was released by the sync below
+                rc = run_group(D, P, table_c ? d_bases : d_bases + clo, d_inf ? d_inf + clo : nullptr, D.scalars[slot].as<uint8_t>(),
+                               nullptr, 0, stride, form, table_stride, val_offset + (table_c ? clo : 0), &launches, 1, ci > 0);
+                if (rc) return rc;
+                COZK_CUDA(cudaStreamSynchronize(D.stream));
+                add_stage_times(D, 1, 3);
+            }
+            rc = run_group(D, P, d_bases, d_inf, nullptr, nullptr, 0, stride, form, table_stride, val_offset, &launches, 2, false);
+            if (rc) return rc;
+            if (!D.finish_on_host) COZK_CUDA(cudaMemcpyAsync(pass_out, D.out.p, 72, cudaMemcpyDeviceToHost, D.stream));
+            COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
+            COZK_CUDA(cudaStreamSynchronize(D.stream));
+            add_stage_times(D, 4, 5);
+            if (D.finish_on_host) {
+                auto h0 = std::chrono::steady_clock::now();
+                FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out};
+                finish_body(0, F);
+                host_finish_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+            }
+            continue;
+        }
 
         // vectors per group: bounded by the pair budget
         MsmPlan probe = make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, table_c);
@@ -750,6 +810,13 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "group_pairs")) {
         if (value < 1) return COZK_ERR_INVALID_ARG;
         ctx->opt_group_pairs = value;
+    } else if (!strcmp(name, "stream_min_points")) {
+        // a single host-resident vector of at least this many points is streamed in chunks (0 = never)
+        if (value < 0) return COZK_ERR_INVALID_ARG;
+        ctx->opt_stream_min_points = value;
+    } else if (!strcmp(name, "stream_chunks")) {
+        if (value < 1 || value > 64) return COZK_ERR_INVALID_ARG;
+        ctx->opt_stream_chunks = value;
     } else if (!strcmp(name, "table_window")) {
         // window size of the tables of SRS registered from now on (0 = choose from the SRS length)
         if (value != 0 && (value < (long)C_MIN || value > (long)C_MAX)) return COZK_ERR_INVALID_ARG;

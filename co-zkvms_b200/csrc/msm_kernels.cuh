@@ -173,7 +173,14 @@ struct AccumulateArgs {
     xyzz* buckets;            // [g*W*B]
     uint32_t* pkeys;          // [2*T] partial keys out, T = ceil(m/L)
     xyzz* ppts;               // [2*T] partial sums out
+    int merge;                // 0: a finished run overwrites its bucket; 1: it is added to what the bucket already holds
+                              // (one MSM streamed in several point chunks through the same bucket set)
 };
+
+COZK_HD void emit_bucket(const AccumulateArgs& A, uint32_t key, const xyzz& sum) {
+    if (A.merge) store_xyzz(&A.buckets[key], xyzz_add(load_xyzz(&A.buckets[key]), sum));
+    else store_xyzz(&A.buckets[key], sum);
+}
 
 template <int L, bool LEVEL1>
 COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
@@ -195,7 +202,7 @@ COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
                     key0 = cur;
                     store_xyzz(&A.ppts[2 * t], acc);
                 } else {
-                    store_xyzz(&A.buckets[cur], acc);
+                    emit_bucket(A, cur, acc);
                 }
             }
             acc = xyzz_identity();
@@ -218,7 +225,7 @@ COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
     if (cur != KEY_MASK) {
         bool lo = first_run && left_open;
         if (!lo && !right_open) {
-            store_xyzz(&A.buckets[cur], acc);
+            emit_bucket(A, cur, acc);
         } else if (first_run) {
             // the whole chunk is one run, open on at least one side: sum in slot 0, a filler keeps the run contiguous
             key0 = cur;

@@ -22,7 +22,7 @@ def lib():
                                    os.path.join(HERE, "emul.cpp")])
         L = ctypes.CDLL(LIB)
         vp, sz, u32, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
-        L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp, u32, sz, sz]
+        L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp, u32, sz, sz, u32]
         L.emul_field_op.argtypes = [ci, vp, vp, vp, sz]
         L.emul_g1_op.argtypes = [ci, vp, vp, vp, sz]
         _lib = L
@@ -33,7 +33,8 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
-def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None, table_c=0, n=None, base_offset=0):
+def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None, table_c=0, n=None, base_offset=0,
+        stream_chunks=1):
     """scalars: (g*n, stride) uint8 laid out vector after vector.  table_c != 0: `bases` is the whole registered SRS,
     a table of 2^(table_c*w) * P rows is built from it and the call covers [base_offset, base_offset + n)."""
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
@@ -44,7 +45,7 @@ def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None, tabl
     st = np.zeros(4, np.uint32)
     inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
     rc = lib().emul_msm(_p(bases), n, _p(scalars), n * stride, stride, form, g, bits, c, _p(inf), _p(out), _p(st),
-                        table_c, srs_n, base_offset)
+                        table_c, srs_n, base_offset, stream_chunks)
     assert rc == 0, rc
     return out, st
 

@@ -22,7 +22,7 @@ extern "C" {
 // bases: n x 64 B; scalars: g vectors, vector v at scalars + v*vector_stride, element i at + i*stride; out: g x 72 B
 int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vector_stride, size_t stride, int form,
              uint32_t g, uint32_t max_bits, uint32_t force_c, const uint8_t* infinity, uint8_t* out, uint32_t* stats,
-             uint32_t table_c, size_t srs_n, size_t base_offset) {
+             uint32_t table_c, size_t srs_n, size_t base_offset, uint32_t stream_chunks) {
     if (n == 0) {
         for (uint32_t v = 0; v < g; ++v) {
             memset(out + 72 * v, 0, 72);
@@ -42,42 +42,51 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         for (size_t i = 0; i < srs_n; ++i) table_body(i, TA);
         base_ptr = table.data();
     }
-    std::vector<uint32_t> keys(P.m), vals(P.m);
-    DecomposeArgs D{scalars, nullptr, vector_stride, stride, form, n, g, P.c, P.W, infinity, keys.data(), vals.data(),
-                    P.Wb, table_c ? srs_n : 0, table_c ? base_offset : 0};
-    for (size_t t = 0; t < (size_t)g * n; ++t) decompose_body(t, D);
-
-    std::vector<size_t> order(P.m);
-    std::iota(order.begin(), order.end(), (size_t)0);
-    uint32_t mask = P.sort_bits >= 32 ? 0xFFFFFFFFu : ((1u << P.sort_bits) - 1u);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return (keys[a] & mask) < (keys[b] & mask); });
-    std::vector<uint32_t> sk(P.m), sv(P.m);
-    for (size_t i = 0; i < P.m; ++i) {
-        sk[i] = keys[order[i]];
-        sv[i] = vals[order[i]];
-    }
-
     std::vector<xyzz> buckets(P.total_buckets);
     memset(buckets.data(), 0, buckets.size() * sizeof(xyzz));
+    // stream_chunks > 1 (single vector only): the engine's streamed mode - the point range goes through decompose, sort
+    // and accumulate in chunks that MERGE into one bucket set
+    size_t chunks = (stream_chunks > 1 && g == 1) ? stream_chunks : 1;
+    size_t cn_max = (((n + chunks - 1) / chunks) + 31) & ~(size_t)31;
+    chunks = (n + cn_max - 1) / cn_max;
     std::vector<uint32_t> pk_in, pk_out;
     std::vector<xyzz> pp_in, pp_out;
-    for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
-        size_t m = P.acc_entries[lvl];
-        const int tile = P.acc_tile[lvl];
-        size_t T = (m + tile - 1) / tile;
-        pk_out.assign(2 * T, 0xDEADBEEFu);
-        pp_out.assign(2 * T, xyzz_identity());
-        AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), base_ptr,
-                         pp_in.data(), buckets.data(), pk_out.data(), pp_out.data()};
-        for (size_t t = 0; t < T; ++t) {
-            // levels >= 2 run on the GPU as the block-cooperative k_segscan, whose output contract is this body with
-            // one "thread" per tile of ACC_TILE slots
-            if (lvl == 0) accumulate_body<ACC_L, true>(t, A);
-            else if (tile == ACC_L) accumulate_body<ACC_L, false>(t, A);
-            else accumulate_body<ACC_TILE, false>(t, A);
+    for (size_t ci = 0; ci < chunks; ++ci) {
+        size_t clo = ci * cn_max, cn = std::min(cn_max, n - clo);
+        MsmPlan Pc = chunks == 1 ? P : make_plan(cn, g, max_bits, (size_t)1 << 24, P.c, table_c);
+        std::vector<uint32_t> keys(Pc.m), vals(Pc.m);
+        DecomposeArgs D{scalars + clo * stride, nullptr, vector_stride, stride, form, cn, g, Pc.c, Pc.W,
+                        infinity ? infinity + clo : nullptr, keys.data(), vals.data(),
+                        Pc.Wb, table_c ? srs_n : 0, table_c ? base_offset + clo : 0};
+        for (size_t t = 0; t < (size_t)g * cn; ++t) decompose_body(t, D);
+        std::vector<size_t> order(Pc.m);
+        std::iota(order.begin(), order.end(), (size_t)0);
+        uint32_t mask = Pc.sort_bits >= 32 ? 0xFFFFFFFFu : ((1u << Pc.sort_bits) - 1u);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return (keys[a] & mask) < (keys[b] & mask); });
+        std::vector<uint32_t> sk(Pc.m), sv(Pc.m);
+        for (size_t i = 0; i < Pc.m; ++i) {
+            sk[i] = keys[order[i]];
+            sv[i] = vals[order[i]];
         }
-        pk_in.swap(pk_out);
-        pp_in.swap(pp_out);
+        const affine* chunk_bases = table_c ? base_ptr : base_ptr + clo;
+        for (size_t lvl = 0; lvl < Pc.acc_entries.size(); ++lvl) {
+            size_t m = Pc.acc_entries[lvl];
+            const int tile = Pc.acc_tile[lvl];
+            size_t T = (m + tile - 1) / tile;
+            pk_out.assign(2 * T, 0xDEADBEEFu);
+            pp_out.assign(2 * T, xyzz_identity());
+            AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), chunk_bases,
+                             pp_in.data(), buckets.data(), pk_out.data(), pp_out.data(), ci > 0 ? 1 : 0};
+            for (size_t t = 0; t < T; ++t) {
+                // levels >= 2 run on the GPU as the block-cooperative k_segscan, whose output contract is this body with
+                // one "thread" per tile of ACC_TILE slots
+                if (lvl == 0) accumulate_body<ACC_L, true>(t, A);
+                else if (tile == ACC_L) accumulate_body<ACC_L, false>(t, A);
+                else accumulate_body<ACC_TILE, false>(t, A);
+            }
+            pk_in.swap(pk_out);
+            pp_in.swap(pp_out);
+        }
     }
     // the top level must not leave any open run
     if (P.acc_entries.size() > 1 || P.m > 0)
@@ -88,14 +97,14 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     GroupArgs GA{buckets.data(), gs.data(), gw.data(), P.group_l, windows * P.G};
     for (size_t t = 0; t < GA.threads; ++t) group_body(t, GA);
     // on the GPU these two levels are k_treesum (masked, then plain); same output contract as the bodies below
-    uint32_t chunks = P.sum_chunks;
-    std::vector<xyzz> cur(windows * P.NS * chunks), nxt;
-    BitsumArgs BA{gs.data(), gw.data(), cur.data(), P.G, P.NS, P.sum_chunk, chunks, windows * P.NS * chunks};
+    uint32_t schunks = P.sum_chunks;
+    std::vector<xyzz> cur(windows * P.NS * schunks), nxt;
+    BitsumArgs BA{gs.data(), gw.data(), cur.data(), P.G, P.NS, P.sum_chunk, schunks, windows * P.NS * schunks};
     for (size_t t = 0; t < BA.threads; ++t) bitsum_body(t, BA);
-    if (chunks > 1) {
+    if (schunks > 1) {
         size_t threads = windows * P.NS;
         nxt.assign(threads, xyzz_identity());
-        PlainSumArgs SA{cur.data(), nxt.data(), chunks, threads};
+        PlainSumArgs SA{cur.data(), nxt.data(), schunks, threads};
         for (size_t t = 0; t < threads; ++t) plainsum_body(t, SA);
         cur.swap(nxt);
     }

@@ -144,3 +144,22 @@ def test_precomputed_table_mode(orc):
     small = orc.gen_scalars("small16", 3, n_srs)
     got, st = emul.msm(bases, small, bits=16, table_c=8)
     assert st[1] == 3 and (got[0] == orc.msm(bases, small)).all()
+
+
+def test_streamed_chunks_merge_into_one_bucket_set(orc):
+    """One vector fed in point chunks (the engine's H2D-overlap mode): later chunks ADD to the buckets of earlier ones."""
+    n = 700
+    bases = orc.gen_bases(9, n)
+    for dist in ("uniform", "const", "wminus", "zero_half"):
+        sc = orc.gen_scalars(dist, 21, n)
+        want = orc.msm(bases, sc)
+        for chunks, c, tc in ((2, 0, 0), (4, 6, 0), (5, 0, 7), (3, 0, 11)):
+            got, _ = emul.msm(bases, sc, c=c, table_c=tc, stream_chunks=chunks)
+            assert (got[0] == want).all(), (dist, chunks, c, tc)
+    inf = np.zeros(n, np.uint8)
+    inf[::5] = 1
+    u = orc.gen_scalars("uniform", 4, n)
+    masked = u.copy()
+    masked[::5] = 0
+    got, _ = emul.msm(bases, u, infinity=inf, stream_chunks=3)
+    assert (got[0] == orc.msm(bases, masked)).all()

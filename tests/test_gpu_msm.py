@@ -314,3 +314,28 @@ def test_large_batch_of_tiny_vectors(ctx, orc):
         assert (got[j] == orc.msm(bases, vecs[j])).all(), j
     assert (got[k - 1] == orc.msm(bases, vecs[k - 1])).all()
     ctx.srs_release(srs)
+
+
+def test_streamed_host_vector(cozk, orc):
+    """A long host-resident vector is streamed in point chunks through one bucket set (H2D of chunk i+1 overlaps the
+    compute of chunk i): same bytes as the one-shot path, with and without the SRS table, Rep3 stride, odd lengths."""
+    n = (1 << 16) + 777
+    bases = orc.gen_bases(21, n)
+    with cozk.Context() as c2:
+        c2.set_option("stream_min_points", 1 << 12)
+        srs_t = c2.srs_register(bases)
+        c2.set_option("table_max_mib", 0)
+        srs_p = c2.srs_register(bases)
+        for dist in ("uniform", "const", "wminus"):
+            sc = orc.gen_scalars(dist, 31, n, stride=64)
+            want = orc.msm(bases, sc)
+            for chunks in (2, 4, 7):
+                c2.set_option("stream_chunks", chunks)
+                assert (c2.msm_batch(srs_t, [sc], n=n, stride=64)[0] == want).all(), (dist, chunks, "table")
+                assert (c2.msm_batch(srs_p, [sc], n=n, stride=64)[0] == want).all(), (dist, chunks, "plain")
+        sc = orc.gen_scalars("uniform", 32, n)
+        c2.set_option("stream_chunks", 3)
+        got = c2.msm_batch(srs_t, [sc], n=50001, base_offset=1234)
+        assert (got[0] == orc.msm(bases[1234:1234 + 50001], sc[:50001])).all()
+        c2.srs_release(srs_t)
+        c2.srs_release(srs_p)

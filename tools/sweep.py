@@ -20,6 +20,8 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--window", type=int, default=0)
 ap.add_argument("--stride", type=int, default=32)
 ap.add_argument("--bits", type=int, default=0)
+ap.add_argument("--stream-min", type=int, default=-1, help="stream_min_points option (-1 default, 0 never)")
+ap.add_argument("--stream-chunks", type=int, default=0)
 ap.add_argument("--table-window", type=int, default=-1, help="-1 auto, 0 no table, else forced table window")
 ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
@@ -27,6 +29,10 @@ args = ap.parse_args()
 ctx = cozk.Context()
 if args.window:
     ctx.set_option("window", args.window)
+if args.stream_min >= 0:
+    ctx.set_option("stream_min_points", args.stream_min)
+if args.stream_chunks:
+    ctx.set_option("stream_chunks", args.stream_chunks)
 if args.table_window == 0:
     ctx.set_option("table_max_mib", 0)
 elif args.table_window > 0:
