@@ -56,7 +56,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     std::mutex mu;  // one MSM at a time per device
-    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, pk[2], pp[2], rs[2], rw[2], out, flush;
+    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2, pk[2], pp[2], rs[2], rw[2], out, flush;
     cudaEvent_t ev[8] = {};
     cudaEvent_t copy_done[2] = {};
     double stats[12] = {};
@@ -89,8 +89,8 @@ struct cozk_ctx {
     uint64_t next_handle = 1;
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
-    long opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never)
-    long opt_stream_chunks = 4;
+    long opt_stream_min_points = 1L << 23;  // host-resident single vectors this long are streamed in chunks (0 = never)
+    long opt_stream_chunks = 2;              // measured: 2 chunks give +5-7 % end to end at 2^24-2^25, 4 chunks lose it again to the merge passes
     long opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     long opt_table_max_bytes = 16L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table; 0 disables tables
 };

@@ -23,7 +23,7 @@ void set_error(const std::string& msg) { g_error = msg; }
 Device::~Device() {
     cudaSetDevice(id);
     DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
-                      &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush};
+                      &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush, &buckets2};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : copy_done) if (e) cudaEventDestroy(e);
@@ -38,6 +38,9 @@ __global__ void __launch_bounds__(256) k_decompose(DecomposeArgs A) {
 template <int L, bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<L, LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+__global__ void __launch_bounds__(128, 3) k_merge(MergeArgs A) {
+    merge_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
 __global__ void __launch_bounds__(128, 3) k_group(GroupArgs A) {
     group_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
@@ -212,7 +215,12 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     COZK_CUDA(cudaEventRecord(D.ev[3], st));
 
     // 3 accumulate, level by level
-    if (!merge) COZK_CUDA(cudaMemsetAsync(D.buckets.p, 0, P.total_buckets * sizeof(xyzz), st));
+    xyzz* bucket_dst = D.buckets.as<xyzz>();
+    if (merge) {
+        if ((rc = D.buckets2.ensure(P.total_buckets * sizeof(xyzz)))) return rc;
+        bucket_dst = D.buckets2.as<xyzz>();
+    }
+    COZK_CUDA(cudaMemsetAsync(bucket_dst, 0, P.total_buckets * sizeof(xyzz), st));
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
         size_t m = P.acc_entries[lvl];
         const int tile = P.acc_tile[lvl];
@@ -226,13 +234,18 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
                          D.vals_b.as<uint32_t>(),
                          d_bases,
                          lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
-                         D.buckets.as<xyzz>(),
+                         bucket_dst,
                          pk_out.as<uint32_t>(),
-                         pp_out.as<xyzz>(),
-                         merge ? 1 : 0};
+                         pp_out.as<xyzz>()};
         if (lvl == 0) k_accumulate<ACC_L, true><<<grid_for(T, 128), 128, 0, st>>>(A);
         else if (tile == ACC_L) k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
         else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+    }
+    if (merge) {
+        MergeArgs MA{D.buckets.as<xyzz>(), bucket_dst, P.total_buckets};
+        k_merge<<<grid_for(P.total_buckets, 128), 128, 0, st>>>(MA);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
     }

@@ -173,13 +173,24 @@ struct AccumulateArgs {
     xyzz* buckets;            // [g*W*B]
     uint32_t* pkeys;          // [2*T] partial keys out, T = ceil(m/L)
     xyzz* ppts;               // [2*T] partial sums out
-    int merge;                // 0: a finished run overwrites its bucket; 1: it is added to what the bucket already holds
-                              // (one MSM streamed in several point chunks through the same bucket set)
 };
 
-COZK_HD void emit_bucket(const AccumulateArgs& A, uint32_t key, const xyzz& sum) {
-    if (A.merge) store_xyzz(&A.buckets[key], xyzz_add(load_xyzz(&A.buckets[key]), sum));
-    else store_xyzz(&A.buckets[key], sum);
+COZK_HD void emit_bucket(const AccumulateArgs& A, uint32_t key, const xyzz& sum) { store_xyzz(&A.buckets[key], sum); }
+
+// Streamed MSM (one vector fed in point chunks): every chunk after the first accumulates into a scratch bucket set,
+// which is then added to the main one - a dense pass, one thread per bucket.  (Adding inside the accumulate kernel
+// at the moment a run closes was measured 2x slower: lanes close their runs at different iterations, so the 14
+// multiplications of the addition ran once per lane instead of once per warp.)
+struct MergeArgs {
+    xyzz* buckets;
+    const xyzz* scratch;
+    size_t total;
+};
+COZK_HD void merge_body(size_t b, const MergeArgs& A) {
+    if (b >= A.total) return;
+    xyzz s = load_xyzz(&A.scratch[b]);
+    if (xyzz_is_identity(s)) return;
+    store_xyzz(&A.buckets[b], xyzz_add(load_xyzz(&A.buckets[b]), s));
 }
 
 template <int L, bool LEVEL1>

@@ -69,6 +69,11 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             sv[i] = vals[order[i]];
         }
         const affine* chunk_bases = table_c ? base_ptr : base_ptr + clo;
+        std::vector<xyzz> scratch;
+        if (ci > 0) {
+            scratch.resize(P.total_buckets);
+            memset(scratch.data(), 0, scratch.size() * sizeof(xyzz));
+        }
         for (size_t lvl = 0; lvl < Pc.acc_entries.size(); ++lvl) {
             size_t m = Pc.acc_entries[lvl];
             const int tile = Pc.acc_tile[lvl];
@@ -76,7 +81,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             pk_out.assign(2 * T, 0xDEADBEEFu);
             pp_out.assign(2 * T, xyzz_identity());
             AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), chunk_bases,
-                             pp_in.data(), buckets.data(), pk_out.data(), pp_out.data(), ci > 0 ? 1 : 0};
+                             pp_in.data(), ci > 0 ? scratch.data() : buckets.data(), pk_out.data(), pp_out.data()};
             for (size_t t = 0; t < T; ++t) {
                 // levels >= 2 run on the GPU as the block-cooperative k_segscan, whose output contract is this body with
                 // one "thread" per tile of ACC_TILE slots
@@ -86,6 +91,10 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             }
             pk_in.swap(pk_out);
             pp_in.swap(pp_out);
+        }
+        if (ci > 0) {
+            MergeArgs MA{buckets.data(), scratch.data(), P.total_buckets};
+            for (size_t b = 0; b < P.total_buckets; ++b) merge_body(b, MA);
         }
     }
     // the top level must not leave any open run
