@@ -17,13 +17,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcozk_msm.so")
-SOURCES = ["msm.cu", "aux.cu", "pst13.cu", "fixed_base.cu"]
-HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp"]
+SOURCES = ["msm.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
+HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "rep3_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 MONT, CANON = 0, 1
-OK, ERR_INVALID_ARG, ERR_KEY_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_BAD_HANDLE = 0, -1, -2, -3, -4, -5
+OK, ERR_INVALID_ARG, ERR_KEY_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_BAD_HANDLE, ERR_WIRE = 0, -1, -2, -3, -4, -5, -6
 DIST = {"uniform": 0, "const": 1, "wminus": 2, "dup": 3, "small16": 4, "zero_half": 5}
 
 # every symbol include/cozk_msm.h and csrc/pst13.hpp declare (checked by tests/test_abi.py without a GPU)
@@ -36,6 +36,10 @@ ABI_SYMBOLS = [
     "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_open",
     "cozk_pst13_combine_commitment_shares", "cozk_pst13_coordinate_prove", "cozk_combine_comm",
     "cozk_fixed_base_batch_mul",
+    # include/cozk_rep3.h
+    "cozk_poly_upload", "cozk_poly_from_device", "cozk_poly_from_wire", "cozk_poly_release", "cozk_poly_info", "cozk_poly_download",
+    "cozk_pst13_batch_commit_polys", "cozk_rep3_linear_combination", "cozk_rep3_evaluate_at_chi", "cozk_srs_pair_sums",
+    "cozk_pst13_open_poly", "cozk_pst13_open_paired", "cozk_rep3_last_stats",
 ]
 
 
@@ -48,7 +52,7 @@ class CozkError(RuntimeError):
 def build(force=False, verbose=False):
     """Compile libcozk_msm.so for sm_100a with nvcc (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", "cozk_msm.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", h) for h in ("cozk_msm.h", "cozk_rep3.h")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
         return LIB_PATH
@@ -106,6 +110,20 @@ def lib():
     L.cozk_pst13_coordinate_prove.argtypes = [vp, sz, sz, vp]
     L.cozk_combine_comm.argtypes = [vp, sz, vp]
     L.cozk_fixed_base_batch_mul.argtypes = [vp, vp, vp, sz, sz, ci, vp, ctypes.POINTER(u64)]
+    pu64 = ctypes.POINTER(u64)
+    L.cozk_poly_upload.argtypes = [vp, ci, vp, sz, ci, pu64]
+    L.cozk_poly_from_device.argtypes = [vp, ci, vp, sz, ci, pu64]
+    L.cozk_poly_from_wire.argtypes = [vp, ci, vp, sz, ci, pu64, ctypes.POINTER(sz)]
+    L.cozk_poly_release.argtypes = [vp, u64]
+    L.cozk_poly_info.argtypes = [vp, u64, ctypes.POINTER(sz), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.cozk_poly_download.argtypes = [vp, u64, vp]
+    L.cozk_pst13_batch_commit_polys.argtypes = [vp, u64, pu64, sz, ci, vp, ctypes.POINTER(ctypes.c_uint8)]
+    L.cozk_rep3_linear_combination.argtypes = [vp, pu64, vp, sz, ci, pu64]
+    L.cozk_rep3_evaluate_at_chi.argtypes = [vp, pu64, sz, vp, sz, vp]
+    L.cozk_srs_pair_sums.argtypes = [vp, u64, pu64]
+    L.cozk_pst13_open_poly.argtypes = [vp, pu64, pu64, sz, u64, vp, vp, vp]
+    L.cozk_pst13_open_paired.argtypes = [vp, pu64, pu64, sz, vp, sz, vp, ci, vp, vp]
+    L.cozk_rep3_last_stats.argtypes = [vp, cd]
     _lib = L
     return L
 
@@ -337,3 +355,4 @@ def g1_sum(points72):
 
 
 from . import pst13  # noqa: E402  (host-side mirror of the reference's PST13 / MultilinearPC interface)
+from . import rep3  # noqa: E402  (device-resident Rep3 polynomials: include/cozk_rep3.h)

@@ -73,10 +73,28 @@ struct SrsEntry {
     uint32_t table_W = 1;            // rows
 };
 
+// A device-resident polynomial (include/cozk_rep3.h).  d_data holds `total` coefficients; the handle covers
+// [lo, lo + len) of them (Rep3DensePolynomial::chunk_range).
+struct PolyEntry {
+    int dev = 0;            // index into cozk_ctx::devs
+    uint32_t kind = 0;      // POLY_SHARED / POLY_MONT / POLY_CANON (rep3_kernels.cuh)
+    int user_kind = 0;      // the COZK_POLY_* constant it was created as
+    unsigned bits = 0;      // max_num_bits hint for the MSM (8/16/32/64 for small unsigned kinds, 0 otherwise)
+    uint8_t* d_data = nullptr;
+    size_t total = 0, lo = 0, len = 0;
+    size_t elem_bytes() const { return kind == 0 ? 64 : 32; }
+    const uint8_t* chunk() const { return d_data + lo * elem_bytes(); }
+};
+
 }  // namespace cozk
 
 struct cozk_ctx;
 namespace cozk {
+// Register n points that already live on device `device_index` (d_inf: optional per-point infinity flags, device memory).
+int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out);
+// PST13 opening over evaluations that are already on device 0 of the context as a dense Montgomery vector (consumed).
+int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, fr* d_r0,
+                      const void* point, void* out_proofs, void* out_eval);
 // The one entry every public MSM call funnels into (msm.cu).  only_device < 0: use all devices of the context.
 int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offset, size_t n, const void* const* host_scalars,
                  const void* const* dev_scalars, size_t k, size_t stride, int form, unsigned max_bits, void* out);
@@ -86,6 +104,8 @@ struct cozk_ctx {
     std::vector<std::unique_ptr<cozk::Device>> devs;
     std::mutex mu;  // guards the SRS table and options
     std::map<uint64_t, cozk::SrsEntry> srs;
+    std::map<uint64_t, cozk::PolyEntry> polys;
+    double rep3_stats[8] = {};
     uint64_t next_handle = 1;
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)

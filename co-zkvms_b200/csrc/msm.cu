@@ -589,6 +589,82 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
     return COZK_OK;
 }
 
+// rows of the precomputed table for an SRS of n points under the context's memory policy (1 = bases only)
+static void srs_table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t* W) {
+    *c = 0;
+    *W = 1;
+    if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
+    uint32_t tc = ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
+    uint32_t tw = windows_for(254, tc);
+    if ((double)tw * (double)n * sizeof(affine) > (double)ctx->opt_table_max_bytes) return;
+    if ((double)tw * (double)n >= 2147483647.0) return;  // table indices share 31 bits with the point index; all-ones is the skip mark
+    *c = tc;
+    *W = tw;
+}
+static int srs_build_table(Device& D, affine* d_table, size_t n, uint32_t c, uint32_t W) {
+    if (W <= 1 || n == 0) return COZK_OK;
+    TableArgs A{d_table, n, c, W};
+    k_build_table<<<grid_for(n, 128), 128, 0, D.stream>>>(A);
+    COZK_CUDA(cudaGetLastError());
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    return COZK_OK;
+}
+
+// Bases (and optional infinity flags) that already live on one device of the context: copied device-to-device, every
+// other device gets a peer copy; the precomputed table is built on each.
+int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out) {
+    if (!ctx || !out || (!d_bases64 && n) || device_index < 0 || device_index >= (int)ctx->devs.size()) {
+        set_error("bad argument");
+        return COZK_ERR_INVALID_ARG;
+    }
+    SrsEntry S;
+    S.n = n;
+    srs_table_shape(ctx, n, &S.table_c, &S.table_W);
+    auto undo = [&]() {
+        for (size_t j = 0; j < S.d_bases.size(); ++j) {
+            cudaSetDevice(ctx->devs[j]->id);
+            if (S.d_bases[j]) cudaFree(S.d_bases[j]);
+            if (S.d_inf[j]) cudaFree(S.d_inf[j]);
+        }
+    };
+    bool any_inf = false;
+    if (d_inf && n) {
+        std::vector<uint8_t> flags(n);
+        COZK_CUDA(cudaSetDevice(ctx->devs[device_index]->id));
+        COZK_CUDA(cudaMemcpy(flags.data(), d_inf, n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n && !any_inf; ++i) any_inf = flags[i] != 0;
+    }
+    for (size_t di = 0; di < ctx->devs.size(); ++di) {
+        Device& D = *ctx->devs[di];
+        affine* d = nullptr;
+        uint8_t* dinf = nullptr;
+        cudaError_t e = cudaSetDevice(D.id);
+        if (e == cudaSuccess) e = cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine));
+        if (e == cudaSuccess) e = cudaMemcpyPeer(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine));
+        if (e == cudaSuccess && any_inf) e = cudaMalloc(&dinf, n);
+        if (e == cudaSuccess && any_inf) e = cudaMemcpyPeer(dinf, D.id, d_inf, ctx->devs[device_index]->id, n);
+        int rc = COZK_OK;
+        if (e != cudaSuccess) {
+            set_error(std::string("SRS registration failed: ") + cudaGetErrorString(e));
+            rc = COZK_ERR_CUDA;
+        } else {
+            rc = srs_build_table(D, d, n, S.table_c, S.table_W);
+        }
+        if (rc) {
+            if (d) cudaFree(d);
+            if (dinf) cudaFree(dinf);
+            undo();
+            return rc;
+        }
+        S.d_bases.push_back(d);
+        S.d_inf.push_back(dinf);
+    }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    *out = ctx->next_handle++;
+    ctx->srs[*out] = S;
+    return COZK_OK;
+}
+
 }  // namespace cozk
 
 using namespace cozk;
@@ -640,6 +716,10 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
 
 void cozk_destroy(cozk_ctx* ctx) {
     if (!ctx) return;
+    for (auto& kv : ctx->polys) {
+        cudaSetDevice(ctx->devs[kv.second.dev]->id);
+        if (kv.second.d_data) cudaFree(kv.second.d_data);
+    }
     for (auto& kv : ctx->srs) {
         for (size_t d = 0; d < kv.second.d_bases.size(); ++d) {
             cudaSetDevice(ctx->devs[d]->id);
@@ -652,27 +732,6 @@ void cozk_destroy(cozk_ctx* ctx) {
 
 int cozk_device_count(const cozk_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
-// rows of the precomputed table for an SRS of n points under the context's memory policy (1 = bases only)
-static void table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t* W) {
-    *c = 0;
-    *W = 1;
-    if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
-    uint32_t tc = ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
-    uint32_t tw = windows_for(254, tc);
-    if ((double)tw * (double)n * sizeof(affine) > (double)ctx->opt_table_max_bytes) return;
-    if ((double)tw * (double)n >= 2147483647.0) return;  // table indices share 31 bits with the point index; all-ones is the skip mark
-    *c = tc;
-    *W = tw;
-}
-static int build_table(Device& D, affine* d_table, size_t n, uint32_t c, uint32_t W) {
-    if (W <= 1 || n == 0) return COZK_OK;
-    TableArgs A{d_table, n, c, W};
-    k_build_table<<<grid_for(n, 128), 128, 0, D.stream>>>(A);
-    COZK_CUDA(cudaGetLastError());
-    COZK_CUDA(cudaStreamSynchronize(D.stream));
-    return COZK_OK;
-}
-
 int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out) {
     if (!ctx || !out || (!bases && n) || stride_bytes < 64) {
         set_error("null pointer or stride < 64");
@@ -680,7 +739,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
     }
     SrsEntry S;
     S.n = n;
-    table_shape(ctx, n, &S.table_c, &S.table_W);
+    srs_table_shape(ctx, n, &S.table_c, &S.table_W);
     bool any_inf = false;
     if (infinity)
         for (size_t i = 0; i < n && !any_inf; ++i) any_inf = infinity[i] != 0;
@@ -700,7 +759,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         }
         S.d_bases.push_back(d);
         S.d_inf.push_back(di);
-        int rc = build_table(*D, d, n, S.table_c, S.table_W);
+        int rc = srs_build_table(*D, d, n, S.table_c, S.table_W);
         if (rc) {
             // nothing registered yet: give back what was allocated so far
             for (size_t j = 0; j < S.d_bases.size(); ++j) {
@@ -718,35 +777,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
 }
 
 int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_bases64, size_t n, cozk_srs* out) {
-    if (!ctx || !out || (!d_bases64 && n) || device_index < 0 || device_index >= (int)ctx->devs.size()) {
-        set_error("bad argument");
-        return COZK_ERR_INVALID_ARG;
-    }
-    SrsEntry S;
-    S.n = n;
-    table_shape(ctx, n, &S.table_c, &S.table_W);
-    for (size_t di = 0; di < ctx->devs.size(); ++di) {
-        Device& D = *ctx->devs[di];
-        COZK_CUDA(cudaSetDevice(D.id));
-        affine* d = nullptr;
-        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine)));
-        COZK_CUDA(cudaMemcpyPeer(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine)));
-        int rc = build_table(D, d, n, S.table_c, S.table_W);
-        if (rc) {
-            cudaFree(d);
-            for (size_t j = 0; j < S.d_bases.size(); ++j) {
-                cudaSetDevice(ctx->devs[j]->id);
-                cudaFree(S.d_bases[j]);
-            }
-            return rc;
-        }
-        S.d_bases.push_back(d);
-        S.d_inf.push_back(nullptr);
-    }
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    *out = ctx->next_handle++;
-    ctx->srs[*out] = S;
-    return COZK_OK;
+    return srs_register_from_device(ctx, device_index, d_bases64, nullptr, n, out);
 }
 
 int cozk_srs_release(cozk_ctx* ctx, cozk_srs srs) {

@@ -1,6 +1,7 @@
 // Host-side mirror of the reference's PST13 / MultilinearPC interface for the MSM path (see pst13.hpp), plus the
 // two small kernels PST13's opening needs between its MSMs (fold r -> q, r').
 #include "pst13.hpp"
+#include "../../include/cozk_rep3.h"
 
 #include <cstring>
 #include <map>
@@ -20,13 +21,18 @@ __global__ void k_gather_fr(const uint8_t* src, size_t stride, fr* dst, size_t n
 
 // One level of open() (pst13.rs:454-459):  q[b] = r[2b+1] - r[2b];  r'[b] = r[2b]*(1-t) + r[2b+1]*t = r[2b] + t*q[b];
 // the MSM scalars are q duplicated: scalars[2b] = scalars[2b+1] = q[b].
-__global__ void k_open_fold(const fr* r, fr t, fr* q_dup, fr* r_next, size_t half) {
+// dup == 0 (pair-sum SRS): q is written once per pair.
+__global__ void k_open_fold(const fr* r, fr t, fr* q_out, fr* r_next, size_t half, int dup) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= half) return;
     fr lo = load_fq(&r[2 * b]), hi = load_fq(&r[2 * b + 1]);
     fr q = fr_sub(hi, lo);
-    store_fq(&q_dup[2 * b], q);
-    store_fq(&q_dup[2 * b + 1], q);
+    if (dup) {
+        store_fq(&q_out[2 * b], q);
+        store_fq(&q_out[2 * b + 1], q);
+    } else {
+        store_fq(&q_out[b], q);
+    }
     store_fq(&r_next[b], fr_add(lo, fr_mul(t, q)));
 }
 
@@ -126,17 +132,8 @@ int cozk_pst13_batch_commit_rep3(cozk_ctx* ctx, cozk_srs srs, const void* const*
     return COZK_OK;
 }
 
-int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const void* evals, size_t stride_bytes,
-                    const void* point, int form, void* out_proofs, void* out_eval) {
-    if (!ctx || !level_srs || !evals || !point || !out_proofs || !out_eval || nv == 0 || nv > 30) {
-        set_error("null pointer or bad nv");
-        return COZK_ERR_INVALID_ARG;
-    }
-    if (form != COZK_MONT || stride_bytes < 32 || (stride_bytes & 15)) {
-        set_error("open() takes Montgomery-form Fr values at a stride that is a multiple of 16");
-        return COZK_ERR_INVALID_ARG;
-    }
-    // assert_eq!(nv, ck.nv): every level must hold exactly 2^(nv-i) points
+static int open_check_levels(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv) {
+    // assert_eq!(nv, ck.nv): every level must hold exactly 2^(nv-i) points (pair sums: half of that)
     for (size_t i = 0; i < nv; ++i) {
         size_t len = 0;
         int rc = cozk_srs_len(ctx, level_srs[i], &len);
@@ -145,15 +142,75 @@ int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const v
             set_error("Invalid size of polynomial: SRS level length does not match nv");
             return COZK_ERR_KEY_LENGTH;
         }
+        if (level_pairs) {
+            rc = cozk_srs_len(ctx, level_pairs[i], &len);
+            if (rc) return rc;
+            if (len != ((size_t)1 << (nv - i - 1))) {
+                set_error("pair-sum SRS level length does not match nv");
+                return COZK_ERR_KEY_LENGTH;
+            }
+        }
     }
+    return COZK_OK;
+}
+
+int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const void* evals, size_t stride_bytes,
+                    const void* point, int form, void* out_proofs, void* out_eval) {
+    return cozk_pst13_open_paired(ctx, level_srs, nullptr, nv, evals, stride_bytes, point, form, out_proofs, out_eval);
+}
+
+int cozk_pst13_open_paired(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv,
+                           const void* evals, size_t stride_bytes, const void* point, int form, void* out_proofs,
+                           void* out_eval) {
+    if (!ctx || !level_srs || !evals || !point || !out_proofs || !out_eval || nv == 0 || nv > 30) {
+        set_error("null pointer or bad nv");
+        return COZK_ERR_INVALID_ARG;
+    }
+    if (form != COZK_MONT || stride_bytes < 32 || (stride_bytes & 15)) {
+        set_error("open() takes Montgomery-form Fr values at a stride that is a multiple of 16");
+        return COZK_ERR_INVALID_ARG;
+    }
+    int rc = open_check_levels(ctx, level_srs, level_pairs, nv);
+    if (rc) return rc;
     Device& D = *ctx->devs[0];
     size_t n = (size_t)1 << nv;
     uint8_t* d_in = nullptr;
-    fr *d_r[2] = {nullptr, nullptr}, *d_q = nullptr;
+    fr* d_r0 = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(D.mu);
+        cudaError_t e = cudaSetDevice(D.id);
+        size_t in_bytes = (n - 1) * stride_bytes + 32;
+        if (e == cudaSuccess) e = cudaMalloc(&d_in, in_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&d_r0, n * sizeof(fr));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, evals, in_bytes, cudaMemcpyHostToDevice, D.stream);
+        if (e == cudaSuccess) {
+            k_gather_fr<<<(unsigned)((n + 255) / 256), 256, 0, D.stream>>>(d_in, stride_bytes, d_r0, n);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        if (d_in) cudaFree(d_in);
+        if (e != cudaSuccess) {
+            if (d_r0) cudaFree(d_r0);
+            set_error(std::string("open(): staging the evaluations failed: ") + cudaGetErrorString(e));
+            return COZK_ERR_CUDA;
+        }
+    }
+    return pst13_open_device(ctx, level_srs, level_pairs, nv, d_r0, point, out_proofs, out_eval);
+}
+
+}  // extern "C"
+
+namespace cozk {
+
+// d_r0: 2^nv dense Montgomery evaluations on device 0, owned by this call from here on.
+int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, fr* d_r0,
+                      const void* point, void* out_proofs, void* out_eval) {
+    Device& D = *ctx->devs[0];
+    size_t n = (size_t)1 << nv;
+    fr *d_r[2] = {d_r0, nullptr}, *d_q = nullptr;
     int rc = COZK_OK;
     auto cleanup = [&]() {
         cudaSetDevice(D.id);
-        if (d_in) cudaFree(d_in);
         if (d_r[0]) cudaFree(d_r[0]);
         if (d_r[1]) cudaFree(d_r[1]);
         if (d_q) cudaFree(d_q);
@@ -170,15 +227,8 @@ int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const v
     {
         std::lock_guard<std::mutex> lock(D.mu);
         OPEN_CUDA(cudaSetDevice(D.id));
-        size_t in_bytes = (n - 1) * stride_bytes + 32;
-        OPEN_CUDA(cudaMalloc(&d_in, in_bytes));
-        OPEN_CUDA(cudaMalloc(&d_r[0], n * sizeof(fr)));
         OPEN_CUDA(cudaMalloc(&d_r[1], (n / 2 + 1) * sizeof(fr)));
-        OPEN_CUDA(cudaMalloc(&d_q, n * sizeof(fr)));
-        OPEN_CUDA(cudaMemcpyAsync(d_in, evals, in_bytes, cudaMemcpyHostToDevice, D.stream));
-        k_gather_fr<<<(unsigned)((n + 255) / 256), 256, 0, D.stream>>>(d_in, stride_bytes, d_r[0], n);
-        OPEN_CUDA(cudaGetLastError());
-        OPEN_CUDA(cudaStreamSynchronize(D.stream));
+        OPEN_CUDA(cudaMalloc(&d_q, (level_pairs ? n / 2 + 1 : n) * sizeof(fr)));
     }
     const uint8_t* pt = reinterpret_cast<const uint8_t*>(point);
     uint8_t* proofs = reinterpret_cast<uint8_t*>(out_proofs);
@@ -190,12 +240,17 @@ int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const v
         {
             std::lock_guard<std::mutex> lock(D.mu);
             OPEN_CUDA(cudaSetDevice(D.id));
-            k_open_fold<<<(unsigned)((half + 127) / 128), 128, 0, D.stream>>>(d_r[cur], t, d_q, d_r[cur ^ 1], half);
+            k_open_fold<<<(unsigned)((half + 127) / 128), 128, 0, D.stream>>>(d_r[cur], t, d_q, d_r[cur ^ 1], half,
+                                                                             level_pairs ? 0 : 1);
             OPEN_CUDA(cudaGetLastError());
             OPEN_CUDA(cudaStreamSynchronize(D.stream));
         }
         const void* vec[1] = {d_q};
-        rc = msm_dispatch(ctx, 0, level_srs[i], 0, 2 * half, nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
+        // with pair sums: sum_b q[b] * (P[2b] + P[2b+1]) over `half` points; without: q duplicated over 2 * half points
+        if (level_pairs)
+            rc = msm_dispatch(ctx, 0, level_pairs[i], 0, half, nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
+        else
+            rc = msm_dispatch(ctx, 0, level_srs[i], 0, 2 * half, nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
         if (rc) {
             cleanup();
             return rc;
@@ -211,6 +266,10 @@ int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const v
 #undef OPEN_CUDA
     return COZK_OK;
 }
+
+}  // namespace cozk
+
+extern "C" {
 
 int cozk_pst13_combine_commitment_shares(const void* commitments, size_t count, void* out_commitment) {
     if (!commitments || !out_commitment || count == 0) {

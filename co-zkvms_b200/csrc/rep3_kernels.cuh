@@ -1,0 +1,274 @@
+// Thread bodies for the steps on either side of the MSM: they keep a party's
+// share device-resident from the moment it arrives until the opening proof leaves.
+//
+//   N2  ingest         ark-serialize wire image of Rep3DensePolynomial coefficients (32-byte little-endian CANONICAL
+//                      integers, a || b per coefficient) -> the in-memory image (Fr Montgomery) the MSM reads at stride 64.
+//                      Reference: `receive_request` -> `deserialize_uncompressed_unchecked`
+//                      (mpc-net/src/rep3/quic/worker.rs:206-219), struct layout co-jolt/src/poly/dense_mlpoly.rs:23-32,
+//                      share layout mpc-types/src/protocols/rep3/arithmetic/types.rs:22-29.
+//   N4  linear combination   joint[i] = sum_j coeff_j * poly_j[i] over shared (both halves) and public polynomials, the
+//                      public terms added to share a on party 0 and share b on party 1
+//                      (co-jolt/src/poly/multilinear_polynomial.rs:196-296; Rep3DensePolynomial::linear_combination,
+//                      co-jolt/src/poly/dense_mlpoly.rs:186-224), and chi dot products
+//                      (evaluate_at_chi, dense_mlpoly.rs:160-181: sum_i (a_i + b_i)/2 * chi_i, an additive share).
+//   N1  pair sums      S[b] = P[2b] + P[2b+1]: open() feeds every quotient scalar to two adjacent bases
+//                      (co-jolt/src/poly/commitment/pst13.rs:459), so its MSM equals a half-size MSM over pair sums.
+//
+// Like msm_kernels.cuh, every body is a pure function of its thread index and compiles for the host emulation tier.
+//
+// Lazy reduction: a sum of products is accumulated as a plain 576-bit integer (64 limb products per term instead of
+// the 136 of a Montgomery multiplication) and reduced once per output element.
+#pragma once
+#include "msm_kernels.cuh"
+
+namespace cozk {
+
+// R^2 mod r (to Montgomery form: fr_mul(x, R2) = x * R)
+#define COZK_FR_R2 {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}
+// (r + 1) / 2, Montgomery form: the TWO_INV of snarks-core/src/field.rs:6 as the kernels need it
+#define COZK_FR_TWO_INV_MONT {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au}
+
+COZK_HD bool fr_is_canonical(const fr& a) {
+    const uint32_t mod[8] = COZK_FR_MOD;
+    uint32_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t d = (uint64_t)a.v[i] - mod[i] - br;
+        br = (uint32_t)(d >> 32) & 1u;
+    }
+    return br != 0;  // a < r
+}
+COZK_HD fr fr_const(const uint32_t (&c)[8]) {
+    fr r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = c[i];
+    return r;
+}
+COZK_HD fr fr_mont_from_canon(const fr& a) {
+    const uint32_t r2[8] = COZK_FR_R2;
+    return fr_mul(a, fr_const(r2));
+}
+COZK_HD fr fr_neg(const fr& a) { return fr_sub(fq_zero(), a); }
+
+// ------------------------------------------------------------------------------------------------ lazy accumulator
+struct fr_wide {
+    uint32_t v[18];
+};
+COZK_HD fr_wide fr_wide_zero() {
+    fr_wide w;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) w.v[i] = 0;
+    return w;
+}
+// acc += a * b  (plain integers; a, b < 2^256; the caller keeps the number of terms below 2^64)
+COZK_HD void fr_wide_mac(fr_wide& acc, const fr& a, const fr& b) {
+    uint32_t t[16];
+#if defined(__CUDA_ARCH__)
+    mulwide_ptx(t, a.v, b.v);
+#else
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; ++j) {
+            c += (uint64_t)a.v[j] * b.v[i] + t[i + j];
+            t[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+        t[i + 8] = (uint32_t)c;
+    }
+#endif
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        c += (uint64_t)acc.v[i] + t[i];
+        acc.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    c += acc.v[16];
+    acc.v[16] = (uint32_t)c;
+    acc.v[17] += (uint32_t)(c >> 32);
+}
+// acc * R^-1 mod r, fully reduced.  With acc = lo + hi * 2^256 + top * 2^512:
+//     acc / R = lo / R + hi + top * 2^256  (mod r)  =  from_mont(lo) + hi + to_mont(top)
+COZK_HD fr fr_wide_reduce(const fr_wide& acc) {
+    fr lo, hi, top = fq_zero();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        lo.v[i] = acc.v[i];
+        hi.v[i] = acc.v[8 + i];
+    }
+    top.v[0] = acc.v[16];
+    top.v[1] = acc.v[17];
+    fr r = fr_add(fr_from_mont(fr_reduce_canon(lo)), fr_reduce_canon(hi));
+    if (top.v[0] | top.v[1]) r = fr_add(r, fr_mont_from_canon(top));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ N2 ingest
+struct IngestArgs {
+    uint8_t* data;   // n_fr field elements, 32 B each, canonical little-endian -> Montgomery, in place
+    size_t n_fr;
+    uint32_t* bad;   // set to 1 when an element is >= r (ark-serialize rejects it: SerializationError::InvalidData)
+};
+COZK_HD void ingest_body(size_t t, const IngestArgs& A) {
+    if (t >= A.n_fr) return;
+    fr x = load_fq(A.data + 32 * t);
+    if (!fr_is_canonical(x)) {
+        *A.bad = 1;  // every writer stores the same value
+        return;
+    }
+    store_fq(A.data + 32 * t, fr_mont_from_canon(x));
+}
+
+// small public scalars (MultilinearPolynomial::{U8,U16,U32,U64,I64}Scalars, co-jolt/src/poly/multilinear_polynomial.rs:226-268)
+// -> 32-byte canonical integers; a negative i64 becomes r - |v| (what F::from_i64 gives)
+struct WidenArgs {
+    const uint8_t* src;
+    uint32_t elem_bytes;  // 1, 2, 4, 8
+    uint32_t is_signed;   // only with elem_bytes == 8
+    size_t n;
+    uint8_t* dst;         // n x 32 B
+};
+COZK_HD void widen_body(size_t t, const WidenArgs& A) {
+    if (t >= A.n) return;
+    uint64_t v = 0;
+    for (uint32_t k = 0; k < A.elem_bytes; ++k) v |= (uint64_t)A.src[t * A.elem_bytes + k] << (8 * k);
+    fr x = fq_zero();
+    bool neg = A.is_signed && (v >> 63);
+    if (neg) v = (uint64_t)0 - v;
+    x.v[0] = (uint32_t)v;
+    x.v[1] = (uint32_t)(v >> 32);
+    if (neg) {
+        const uint32_t mod[8] = COZK_FR_MOD;
+        uint32_t br = 0;
+        fr y;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint64_t d = (uint64_t)mod[i] - x.v[i] - br;
+            y.v[i] = (uint32_t)d;
+            br = (uint32_t)(d >> 32) & 1u;
+        }
+        x = y;
+    }
+    store_fq(A.dst + 32 * t, x);
+}
+
+// ------------------------------------------------------------------------------------------------ N4 linear combination
+constexpr uint32_t POLY_SHARED = 0;  // Rep3PrimeFieldShare{a, b}: 64 B per coefficient, Fr Montgomery
+constexpr uint32_t POLY_MONT = 1;    // public LargeScalars: 32 B per coefficient, Fr Montgomery
+constexpr uint32_t POLY_CANON = 2;   // public small scalars widened to 32-byte canonical integers
+
+struct PolyDesc {
+    const uint8_t* data;  // coefficient 0 of the polynomial's chunk_range
+    uint64_t len;
+    uint32_t kind;
+    uint32_t pad;
+};
+struct LincombArgs {
+    const PolyDesc* polys;  // k descriptors
+    const fr* coeffs;       // k x 2: [2j] = coeff_j (Montgomery), [2j+1] = coeff_j * R = fr_mont_from_canon(coeff_j): times a CANONICAL value it gives the Montgomery product
+    uint32_t k;
+    uint32_t party;         // PartyID 0, 1, 2
+    uint32_t shared_out;    // 1: out is AoS shares (64 B), 0: every input is public, out is dense Montgomery (32 B)
+    size_t n;               // max length
+    uint8_t* out;
+};
+// thread i: element i of the joint polynomial
+COZK_HD void lincomb_body(size_t i, const LincombArgs& A) {
+    if (i >= A.n) return;
+    fr_wide sa = fr_wide_zero(), sb = fr_wide_zero(), pub = fr_wide_zero();
+    for (uint32_t j = 0; j < A.k; ++j) {
+        const PolyDesc d = A.polys[j];
+        if (i >= d.len) continue;
+        if (d.kind == POLY_SHARED) {
+            fr c = load_fq(&A.coeffs[2 * j]);
+            fr_wide_mac(sa, load_fq(d.data + 64 * i), c);
+            fr_wide_mac(sb, load_fq(d.data + 64 * i + 32), c);
+        } else {
+            fr c = load_fq(&A.coeffs[2 * j + (d.kind == POLY_CANON ? 1 : 0)]);
+            fr_wide_mac(pub, load_fq(d.data + 32 * i), c);
+        }
+    }
+    fr p = fr_wide_reduce(pub);
+    if (!A.shared_out) {
+        store_fq(A.out + 32 * i, p);
+        return;
+    }
+    fr a = fr_wide_reduce(sa), b = fr_wide_reduce(sb);
+    // rep3 add_public: the public value joins share a on party 0 and share b on party 1 (party 2 holds neither copy of t0)
+    if (A.party == 0) a = fr_add(a, p);
+    if (A.party == 1) b = fr_add(b, p);
+    store_fq(A.out + 64 * i, a);
+    store_fq(A.out + 64 * i + 32, b);
+}
+
+// chi dot product, stage 1: thread t of T sums its strided slice; out[poly * T + t] (Montgomery, reduced).
+// Shared polynomial: (a_i + b_i) * chi_i (the 1/2 of into_additive is applied once, in stage 2); public: v_i * chi_i.
+struct ChiArgs {
+    const PolyDesc* polys;
+    uint32_t k;
+    const fr* chis;   // n values, Montgomery
+    size_t n;
+    uint32_t T;       // threads per polynomial
+    fr* partial;      // k x T
+};
+COZK_HD void chi_partial_body(size_t tid, const ChiArgs& A) {
+    if (tid >= (size_t)A.k * A.T) return;
+    uint32_t j = (uint32_t)(tid / A.T), t = (uint32_t)(tid - (size_t)j * A.T);
+    const PolyDesc d = A.polys[j];
+    fr_wide acc = fr_wide_zero();
+    size_t lim = d.len < A.n ? d.len : A.n;
+    for (size_t i = t; i < lim; i += A.T) {
+        fr chi = load_fq(&A.chis[i]);
+        fr v;
+        if (d.kind == POLY_SHARED) {
+            v = fr_add(load_fq(d.data + 64 * i), load_fq(d.data + 64 * i + 32));
+        } else {
+            v = load_fq(d.data + 32 * i);
+            if (d.kind == POLY_CANON) v = fr_mont_from_canon(v);
+        }
+        fr_wide_mac(acc, v, chi);
+    }
+    store_fq(&A.partial[tid], fr_wide_reduce(acc));
+}
+// stage 2: one thread per polynomial adds the T partial sums and applies TWO_INV for shared polynomials
+COZK_HD void chi_final_body(size_t j, const ChiArgs& A, fr* out) {
+    if (j >= A.k) return;
+    fr s = fq_zero();
+    for (uint32_t t = 0; t < A.T; ++t) s = fr_add(s, load_fq(&A.partial[j * A.T + t]));
+    if (A.polys[j].kind == POLY_SHARED) {
+        const uint32_t h[8] = COZK_FR_TWO_INV_MONT;
+        s = fr_mul(s, fr_const(h));
+    }
+    store_fq(&out[j], s);
+}
+
+// ------------------------------------------------------------------------------------------------ N1 pair sums
+struct PairSumArgs {
+    const affine* bases;      // 2 * half points
+    const uint8_t* infinity;  // optional flags of the inputs
+    size_t half;
+    affine* out;              // half points
+    uint8_t* out_inf;         // half flags (P + (-P), or both inputs at infinity)
+};
+COZK_HD void pair_sum_body(size_t b, const PairSumArgs& A) {
+    if (b >= A.half) return;
+    bool i0 = A.infinity && A.infinity[2 * b], i1 = A.infinity && A.infinity[2 * b + 1];
+    xyzz s = xyzz_identity();
+    if (!i0) s = xyzz_from_affine(load_affine(&A.bases[2 * b]));
+    if (!i1) s = xyzz_madd(s, load_affine(&A.bases[2 * b + 1]));
+    alignas(16) uint8_t w[72];
+    xyzz_to_wire(s, w);
+    affine r;
+    const uint32_t* ww = reinterpret_cast<const uint32_t*>(w);
+    for (int i = 0; i < 8; ++i) {
+        r.x.v[i] = ww[i];
+        r.y.v[i] = ww[8 + i];
+    }
+    store_fq(&A.out[b].x, r.x);
+    store_fq(&A.out[b].y, r.y);
+    A.out_inf[b] = w[64];
+}
+
+}  // namespace cozk

@@ -1,0 +1,645 @@
+// Device-resident Rep3 polynomials (include/cozk_rep3.h): wire ingestion (N2), linear combination and chi dot products
+// (N4), pair-sum SRS and the opening of a resident polynomial (N1).  Thread bodies live in rep3_kernels.cuh.
+#include "../../include/cozk_rep3.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "engine.hpp"
+#include "pst13.hpp"
+#include "rep3_kernels.cuh"
+
+namespace cozk {
+
+__global__ void __launch_bounds__(256) k_ingest(IngestArgs A) { ingest_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(256) k_widen(WidenArgs A) { widen_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(128) k_lincomb(LincombArgs A) { lincomb_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void k_chi_final(ChiArgs A, fr* out) { chi_final_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A, out); }
+__global__ void __launch_bounds__(128) k_pair_sum(PairSumArgs A) { pair_sum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+// dense[i] = src[i * stride]: share a of an AoS share array (stride 64) or a plain copy (stride 32)
+__global__ void k_take_fr(const uint8_t* src, size_t stride, fr* dst, size_t n, int canon) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    fr v = load_fq(src + t * stride);
+    if (canon) v = fr_mont_from_canon(v);
+    store_fq(&dst[t], v);
+}
+
+static inline unsigned blocks_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
+
+static int check_device(cozk_ctx* ctx, int device_index) {
+    if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size()) {
+        set_error("null context or device index out of range");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return COZK_OK;
+}
+
+static int lookup(cozk_ctx* ctx, cozk_poly h, PolyEntry* out) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->polys.find(h);
+    if (it == ctx->polys.end()) {
+        set_error("unknown polynomial handle");
+        return COZK_ERR_BAD_HANDLE;
+    }
+    *out = it->second;
+    return COZK_OK;
+}
+
+static cozk_poly publish(cozk_ctx* ctx, const PolyEntry& E) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cozk_poly h = ctx->next_handle++;
+    ctx->polys[h] = E;
+    return h;
+}
+
+struct StageTimer {
+    Device& D;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit StageTimer(Device& d) : D(d) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    ~StageTimer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+    void start() { cudaEventRecord(a, D.stream); }
+    double stop() {
+        cudaEventRecord(b, D.stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+};
+
+// little-endian reader over the wire image
+struct Reader {
+    const uint8_t* p;
+    size_t n, off = 0;
+    bool ok = true;
+    uint64_t u64() {
+        if (!ok || n - off < 8) {
+            ok = false;
+            return 0;
+        }
+        uint64_t v;
+        memcpy(&v, p + off, 8);
+        off += 8;
+        return v;
+    }
+    uint8_t u8() {
+        if (!ok || n - off < 1) {
+            ok = false;
+            return 0;
+        }
+        return p[off++];
+    }
+    // skips count * 64 bytes; false when the image is too short (also guards count * 64 against overflow)
+    bool skip_shares(uint64_t count) {
+        if (!ok || count > (n - off) / 64) {
+            ok = false;
+            return false;
+        }
+        off += (size_t)count * 64;
+        return true;
+    }
+};
+
+}  // namespace cozk
+
+using namespace cozk;
+
+extern "C" {
+
+int cozk_poly_upload(cozk_ctx* ctx, int device_index, const void* coeffs, size_t len, int kind, cozk_poly* out) {
+    int rc = check_device(ctx, device_index);
+    if (rc) return rc;
+    if (!out || (!coeffs && len) || kind < COZK_POLY_SHARED || kind > COZK_POLY_I64) {
+        set_error("null pointer or unknown polynomial kind");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Device& D = *ctx->devs[device_index];
+    PolyEntry E;
+    E.dev = device_index;
+    E.user_kind = kind;
+    E.total = E.len = len;
+    static const unsigned small_bytes[7] = {0, 0, 1, 2, 4, 8, 8};
+    E.kind = kind == COZK_POLY_SHARED ? POLY_SHARED : (kind == COZK_POLY_PUBLIC ? POLY_MONT : POLY_CANON);
+    E.bits = (kind >= COZK_POLY_U8 && kind <= COZK_POLY_U64) ? 8 * small_bytes[kind] : 0;
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    StageTimer T(D);
+    uint8_t* d = nullptr;
+    COZK_CUDA(cudaMalloc(&d, std::max<size_t>(len, 1) * E.elem_bytes()));
+    E.d_data = d;
+    double h2d = 0, conv = 0;
+    cudaError_t e = cudaSuccess;
+    if (kind <= COZK_POLY_PUBLIC) {
+        T.start();
+        e = cudaMemcpyAsync(d, coeffs, len * E.elem_bytes(), cudaMemcpyHostToDevice, D.stream);
+        h2d = T.stop();
+    } else if (len) {
+        uint8_t* raw = nullptr;
+        size_t rb = len * small_bytes[kind];
+        e = cudaMalloc(&raw, rb);
+        if (e == cudaSuccess) {
+            T.start();
+            e = cudaMemcpyAsync(raw, coeffs, rb, cudaMemcpyHostToDevice, D.stream);
+            h2d = T.stop();
+        }
+        if (e == cudaSuccess) {
+            WidenArgs A{raw, small_bytes[kind], kind == COZK_POLY_I64 ? 1u : 0u, len, d};
+            T.start();
+            k_widen<<<blocks_for(len, 256), 256, 0, D.stream>>>(A);
+            e = cudaGetLastError();
+            conv = T.stop();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        if (raw) cudaFree(raw);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        set_error(std::string("polynomial upload failed: ") + cudaGetErrorString(e));
+        return COZK_ERR_CUDA;
+    }
+    ctx->rep3_stats[0] = h2d;
+    ctx->rep3_stats[1] = conv;
+    *out = publish(ctx, E);
+    return COZK_OK;
+}
+
+int cozk_poly_from_device(cozk_ctx* ctx, int device_index, const void* d_coeffs, size_t len, int kind, cozk_poly* out) {
+    int rc = check_device(ctx, device_index);
+    if (rc) return rc;
+    if (!out || (!d_coeffs && len) || (kind != COZK_POLY_SHARED && kind != COZK_POLY_PUBLIC)) {
+        set_error("null pointer, or a kind other than SHARED / PUBLIC");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Device& D = *ctx->devs[device_index];
+    PolyEntry E;
+    E.dev = device_index;
+    E.user_kind = kind;
+    E.kind = kind == COZK_POLY_SHARED ? POLY_SHARED : POLY_MONT;
+    E.total = E.len = len;
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    uint8_t* d = nullptr;
+    COZK_CUDA(cudaMalloc(&d, std::max<size_t>(len, 1) * E.elem_bytes()));
+    cudaError_t e = cudaMemcpyAsync(d, d_coeffs, len * E.elem_bytes(), cudaMemcpyDeviceToDevice, D.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        set_error(std::string("polynomial copy failed: ") + cudaGetErrorString(e));
+        return COZK_ERR_CUDA;
+    }
+    E.d_data = d;
+    *out = publish(ctx, E);
+    return COZK_OK;
+}
+
+int cozk_poly_from_wire(cozk_ctx* ctx, int device_index, const void* bytes, size_t nbytes, int tagged, cozk_poly* out,
+                        size_t* consumed) {
+    int rc = check_device(ctx, device_index);
+    if (rc) return rc;
+    if (!bytes || !out) {
+        set_error("null pointer");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Reader R{reinterpret_cast<const uint8_t*>(bytes), nbytes};
+    if (tagged) {
+        uint8_t tag = R.u8();
+        if (R.ok && tag != 1) {
+            set_error(tag == 0 ? "Rep3MultilinearPolynomial::Public on the wire: jolt-core's MultilinearPolynomial format is not "
+                                 "defined in the reference tree; upload it with cozk_poly_upload"
+                               : "unknown Rep3MultilinearPolynomial discriminant");
+            return COZK_ERR_WIRE;
+        }
+    }
+    uint64_t num_vars = R.u64();
+    uint64_t n_coeffs = R.u64();
+    size_t coeff_off = R.off;
+    R.skip_shares(n_coeffs);
+    uint64_t n_bound = R.u64();
+    R.skip_shares(n_bound);
+    uint8_t has_scratch = R.u8();
+    if (R.ok && has_scratch > 1) {
+        set_error("wire image: Option discriminant is not 0/1");
+        return COZK_ERR_WIRE;
+    }
+    if (has_scratch) R.skip_shares(R.u64());
+    uint64_t len = R.u64();
+    uint64_t lo = R.u64(), hi = R.u64();
+    if (!R.ok) {
+        set_error("wire image: unexpected end of input");
+        return COZK_ERR_WIRE;
+    }
+    if (lo > hi || hi > n_coeffs || num_vars > 63) {
+        set_error("wire image: chunk_range outside the coefficient vector");
+        return COZK_ERR_WIRE;
+    }
+    (void)len;  // the reference's own accessors (coeffs_ref, copy_share_a) go by chunk_range
+    Device& D = *ctx->devs[device_index];
+    PolyEntry E;
+    E.dev = device_index;
+    E.user_kind = COZK_POLY_SHARED;
+    E.kind = POLY_SHARED;
+    E.total = (size_t)n_coeffs;
+    E.lo = (size_t)lo;
+    E.len = (size_t)(hi - lo);
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    StageTimer T(D);
+    uint8_t* d = nullptr;
+    uint32_t* d_bad = nullptr;
+    COZK_CUDA(cudaMalloc(&d, std::max<size_t>(E.total, 1) * 64 + 16));
+    cudaError_t e = cudaMalloc(&d_bad, 4);
+    uint32_t bad = 0;
+    double h2d = 0, conv = 0;
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, D.stream);
+    if (e == cudaSuccess) {
+        T.start();
+        e = cudaMemcpyAsync(d, R.p + coeff_off, E.total * 64, cudaMemcpyHostToDevice, D.stream);
+        h2d = T.stop();
+    }
+    if (e == cudaSuccess && E.total) {
+        IngestArgs A{d, 2 * E.total, d_bad};
+        T.start();
+        k_ingest<<<blocks_for(A.n_fr, 256), 256, 0, D.stream>>>(A);
+        e = cudaGetLastError();
+        conv = T.stop();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, D.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    if (d_bad) cudaFree(d_bad);
+    if (e != cudaSuccess || bad) {
+        cudaFree(d);
+        if (e != cudaSuccess) {
+            set_error(std::string("wire ingestion failed: ") + cudaGetErrorString(e));
+            return COZK_ERR_CUDA;
+        }
+        set_error("wire image: field element is not below the modulus");
+        return COZK_ERR_WIRE;
+    }
+    E.d_data = d;
+    ctx->rep3_stats[0] = h2d;
+    ctx->rep3_stats[1] = conv;
+    if (consumed) *consumed = R.off;
+    *out = publish(ctx, E);
+    return COZK_OK;
+}
+
+int cozk_poly_release(cozk_ctx* ctx, cozk_poly poly) {
+    if (!ctx) return COZK_ERR_INVALID_ARG;
+    PolyEntry E;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->polys.find(poly);
+        if (it == ctx->polys.end()) {
+            set_error("unknown polynomial handle");
+            return COZK_ERR_BAD_HANDLE;
+        }
+        E = it->second;
+        ctx->polys.erase(it);
+    }
+    Device& D = *ctx->devs[E.dev];
+    std::lock_guard<std::mutex> lock(D.mu);
+    cudaSetDevice(D.id);
+    if (E.d_data) cudaFree(E.d_data);
+    return COZK_OK;
+}
+
+int cozk_poly_info(cozk_ctx* ctx, cozk_poly poly, size_t* len, int* kind, int* device_index) {
+    if (!ctx) return COZK_ERR_INVALID_ARG;
+    PolyEntry E;
+    int rc = lookup(ctx, poly, &E);
+    if (rc) return rc;
+    if (len) *len = E.len;
+    if (kind) *kind = E.user_kind;
+    if (device_index) *device_index = E.dev;
+    return COZK_OK;
+}
+
+int cozk_poly_download(cozk_ctx* ctx, cozk_poly poly, void* out) {
+    if (!ctx || !out) {
+        set_error("null pointer");
+        return COZK_ERR_INVALID_ARG;
+    }
+    PolyEntry E;
+    int rc = lookup(ctx, poly, &E);
+    if (rc) return rc;
+    Device& D = *ctx->devs[E.dev];
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    COZK_CUDA(cudaMemcpy(out, E.chunk(), E.len * E.elem_bytes(), cudaMemcpyDeviceToHost));
+    return COZK_OK;
+}
+
+int cozk_pst13_batch_commit_polys(cozk_ctx* ctx, cozk_srs srs, const cozk_poly* polys, size_t k, int commit_to_public,
+                                  void* out_commitments, uint8_t* present) {
+    if (!ctx || !polys || !out_commitments || !present || k == 0) {
+        set_error("null pointer or k == 0");
+        return COZK_ERR_INVALID_ARG;
+    }
+    std::vector<PolyEntry> E(k);
+    for (size_t j = 0; j < k; ++j) {
+        int rc = lookup(ctx, polys[j], &E[j]);
+        if (rc) return rc;
+    }
+    size_t n = E[0].len;
+    unsigned nv = 0;
+    while (((size_t)1 << nv) < n) ++nv;
+    if (n == 0 || ((size_t)1 << nv) != n) {
+        set_error("polynomial length must be a power of two");
+        return COZK_ERR_INVALID_ARG;
+    }
+    for (size_t j = 0; j < k; ++j) {
+        if (E[j].len != n) {
+            set_error("batch_commit: polynomials must have equal lengths");  // assert at pst13.rs:307-309
+            return COZK_ERR_INVALID_ARG;
+        }
+    }
+    uint8_t* out = reinterpret_cast<uint8_t*>(out_commitments);
+    memset(out, 0, k * COZK_COMMITMENT_BYTES);
+    // one MSM batch per (device, scalar layout, bit-width hint)
+    struct Key {
+        int dev;
+        uint32_t kind;
+        unsigned bits;
+        bool operator<(const Key& o) const {
+            return dev != o.dev ? dev < o.dev : (kind != o.kind ? kind < o.kind : bits < o.bits);
+        }
+    };
+    std::map<Key, std::vector<size_t>> groups;
+    for (size_t j = 0; j < k; ++j) {
+        bool shared = E[j].kind == POLY_SHARED;
+        present[j] = (shared || commit_to_public) ? 1 : 0;
+        if (present[j]) groups[Key{E[j].dev, E[j].kind, E[j].bits}].push_back(j);
+    }
+    uint64_t nv64 = nv;
+    for (auto& kv : groups) {
+        std::vector<const void*> ptrs;
+        for (size_t j : kv.second) ptrs.push_back(E[j].chunk());
+        std::vector<uint8_t> pts(ptrs.size() * 72);
+        size_t stride = kv.first.kind == POLY_SHARED ? 64 : 32;
+        int form = kv.first.kind == POLY_CANON ? COZK_CANON : COZK_MONT;
+        int rc = msm_dispatch(ctx, kv.first.dev, srs, 0, n, nullptr, ptrs.data(), ptrs.size(), stride, form, kv.first.bits, pts.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < kv.second.size(); ++i) {
+            uint8_t* o = out + COZK_COMMITMENT_BYTES * kv.second[i];
+            memcpy(o, &nv64, 8);
+            memcpy(o + 8, &pts[72 * i], 72);
+        }
+    }
+    return COZK_OK;
+}
+
+int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const void* coeffs, size_t k, int party_id,
+                                 cozk_poly* out) {
+    if (!ctx || !polys || !coeffs || !out || k == 0 || k > 0xFFFFFFFFu || party_id < 0 || party_id > 2) {
+        set_error("null pointer, k == 0 or party id outside 0..2");
+        return COZK_ERR_INVALID_ARG;
+    }
+    std::vector<PolyEntry> E(k);
+    size_t max_len = 0, max_shared = 0;
+    bool any_shared = false;
+    for (size_t j = 0; j < k; ++j) {
+        int rc = lookup(ctx, polys[j], &E[j]);
+        if (rc) return rc;
+        if (E[j].dev != E[0].dev) {
+            set_error("linear_combination: all polynomials must live on one device");
+            return COZK_ERR_INVALID_ARG;
+        }
+        max_len = std::max(max_len, E[j].len);
+        if (E[j].kind == POLY_SHARED) {
+            any_shared = true;
+            max_shared = std::max(max_shared, E[j].len);
+        }
+    }
+    if (any_shared && max_shared < max_len) {
+        // the reference leaves such an index as SharedOrPublic::Public and panics in as_shared() ("Not an arithmetic share")
+        set_error("linear_combination: a public polynomial is longer than every shared one");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Device& D = *ctx->devs[E[0].dev];
+    // coefficient pairs: [2j] = c_j (Montgomery), [2j+1] = c_j * R for terms whose values are canonical integers
+    std::vector<fr> hc(2 * k);
+    const uint8_t* cb = reinterpret_cast<const uint8_t*>(coeffs);
+    for (size_t j = 0; j < k; ++j) {
+        memcpy(hc[2 * j].v, cb + 32 * j, 32);
+        hc[2 * j + 1] = fr_mont_from_canon(hc[2 * j]);
+    }
+    std::vector<PolyDesc> hd(k);
+    double bytes = 0;
+    for (size_t j = 0; j < k; ++j) {
+        hd[j] = PolyDesc{E[j].chunk(), E[j].len, E[j].kind, 0};
+        bytes += (double)E[j].len * E[j].elem_bytes();
+    }
+    PolyEntry O;
+    O.dev = E[0].dev;
+    O.kind = any_shared ? POLY_SHARED : POLY_MONT;
+    O.user_kind = any_shared ? COZK_POLY_SHARED : COZK_POLY_PUBLIC;
+    O.total = O.len = max_len;
+    bytes += (double)max_len * O.elem_bytes();
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    PolyDesc* d_desc = nullptr;
+    fr* d_coef = nullptr;
+    uint8_t* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_desc, k * sizeof(PolyDesc));
+    if (e == cudaSuccess) e = cudaMalloc(&d_coef, 2 * k * sizeof(fr));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, std::max<size_t>(max_len, 1) * O.elem_bytes());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), k * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_coef, hc.data(), 2 * k * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
+    double ms = 0;
+    if (e == cudaSuccess && max_len) {
+        LincombArgs A{d_desc, d_coef, (uint32_t)k, (uint32_t)party_id, any_shared ? 1u : 0u, max_len, d_out};
+        StageTimer T(D);
+        T.start();
+        k_lincomb<<<blocks_for(max_len, 128), 128, 0, D.stream>>>(A);
+        e = cudaGetLastError();
+        ms = T.stop();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    if (d_desc) cudaFree(d_desc);
+    if (d_coef) cudaFree(d_coef);
+    if (e != cudaSuccess) {
+        if (d_out) cudaFree(d_out);
+        set_error(std::string("linear_combination failed: ") + cudaGetErrorString(e));
+        return COZK_ERR_CUDA;
+    }
+    O.d_data = d_out;
+    ctx->rep3_stats[2] = ms;
+    ctx->rep3_stats[4] = bytes;
+    *out = publish(ctx, O);
+    return COZK_OK;
+}
+
+int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, const void* chis, size_t n, void* out_evals) {
+    if (!ctx || !polys || !chis || !out_evals || k == 0 || k > 0xFFFFFFFFu) {
+        set_error("null pointer or k == 0");
+        return COZK_ERR_INVALID_ARG;
+    }
+    std::vector<PolyEntry> E(k);
+    for (size_t j = 0; j < k; ++j) {
+        int rc = lookup(ctx, polys[j], &E[j]);
+        if (rc) return rc;
+        if (E[j].dev != E[0].dev) {
+            set_error("evaluate_at_chi: all polynomials must live on one device");
+            return COZK_ERR_INVALID_ARG;
+        }
+        if (E[j].len != n) {
+            set_error("evaluate_at_chi: polynomial and chi lengths differ");  // zip_eq panics
+            return COZK_ERR_INVALID_ARG;
+        }
+    }
+    Device& D = *ctx->devs[E[0].dev];
+    std::vector<PolyDesc> hd(k);
+    for (size_t j = 0; j < k; ++j) hd[j] = PolyDesc{E[j].chunk(), E[j].len, E[j].kind, 0};
+    // threads per polynomial: enough to fill the chip a few times over, never more than one element per thread
+    uint32_t T = 32;
+    while ((size_t)T * 2 <= n && (size_t)T * k < (size_t)D.sm_count * 2048 && T < 4096) T *= 2;
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    PolyDesc* d_desc = nullptr;
+    fr *d_chis = nullptr, *d_part = nullptr, *d_res = nullptr;
+    cudaError_t e = cudaMalloc(&d_desc, k * sizeof(PolyDesc));
+    if (e == cudaSuccess) e = cudaMalloc(&d_chis, std::max<size_t>(n, 1) * sizeof(fr));
+    if (e == cudaSuccess) e = cudaMalloc(&d_part, k * (size_t)T * sizeof(fr));
+    if (e == cudaSuccess) e = cudaMalloc(&d_res, k * sizeof(fr));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), k * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_chis, chis, n * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
+    double ms = 0;
+    if (e == cudaSuccess) {
+        ChiArgs A{d_desc, (uint32_t)k, d_chis, n, T, d_part};
+        StageTimer St(D);
+        St.start();
+        k_chi_partial<<<blocks_for(k * (size_t)T, 128), 128, 0, D.stream>>>(A);
+        k_chi_final<<<blocks_for(k, 64), 64, 0, D.stream>>>(A, d_res);
+        e = cudaGetLastError();
+        ms = St.stop();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_evals, d_res, k * sizeof(fr), cudaMemcpyDeviceToHost, D.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    for (void* p : {(void*)d_desc, (void*)d_chis, (void*)d_part, (void*)d_res})
+        if (p) cudaFree(p);
+    if (e != cudaSuccess) {
+        set_error(std::string("evaluate_at_chi failed: ") + cudaGetErrorString(e));
+        return COZK_ERR_CUDA;
+    }
+    ctx->rep3_stats[3] = ms;
+    return COZK_OK;
+}
+
+int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
+    if (!ctx || !out) {
+        set_error("null pointer");
+        return COZK_ERR_INVALID_ARG;
+    }
+    SrsEntry S;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->srs.find(srs);
+        if (it == ctx->srs.end()) {
+            set_error("unknown SRS handle");
+            return COZK_ERR_BAD_HANDLE;
+        }
+        S = it->second;
+    }
+    if (S.n == 0 || (S.n & 1)) {
+        set_error("pair sums need an even, non-zero number of bases");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Device& D = *ctx->devs[0];
+    size_t half = S.n / 2;
+    affine* d_out = nullptr;
+    uint8_t* d_inf = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(D.mu);
+        COZK_CUDA(cudaSetDevice(D.id));
+        cudaError_t e = cudaMalloc(&d_out, half * sizeof(affine));
+        if (e == cudaSuccess) e = cudaMalloc(&d_inf, half);
+        if (e == cudaSuccess) {
+            PairSumArgs A{S.d_bases[0], S.d_inf[0], half, d_out, d_inf};  // row 0 of the table = the bases themselves
+            k_pair_sum<<<blocks_for(half, 128), 128, 0, D.stream>>>(A);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        if (e != cudaSuccess) {
+            if (d_out) cudaFree(d_out);
+            if (d_inf) cudaFree(d_inf);
+            set_error(std::string("pair sums failed: ") + cudaGetErrorString(e));
+            return COZK_ERR_CUDA;
+        }
+    }
+    int rc = srs_register_from_device(ctx, 0, d_out, d_inf, half, out);
+    std::lock_guard<std::mutex> lock(D.mu);
+    cudaSetDevice(D.id);
+    cudaFree(d_out);
+    cudaFree(d_inf);
+    return rc;
+}
+
+int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, cozk_poly poly,
+                         const void* point, void* out_proofs, void* out_eval) {
+    if (!ctx || !level_srs || !point || !out_proofs || !out_eval || nv == 0 || nv > 30) {
+        set_error("null pointer or bad nv");
+        return COZK_ERR_INVALID_ARG;
+    }
+    PolyEntry E;
+    int rc = lookup(ctx, poly, &E);
+    if (rc) return rc;
+    if (E.dev != 0) {
+        set_error("open(): the polynomial must live on device 0 of the context");
+        return COZK_ERR_INVALID_ARG;
+    }
+    size_t n = (size_t)1 << nv;
+    if (E.len != n) {
+        set_error("Invalid size of polynomial");  // assert_eq!(nv, ck.nv), pst13.rs:438
+        return COZK_ERR_KEY_LENGTH;
+    }
+    for (size_t i = 0; i < nv; ++i) {
+        size_t len = 0;
+        rc = cozk_srs_len(ctx, level_srs[i], &len);
+        if (rc) return rc;
+        size_t plen = len / 2;
+        if (level_pairs) {
+            rc = cozk_srs_len(ctx, level_pairs[i], &plen);
+            if (rc) return rc;
+        }
+        if (len != ((size_t)1 << (nv - i)) || plen != len / 2) {
+            set_error("Invalid size of polynomial: SRS level length does not match nv");
+            return COZK_ERR_KEY_LENGTH;
+        }
+    }
+    Device& D = *ctx->devs[0];
+    fr* d_r0 = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(D.mu);
+        COZK_CUDA(cudaSetDevice(D.id));
+        COZK_CUDA(cudaMalloc(&d_r0, n * sizeof(fr)));
+        // copy_share_a (dense_mlpoly.rs:102-110) as a strided device read
+        k_take_fr<<<blocks_for(n, 256), 256, 0, D.stream>>>(E.chunk(), E.elem_bytes(), d_r0, n, E.kind == POLY_CANON ? 1 : 0);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        if (e != cudaSuccess) {
+            cudaFree(d_r0);
+            set_error(std::string("open(): gathering share a failed: ") + cudaGetErrorString(e));
+            return COZK_ERR_CUDA;
+        }
+    }
+    return pst13_open_device(ctx, level_srs, level_pairs, nv, d_r0, point, out_proofs, out_eval);
+}
+
+int cozk_rep3_last_stats(cozk_ctx* ctx, double* out8) {
+    if (!ctx || !out8) return COZK_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->rep3_stats[i];
+    return COZK_OK;
+}
+
+}  // extern "C"

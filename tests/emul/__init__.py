@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         deps = [os.path.join(HERE, "emul.cpp")] + [os.path.join(CSRC, f) for f in
-                                                   ("field.cuh", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp")]
+                                                   ("field.cuh", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp", "rep3_kernels.cuh")]
         if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB,
@@ -25,6 +25,12 @@ def lib():
         L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp, u32, sz, sz, u32]
         L.emul_field_op.argtypes = [ci, vp, vp, vp, sz]
         L.emul_g1_op.argtypes = [ci, vp, vp, vp, sz]
+        L.emul_ingest.argtypes = [vp, sz, vp]
+        L.emul_widen.argtypes = [vp, u32, u32, sz, vp]
+        L.emul_lincomb.argtypes = [vp, vp, vp, u32, vp, u32, u32, sz, vp]
+        L.emul_chi.argtypes = [vp, vp, vp, u32, vp, sz, u32, vp]
+        L.emul_pair_sum.argtypes = [vp, vp, sz, vp, vp]
+        L.emul_wide_dot.argtypes = [vp, vp, sz, u32, vp]
         _lib = L
     return _lib
 
@@ -66,4 +72,67 @@ def g1_op(op, a, b=None):
     bb = np.ascontiguousarray(b, dtype=np.uint8) if b is not None else None
     out = np.zeros_like(a)
     lib().emul_g1_op(ops[op], _p(a), _p(bb), _p(out), a.shape[0])
+    return out
+
+
+# ---- rep3_kernels.cuh bodies (rows N1, N2, N4)
+KIND = {"shared": 0, "mont": 1, "canon": 2}
+
+
+def ingest(data):
+    """data: (n, 32) canonical little-endian -> Montgomery, in place.  Returns the `bad` flag."""
+    bad = np.zeros(1, np.uint32)
+    lib().emul_ingest(_p(data), data.shape[0], _p(bad))
+    return int(bad[0])
+
+
+def widen(raw, elem_bytes, signed=False):
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    n = raw.size // elem_bytes
+    out = np.zeros((n, 32), np.uint8)
+    lib().emul_widen(_p(raw), elem_bytes, 1 if signed else 0, n, _p(out))
+    return out
+
+
+def _descs(polys):
+    arrs = [np.ascontiguousarray(a, dtype=np.uint8) for _, a in polys]
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    lens = np.array([a.shape[0] for a in arrs], np.uint64)
+    kinds = np.array([KIND[k] for k, _ in polys], np.uint32)
+    return arrs, ptrs, lens, kinds
+
+
+def lincomb(polys, coeffs, party):
+    """polys: list of (kind, array): "shared" (n, 64) Montgomery AoS, "mont" (n, 32), "canon" (n, 32)."""
+    arrs, ptrs, lens, kinds = _descs(polys)
+    shared_out = 1 if any(k == "shared" for k, _ in polys) else 0
+    n = int(lens.max())
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint8)
+    out = np.zeros((n, 64 if shared_out else 32), np.uint8)
+    lib().emul_lincomb(ptrs, _p(lens), _p(kinds), len(arrs), _p(coeffs), party, shared_out, n, _p(out))
+    return out
+
+
+def chi(polys, chis, T=32):
+    arrs, ptrs, lens, kinds = _descs(polys)
+    chis = np.ascontiguousarray(chis, dtype=np.uint8)
+    out = np.zeros((len(arrs), 32), np.uint8)
+    lib().emul_chi(ptrs, _p(lens), _p(kinds), len(arrs), _p(chis), chis.shape[0], T, _p(out))
+    return out
+
+
+def pair_sum(bases, infinity=None):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    half = bases.shape[0] // 2
+    inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
+    out, oi = np.zeros((half, 64), np.uint8), np.zeros(half, np.uint8)
+    lib().emul_pair_sum(_p(bases), _p(inf), half, _p(out), _p(oi))
+    return out, oi
+
+
+def wide_dot(a, b, repeat=1):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.zeros(32, np.uint8)
+    lib().emul_wide_dot(_p(a), _p(b), a.shape[0], repeat, _p(out))
     return out

@@ -13,6 +13,7 @@
 
 #include "../../co-zkvms_b200/csrc/msm_kernels.cuh"
 #include "../../co-zkvms_b200/csrc/msm_plan.hpp"
+#include "../../co-zkvms_b200/csrc/rep3_kernels.cuh"
 #include "../../experiments/radix29/curve29.cuh"
 
 using namespace cozk;
@@ -192,5 +193,51 @@ void emul_g1_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t
         }
         xyzz_to_wire(r, out + 72 * i);
     }
+}
+
+// ---------------------------------------------------------------------------------------------- rep3_kernels.cuh bodies
+void emul_ingest(uint8_t* data, size_t n_fr, uint32_t* bad) {
+    IngestArgs A{data, n_fr, bad};
+    for (size_t t = 0; t < n_fr; ++t) ingest_body(t, A);
+}
+void emul_widen(const uint8_t* src, uint32_t elem_bytes, uint32_t is_signed, size_t n, uint8_t* dst) {
+    WidenArgs A{src, elem_bytes, is_signed, n, dst};
+    for (size_t t = 0; t < n; ++t) widen_body(t, A);
+}
+static std::vector<PolyDesc> make_descs(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* kinds, uint32_t k) {
+    std::vector<PolyDesc> d(k);
+    for (uint32_t j = 0; j < k; ++j) d[j] = PolyDesc{ptrs[j], lens[j], kinds[j], 0};
+    return d;
+}
+// coeffs: k x 32 B Montgomery; out: n x 64 B (shared_out) or n x 32 B
+void emul_lincomb(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* kinds, uint32_t k, const uint8_t* coeffs,
+                  uint32_t party, uint32_t shared_out, size_t n, uint8_t* out) {
+    std::vector<PolyDesc> d = make_descs(ptrs, lens, kinds, k);
+    std::vector<fr> c(2 * (size_t)k);
+    for (uint32_t j = 0; j < k; ++j) {
+        c[2 * j] = load_fq(coeffs + 32 * j);
+        c[2 * j + 1] = fr_mont_from_canon(c[2 * j]);
+    }
+    LincombArgs A{d.data(), c.data(), k, party, shared_out, n, out};
+    for (size_t i = 0; i < n; ++i) lincomb_body(i, A);
+}
+void emul_chi(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* kinds, uint32_t k, const uint8_t* chis, size_t n,
+              uint32_t T, uint8_t* out) {
+    std::vector<PolyDesc> d = make_descs(ptrs, lens, kinds, k);
+    std::vector<fr> part((size_t)k * T);
+    ChiArgs A{d.data(), k, reinterpret_cast<const fr*>(chis), n, T, part.data()};
+    for (size_t t = 0; t < (size_t)k * T; ++t) chi_partial_body(t, A);
+    for (size_t j = 0; j < k; ++j) chi_final_body(j, A, reinterpret_cast<fr*>(out));
+}
+void emul_pair_sum(const uint8_t* bases, const uint8_t* infinity, size_t half, uint8_t* out, uint8_t* out_inf) {
+    PairSumArgs A{reinterpret_cast<const affine*>(bases), infinity, half, reinterpret_cast<affine*>(out), out_inf};
+    for (size_t b = 0; b < half; ++b) pair_sum_body(b, A);
+}
+// out = (sum_i a_i * b_i) / R mod r through the lazy accumulator, `repeat` times over (pushes the top limbs)
+void emul_wide_dot(const uint8_t* a, const uint8_t* b, size_t n, uint32_t repeat, uint8_t* out) {
+    fr_wide acc = fr_wide_zero();
+    for (uint32_t r = 0; r < repeat; ++r)
+        for (size_t i = 0; i < n; ++i) fr_wide_mac(acc, load_fq(a + 32 * i), load_fq(b + 32 * i));
+    store_fq(out, fr_wide_reduce(acc));
 }
 }

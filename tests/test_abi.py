@@ -20,8 +20,8 @@ def _declared(path):
 
 def test_library_exports_every_declared_symbol(cozk):
     L = cozk.lib()
-    declared = _declared(os.path.join(ROOT, "include", "cozk_msm.h")) + _declared(
-        os.path.join(ROOT, "co-zkvms_b200", "csrc", "pst13.hpp"))
+    declared = (_declared(os.path.join(ROOT, "include", "cozk_msm.h")) + _declared(os.path.join(ROOT, "include", "cozk_rep3.h"))
+                + _declared(os.path.join(ROOT, "co-zkvms_b200", "csrc", "pst13.hpp")))
     assert len(declared) >= 25
     for name in declared:
         assert hasattr(L, name), name

@@ -209,6 +209,53 @@ def gen_mul(mod, square=False):
     return pg
 
 
+def gen_mulwide():
+    """r[0..15] = a * b as a plain 512-bit integer (no reduction): the product half of a lazily reduced
+    multiply-accumulate (rep3_kernels.cuh: linear combinations of shared polynomials, chi dot products).  Same EV/OD
+    split as gen_mul so that every product lands on an aligned register pair: EV collects the products whose limb
+    position i+j is even, OD (weight 2^32) the odd ones.  64 wide multiply-adds."""
+    pg = Prog()
+    a = ["a%d" % k for k in range(8)]
+    b = ["b%d" % k for k in range(8)]
+    ev = [pg.new("e") for _ in range(16)]
+    od = [pg.new("o") for _ in range(16)]
+    for k in range(4):
+        pg.emit("mul.wide", (ev[2 * k], ev[2 * k + 1]), a[2 * k], b[0])
+        pg.emit("mul.wide", (od[2 * k], od[2 * k + 1]), a[2 * k + 1], b[0])
+    for k in range(8, 16):
+        pg.emit("mov", ev[k], 0)
+        pg.emit("mov", od[k], 0)
+
+    def chain(acc, start, mults, bi):
+        for k, aj in enumerate(mults):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", acc[start + 2 * k], aj, bi, acc[start + 2 * k])
+            pg.emit("madc.hi.cc", acc[start + 2 * k + 1], aj, bi, acc[start + 2 * k + 1])
+        if start + 8 <= 15:
+            pg.emit("addc", acc[start + 8], acc[start + 8], 0)
+
+    for i in range(1, 8):
+        even_a, odd_a = [a[0], a[2], a[4], a[6]], [a[1], a[3], a[5], a[7]]
+        if i % 2 == 0:
+            chain(ev, i, even_a, b[i])      # positions i+2k (even)
+            chain(od, i, odd_a, b[i])       # positions i+2k+1 -> OD index i+2k
+        else:
+            chain(ev, i + 1, odd_a, b[i])   # positions i+2k+1 (even)
+            chain(od, i - 1, even_a, b[i])  # positions i+2k (odd) -> OD index i+2k-1
+    pg.emit("mov", "r0", ev[0])
+    for k in range(1, 16):
+        pg.emit("add.cc" if k == 1 else ("addc.cc" if k < 15 else "addc"), "r%d" % k, ev[k], od[k - 1])
+    return pg
+
+
+def run_mulwide(pg, x, y):
+    env = {}
+    for k in range(8):
+        env["a%d" % k] = (x >> (32 * k)) & M32
+        env["b%d" % k] = (y >> (32 * k)) & M32
+    out = pg.run(env)
+    return sum(out["r%d" % k] << (32 * k) for k in range(16))
+
+
 def gen_add(mod):
     pg = Prog()
     t = [pg.new("t") for _ in range(8)]
@@ -255,6 +302,13 @@ def self_check(trials=300, seed=1):
             assert run_binop(ps, x, 0) == x * x * Rinv[mod] % mod, ("sqr", hex(x))
             assert run_binop(pa, x, y) == (x + y) % mod, ("add", hex(x), hex(y))
             assert run_binop(pb, x, y) == (x - y) % mod, ("sub", hex(x), hex(y))
+    pw = gen_mulwide()
+    full = (1 << 256) - 1
+    wvals = [0, 1, full, full - 1, 1 << 255, M32, (1 << 224) - 1, R - 1, P - 1] + [rnd.randrange(1 << 256) for _ in range(trials)]
+    for i, x in enumerate(wvals):
+        y = wvals[(i * 5 + 2) % len(wvals)]
+        assert run_mulwide(pw, x, y) == x * y, ("mulwide", hex(x), hex(y))
+    assert run_mulwide(pw, full, full) == full * full
     return True
 
 
@@ -284,6 +338,26 @@ def emit_fn(name, pg, nin):
             % (nmul, name, sig, body, outs, ins))
 
 
+def emit_fn_wide(name, pg):
+    names = {}
+    idx = 0
+    for k in range(16):
+        names["r%d" % k] = "%%%d" % idx
+        idx += 1
+    for pre in ("a", "b"):
+        for k in range(8):
+            names["%s%d" % (pre, k)] = "%%%d" % idx
+            idx += 1
+    lines = pg.ptx(names)
+    body = "\n".join('        "%s\\n\\t"' % ln for ln in lines)
+    outs = ", ".join('"=r"(r[%d])' % k for k in range(16))
+    ins = ", ".join('"r"(a[%d])' % k for k in range(8)) + ", " + ", ".join('"r"(b[%d])' % k for k in range(8))
+    nmul = sum(1 for i in pg.ins if i[0] == "mul.wide" or (i[0].startswith("mad") and ".lo" in i[0]))
+    return ("// %d wide multiply(-add)s: the 512-bit product a * b, not reduced\n"
+            "__device__ __forceinline__ void %s(uint32_t (&r)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {\n"
+            "    asm(\n%s\n        : %s\n        : %s);\n}\n" % (nmul, name, body, outs, ins))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("-o", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "co-zkvms_b200", "csrc", "field_ptx.inc"))
@@ -299,6 +373,7 @@ def main():
     parts.append(emit_fn("fr_mul_ptx", gen_mul(R), 2))
     parts.append(emit_fn("fr_add_ptx", gen_add(R), 2))
     parts.append(emit_fn("fr_sub_ptx", gen_sub(R), 2))
+    parts.append(emit_fn_wide("mulwide_ptx", gen_mulwide()))
     with open(args.o, "w") as f:
         f.write("\n".join(parts))
     print("wrote", os.path.normpath(args.o))
