@@ -39,7 +39,8 @@ ABI_SYMBOLS = [
     # include/cozk_rep3.h
     "cozk_poly_upload", "cozk_poly_from_device", "cozk_poly_from_wire", "cozk_poly_release", "cozk_poly_info", "cozk_poly_download",
     "cozk_pst13_batch_commit_polys", "cozk_rep3_linear_combination", "cozk_rep3_evaluate_at_chi", "cozk_srs_pair_sums",
-    "cozk_pst13_open_poly", "cozk_pst13_open_paired", "cozk_rep3_last_stats",
+    "cozk_pst13_open_key_create", "cozk_pst13_open_key_release", "cozk_pst13_open_poly", "cozk_pst13_open_keyed",
+    "cozk_rep3_last_stats",
 ]
 
 
@@ -121,8 +122,10 @@ def lib():
     L.cozk_rep3_linear_combination.argtypes = [vp, pu64, vp, sz, ci, pu64]
     L.cozk_rep3_evaluate_at_chi.argtypes = [vp, pu64, sz, vp, sz, vp]
     L.cozk_srs_pair_sums.argtypes = [vp, u64, pu64]
-    L.cozk_pst13_open_poly.argtypes = [vp, pu64, pu64, sz, u64, vp, vp, vp]
-    L.cozk_pst13_open_paired.argtypes = [vp, pu64, pu64, sz, vp, sz, vp, ci, vp, vp]
+    L.cozk_pst13_open_key_create.argtypes = [vp, pu64, sz, pu64]
+    L.cozk_pst13_open_key_release.argtypes = [vp, u64]
+    L.cozk_pst13_open_poly.argtypes = [vp, pu64, sz, u64, u64, vp, vp, vp]
+    L.cozk_pst13_open_keyed.argtypes = [vp, u64, vp, sz, vp, ci, vp, vp]
     L.cozk_rep3_last_stats.argtypes = [vp, cd]
     _lib = L
     return L

@@ -323,14 +323,22 @@ int cozk_dev_upload(cozk_ctx* ctx, int device_index, void* dst, const void* src,
     Device* D;
     int rc = get_device(ctx, device_index, &D);
     if (rc) return rc;
-    COZK_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    // on the engine's stream, then synchronised: a pageable cudaMemcpy only guarantees that the data has been staged, and
+    // its DMA (legacy default stream) is not ordered before kernels on the engine's non-blocking streams
+    std::lock_guard<std::mutex> lock(D->mu);
+    COZK_CUDA(cudaSetDevice(D->id));
+    COZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, D->stream));
+    COZK_CUDA(cudaStreamSynchronize(D->stream));
     return COZK_OK;
 }
 int cozk_dev_download(cozk_ctx* ctx, int device_index, void* dst, const void* src, size_t bytes) {
     Device* D;
     int rc = get_device(ctx, device_index, &D);
     if (rc) return rc;
-    COZK_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    std::lock_guard<std::mutex> lock(D->mu);
+    COZK_CUDA(cudaSetDevice(D->id));
+    COZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, D->stream));
+    COZK_CUDA(cudaStreamSynchronize(D->stream));
     return COZK_OK;
 }
 int cozk_host_alloc_pinned(size_t bytes, void** out) {

@@ -57,6 +57,8 @@ struct Device {
     cudaStream_t copy_stream = nullptr;
     std::mutex mu;  // one MSM at a time per device
     DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2, pk[2], pp[2], rs[2], rw[2], out, flush;
+    std::mutex open_mu;  // one PST13 opening at a time per device: it owns the four buffers below across its MSM calls
+    DevBuf open_in, open_r[2], open_q, open_qs;
     cudaEvent_t ev[8] = {};
     cudaEvent_t copy_done[2] = {};
     double stats[12] = {};
@@ -86,15 +88,38 @@ struct PolyEntry {
     const uint8_t* chunk() const { return d_data + lo * elem_bytes(); }
 };
 
+// Setup-time data of the PST13 opening (include/cozk_rep3.h): pair sums of every SRS level, the small levels
+// concatenated into one SRS so that a single batched MSM serves all of them.
+struct OpenKey {
+    size_t nv = 0;
+    std::vector<cozk_srs> level_srs;   // as given by the caller (not owned)
+    std::vector<cozk_srs> pair_srs;    // owned: pair sums of level i, i < first_small
+    size_t first_small = 0;            // levels [first_small, nv) go through one batched MSM
+    cozk_srs small_srs = 0;            // owned: pair sums of the small levels, level after level
+    size_t small_n = 0;
+    std::vector<size_t> small_off;     // offset of level first_small + j inside small_srs
+};
+
 }  // namespace cozk
 
 struct cozk_ctx;
 namespace cozk {
 // Register n points that already live on device `device_index` (d_inf: optional per-point infinity flags, device memory).
 int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out);
-// PST13 opening over evaluations that are already on device 0 of the context as a dense Montgomery vector (consumed).
-int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, fr* d_r0,
+// Where the 2^nv evaluations of an opening come from: host memory (staged through a scratch buffer) or device 0.
+struct OpenSource {
+    const void* host = nullptr;      // element i at host + i * stride
+    const uint8_t* dev = nullptr;    // element i at dev + i * stride (share a of an AoS share array: stride 64)
+    size_t stride = 32;
+    int canon = 0;                   // device source holds canonical integers (small-scalar public polynomial)
+};
+// PST13 opening on device 0.  key == nullptr: the reference's schedule (one MSM per level over duplicated scalars);
+// else pair sums + one batched MSM for the small levels.
+int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const OpenKey* key, size_t nv, const OpenSource& src,
                       const void* point, void* out_proofs, void* out_eval);
+// S[b] = P[2b] + P[2b+1] of a registered SRS into caller-provided device buffers on device 0 (half = n / 2 entries each).
+int srs_pair_sums_into(cozk_ctx* ctx, cozk_srs srs, affine* d_out, uint8_t* d_inf, size_t* half_out);
+int open_key_lookup(cozk_ctx* ctx, uint64_t h, OpenKey* out);
 // The one entry every public MSM call funnels into (msm.cu).  only_device < 0: use all devices of the context.
 int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offset, size_t n, const void* const* host_scalars,
                  const void* const* dev_scalars, size_t k, size_t stride, int form, unsigned max_bits, void* out);
@@ -105,6 +130,8 @@ struct cozk_ctx {
     std::mutex mu;  // guards the SRS table and options
     std::map<uint64_t, cozk::SrsEntry> srs;
     std::map<uint64_t, cozk::PolyEntry> polys;
+    std::map<uint64_t, cozk::OpenKey> open_keys;
+    long opt_open_small_log2 = 14;   // opening levels with at most 2^this quotient values share one batched MSM (measured: 10..14 -> 19.4 .. 18.1 ms at nv = 22)
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;
     long opt_window = 0;             // 0 = choose per call

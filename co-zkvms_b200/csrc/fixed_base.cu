@@ -96,7 +96,8 @@ extern "C" int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, cons
             // multiples of the identity are the identity
             std::vector<uint8_t> ident(std::max<size_t>(n, 1) * 72, 0);
             for (size_t i = 0; i < n; ++i) ident[72 * i + 64] = 1;
-            FB_CUDA(cudaMemcpy(d_out, ident.data(), n * 72, cudaMemcpyHostToDevice));
+            FB_CUDA(cudaMemcpyAsync(d_out, ident.data(), n * 72, cudaMemcpyHostToDevice, D.stream));
+            FB_CUDA(cudaStreamSynchronize(D.stream));
         } else {
             affine base;
             memcpy(base.x.v, b, 32);

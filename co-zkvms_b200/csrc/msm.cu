@@ -23,7 +23,8 @@ void set_error(const std::string& msg) { g_error = msg; }
 Device::~Device() {
     cudaSetDevice(id);
     DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
-                      &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush, &buckets2};
+                      &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush, &buckets2,
+                      &open_in, &open_r[0], &open_r[1], &open_q, &open_qs};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : copy_done) if (e) cudaEventDestroy(e);
@@ -748,15 +749,19 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         affine* d = nullptr;
         uint8_t* di = nullptr;
         COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine)));
+        // Copies go through the engine's own stream and are synchronised there.  A plain cudaMemcpy from pageable memory
+        // returns once the data is STAGED - its DMA runs on the legacy default stream, which the engine's non-blocking
+        // streams do not wait for, so the table build could read row 0 before the tail of the copy had landed.
         if (stride_bytes == 64) {
-            COZK_CUDA(cudaMemcpy(d, bases, n * 64, cudaMemcpyHostToDevice));
+            COZK_CUDA(cudaMemcpyAsync(d, bases, n * 64, cudaMemcpyHostToDevice, D->stream));
         } else {
-            COZK_CUDA(cudaMemcpy2D(d, 64, bases, stride_bytes, 64, n, cudaMemcpyHostToDevice));
+            COZK_CUDA(cudaMemcpy2DAsync(d, 64, bases, stride_bytes, 64, n, cudaMemcpyHostToDevice, D->stream));
         }
         if (any_inf) {
             COZK_CUDA(cudaMalloc(&di, n));
-            COZK_CUDA(cudaMemcpy(di, infinity, n, cudaMemcpyHostToDevice));
+            COZK_CUDA(cudaMemcpyAsync(di, infinity, n, cudaMemcpyHostToDevice, D->stream));
         }
+        COZK_CUDA(cudaStreamSynchronize(D->stream));
         S.d_bases.push_back(d);
         S.d_inf.push_back(di);
         int rc = srs_build_table(*D, d, n, S.table_c, S.table_W);
@@ -865,6 +870,10 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // window size of the tables of SRS registered from now on (0 = choose from the SRS length)
         if (value != 0 && (value < (long)C_MIN || value > (long)C_MAX)) return COZK_ERR_INVALID_ARG;
         ctx->opt_table_window = value;
+    } else if (!strcmp(name, "open_small_log2")) {
+        // opening keys created from now on: levels with at most 2^value quotient scalars share one batched MSM (0 = none)
+        if (value < 0 || value > 20) return COZK_ERR_INVALID_ARG;
+        ctx->opt_open_small_log2 = value;
     } else if (!strcmp(name, "table_max_mib")) {
         // memory an SRS registered from now on may spend on its 2^(c*w) * P table; 0 = no tables
         if (value < 0) return COZK_ERR_INVALID_ARG;

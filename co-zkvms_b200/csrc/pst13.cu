@@ -3,20 +3,27 @@
 #include "pst13.hpp"
 #include "../../include/cozk_rep3.h"
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
 
 #include "engine.hpp"
-#include "msm_kernels.cuh"
+#include "rep3_kernels.cuh"
 
 namespace cozk {
 
 // dense[i] = strided[i * stride]   (share `a` of an AoS Rep3 share array, or a plain copy when stride == 32)
-__global__ void k_gather_fr(const uint8_t* src, size_t stride, fr* dst, size_t n) {
+// canon: the source holds canonical integers (a widened small-scalar polynomial): converted to Montgomery form on the way
+__global__ void k_gather_fr(const uint8_t* src, size_t stride, fr* dst, size_t n, int canon) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    store_fq(&dst[t], load_fq(src + t * stride));
+    fr v = load_fq(src + t * stride);
+    if (canon) v = fr_mont_from_canon(v);
+    store_fq(&dst[t], v);
 }
 
 // One level of open() (pst13.rs:454-459):  q[b] = r[2b+1] - r[2b];  r'[b] = r[2b]*(1-t) + r[2b+1]*t = r[2b] + t*q[b];
@@ -132,8 +139,8 @@ int cozk_pst13_batch_commit_rep3(cozk_ctx* ctx, cozk_srs srs, const void* const*
     return COZK_OK;
 }
 
-static int open_check_levels(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv) {
-    // assert_eq!(nv, ck.nv): every level must hold exactly 2^(nv-i) points (pair sums: half of that)
+static int open_check_levels(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv) {
+    // assert_eq!(nv, ck.nv): every level must hold exactly 2^(nv-i) points
     for (size_t i = 0; i < nv; ++i) {
         size_t len = 0;
         int rc = cozk_srs_len(ctx, level_srs[i], &len);
@@ -142,27 +149,13 @@ static int open_check_levels(cozk_ctx* ctx, const cozk_srs* level_srs, const coz
             set_error("Invalid size of polynomial: SRS level length does not match nv");
             return COZK_ERR_KEY_LENGTH;
         }
-        if (level_pairs) {
-            rc = cozk_srs_len(ctx, level_pairs[i], &len);
-            if (rc) return rc;
-            if (len != ((size_t)1 << (nv - i - 1))) {
-                set_error("pair-sum SRS level length does not match nv");
-                return COZK_ERR_KEY_LENGTH;
-            }
-        }
     }
     return COZK_OK;
 }
 
-int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const void* evals, size_t stride_bytes,
-                    const void* point, int form, void* out_proofs, void* out_eval) {
-    return cozk_pst13_open_paired(ctx, level_srs, nullptr, nv, evals, stride_bytes, point, form, out_proofs, out_eval);
-}
-
-int cozk_pst13_open_paired(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv,
-                           const void* evals, size_t stride_bytes, const void* point, int form, void* out_proofs,
-                           void* out_eval) {
-    if (!ctx || !level_srs || !evals || !point || !out_proofs || !out_eval || nv == 0 || nv > 30) {
+static int open_check_args(cozk_ctx* ctx, const void* evals, const void* point, void* out_proofs, void* out_eval, size_t nv,
+                           size_t stride_bytes, int form) {
+    if (!ctx || !evals || !point || !out_proofs || !out_eval || nv == 0 || nv > 30) {
         set_error("null pointer or bad nv");
         return COZK_ERR_INVALID_ARG;
     }
@@ -170,51 +163,151 @@ int cozk_pst13_open_paired(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_
         set_error("open() takes Montgomery-form Fr values at a stride that is a multiple of 16");
         return COZK_ERR_INVALID_ARG;
     }
-    int rc = open_check_levels(ctx, level_srs, level_pairs, nv);
+    return COZK_OK;
+}
+
+int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const void* evals, size_t stride_bytes,
+                    const void* point, int form, void* out_proofs, void* out_eval) {
+    int rc = open_check_args(ctx, evals, point, out_proofs, out_eval, nv, stride_bytes, form);
     if (rc) return rc;
-    Device& D = *ctx->devs[0];
-    size_t n = (size_t)1 << nv;
-    uint8_t* d_in = nullptr;
-    fr* d_r0 = nullptr;
+    if (!level_srs) {
+        set_error("null pointer");
+        return COZK_ERR_INVALID_ARG;
+    }
+    rc = open_check_levels(ctx, level_srs, nv);
+    if (rc) return rc;
+    OpenSource src;
+    src.host = evals;
+    src.stride = stride_bytes;
+    return pst13_open_device(ctx, level_srs, nullptr, nv, src, point, out_proofs, out_eval);
+}
+
+int cozk_pst13_open_keyed(cozk_ctx* ctx, cozk_open_key key, const void* evals, size_t stride_bytes, const void* point,
+                          int form, void* out_proofs, void* out_eval) {
+    OpenKey K;
+    if (!ctx) return COZK_ERR_INVALID_ARG;
+    int rc = open_key_lookup(ctx, key, &K);
+    if (rc) return rc;
+    rc = open_check_args(ctx, evals, point, out_proofs, out_eval, K.nv, stride_bytes, form);
+    if (rc) return rc;
+    OpenSource src;
+    src.host = evals;
+    src.stride = stride_bytes;
+    return pst13_open_device(ctx, K.level_srs.data(), &K, K.nv, src, point, out_proofs, out_eval);
+}
+
+int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, cozk_open_key* out) {
+    if (!ctx || !level_srs || !out || nv == 0 || nv > 30) {
+        set_error("null pointer or bad nv");
+        return COZK_ERR_INVALID_ARG;
+    }
+    int rc = open_check_levels(ctx, level_srs, nv);
+    if (rc) return rc;
+    OpenKey K;
+    K.nv = nv;
+    K.level_srs.assign(level_srs, level_srs + nv);
+    size_t small_log2;
     {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        small_log2 = (size_t)ctx->opt_open_small_log2;
+    }
+    // level i has 2^(nv-1-i) quotient scalars; the levels with at most 2^small_log2 of them are batched (none if 0)
+    K.first_small = small_log2 == 0 ? nv : (nv > small_log2 + 1 ? nv - small_log2 - 1 : 0);
+    K.small_n = K.first_small < nv ? ((size_t)1 << (nv - K.first_small)) - 1 : 0;
+    Device& D = *ctx->devs[0];
+    affine* d_small = nullptr;
+    uint8_t* d_small_inf = nullptr;
+    auto fail = [&](int code) {
+        for (cozk_srs h : K.pair_srs) cozk_srs_release(ctx, h);
+        cudaSetDevice(D.id);
+        if (d_small) cudaFree(d_small);
+        if (d_small_inf) cudaFree(d_small_inf);
+        return code;
+    };
+    if (K.small_n) {
         std::lock_guard<std::mutex> lock(D.mu);
         cudaError_t e = cudaSetDevice(D.id);
-        size_t in_bytes = (n - 1) * stride_bytes + 32;
-        if (e == cudaSuccess) e = cudaMalloc(&d_in, in_bytes);
-        if (e == cudaSuccess) e = cudaMalloc(&d_r0, n * sizeof(fr));
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, evals, in_bytes, cudaMemcpyHostToDevice, D.stream);
-        if (e == cudaSuccess) {
-            k_gather_fr<<<(unsigned)((n + 255) / 256), 256, 0, D.stream>>>(d_in, stride_bytes, d_r0, n);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-        if (d_in) cudaFree(d_in);
+        if (e == cudaSuccess) e = cudaMalloc(&d_small, K.small_n * sizeof(affine));
+        if (e == cudaSuccess) e = cudaMalloc(&d_small_inf, K.small_n);
         if (e != cudaSuccess) {
-            if (d_r0) cudaFree(d_r0);
-            set_error(std::string("open(): staging the evaluations failed: ") + cudaGetErrorString(e));
-            return COZK_ERR_CUDA;
+            set_error(std::string("open key: allocation failed: ") + cudaGetErrorString(e));
+            return fail(COZK_ERR_CUDA);
         }
     }
-    return pst13_open_device(ctx, level_srs, level_pairs, nv, d_r0, point, out_proofs, out_eval);
+    size_t off = 0;
+    for (size_t i = 0; i < nv; ++i) {
+        size_t half = (size_t)1 << (nv - 1 - i);
+        if (i < K.first_small) {
+            cozk_srs h = 0;
+            rc = cozk_srs_pair_sums(ctx, level_srs[i], &h);
+            if (rc) return fail(rc);
+            K.pair_srs.push_back(h);
+        } else {
+            size_t got = 0;
+            rc = srs_pair_sums_into(ctx, level_srs[i], d_small + off, d_small_inf + off, &got);
+            if (rc) return fail(rc);
+            K.small_off.push_back(off);
+            off += half;
+        }
+    }
+    if (K.small_n) {
+        rc = srs_register_from_device(ctx, 0, d_small, d_small_inf, K.small_n, &K.small_srs);
+        if (rc) return fail(rc);
+        std::lock_guard<std::mutex> lock(D.mu);
+        cudaSetDevice(D.id);
+        cudaFree(d_small);
+        cudaFree(d_small_inf);
+    }
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    *out = ctx->next_handle++;
+    ctx->open_keys[*out] = K;
+    return COZK_OK;
+}
+
+int cozk_pst13_open_key_release(cozk_ctx* ctx, cozk_open_key key) {
+    if (!ctx) return COZK_ERR_INVALID_ARG;
+    OpenKey K;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->open_keys.find(key);
+        if (it == ctx->open_keys.end()) {
+            set_error("unknown opening key");
+            return COZK_ERR_BAD_HANDLE;
+        }
+        K = it->second;
+        ctx->open_keys.erase(it);
+    }
+    for (cozk_srs h : K.pair_srs) cozk_srs_release(ctx, h);
+    if (K.small_srs) cozk_srs_release(ctx, K.small_srs);
+    return COZK_OK;
 }
 
 }  // extern "C"
 
 namespace cozk {
 
-// d_r0: 2^nv dense Montgomery evaluations on device 0, owned by this call from here on.
-int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, fr* d_r0,
+int open_key_lookup(cozk_ctx* ctx, uint64_t h, OpenKey* out) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->open_keys.find(h);
+    if (it == ctx->open_keys.end()) {
+        set_error("unknown opening key");
+        return COZK_ERR_BAD_HANDLE;
+    }
+    *out = it->second;
+    return COZK_OK;
+}
+
+// The evaluations are brought into a dense Montgomery vector on device 0 (copy_share_a, dense_mlpoly.rs:102-110, as a strided
+// read).  All nv folds run back to back on the stream (pst13.rs:454-458); the MSMs follow: without a key one per level over
+// the duplicated quotient scalars (the reference's schedule, pst13.rs:459-469); with a key one per large level over its pair
+// sums and ONE batched MSM for all small levels - level j's scalar vector is zero outside its own slice of the concatenated
+// small SRS, so the batch returns every level's sum separately.  Scratch memory is the device's grow-only open_* buffers.
+int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const OpenKey* key, size_t nv, const OpenSource& src,
                       const void* point, void* out_proofs, void* out_eval) {
     Device& D = *ctx->devs[0];
+    std::lock_guard<std::mutex> open_lock(D.open_mu);
     size_t n = (size_t)1 << nv;
-    fr *d_r[2] = {d_r0, nullptr}, *d_q = nullptr;
-    int rc = COZK_OK;
-    auto cleanup = [&]() {
-        cudaSetDevice(D.id);
-        if (d_r[0]) cudaFree(d_r[0]);
-        if (d_r[1]) cudaFree(d_r[1]);
-        if (d_q) cudaFree(d_q);
-    };
+    auto cleanup = [&]() {};
 #define OPEN_CUDA(call)                                                                  \
     do {                                                                                 \
         cudaError_t e__ = (call);                                                        \
@@ -224,47 +317,79 @@ int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* 
             return COZK_ERR_CUDA;                                                        \
         }                                                                                \
     } while (0)
-    {
-        std::lock_guard<std::mutex> lock(D.mu);
-        OPEN_CUDA(cudaSetDevice(D.id));
-        OPEN_CUDA(cudaMalloc(&d_r[1], (n / 2 + 1) * sizeof(fr)));
-        OPEN_CUDA(cudaMalloc(&d_q, (level_pairs ? n / 2 + 1 : n) * sizeof(fr)));
+    const size_t first_small = key ? key->first_small : nv;
+    const size_t g_small = nv - first_small;
+    // quotient vectors of the individually opened levels, one after the other: level i at q_off[i]
+    std::vector<size_t> q_off(nv, 0);
+    size_t q_total = 0;
+    for (size_t i = 0; i < first_small; ++i) {
+        q_off[i] = q_total;
+        q_total += key ? ((size_t)1 << (nv - 1 - i)) : ((size_t)1 << (nv - i));
     }
     const uint8_t* pt = reinterpret_cast<const uint8_t*>(point);
     uint8_t* proofs = reinterpret_cast<uint8_t*>(out_proofs);
     int cur = 0;
-    for (size_t i = 0; i < nv; ++i) {
-        size_t k = nv - i, half = (size_t)1 << (k - 1);
-        fr t;
-        memcpy(t.v, pt + 32 * i, 32);
-        {
-            std::lock_guard<std::mutex> lock(D.mu);
-            OPEN_CUDA(cudaSetDevice(D.id));
-            k_open_fold<<<(unsigned)((half + 127) / 128), 128, 0, D.stream>>>(d_r[cur], t, d_q, d_r[cur ^ 1], half,
-                                                                             level_pairs ? 0 : 1);
-            OPEN_CUDA(cudaGetLastError());
-            OPEN_CUDA(cudaStreamSynchronize(D.stream));
-        }
-        const void* vec[1] = {d_q};
-        // with pair sums: sum_b q[b] * (P[2b] + P[2b+1]) over `half` points; without: q duplicated over 2 * half points
-        if (level_pairs)
-            rc = msm_dispatch(ctx, 0, level_pairs[i], 0, half, nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
-        else
-            rc = msm_dispatch(ctx, 0, level_srs[i], 0, 2 * half, nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
-        if (rc) {
-            cleanup();
-            return rc;
-        }
-        cur ^= 1;
-    }
+    fr *d_r[2] = {nullptr, nullptr}, *d_q = nullptr, *d_qs = nullptr;
     {
         std::lock_guard<std::mutex> lock(D.mu);
         OPEN_CUDA(cudaSetDevice(D.id));
-        OPEN_CUDA(cudaMemcpy(out_eval, d_r[cur], 32, cudaMemcpyDeviceToHost));
+        int rc0 = D.open_r[0].ensure(n * sizeof(fr));
+        if (!rc0) rc0 = D.open_r[1].ensure((n / 2 + 1) * sizeof(fr));
+        if (!rc0) rc0 = D.open_q.ensure(std::max<size_t>(q_total, 1) * sizeof(fr));
+        if (!rc0 && g_small) rc0 = D.open_qs.ensure(g_small * key->small_n * sizeof(fr));
+        if (!rc0 && src.host) rc0 = D.open_in.ensure((n - 1) * src.stride + 32);
+        if (rc0) return rc0;
+        d_r[0] = D.open_r[0].as<fr>();
+        d_r[1] = D.open_r[1].as<fr>();
+        d_q = D.open_q.as<fr>();
+        d_qs = D.open_qs.as<fr>();
+        const uint8_t* from = src.dev;
+        if (src.host) {
+            OPEN_CUDA(cudaMemcpyAsync(D.open_in.p, src.host, (n - 1) * src.stride + 32, cudaMemcpyHostToDevice, D.stream));
+            from = D.open_in.as<uint8_t>();
+        }
+        k_gather_fr<<<(unsigned)((n + 255) / 256), 256, 0, D.stream>>>(from, src.stride, d_r[0], n, src.canon);
+        OPEN_CUDA(cudaGetLastError());
+        if (g_small) OPEN_CUDA(cudaMemsetAsync(d_qs, 0, g_small * key->small_n * sizeof(fr), D.stream));
+        for (size_t i = 0; i < nv; ++i) {
+            size_t half = (size_t)1 << (nv - 1 - i);
+            fr t;
+            memcpy(t.v, pt + 32 * i, 32);
+            fr* q_out = i < first_small ? d_q + q_off[i] : d_qs + (i - first_small) * key->small_n + key->small_off[i - first_small];
+            k_open_fold<<<(unsigned)((half + 127) / 128), 128, 0, D.stream>>>(d_r[cur], t, q_out, d_r[cur ^ 1], half, key ? 0 : 1);
+            OPEN_CUDA(cudaGetLastError());
+            cur ^= 1;
+        }
+        OPEN_CUDA(cudaMemcpyAsync(out_eval, d_r[cur], 32, cudaMemcpyDeviceToHost, D.stream));
+        OPEN_CUDA(cudaStreamSynchronize(D.stream));
     }
-    cleanup();
+    int rc = COZK_OK;
+    const bool trace = getenv("COZK_OPEN_TRACE") != nullptr;  // per-stage wall times on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
+    auto t_start = now();
+    for (size_t i = 0; i < first_small && !rc; ++i) {
+        auto t0 = now();
+        const void* vec[1] = {d_q + q_off[i]};
+        if (key)
+            rc = msm_dispatch(ctx, 0, key->pair_srs[i], 0, (size_t)1 << (nv - 1 - i), nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
+        else
+            rc = msm_dispatch(ctx, 0, level_srs[i], 0, (size_t)1 << (nv - i), nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
+        if (trace) fprintf(stderr, "[open] level %zu: %.3f ms\n", i, ms_since(t0));
+    }
+    if (!rc && g_small) {
+        auto t0 = now();
+        std::vector<const void*> vecs(g_small);
+        for (size_t j = 0; j < g_small; ++j) vecs[j] = d_qs + j * key->small_n;
+        rc = msm_dispatch(ctx, 0, key->small_srs, 0, key->small_n, nullptr, vecs.data(), g_small, 32, COZK_MONT, 0,
+                          proofs + 72 * first_small);
+        if (trace) fprintf(stderr, "[open] %zu small levels in one batch of %zu points: %.3f ms\n", g_small, key->small_n, ms_since(t0));
+    }
+    if (trace) fprintf(stderr, "[open] MSMs %.3f ms\n", ms_since(t_start));
 #undef OPEN_CUDA
-    return COZK_OK;
+    return rc;
 }
 
 }  // namespace cozk

@@ -65,6 +65,30 @@ COZK_HD void fr_wide_mac(fr_wide& acc, const fr& a, const fr& b) {
     uint32_t t[16];
 #if defined(__CUDA_ARCH__)
     mulwide_ptx(t, a.v, b.v);
+    // one 18-limb carry chain (IADD3 / IADD3.X); written as PTX so that the carries stay in the flag
+    asm("add.cc.u32 %0, %0, %18;\n\t"
+        "addc.cc.u32 %1, %1, %19;\n\t"
+        "addc.cc.u32 %2, %2, %20;\n\t"
+        "addc.cc.u32 %3, %3, %21;\n\t"
+        "addc.cc.u32 %4, %4, %22;\n\t"
+        "addc.cc.u32 %5, %5, %23;\n\t"
+        "addc.cc.u32 %6, %6, %24;\n\t"
+        "addc.cc.u32 %7, %7, %25;\n\t"
+        "addc.cc.u32 %8, %8, %26;\n\t"
+        "addc.cc.u32 %9, %9, %27;\n\t"
+        "addc.cc.u32 %10, %10, %28;\n\t"
+        "addc.cc.u32 %11, %11, %29;\n\t"
+        "addc.cc.u32 %12, %12, %30;\n\t"
+        "addc.cc.u32 %13, %13, %31;\n\t"
+        "addc.cc.u32 %14, %14, %32;\n\t"
+        "addc.cc.u32 %15, %15, %33;\n\t"
+        "addc.cc.u32 %16, %16, 0;\n\t"
+        "addc.u32 %17, %17, 0;\n\t"
+        : "+r"(acc.v[0]), "+r"(acc.v[1]), "+r"(acc.v[2]), "+r"(acc.v[3]), "+r"(acc.v[4]), "+r"(acc.v[5]), "+r"(acc.v[6]),
+          "+r"(acc.v[7]), "+r"(acc.v[8]), "+r"(acc.v[9]), "+r"(acc.v[10]), "+r"(acc.v[11]), "+r"(acc.v[12]), "+r"(acc.v[13]),
+          "+r"(acc.v[14]), "+r"(acc.v[15]), "+r"(acc.v[16]), "+r"(acc.v[17])
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]), "r"(t[9]),
+          "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
 #else
 #pragma unroll
     for (int i = 0; i < 16; ++i) t[i] = 0;
@@ -77,9 +101,7 @@ COZK_HD void fr_wide_mac(fr_wide& acc, const fr& a, const fr& b) {
         }
         t[i + 8] = (uint32_t)c;
     }
-#endif
     uint64_t c = 0;
-#pragma unroll
     for (int i = 0; i < 16; ++i) {
         c += (uint64_t)acc.v[i] + t[i];
         acc.v[i] = (uint32_t)c;
@@ -88,6 +110,7 @@ COZK_HD void fr_wide_mac(fr_wide& acc, const fr& a, const fr& b) {
     c += acc.v[16];
     acc.v[16] = (uint32_t)c;
     acc.v[17] += (uint32_t)(c >> 32);
+#endif
 }
 // acc * R^-1 mod r, fully reduced.  With acc = lo + hi * 2^256 + top * 2^512:
 //     acc / R = lo / R + hi + top * 2^256  (mod r)  =  from_mont(lo) + hi + to_mont(top)
@@ -174,20 +197,40 @@ struct LincombArgs {
     size_t n;               // max length
     uint8_t* out;
 };
-// thread i: element i of the joint polynomial
+// One term of element i: the two field elements it contributes (x = a / the public value, y = b) and where they go.
+struct LincombTerm {
+    fr x, y;
+    uint32_t kind;  // POLY_* or 0xFFFFFFFF when polynomial j does not reach index i
+};
+COZK_HD LincombTerm lincomb_fetch(size_t i, uint32_t j, const LincombArgs& A) {
+    LincombTerm t;
+    const PolyDesc d = A.polys[j];
+    t.kind = i < d.len ? d.kind : 0xFFFFFFFFu;
+    t.x = fq_zero();
+    t.y = fq_zero();
+    if (t.kind == POLY_SHARED) {
+        t.x = load_fq(d.data + 64 * i);
+        t.y = load_fq(d.data + 64 * i + 32);
+    } else if (t.kind != 0xFFFFFFFFu) {
+        t.x = load_fq(d.data + 32 * i);
+    }
+    return t;
+}
+// thread i: element i of the joint polynomial.  The loads of term j+1 are issued before the multiplications of term j.
 COZK_HD void lincomb_body(size_t i, const LincombArgs& A) {
     if (i >= A.n) return;
     fr_wide sa = fr_wide_zero(), sb = fr_wide_zero(), pub = fr_wide_zero();
+    LincombTerm next = lincomb_fetch(i, 0, A);
     for (uint32_t j = 0; j < A.k; ++j) {
-        const PolyDesc d = A.polys[j];
-        if (i >= d.len) continue;
-        if (d.kind == POLY_SHARED) {
+        const LincombTerm cur = next;
+        if (j + 1 < A.k) next = lincomb_fetch(i, j + 1, A);
+        if (cur.kind == POLY_SHARED) {
             fr c = load_fq(&A.coeffs[2 * j]);
-            fr_wide_mac(sa, load_fq(d.data + 64 * i), c);
-            fr_wide_mac(sb, load_fq(d.data + 64 * i + 32), c);
-        } else {
-            fr c = load_fq(&A.coeffs[2 * j + (d.kind == POLY_CANON ? 1 : 0)]);
-            fr_wide_mac(pub, load_fq(d.data + 32 * i), c);
+            fr_wide_mac(sa, cur.x, c);
+            fr_wide_mac(sb, cur.y, c);
+        } else if (cur.kind != 0xFFFFFFFFu) {
+            fr c = load_fq(&A.coeffs[2 * j + (cur.kind == POLY_CANON ? 1 : 0)]);
+            fr_wide_mac(pub, cur.x, c);
         }
     }
     fr p = fr_wide_reduce(pub);
@@ -213,35 +256,53 @@ struct ChiArgs {
     uint32_t T;       // threads per polynomial
     fr* partial;      // k x T
 };
+COZK_HD fr chi_value(const PolyDesc& d, size_t i) {
+    if (d.kind == POLY_SHARED) return fr_add(load_fq(d.data + 64 * i), load_fq(d.data + 64 * i + 32));
+    fr v = load_fq(d.data + 32 * i);
+    return d.kind == POLY_CANON ? fr_mont_from_canon(v) : v;
+}
 COZK_HD void chi_partial_body(size_t tid, const ChiArgs& A) {
     if (tid >= (size_t)A.k * A.T) return;
     uint32_t j = (uint32_t)(tid / A.T), t = (uint32_t)(tid - (size_t)j * A.T);
     const PolyDesc d = A.polys[j];
     fr_wide acc = fr_wide_zero();
     size_t lim = d.len < A.n ? d.len : A.n;
-    for (size_t i = t; i < lim; i += A.T) {
-        fr chi = load_fq(&A.chis[i]);
-        fr v;
-        if (d.kind == POLY_SHARED) {
-            v = fr_add(load_fq(d.data + 64 * i), load_fq(d.data + 64 * i + 32));
-        } else {
-            v = load_fq(d.data + 32 * i);
-            if (d.kind == POLY_CANON) v = fr_mont_from_canon(v);
-        }
-        fr_wide_mac(acc, v, chi);
+    size_t i = t;
+    // four elements per round: their loads are all issued before the first multiplication
+    for (; i + 3 * (size_t)A.T < lim; i += 4 * (size_t)A.T) {
+        fr v0 = chi_value(d, i), v1 = chi_value(d, i + A.T), v2 = chi_value(d, i + 2 * (size_t)A.T), v3 = chi_value(d, i + 3 * (size_t)A.T);
+        fr c0 = load_fq(&A.chis[i]), c1 = load_fq(&A.chis[i + A.T]), c2 = load_fq(&A.chis[i + 2 * (size_t)A.T]),
+           c3 = load_fq(&A.chis[i + 3 * (size_t)A.T]);
+        fr_wide_mac(acc, v0, c0);
+        fr_wide_mac(acc, v1, c1);
+        fr_wide_mac(acc, v2, c2);
+        fr_wide_mac(acc, v3, c3);
     }
+    for (; i < lim; i += A.T) fr_wide_mac(acc, chi_value(d, i), load_fq(&A.chis[i]));
     store_fq(&A.partial[tid], fr_wide_reduce(acc));
 }
-// stage 2: one thread per polynomial adds the T partial sums and applies TWO_INV for shared polynomials
-COZK_HD void chi_final_body(size_t j, const ChiArgs& A, fr* out) {
-    if (j >= A.k) return;
+// stage 2 (run twice: T -> 64 -> 1 partial sums per polynomial, so that no thread walks a long chain of dependent loads):
+// thread j * Tout + t adds the partial sums s = t, t + Tout, ... < Tin of polynomial j; the last pass applies the TWO_INV of
+// into_additive for shared polynomials.
+struct ChiReduceArgs {
+    const PolyDesc* polys;
+    uint32_t k;
+    const fr* in;
+    uint32_t Tin;
+    fr* out;
+    uint32_t Tout;
+    uint32_t last;
+};
+COZK_HD void chi_reduce_body(size_t tid, const ChiReduceArgs& A) {
+    if (tid >= (size_t)A.k * A.Tout) return;
+    uint32_t j = (uint32_t)(tid / A.Tout), t = (uint32_t)(tid - (size_t)j * A.Tout);
     fr s = fq_zero();
-    for (uint32_t t = 0; t < A.T; ++t) s = fr_add(s, load_fq(&A.partial[j * A.T + t]));
-    if (A.polys[j].kind == POLY_SHARED) {
+    for (uint32_t i = t; i < A.Tin; i += A.Tout) s = fr_add(s, load_fq(&A.in[(size_t)j * A.Tin + i]));
+    if (A.last && A.polys[j].kind == POLY_SHARED) {
         const uint32_t h[8] = COZK_FR_TWO_INV_MONT;
         s = fr_mul(s, fr_const(h));
     }
-    store_fq(&out[j], s);
+    store_fq(&A.out[tid], s);
 }
 
 // ------------------------------------------------------------------------------------------------ N1 pair sums

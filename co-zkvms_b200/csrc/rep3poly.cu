@@ -15,19 +15,24 @@ namespace cozk {
 
 __global__ void __launch_bounds__(256) k_ingest(IngestArgs A) { ingest_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(256) k_widen(WidenArgs A) { widen_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
-__global__ void __launch_bounds__(128) k_lincomb(LincombArgs A) { lincomb_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
-__global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
-__global__ void k_chi_final(ChiArgs A, fr* out) { chi_final_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A, out); }
-__global__ void __launch_bounds__(128) k_pair_sum(PairSumArgs A) { pair_sum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
-// dense[i] = src[i * stride]: share a of an AoS share array (stride 64) or a plain copy (stride 32)
-__global__ void k_take_fr(const uint8_t* src, size_t stride, fr* dst, size_t n, int canon) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    fr v = load_fq(src + t * stride);
-    if (canon) v = fr_mont_from_canon(v);
-    store_fq(&dst[t], v);
+// descriptors and coefficients are the same for every thread: each block stages them in shared memory once
+// (k * (24 + 64) bytes) so that the inner loop reads them with broadcast loads instead of going through L1/L2
+__global__ void __launch_bounds__(128, 4) k_lincomb(LincombArgs A, int staged) {
+    extern __shared__ uint4 lincomb_smem[];
+    if (staged) {
+        PolyDesc* sd = reinterpret_cast<PolyDesc*>(lincomb_smem);
+        fr* sc = reinterpret_cast<fr*>(reinterpret_cast<uint8_t*>(lincomb_smem) + (((size_t)A.k * sizeof(PolyDesc) + 15) & ~(size_t)15));
+        for (uint32_t j = threadIdx.x; j < A.k; j += blockDim.x) sd[j] = A.polys[j];
+        for (uint32_t j = threadIdx.x; j < 2 * A.k; j += blockDim.x) store_fq(&sc[j], load_fq(&A.coeffs[j]));
+        __syncthreads();
+        A.polys = sd;
+        A.coeffs = sc;
+    }
+    lincomb_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
-
+__global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void k_chi_reduce(ChiReduceArgs A) { chi_reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(128) k_pair_sum(PairSumArgs A) { pair_sum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 static inline unsigned blocks_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
 static int check_device(cozk_ctx* ctx, int device_index) {
@@ -109,6 +114,33 @@ struct Reader {
         return true;
     }
 };
+
+int srs_pair_sums_into(cozk_ctx* ctx, cozk_srs srs, affine* d_out, uint8_t* d_inf, size_t* half_out) {
+    SrsEntry S;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        auto it = ctx->srs.find(srs);
+        if (it == ctx->srs.end()) {
+            set_error("unknown SRS handle");
+            return COZK_ERR_BAD_HANDLE;
+        }
+        S = it->second;
+    }
+    if (S.n == 0 || (S.n & 1)) {
+        set_error("pair sums need an even, non-zero number of bases");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Device& D = *ctx->devs[0];
+    size_t half = S.n / 2;
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    PairSumArgs A{S.d_bases[0], S.d_inf[0], half, d_out, d_inf};  // row 0 of the table = the bases themselves
+    k_pair_sum<<<blocks_for(half, 128), 128, 0, D.stream>>>(A);
+    COZK_CUDA(cudaGetLastError());
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    if (half_out) *half_out = half;
+    return COZK_OK;
+}
 
 }  // namespace cozk
 
@@ -336,7 +368,8 @@ int cozk_poly_download(cozk_ctx* ctx, cozk_poly poly, void* out) {
     Device& D = *ctx->devs[E.dev];
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
-    COZK_CUDA(cudaMemcpy(out, E.chunk(), E.len * E.elem_bytes(), cudaMemcpyDeviceToHost));
+    COZK_CUDA(cudaMemcpyAsync(out, E.chunk(), E.len * E.elem_bytes(), cudaMemcpyDeviceToHost, D.stream));
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
     return COZK_OK;
 }
 
@@ -461,7 +494,9 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
         LincombArgs A{d_desc, d_coef, (uint32_t)k, (uint32_t)party_id, any_shared ? 1u : 0u, max_len, d_out};
         StageTimer T(D);
         T.start();
-        k_lincomb<<<blocks_for(max_len, 128), 128, 0, D.stream>>>(A);
+        size_t smem = (((size_t)k * sizeof(PolyDesc) + 15) & ~(size_t)15) + 2 * k * sizeof(fr);
+        int staged = smem <= 40 * 1024 ? 1 : 0;  // k <= 465; longer lists read the tables from global memory
+        k_lincomb<<<blocks_for(max_len, 128), 128, staged ? smem : 0, D.stream>>>(A, staged);
         e = cudaGetLastError();
         ms = T.stop();
     }
@@ -507,10 +542,12 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
     PolyDesc* d_desc = nullptr;
-    fr *d_chis = nullptr, *d_part = nullptr, *d_res = nullptr;
+    fr *d_chis = nullptr, *d_part = nullptr, *d_mid = nullptr, *d_res = nullptr;
+    const uint32_t Tmid = T < 64 ? T : 64;
     cudaError_t e = cudaMalloc(&d_desc, k * sizeof(PolyDesc));
     if (e == cudaSuccess) e = cudaMalloc(&d_chis, std::max<size_t>(n, 1) * sizeof(fr));
     if (e == cudaSuccess) e = cudaMalloc(&d_part, k * (size_t)T * sizeof(fr));
+    if (e == cudaSuccess) e = cudaMalloc(&d_mid, k * (size_t)Tmid * sizeof(fr));
     if (e == cudaSuccess) e = cudaMalloc(&d_res, k * sizeof(fr));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), k * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_chis, chis, n * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
@@ -520,13 +557,15 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
         StageTimer St(D);
         St.start();
         k_chi_partial<<<blocks_for(k * (size_t)T, 128), 128, 0, D.stream>>>(A);
-        k_chi_final<<<blocks_for(k, 64), 64, 0, D.stream>>>(A, d_res);
+        ChiReduceArgs R1{d_desc, (uint32_t)k, d_part, T, d_mid, Tmid, 0}, R2{d_desc, (uint32_t)k, d_mid, Tmid, d_res, 1, 1};
+        k_chi_reduce<<<blocks_for(k * (size_t)Tmid, 64), 64, 0, D.stream>>>(R1);
+        k_chi_reduce<<<blocks_for(k, 64), 64, 0, D.stream>>>(R2);
         e = cudaGetLastError();
         ms = St.stop();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_evals, d_res, k * sizeof(fr), cudaMemcpyDeviceToHost, D.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-    for (void* p : {(void*)d_desc, (void*)d_chis, (void*)d_part, (void*)d_res})
+    for (void* p : {(void*)d_desc, (void*)d_chis, (void*)d_part, (void*)d_mid, (void*)d_res})
         if (p) cudaFree(p);
     if (e != cudaSuccess) {
         set_error(std::string("evaluate_at_chi failed: ") + cudaGetErrorString(e));
@@ -541,22 +580,15 @@ int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
         set_error("null pointer");
         return COZK_ERR_INVALID_ARG;
     }
-    SrsEntry S;
-    {
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        auto it = ctx->srs.find(srs);
-        if (it == ctx->srs.end()) {
-            set_error("unknown SRS handle");
-            return COZK_ERR_BAD_HANDLE;
-        }
-        S = it->second;
-    }
-    if (S.n == 0 || (S.n & 1)) {
+    size_t n = 0;
+    int rc = cozk_srs_len(ctx, srs, &n);
+    if (rc) return rc;
+    if (n == 0 || (n & 1)) {
         set_error("pair sums need an even, non-zero number of bases");
         return COZK_ERR_INVALID_ARG;
     }
     Device& D = *ctx->devs[0];
-    size_t half = S.n / 2;
+    size_t half = n / 2;
     affine* d_out = nullptr;
     uint8_t* d_inf = nullptr;
     {
@@ -564,20 +596,14 @@ int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
         COZK_CUDA(cudaSetDevice(D.id));
         cudaError_t e = cudaMalloc(&d_out, half * sizeof(affine));
         if (e == cudaSuccess) e = cudaMalloc(&d_inf, half);
-        if (e == cudaSuccess) {
-            PairSumArgs A{S.d_bases[0], S.d_inf[0], half, d_out, d_inf};  // row 0 of the table = the bases themselves
-            k_pair_sum<<<blocks_for(half, 128), 128, 0, D.stream>>>(A);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
         if (e != cudaSuccess) {
             if (d_out) cudaFree(d_out);
-            if (d_inf) cudaFree(d_inf);
-            set_error(std::string("pair sums failed: ") + cudaGetErrorString(e));
+            set_error(std::string("pair sums: allocation failed: ") + cudaGetErrorString(e));
             return COZK_ERR_CUDA;
         }
     }
-    int rc = srs_register_from_device(ctx, 0, d_out, d_inf, half, out);
+    rc = srs_pair_sums_into(ctx, srs, d_out, d_inf, &half);
+    if (!rc) rc = srs_register_from_device(ctx, 0, d_out, d_inf, half, out);
     std::lock_guard<std::mutex> lock(D.mu);
     cudaSetDevice(D.id);
     cudaFree(d_out);
@@ -585,14 +611,36 @@ int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
     return rc;
 }
 
-int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, cozk_poly poly,
+int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, cozk_open_key key, cozk_poly poly,
                          const void* point, void* out_proofs, void* out_eval) {
-    if (!ctx || !level_srs || !point || !out_proofs || !out_eval || nv == 0 || nv > 30) {
-        set_error("null pointer or bad nv");
+    if (!ctx || !point || !out_proofs || !out_eval || (!level_srs && !key)) {
+        set_error("null pointer");
         return COZK_ERR_INVALID_ARG;
     }
+    OpenKey K;
+    int rc = COZK_OK;
+    if (key) {
+        rc = open_key_lookup(ctx, key, &K);
+        if (rc) return rc;
+        nv = K.nv;
+        level_srs = K.level_srs.data();
+    } else {
+        if (nv == 0 || nv > 30) {
+            set_error("bad nv");
+            return COZK_ERR_INVALID_ARG;
+        }
+        for (size_t i = 0; i < nv; ++i) {
+            size_t len = 0;
+            rc = cozk_srs_len(ctx, level_srs[i], &len);
+            if (rc) return rc;
+            if (len != ((size_t)1 << (nv - i))) {
+                set_error("Invalid size of polynomial: SRS level length does not match nv");
+                return COZK_ERR_KEY_LENGTH;
+            }
+        }
+    }
     PolyEntry E;
-    int rc = lookup(ctx, poly, &E);
+    rc = lookup(ctx, poly, &E);
     if (rc) return rc;
     if (E.dev != 0) {
         set_error("open(): the polynomial must live on device 0 of the context");
@@ -603,37 +651,11 @@ int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_sr
         set_error("Invalid size of polynomial");  // assert_eq!(nv, ck.nv), pst13.rs:438
         return COZK_ERR_KEY_LENGTH;
     }
-    for (size_t i = 0; i < nv; ++i) {
-        size_t len = 0;
-        rc = cozk_srs_len(ctx, level_srs[i], &len);
-        if (rc) return rc;
-        size_t plen = len / 2;
-        if (level_pairs) {
-            rc = cozk_srs_len(ctx, level_pairs[i], &plen);
-            if (rc) return rc;
-        }
-        if (len != ((size_t)1 << (nv - i)) || plen != len / 2) {
-            set_error("Invalid size of polynomial: SRS level length does not match nv");
-            return COZK_ERR_KEY_LENGTH;
-        }
-    }
-    Device& D = *ctx->devs[0];
-    fr* d_r0 = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(D.mu);
-        COZK_CUDA(cudaSetDevice(D.id));
-        COZK_CUDA(cudaMalloc(&d_r0, n * sizeof(fr)));
-        // copy_share_a (dense_mlpoly.rs:102-110) as a strided device read
-        k_take_fr<<<blocks_for(n, 256), 256, 0, D.stream>>>(E.chunk(), E.elem_bytes(), d_r0, n, E.kind == POLY_CANON ? 1 : 0);
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-        if (e != cudaSuccess) {
-            cudaFree(d_r0);
-            set_error(std::string("open(): gathering share a failed: ") + cudaGetErrorString(e));
-            return COZK_ERR_CUDA;
-        }
-    }
-    return pst13_open_device(ctx, level_srs, level_pairs, nv, d_r0, point, out_proofs, out_eval);
+    OpenSource src;
+    src.dev = E.chunk();
+    src.stride = E.elem_bytes();
+    src.canon = E.kind == POLY_CANON ? 1 : 0;
+    return pst13_open_device(ctx, level_srs, key ? &K : nullptr, nv, src, point, out_proofs, out_eval);
 }
 
 int cozk_rep3_last_stats(cozk_ctx* ctx, double* out8) {

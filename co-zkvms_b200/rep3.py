@@ -136,49 +136,50 @@ def pair_sums(ctx, srs):
     return h.value
 
 
-def derive_pairs(setup):
-    """Adds `level_pairs` to a PST13Setup: the pair-sum SRS of every level (setup-time work)."""
-    setup.level_pairs = [pair_sums(setup.ctx, h) for h in setup.level_srs]
+def create_open_key(setup, nv=None):
+    """Adds `open_key` to a PST13Setup: pair sums of every level, small levels concatenated (setup-time work)."""
+    nv = len(setup.level_srs) if nv is None else nv
+    srs = (ctypes.c_uint64 * nv)(*setup.level_srs[:nv])
+    h = ctypes.c_uint64()
+    _check(_lib().cozk_pst13_open_key_create(setup.ctx.handle, srs, nv, ctypes.byref(h)))
+    setup.open_key = h.value
     return setup
 
 
-def release_pairs(setup):
-    for h in getattr(setup, "level_pairs", []) or []:
-        setup.ctx.srs_release(h)
-    setup.level_pairs = []
+def release_open_key(setup):
+    if getattr(setup, "open_key", 0):
+        _check(_lib().cozk_pst13_open_key_release(setup.ctx.handle, setup.open_key))
+    setup.open_key = 0
 
 
-def prove_rep3(setup, poly, opening_point, paired=True):
+def prove_rep3(setup, poly, opening_point, keyed=True):
     """PST13::prove_rep3 (pst13.rs:125-137) without the network send: the opening point is reversed, share a is opened.
     Returns (proofs (nv, 72), evaluation (32,))."""
     point = np.ascontiguousarray(opening_point, dtype=np.uint8).reshape(-1, 32)[::-1].copy()
-    return open_poly(setup, poly, point, paired=paired)
+    return open_poly(setup, poly, point, keyed=keyed)
 
 
-def open_poly(setup, poly, point, paired=True):
-    """open() (pst13.rs:428-474) on a resident polynomial; `point` in the order open() receives it."""
+def open_poly(setup, poly, point, keyed=True):
+    """open() (pst13.rs:428-474) on a resident polynomial; `point` in the order open() receives it.  keyed: use the
+    setup's opening key (pair sums + batched small levels) when it has one, else the reference's schedule."""
     point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
     nv = point.shape[0]
     srs = (ctypes.c_uint64 * nv)(*setup.level_srs[:nv])
-    pairs = None
-    if paired and getattr(setup, "level_pairs", None):
-        pairs = (ctypes.c_uint64 * nv)(*setup.level_pairs[:nv])
+    key = getattr(setup, "open_key", 0) if keyed else 0
     proofs = np.zeros((nv, 72), dtype=np.uint8)
     ev = np.zeros(32, dtype=np.uint8)
-    _check(_lib().cozk_pst13_open_poly(setup.ctx.handle, srs, pairs, nv, poly.handle, _vp(point), _vp(proofs), _vp(ev)))
+    _check(_lib().cozk_pst13_open_poly(setup.ctx.handle, srs, nv, key, poly.handle, _vp(point), _vp(proofs), _vp(ev)))
     return proofs, ev
 
 
-def open_paired(setup, evals, point, stride=32):
-    """cozk_pst13_open_paired: host evaluations, pair-sum SRS."""
+def open_keyed(setup, evals, point, stride=32):
+    """cozk_pst13_open_keyed: host evaluations, the setup's opening key."""
     evals = np.ascontiguousarray(evals, dtype=np.uint8)
     point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
     nv = point.shape[0]
-    srs = (ctypes.c_uint64 * nv)(*setup.level_srs[:nv])
-    pairs = (ctypes.c_uint64 * nv)(*setup.level_pairs[:nv])
     proofs = np.zeros((nv, 72), dtype=np.uint8)
     ev = np.zeros(32, dtype=np.uint8)
-    _check(_lib().cozk_pst13_open_paired(setup.ctx.handle, srs, pairs, nv, _vp(evals), stride, _vp(point), 0, _vp(proofs), _vp(ev)))
+    _check(_lib().cozk_pst13_open_keyed(setup.ctx.handle, setup.open_key, _vp(evals), stride, _vp(point), 0, _vp(proofs), _vp(ev)))
     return proofs, ev
 
 

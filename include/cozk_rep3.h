@@ -13,9 +13,10 @@
  *   cozk_rep3_linear_combination Rep3MultilinearPolynomial::linear_combination
  *                                          co-jolt/src/poly/multilinear_polynomial.rs:196-296 (call site opening_proof.rs:274-278)
  *   cozk_rep3_evaluate_at_chi    Rep3DensePolynomial::evaluate_at_chi / batch_evaluate  co-jolt/src/poly/dense_mlpoly.rs:160-194
- *   cozk_srs_pair_sums + cozk_pst13_open_poly   open() behind PST13::prove_rep3 (pst13.rs:125-137, :428-474) on the
+ *   cozk_pst13_open_key_create + cozk_pst13_open_poly   open() behind PST13::prove_rep3 (pst13.rs:125-137, :428-474) on the
  *                                          device-resident joint polynomial; every quotient scalar multiplies two adjacent
- *                                          bases (pst13.rs:459), so level i runs as a half-size MSM over P[2b] + P[2b+1].
+ *                                          bases (pst13.rs:459), so level i runs as a half-size MSM over P[2b] + P[2b+1]
+ *                                          (cozk_srs_pair_sums), and the many small levels run as one batched MSM.
  *
  * Formats: Fr in memory = 4 x u64 LE limbs, Montgomery (arkworks); Fr on the wire = 32-byte LE canonical integer
  * (ark-serialize, uncompressed).  A shared polynomial is an array of Rep3PrimeFieldShare{a, b}
@@ -84,16 +85,24 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
 /* out = SRS of n/2 points S[b] = P[2b] + P[2b+1] (n even).  Setup-time work, like the SRS itself. */
 int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out);
 
-/* PST13 opening of a device-resident shared polynomial (share a) or public polynomial of 2^nv coefficients.
- * level_srs[i] = ck.powers_of_g[i] (2^(nv-i) points); level_pairs (may be NULL) = cozk_srs_pair_sums of each level, which
- * halves every MSM.  point / out_proofs / out_eval as cozk_pst13_open. */
-int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv, cozk_poly poly,
+/* Setup-time key of the PST13 opening: the pair sums of every level (each MSM halves), with the levels that hold at most
+ * 2^14 quotient scalars (option "open_small_log2") concatenated into one SRS so that ONE batched MSM opens all of them -
+ * an MSM of a few thousand points is latency-bound, a dozen of them in a row dominate the reference's schedule.
+ * level_srs[i] = ck.powers_of_g[i] (2^(nv-i) points) stay owned by the caller and must outlive the key. */
+typedef uint64_t cozk_open_key;
+int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, cozk_open_key* out);
+int cozk_pst13_open_key_release(cozk_ctx* ctx, cozk_open_key key);
+
+/* PST13 opening of a device-resident shared polynomial (share a) or public polynomial of 2^nv coefficients on device 0.
+ * key != 0: the keyed schedule above (level_srs / nv are taken from the key); key == 0: the reference's schedule, one MSM
+ * per level over the duplicated quotient scalars.  All folds run on the device; nothing but the nv proof points and the
+ * evaluation comes back.  point / out_proofs / out_eval as cozk_pst13_open (csrc/pst13.hpp). */
+int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, cozk_open_key key, cozk_poly poly,
                          const void* point, void* out_proofs, void* out_eval);
 
-/* cozk_pst13_open with the pair-sum SRSs: host evaluations as in cozk_pst13_open (csrc/pst13.hpp). */
-int cozk_pst13_open_paired(cozk_ctx* ctx, const cozk_srs* level_srs, const cozk_srs* level_pairs, size_t nv,
-                           const void* evals, size_t stride_bytes, const void* point, int form, void* out_proofs,
-                           void* out_eval);
+/* cozk_pst13_open with a key: host evaluations as in cozk_pst13_open. */
+int cozk_pst13_open_keyed(cozk_ctx* ctx, cozk_open_key key, const void* evals, size_t stride_bytes, const void* point,
+                          int form, void* out_proofs, void* out_eval);
 
 /* Timings (ms, CUDA events on the engine's stream) of the last call on this thread's context:
  * [0] cozk_poly_from_wire / upload: H2D  [1] ingest kernel  [2] linear combination kernel  [3] chi kernels  [4] bytes moved by [2] */

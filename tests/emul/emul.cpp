@@ -227,7 +227,11 @@ void emul_chi(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* 
     std::vector<fr> part((size_t)k * T);
     ChiArgs A{d.data(), k, reinterpret_cast<const fr*>(chis), n, T, part.data()};
     for (size_t t = 0; t < (size_t)k * T; ++t) chi_partial_body(t, A);
-    for (size_t j = 0; j < k; ++j) chi_final_body(j, A, reinterpret_cast<fr*>(out));
+    uint32_t Tmid = T < 64 ? T : 64;
+    std::vector<fr> mid((size_t)k * Tmid);
+    ChiReduceArgs R1{d.data(), k, part.data(), T, mid.data(), Tmid, 0}, R2{d.data(), k, mid.data(), Tmid, reinterpret_cast<fr*>(out), 1, 1};
+    for (size_t t = 0; t < (size_t)k * Tmid; ++t) chi_reduce_body(t, R1);
+    for (size_t j = 0; j < k; ++j) chi_reduce_body(j, R2);
 }
 void emul_pair_sum(const uint8_t* bases, const uint8_t* infinity, size_t half, uint8_t* out, uint8_t* out_inf) {
     PairSumArgs A{reinterpret_cast<const affine*>(bases), infinity, half, reinterpret_cast<affine*>(out), out_inf};

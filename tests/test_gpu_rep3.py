@@ -188,27 +188,49 @@ def test_evaluate_at_chi(cozk, ctx):
             p.release()
 
 
-@pytest.mark.parametrize("nv", [1, 5, 10])
-def test_open_resident_polynomial_with_pair_sums(cozk, ctx, orc, nv):
-    """open() on a resident polynomial, with and without the pair-sum SRS, against the restated open()."""
+def test_pair_sum_srs(cozk, ctx, orc):
+    """cozk_srs_pair_sums: MSM(P, q duplicated) == MSM(S, q), exceptional pairs included (pst13.rs:459)."""
+    rep3 = cozk.rep3
+    n = 2048
+    bases = orc.gen_bases(3, n)
+    bases[3] = bases[2]
+    bases[5, :32] = bases[4, :32]
+    bases[5, 32:] = H.fq_mont((-pyref.from_mont(H.to_int(bases[4, 32:]), H.P)) % H.P)
+    srs = ctx.srs_register(bases)
+    pairs = rep3.pair_sums(ctx, srs)
+    assert ctx.srs_len(pairs) == n // 2
+    q = orc.gen_scalars("uniform", 8, n // 2)
+    assert (ctx.msm_batch(pairs, q)[0] == orc.msm(bases, np.repeat(q, 2, axis=0))).all()
+    ctx.srs_release(pairs)
+    ctx.srs_release(srs)
+
+
+@pytest.mark.parametrize("nv,small", [(1, 12), (5, 12), (10, 12), (10, 3), (10, 0), (15, 12)])
+def test_open_resident_polynomial_with_key(cozk, ctx, orc, nv, small):
+    """open() on a resident polynomial, with the opening key (pair sums, batched small levels) and with the reference's
+    schedule, against the restated open()."""
     rep3, pst = cozk.rep3, cozk.pst13
     levels = _levels(orc, nv, seed=7)
     if nv >= 5:
         levels[0][3] = levels[0][2]  # P + P inside a pair
         levels[1][1, 32:] = H.fq_mont((-pyref.from_mont(H.to_int(levels[1][0, 32:]), H.P)) % H.P)
         levels[1][1, :32] = levels[1][0, :32]  # P + (-P): the pair sum is the point at infinity
-    setup = rep3.derive_pairs(pst.PST13Setup(ctx, levels))
+    ctx.set_option("open_small_log2", small)
+    try:
+        setup = rep3.create_open_key(pst.PST13Setup(ctx, levels))
+    finally:
+        ctx.set_option("open_small_log2", 14)
     n = 1 << nv
     a, b = _rand_fr(60, n), _rand_fr(62, n)
     point = _rand_fr(61, nv)
     want_proofs, want_ev = _open_reference(orc, levels, a, point)
     poly = rep3.Rep3DensePolynomial.upload(ctx, _shared_mont(list(zip(a, b))))
-    for paired in (True, False):
-        proofs, ev = rep3.open_poly(setup, poly, H.scalars_wire(point), paired=paired)
-        assert (proofs == want_proofs).all(), paired
+    for keyed in (True, False):
+        proofs, ev = rep3.open_poly(setup, poly, H.scalars_wire(point), keyed=keyed)
+        assert (proofs == want_proofs).all(), keyed
         assert pyref.from_mont(H.to_int(ev), R) == want_ev
-    proofs, ev = rep3.open_paired(setup, H.scalars_wire(a), H.scalars_wire(point))
-    assert (proofs == want_proofs).all()
+    proofs, ev = rep3.open_keyed(setup, H.scalars_wire(a), H.scalars_wire(point))
+    assert (proofs == want_proofs).all() and pyref.from_mont(H.to_int(ev), R) == want_ev
     # prove_rep3 reverses the opening point first (pst13.rs:134)
     proofs, _ = rep3.prove_rep3(setup, poly, H.scalars_wire(point[::-1]))
     assert (proofs == want_proofs).all()
@@ -222,7 +244,7 @@ def test_open_resident_polynomial_with_pair_sums(cozk, ctx, orc, nv):
     assert e.value.code == cozk.ERR_KEY_LENGTH
     for p in (poly, dense, wrong):
         p.release()
-    rep3.release_pairs(setup)
+    rep3.release_open_key(setup)
     setup.release()
 
 
@@ -234,7 +256,7 @@ def test_three_party_flow_commit_combine_open(cozk, ctx, orc):
     nv, k = 6, 3
     n = 1 << nv
     levels = _levels(orc, nv, seed=9)
-    setup = rep3.derive_pairs(pst.PST13Setup(ctx, levels))
+    setup = rep3.create_open_key(pst.PST13Setup(ctx, levels))
     secrets = [[pyref.limb(70 + j, i, 0) & 0xFFFFFFFF for i in range(n)] for j in range(k)]
     public = [pyref.limb(80, i, 0) & 0xFF for i in range(n)]
     gamma = pyref.scalar_uniform(81, 0)
@@ -264,5 +286,5 @@ def test_three_party_flow_commit_combine_open(cozk, ctx, orc):
     plain_joint = [(sum(gp[j] * secrets[j][i] for j in range(k)) + gp[k] * public[i]) % R for i in range(n)]
     want_proofs, _ = _open_reference(orc, levels, plain_joint, point)
     assert (pst.coordinate_prove(party_proofs) == want_proofs).all()
-    rep3.release_pairs(setup)
+    rep3.release_open_key(setup)
     setup.release()

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--nv", type=int, default=18)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--small", default="12", help="comma list of open_small_log2 values to try for the keyed opening")
     args = ap.parse_args()
     cozk = importlib.import_module("co-zkvms_b200")
     rep3, pst = cozk.rep3, cozk.pst13
@@ -130,26 +131,29 @@ def main():
         pass
     setup = S()
     setup.ctx, setup.level_srs = ctx, handles
-    t0 = time.perf_counter()
-    rep3.derive_pairs(setup)
-    pairs_s = time.perf_counter() - t0
     m = 1 << nv
     tmp = ctx.testgen_scalars("uniform", 11, m, stride=64)
     poly = rep3.Rep3DensePolynomial.from_device(ctx, tmp, m)
     tmp.free()
     point = ctx.testgen_scalars("uniform", 12, nv).download().reshape(nv, 32)
-    res = {}
-    proofs = {}
-    for paired in (False, True):
-        ts = []
+    def timed_open(keyed):
+        ts, proofs = [], None
         for _ in range(args.reps + 1):
             t0 = time.perf_counter()
-            proofs[paired], _ = rep3.open_poly(setup, poly, point, paired=paired)
+            proofs, _ = rep3.open_poly(setup, poly, point, keyed=keyed)
             ts.append(time.perf_counter() - t0)
-        res[paired] = 1e3 * float(np.median(ts[1:]))
-    print(json.dumps({"experiment": "open", "nv": nv, "unpaired_ms": res[False], "paired_ms": res[True],
-                      "speedup": res[False] / res[True], "pair_sum_setup_s": pairs_s,
-                      "identical_proofs": bool((proofs[False] == proofs[True]).all())}))
+        return 1e3 * float(np.median(ts[1:])), proofs
+    ref_ms, ref_proofs = timed_open(False)
+    for small in [int(x) for x in args.small.split(",")]:
+        ctx.set_option("open_small_log2", small)
+        t0 = time.perf_counter()
+        rep3.create_open_key(setup)
+        key_s = time.perf_counter() - t0
+        key_ms, key_proofs = timed_open(True)
+        print(json.dumps({"experiment": "open", "nv": nv, "open_small_log2": small, "reference_schedule_ms": ref_ms,
+                          "keyed_ms": key_ms, "speedup": ref_ms / key_ms, "open_key_setup_s": key_s,
+                          "identical_proofs": bool((ref_proofs == key_proofs).all())}))
+        rep3.release_open_key(setup)
     ctx.close()
 
 
