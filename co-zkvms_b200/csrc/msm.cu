@@ -705,6 +705,13 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
             return COZK_ERR_NO_DEVICE;
         }
         D->sm_count = prop.multiProcessorCount;
+        {
+            // keep freed stream-ordered allocations (device-resident polynomials, rep3poly.cu) in the pool
+            cudaMemPool_t pool;
+            COZK_CUDA(cudaDeviceGetDefaultMemPool(&pool, id));
+            uint64_t keep = UINT64_MAX;
+            COZK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         COZK_CUDA(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
         COZK_CUDA(cudaStreamCreateWithFlags(&D->copy_stream, cudaStreamNonBlocking));
         for (auto& ev : D->ev) COZK_CUDA(cudaEventCreate(&ev));
@@ -719,7 +726,14 @@ void cozk_destroy(cozk_ctx* ctx) {
     if (!ctx) return;
     for (auto& kv : ctx->polys) {
         cudaSetDevice(ctx->devs[kv.second.dev]->id);
-        if (kv.second.d_data) cudaFree(kv.second.d_data);
+        if (kv.second.d_data) cudaFree(kv.second.d_data);  // also valid for stream-ordered allocations; synchronises
+    }
+    for (auto& D : ctx->devs) {
+        cudaMemPool_t pool;
+        if (cudaSetDevice(D->id) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, D->id) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
     }
     for (auto& kv : ctx->srs) {
         for (size_t d = 0; d < kv.second.d_bases.size(); ++d) {

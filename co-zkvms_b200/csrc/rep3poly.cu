@@ -33,6 +33,15 @@ __global__ void __launch_bounds__(128, 4) k_lincomb(LincombArgs A, int staged) {
 __global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void k_chi_reduce(ChiReduceArgs A) { chi_reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(128) k_pair_sum(PairSumArgs A) { pair_sum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+// Polynomials come and go by the hundred (138 trace polynomials per proof): allocate them stream-ordered from the device's
+// memory pool, whose release threshold cozk_init lifts, so that a freed polynomial's memory is reused instead of being
+// handed back to the driver (cudaMalloc / cudaFree of 64 MiB blocks cost more than the ingestion kernel itself).
+template <class T>
+static inline cudaError_t pool_alloc(Device& D, T** out, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void**>(out), bytes ? bytes : 16, D.stream);
+}
+static inline cudaError_t pool_free(Device& D, void* p) { return cudaFreeAsync(p, D.stream); }
+
 static inline unsigned blocks_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
 static int check_device(cozk_ctx* ctx, int device_index) {
@@ -167,7 +176,7 @@ int cozk_poly_upload(cozk_ctx* ctx, int device_index, const void* coeffs, size_t
     COZK_CUDA(cudaSetDevice(D.id));
     StageTimer T(D);
     uint8_t* d = nullptr;
-    COZK_CUDA(cudaMalloc(&d, std::max<size_t>(len, 1) * E.elem_bytes()));
+    COZK_CUDA(pool_alloc(D, &d, std::max<size_t>(len, 1) * E.elem_bytes()));
     E.d_data = d;
     double h2d = 0, conv = 0;
     cudaError_t e = cudaSuccess;
@@ -178,7 +187,7 @@ int cozk_poly_upload(cozk_ctx* ctx, int device_index, const void* coeffs, size_t
     } else if (len) {
         uint8_t* raw = nullptr;
         size_t rb = len * small_bytes[kind];
-        e = cudaMalloc(&raw, rb);
+        e = pool_alloc(D, &raw, rb);
         if (e == cudaSuccess) {
             T.start();
             e = cudaMemcpyAsync(raw, coeffs, rb, cudaMemcpyHostToDevice, D.stream);
@@ -192,11 +201,11 @@ int cozk_poly_upload(cozk_ctx* ctx, int device_index, const void* coeffs, size_t
             conv = T.stop();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-        if (raw) cudaFree(raw);
+        if (raw) pool_free(D, raw);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
     if (e != cudaSuccess) {
-        cudaFree(d);
+        pool_free(D, d);
         set_error(std::string("polynomial upload failed: ") + cudaGetErrorString(e));
         return COZK_ERR_CUDA;
     }
@@ -222,11 +231,11 @@ int cozk_poly_from_device(cozk_ctx* ctx, int device_index, const void* d_coeffs,
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
     uint8_t* d = nullptr;
-    COZK_CUDA(cudaMalloc(&d, std::max<size_t>(len, 1) * E.elem_bytes()));
+    COZK_CUDA(pool_alloc(D, &d, std::max<size_t>(len, 1) * E.elem_bytes()));
     cudaError_t e = cudaMemcpyAsync(d, d_coeffs, len * E.elem_bytes(), cudaMemcpyDeviceToDevice, D.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
     if (e != cudaSuccess) {
-        cudaFree(d);
+        pool_free(D, d);
         set_error(std::string("polynomial copy failed: ") + cudaGetErrorString(e));
         return COZK_ERR_CUDA;
     }
@@ -289,8 +298,8 @@ int cozk_poly_from_wire(cozk_ctx* ctx, int device_index, const void* bytes, size
     StageTimer T(D);
     uint8_t* d = nullptr;
     uint32_t* d_bad = nullptr;
-    COZK_CUDA(cudaMalloc(&d, std::max<size_t>(E.total, 1) * 64 + 16));
-    cudaError_t e = cudaMalloc(&d_bad, 4);
+    COZK_CUDA(pool_alloc(D, &d, std::max<size_t>(E.total, 1) * 64 + 16));
+    cudaError_t e = pool_alloc(D, &d_bad, 4);
     uint32_t bad = 0;
     double h2d = 0, conv = 0;
     if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, D.stream);
@@ -308,9 +317,9 @@ int cozk_poly_from_wire(cozk_ctx* ctx, int device_index, const void* bytes, size
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, D.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-    if (d_bad) cudaFree(d_bad);
+    if (d_bad) pool_free(D, d_bad);
     if (e != cudaSuccess || bad) {
-        cudaFree(d);
+        pool_free(D, d);
         if (e != cudaSuccess) {
             set_error(std::string("wire ingestion failed: ") + cudaGetErrorString(e));
             return COZK_ERR_CUDA;
@@ -342,7 +351,7 @@ int cozk_poly_release(cozk_ctx* ctx, cozk_poly poly) {
     Device& D = *ctx->devs[E.dev];
     std::lock_guard<std::mutex> lock(D.mu);
     cudaSetDevice(D.id);
-    if (E.d_data) cudaFree(E.d_data);
+    if (E.d_data) pool_free(D, E.d_data);
     return COZK_OK;
 }
 
@@ -484,9 +493,9 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
     PolyDesc* d_desc = nullptr;
     fr* d_coef = nullptr;
     uint8_t* d_out = nullptr;
-    cudaError_t e = cudaMalloc(&d_desc, k * sizeof(PolyDesc));
-    if (e == cudaSuccess) e = cudaMalloc(&d_coef, 2 * k * sizeof(fr));
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, std::max<size_t>(max_len, 1) * O.elem_bytes());
+    cudaError_t e = pool_alloc(D, &d_desc, k * sizeof(PolyDesc));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_coef, 2 * k * sizeof(fr));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_out, std::max<size_t>(max_len, 1) * O.elem_bytes());
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), k * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_coef, hc.data(), 2 * k * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
     double ms = 0;
@@ -501,10 +510,10 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
         ms = T.stop();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-    if (d_desc) cudaFree(d_desc);
-    if (d_coef) cudaFree(d_coef);
+    if (d_desc) pool_free(D, d_desc);
+    if (d_coef) pool_free(D, d_coef);
     if (e != cudaSuccess) {
-        if (d_out) cudaFree(d_out);
+        if (d_out) pool_free(D, d_out);
         set_error(std::string("linear_combination failed: ") + cudaGetErrorString(e));
         return COZK_ERR_CUDA;
     }
@@ -544,11 +553,11 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
     PolyDesc* d_desc = nullptr;
     fr *d_chis = nullptr, *d_part = nullptr, *d_mid = nullptr, *d_res = nullptr;
     const uint32_t Tmid = T < 64 ? T : 64;
-    cudaError_t e = cudaMalloc(&d_desc, k * sizeof(PolyDesc));
-    if (e == cudaSuccess) e = cudaMalloc(&d_chis, std::max<size_t>(n, 1) * sizeof(fr));
-    if (e == cudaSuccess) e = cudaMalloc(&d_part, k * (size_t)T * sizeof(fr));
-    if (e == cudaSuccess) e = cudaMalloc(&d_mid, k * (size_t)Tmid * sizeof(fr));
-    if (e == cudaSuccess) e = cudaMalloc(&d_res, k * sizeof(fr));
+    cudaError_t e = pool_alloc(D, &d_desc, k * sizeof(PolyDesc));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_chis, std::max<size_t>(n, 1) * sizeof(fr));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_part, k * (size_t)T * sizeof(fr));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_mid, k * (size_t)Tmid * sizeof(fr));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_res, k * sizeof(fr));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), k * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_chis, chis, n * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
     double ms = 0;
@@ -566,7 +575,7 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_evals, d_res, k * sizeof(fr), cudaMemcpyDeviceToHost, D.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
     for (void* p : {(void*)d_desc, (void*)d_chis, (void*)d_part, (void*)d_mid, (void*)d_res})
-        if (p) cudaFree(p);
+        if (p) pool_free(D, p);
     if (e != cudaSuccess) {
         set_error(std::string("evaluate_at_chi failed: ") + cudaGetErrorString(e));
         return COZK_ERR_CUDA;
@@ -594,10 +603,10 @@ int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
     {
         std::lock_guard<std::mutex> lock(D.mu);
         COZK_CUDA(cudaSetDevice(D.id));
-        cudaError_t e = cudaMalloc(&d_out, half * sizeof(affine));
-        if (e == cudaSuccess) e = cudaMalloc(&d_inf, half);
+        cudaError_t e = pool_alloc(D, &d_out, half * sizeof(affine));
+        if (e == cudaSuccess) e = pool_alloc(D, &d_inf, half);
         if (e != cudaSuccess) {
-            if (d_out) cudaFree(d_out);
+            if (d_out) pool_free(D, d_out);
             set_error(std::string("pair sums: allocation failed: ") + cudaGetErrorString(e));
             return COZK_ERR_CUDA;
         }
@@ -606,8 +615,8 @@ int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
     if (!rc) rc = srs_register_from_device(ctx, 0, d_out, d_inf, half, out);
     std::lock_guard<std::mutex> lock(D.mu);
     cudaSetDevice(D.id);
-    cudaFree(d_out);
-    cudaFree(d_inf);
+    pool_free(D, d_out);
+    pool_free(D, d_inf);
     return rc;
 }
 
