@@ -117,7 +117,8 @@ extern "C" int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, cons
         }
         if (out_points72 || out_srs) {
             host_out.resize(n * 72);
-            FB_CUDA(cudaMemcpy(host_out.data(), d_out, n * 72, cudaMemcpyDeviceToHost));
+            FB_CUDA(cudaMemcpyAsync(host_out.data(), d_out, n * 72, cudaMemcpyDeviceToHost, D.stream));
+            FB_CUDA(cudaStreamSynchronize(D.stream));
         }
     }
     cleanup();

@@ -632,7 +632,9 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
     if (d_inf && n) {
         std::vector<uint8_t> flags(n);
         COZK_CUDA(cudaSetDevice(ctx->devs[device_index]->id));
-        COZK_CUDA(cudaMemcpy(flags.data(), d_inf, n, cudaMemcpyDeviceToHost));
+        Device& S0 = *ctx->devs[device_index];
+        COZK_CUDA(cudaMemcpyAsync(flags.data(), d_inf, n, cudaMemcpyDeviceToHost, S0.stream));
+        COZK_CUDA(cudaStreamSynchronize(S0.stream));
         for (size_t i = 0; i < n && !any_inf; ++i) any_inf = flags[i] != 0;
     }
     for (size_t di = 0; di < ctx->devs.size(); ++di) {
@@ -641,9 +643,12 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
         uint8_t* dinf = nullptr;
         cudaError_t e = cudaSetDevice(D.id);
         if (e == cudaSuccess) e = cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine));
-        if (e == cudaSuccess) e = cudaMemcpyPeer(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine));
+        // on the destination device's own stream and synchronised there: nothing in this library relies on the legacy
+        // default stream, which its non-blocking streams do not wait for (the source is complete: callers synchronise)
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine), D.stream);
         if (e == cudaSuccess && any_inf) e = cudaMalloc(&dinf, n);
-        if (e == cudaSuccess && any_inf) e = cudaMemcpyPeer(dinf, D.id, d_inf, ctx->devs[device_index]->id, n);
+        if (e == cudaSuccess && any_inf) e = cudaMemcpyPeerAsync(dinf, D.id, d_inf, ctx->devs[device_index]->id, n, D.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
         int rc = COZK_OK;
         if (e != cudaSuccess) {
             set_error(std::string("SRS registration failed: ") + cudaGetErrorString(e));

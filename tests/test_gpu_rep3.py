@@ -248,6 +248,41 @@ def test_open_resident_polynomial_with_key(cozk, ctx, orc, nv, small):
     setup.release()
 
 
+def test_open_key_lifecycle_is_deterministic(cozk, ctx):
+    """Keys, pair-sum SRSs and polynomials created and released in a loop (pooled, stream-ordered allocations): the keyed
+    and the reference schedule must agree every time, and with the first round."""
+    rep3 = cozk.rep3
+    nv = 17
+    handles, start = [], 0
+    for i in range(nv):
+        m = 1 << (nv - i)
+        d = ctx.testgen_bases(3, m, start=start)
+        handles.append(ctx.srs_register_device(d, m))
+        d.free()
+        start += m
+
+    class Setup:
+        pass
+    setup = Setup()
+    setup.ctx, setup.level_srs = ctx, handles
+    point = ctx.testgen_scalars("uniform", 12, nv).download().reshape(nv, 32)
+    first = None
+    for rnd in range(4):
+        tmp = ctx.testgen_scalars("uniform", 11, 1 << nv, stride=64)
+        poly = rep3.Rep3DensePolynomial.from_device(ctx, tmp, 1 << nv)
+        tmp.free()
+        rep3.create_open_key(setup)
+        keyed, _ = rep3.open_poly(setup, poly, point, keyed=True)
+        plain, _ = rep3.open_poly(setup, poly, point, keyed=False)
+        assert (keyed == plain).all(), rnd
+        first = keyed if first is None else first
+        assert (keyed == first).all(), rnd
+        rep3.release_open_key(setup)
+        poly.release()
+    for h in handles:
+        ctx.srs_release(h)
+
+
 def test_three_party_flow_commit_combine_open(cozk, ctx, orc):
     """The reference's flow end to end on resident shares (witness.rs:303-365, opening_proof.rs:255-288, pst13.rs:72-137):
     every party ingests its wire share, commits, forms the joint polynomial and opens it; the coordinator's sums equal
