@@ -39,3 +39,12 @@ def test_multiply_count():
     single = sum(1 for i in pg.ins if i[0] == "mul.lo")
     # 8 rows x (8 a*b + 8 m*p) products + 8 m = 136 integer multiply-adds per field multiplication
     assert wide + pairs + single == 136
+
+
+def test_squaring_multiply_count():
+    """Squaring: 28 cross products + 8 squares + 8 rows x (8 m*p + 1 m) = 108 multiply-adds (a multiplication: 136)."""
+    g = _gen()
+    pg = g.gen_sqr_sos(g.P)
+    pairs = sum(1 for i in pg.ins if i[0].startswith("mad") and ".lo" in i[0])
+    single = sum(1 for i in pg.ins if i[0] == "mul.lo")
+    assert pairs + single == 108

@@ -40,6 +40,7 @@ class Prog:
     def __init__(self):
         self.ins = []
         self.tmp = 0
+        self.allow_wrap = False  # True: a chain top may carry out (modular subtraction adds the modulus back mod 2^256)
 
     def new(self, prefix="t"):
         self.tmp += 1
@@ -75,11 +76,15 @@ class Prog:
                 r = s & M32
                 if op.endswith(".cc"):
                     cf = s >> 32
+                elif op.startswith("madc"):
+                    assert self.allow_wrap or s >> 32 == 0, "carry out of a chain top"
             elif op in ("add", "add.cc", "addc", "addc.cc"):
                 s = src[0] + src[1] + (cf if op.startswith("addc") else 0)
                 r = s & M32
                 if op.endswith(".cc"):
                     cf = s >> 32
+                elif op == "addc":
+                    assert self.allow_wrap or s >> 32 == 0, "carry out of a chain top"
             elif op in ("sub", "sub.cc", "subc", "subc.cc"):
                 s = src[0] - src[1] - (cf if op.startswith("subc") else 0)
                 r = s & M32
@@ -209,6 +214,99 @@ def gen_mul(mod, square=False):
     return pg
 
 
+def redc_tail(pg, t, mod, out):
+    """out = (t[0..15] as a 512-bit integer) / 2^256 mod `mod`, fully reduced, for t < mod * 2^256 + small.
+    t / R = redc(t_lo) + t_hi: the eight reduction rows of gen_mul without the multiplication rows (72 multiply-adds),
+    then one 8-limb addition of the high half.  The stray limb of the previous row is folded into ev[0] first and its
+    carry (weight 2^32) is picked up by the ODD chain of m * p, which therefore runs before the even one; mul.lo in
+    between does not touch the carry flag."""
+    ml = limbs32(mod)
+    n0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    ev = [pg.new("e") for _ in range(9)]
+    od = [pg.new("o") for _ in range(8)]
+    for k in range(8):
+        pg.emit("mov", ev[k], t[k])
+        pg.emit("mov", od[k], 0)
+    pg.emit("mov", ev[8], 0)
+    stray = None
+    for i in range(8):
+        if stray is not None:
+            pg.emit("add.cc", ev[0], ev[0], stray)
+        m = pg.new("m")
+        pg.emit("mul.lo", m, ev[0], n0)
+        for k in range(4):
+            first = "mad.lo.cc" if (k == 0 and stray is None) else "madc.lo.cc"
+            pg.emit(first, od[2 * k], m, ml[2 * k + 1], od[2 * k])
+            pg.emit("madc.hi.cc", od[2 * k + 1], m, ml[2 * k + 1], od[2 * k + 1])
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", ev[2 * k], m, ml[2 * k], ev[2 * k])
+            pg.emit("madc.hi.cc", ev[2 * k + 1], m, ml[2 * k], ev[2 * k + 1])
+        pg.emit("addc", ev[8], ev[8], 0)
+        stray = ev[1]
+        new_od = ev[2:9]
+        z = pg.new("z")
+        pg.emit("mov", z, 0)
+        new_od = new_od + [z]
+        z8 = pg.new("z")
+        pg.emit("mov", z8, 0)
+        ev, od = od + [z8], new_od
+    lo = [stray] + od[0:7]
+    u = [pg.new("u") for _ in range(8)]
+    for k in range(8):
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), u[k], ev[k], lo[k])
+    v = [pg.new("v") for _ in range(8)]
+    for k in range(8):
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), v[k], u[k], t[8 + k])
+    cond_sub(pg, v, mod, out)
+
+
+def sqrwide(pg, a):
+    """t[0..15] = a^2 as a plain integer with 36 multiply-adds: the 28 cross products a_i a_j (i < j) land on aligned
+    pairs of two accumulators (EV: i + j even, OD: i + j odd, weight 2^32), their sum is doubled by one carry chain, and
+    the eight squares a_i^2 are added by one chain over all sixteen limbs."""
+    ev = [pg.new("e") for _ in range(16)]
+    od = [pg.new("o") for _ in range(16)]
+    for k in range(16):
+        pg.emit("mov", ev[k], 0)
+        pg.emit("mov", od[k], 0)
+
+    def chain(acc, start, js, ai):
+        for k, j in enumerate(js):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", acc[start + 2 * k], a[j], ai, acc[start + 2 * k])
+            pg.emit("madc.hi.cc", acc[start + 2 * k + 1], a[j], ai, acc[start + 2 * k + 1])
+        top = start + 2 * len(js)
+        if js and top <= 15:
+            pg.emit("addc", acc[top], acc[top], 0)
+
+    for i in range(7):
+        ev_js = [j for j in range(i + 1, 8) if (i + j) % 2 == 0]
+        od_js = [j for j in range(i + 1, 8) if (i + j) % 2 == 1]
+        if ev_js:
+            chain(ev, i + ev_js[0], ev_js, a[i])          # positions i + j, contiguous pairs
+        if od_js:
+            chain(od, i + od_js[0] - 1, od_js, a[i])      # positions i + j -> OD index i + j - 1
+    s = [pg.new("s") for _ in range(16)]
+    pg.emit("mov", s[0], ev[0])
+    for k in range(1, 16):
+        pg.emit("add.cc" if k == 1 else ("addc.cc" if k < 15 else "addc"), s[k], ev[k], od[k - 1])
+    d = [pg.new("d") for _ in range(16)]
+    for k in range(16):
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 15 else "addc"), d[k], s[k], s[k])
+    for i in range(8):
+        pg.emit("mad.lo.cc" if i == 0 else "madc.lo.cc", d[2 * i], a[i], a[i], d[2 * i])
+        pg.emit("madc.hi.cc" if i < 7 else "madc.hi", d[2 * i + 1], a[i], a[i], d[2 * i + 1])
+    return d
+
+
+def gen_sqr_sos(mod):
+    """r = a^2 / 2^256 mod `mod`: 36 + 72 = 108 multiply-adds instead of 136."""
+    pg = Prog()
+    a = ["a%d" % k for k in range(8)]
+    t = sqrwide(pg, a)
+    redc_tail(pg, t, mod, ["r%d" % k for k in range(8)])
+    return pg
+
+
 def gen_mulwide():
     """r[0..15] = a * b as a plain 512-bit integer (no reduction): the product half of a lazily reduced
     multiply-accumulate (rep3_kernels.cuh: linear combinations of shared polynomials, chi dot products).  Same EV/OD
@@ -267,6 +365,7 @@ def gen_add(mod):
 
 def gen_sub(mod):
     pg = Prog()
+    pg.allow_wrap = True
     ml = limbs32(mod)
     t = [pg.new("t") for _ in range(8)]
     for k in range(8):
@@ -293,7 +392,7 @@ def self_check(trials=300, seed=1):
     rnd = random.Random(seed)
     Rinv = {m: pow(1 << 256, -1, m) for m in (P, R)}
     for mod in (P, R):
-        pm, ps, pa, pb = gen_mul(mod), gen_mul(mod, True), gen_add(mod), gen_sub(mod)
+        pm, ps, pa, pb = gen_mul(mod), gen_sqr_sos(mod), gen_add(mod), gen_sub(mod)
         edge = [0, 1, 2, mod - 1, mod - 2, (1 << 253), (1 << 254) % mod, M32, (1 << 224) - 1, mod >> 1]
         vals = edge + [rnd.randrange(mod) for _ in range(trials)]
         for i, x in enumerate(vals):
@@ -367,7 +466,7 @@ def main():
     parts = ["// GENERATED by tools/gen_field_ptx.py - do not edit.  8 x 32-bit limbs, little-endian, Montgomery R = 2^256.\n"
              "// Every function returns a fully reduced value in [0, modulus).\n"]
     parts.append(emit_fn("fq_mul_ptx", gen_mul(P), 2))
-    parts.append(emit_fn("fq_sqr_ptx", gen_mul(P, True), 1))
+    parts.append(emit_fn("fq_sqr_ptx", gen_sqr_sos(P), 1))
     parts.append(emit_fn("fq_add_ptx", gen_add(P), 2))
     parts.append(emit_fn("fq_sub_ptx", gen_sub(P), 2))
     parts.append(emit_fn("fr_mul_ptx", gen_mul(R), 2))
