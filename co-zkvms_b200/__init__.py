@@ -311,7 +311,7 @@ class Context:
         return buf
 
     def field_op(self, op, a, b=None, device=0):
-        ops = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "fr_from_mont": 5}
+        ops = {"mul": 0, "add": 1, "sub": 2, "sqr": 3, "inv": 4, "fr_from_mont": 5, "mul2_xyyx": 7}
         a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
         n = a.shape[0]
         da = self.alloc(a.nbytes, device).upload(a)

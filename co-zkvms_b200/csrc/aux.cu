@@ -139,6 +139,7 @@ __global__ void k_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* 
         case 2: r = fq_sub(x, y); break;
         case 3: r = fq_sqr(x); break;
         case 4: r = fq_inv(x); break;
+        case 7: r = fq_mul2(x, y, y, x); break;  // 2xy with one reduction
         default: r = fr_from_mont(x); break;
     }
     store_fq(out + 32 * t, r);

@@ -3,7 +3,8 @@
 //   affine  - a finite SRS point as the reference stores it (ark_ec short_weierstrass::Affine{x, y}; the `infinity`
 //             flag travels separately, see include/cozk_msm.h), 64 B.
 //   xyzz    - extended Jacobian accumulator (X, Y, ZZ, ZZZ) with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; ZZ = 0 is the
-//             identity.  128 B.  Mixed addition costs 8M + 2S, full addition 12M + 2S, doubling 6M + 3S.
+//             identity.  128 B.  Mixed addition costs 8M + 2S, full addition 12M + 2S, doubling 6M + 3S; in each of
+//             them Y3 = u*v - w*z is ONE fused product pair (fq_mul2: two products, one Montgomery reduction).
 //
 // The reference's CPU path accumulates in Jacobian `Projective` and normalises with `.into_affine()`
 // (pst13.rs:294, :328, :469); coordinates differ, the group element - and so the affine output - does not.
@@ -54,7 +55,7 @@ COZK_HD xyzz xyzz_dbl_affine(const affine& p) {
     fq xx = fq_sqr(p.x);
     fq M = fq_add(fq_dbl(xx), xx);
     r.X = fq_sub(fq_sqr(M), fq_dbl(S));
-    r.Y = fq_sub(fq_mul(M, fq_sub(S, r.X)), fq_mul(W, p.y));
+    r.Y = fq_mul2(M, fq_sub(S, r.X), W, fq_neg(p.y));
     r.ZZ = V;
     r.ZZZ = W;
     return r;
@@ -70,7 +71,7 @@ COZK_HD xyzz xyzz_dbl(const xyzz& p) {
     fq xx = fq_sqr(p.X);
     fq M = fq_add(fq_dbl(xx), xx);
     r.X = fq_sub(fq_sqr(M), fq_dbl(S));
-    r.Y = fq_sub(fq_mul(M, fq_sub(S, r.X)), fq_mul(W, p.Y));
+    r.Y = fq_mul2(M, fq_sub(S, r.X), W, fq_neg(p.Y));
     r.ZZ = fq_mul(V, p.ZZ);
     r.ZZZ = fq_mul(W, p.ZZZ);
     return r;
@@ -92,7 +93,7 @@ COZK_HD xyzz xyzz_madd(const xyzz& a, const affine& q) {
     fq PPP = fq_mul(P, PP);
     fq Q = fq_mul(a.X, PP);
     r.X = fq_sub(fq_sub(fq_sqr(R), PPP), fq_dbl(Q));
-    r.Y = fq_sub(fq_mul(R, fq_sub(Q, r.X)), fq_mul(a.Y, PPP));
+    r.Y = fq_mul2(R, fq_sub(Q, r.X), fq_neg(a.Y), PPP);
     r.ZZ = fq_mul(a.ZZ, PP);
     r.ZZZ = fq_mul(a.ZZZ, PPP);
     return r;
@@ -117,7 +118,7 @@ COZK_HD xyzz xyzz_add(const xyzz& a, const xyzz& b) {
     fq PPP = fq_mul(P, PP);
     fq Q = fq_mul(U1, PP);
     r.X = fq_sub(fq_sub(fq_sqr(R), PPP), fq_dbl(Q));
-    r.Y = fq_sub(fq_mul(R, fq_sub(Q, r.X)), fq_mul(S1, PPP));
+    r.Y = fq_mul2(R, fq_sub(Q, r.X), fq_neg(S1), PPP);
     r.ZZ = fq_mul(fq_mul(a.ZZ, b.ZZ), PP);
     r.ZZZ = fq_mul(fq_mul(a.ZZZ, b.ZZZ), PPP);
     return r;

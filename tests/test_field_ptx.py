@@ -48,3 +48,13 @@ def test_squaring_multiply_count():
     pairs = sum(1 for i in pg.ins if i[0].startswith("mad") and ".lo" in i[0])
     single = sum(1 for i in pg.ins if i[0] == "mul.lo")
     assert pairs + single == 108
+
+
+def test_fused_product_pair_multiply_count():
+    """a*b + c*d with one reduction: 8 rows x (8 + 8 + 8 m*p + 1 m) = 200 multiply-adds (two multiplications: 272)."""
+    g = _gen()
+    pg = g.gen_mul2(g.P)
+    wide = sum(1 for i in pg.ins if i[0] == "mul.wide")
+    pairs = sum(1 for i in pg.ins if i[0].startswith("mad") and ".lo" in i[0])
+    single = sum(1 for i in pg.ins if i[0] == "mul.lo")
+    assert wide + pairs + single == 200

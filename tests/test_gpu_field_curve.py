@@ -22,6 +22,9 @@ def test_fq_ops_2pow16(ctx, orc):
         want = orc.field_op("fq", op, a.view(np.uint64), b.view(np.uint64)).view(np.uint8)
         assert (ctx.field_op(op, a, b) == want).all(), op
     assert (ctx.field_op("sqr", a) == orc.field_op("fq", "sqr", a.view(np.uint64)).view(np.uint8)).all()
+    # the fused product pair (x*y + y*x with one reduction) = 2xy
+    prod = orc.field_op("fq", "mul", a.view(np.uint64), b.view(np.uint64))
+    assert (ctx.field_op("mul2_xyyx", a, b) == orc.field_op("fq", "add", prod, prod).view(np.uint8)).all()
 
 
 def test_fq_inv_and_fr_from_mont(ctx, orc):

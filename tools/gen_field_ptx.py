@@ -94,6 +94,10 @@ class Prog:
                 r = src[0] if src[2] != 0 else src[1]
             elif op == "and":
                 r = src[0] & src[1]
+            elif op == "xor":
+                r = src[0] ^ src[1]
+            elif op == "addc.wrap":  # top limb of a two's-complement sum: the carry out is meant to be dropped
+                r = (src[0] + src[1] + cf) & M32
             else:
                 raise ValueError(op)
             env[dst] = r
@@ -141,6 +145,10 @@ class Prog:
                 lines.append("mov.u32 %s, %s;" % (o(dst), o(src[0])))
             elif op == "and":
                 lines.append("and.b32 %s, %s, %s;" % (o(dst), o(src[0]), o(src[1])))
+            elif op == "xor":
+                lines.append("xor.b32 %s, %s, %s;" % (o(dst), o(src[0]), o(src[1])))
+            elif op == "addc.wrap":
+                lines.append("addc.u32 %s, %s, %s;" % (o(dst), o(src[0]), o(src[1])))
             else:
                 lines.append("%s.u32 %s, %s;" % (op, o(dst), ", ".join(o(s) for s in src)))
         lines.append("}")
@@ -212,6 +220,81 @@ def gen_mul(mod, square=False):
         pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), t[k], ev[k], lo[k])
     cond_sub(pg, t, mod, ["r%d" % k for k in range(8)])
     return pg
+
+
+def gen_mul2(mod):
+    """r = (a*b + c*d) / 2^256 mod `mod`, fully reduced: both products share ONE Montgomery reduction, so the pair costs
+    8 rows x (8 + 8 + 8 + 1) = 200 multiply-adds instead of 272 (the Y coordinate of every group addition is such a
+    sum: R*(Q - X3) + (-Y1)*PPP).  Same EV/OD split as gen_mul; row i adds a*b_i and c*d_i before the reduction row.
+    T < (3 * 2^32 + 3) * mod < 2^288 throughout and the result is < 2*mod^2/2^256 + mod < 2*mod: one conditional
+    subtraction."""
+    pg = Prog()
+    a = ["a%d" % k for k in range(8)]
+    b = ["b%d" % k for k in range(8)]
+    c = ["c%d" % k for k in range(8)]
+    d = ["d%d" % k for k in range(8)]
+    ml = limbs32(mod)
+    n0 = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    ev = [pg.new("e") for _ in range(9)]
+    od = [pg.new("o") for _ in range(8)]
+    stray = None
+    for i in range(8):
+        bi, di = b[i], d[i]
+        if i == 0:
+            for k in range(4):
+                pg.emit("mul.wide", (ev[2 * k], ev[2 * k + 1]), a[2 * k], bi)
+                pg.emit("mul.wide", (od[2 * k], od[2 * k + 1]), a[2 * k + 1], bi)
+            pg.emit("mov", ev[8], 0)
+        else:
+            pg.emit("add.cc", ev[0], ev[0], stray)
+            for k in range(4):
+                pg.emit("madc.lo.cc", od[2 * k], a[2 * k + 1], bi, od[2 * k])
+                pg.emit("madc.hi.cc", od[2 * k + 1], a[2 * k + 1], bi, od[2 * k + 1])
+            for k in range(4):
+                pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", ev[2 * k], a[2 * k], bi, ev[2 * k])
+                pg.emit("madc.hi.cc", ev[2 * k + 1], a[2 * k], bi, ev[2 * k + 1])
+            pg.emit("addc", ev[8], ev[8], 0)
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", od[2 * k], c[2 * k + 1], di, od[2 * k])
+            pg.emit("madc.hi.cc", od[2 * k + 1], c[2 * k + 1], di, od[2 * k + 1])
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", ev[2 * k], c[2 * k], di, ev[2 * k])
+            pg.emit("madc.hi.cc", ev[2 * k + 1], c[2 * k], di, ev[2 * k + 1])
+        pg.emit("addc", ev[8], ev[8], 0)
+        m = pg.new("m")
+        pg.emit("mul.lo", m, ev[0], n0)
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", ev[2 * k], m, ml[2 * k], ev[2 * k])
+            pg.emit("madc.hi.cc", ev[2 * k + 1], m, ml[2 * k], ev[2 * k + 1])
+        pg.emit("addc", ev[8], ev[8], 0)
+        for k in range(4):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", od[2 * k], m, ml[2 * k + 1], od[2 * k])
+            pg.emit("madc.hi.cc", od[2 * k + 1], m, ml[2 * k + 1], od[2 * k + 1])
+        stray = ev[1]
+        new_od = ev[2:9]
+        z = pg.new("z")
+        pg.emit("mov", z, 0)
+        new_od = new_od + [z]
+        z8 = pg.new("z")
+        pg.emit("mov", z8, 0)
+        ev, od = od + [z8], new_od
+    lo = [stray] + od[0:7]
+    t = [pg.new("r") for _ in range(8)]
+    for k in range(8):
+        pg.emit("add.cc" if k == 0 else ("addc.cc" if k < 7 else "addc"), t[k], ev[k], lo[k])
+    cond_sub(pg, t, mod, ["r%d" % k for k in range(8)])
+    return pg
+
+
+def run_quadop(pg, x, y, z, w):
+    env = {}
+    for k in range(8):
+        env["a%d" % k] = (x >> (32 * k)) & M32
+        env["b%d" % k] = (y >> (32 * k)) & M32
+        env["c%d" % k] = (z >> (32 * k)) & M32
+        env["d%d" % k] = (w >> (32 * k)) & M32
+    out = pg.run(env)
+    return sum(out["r%d" % k] << (32 * k) for k in range(8))
 
 
 def redc_tail(pg, t, mod, out):
@@ -296,6 +379,101 @@ def sqrwide(pg, a):
         pg.emit("mad.lo.cc" if i == 0 else "madc.lo.cc", d[2 * i], a[i], a[i], d[2 * i])
         pg.emit("madc.hi.cc" if i < 7 else "madc.hi", d[2 * i + 1], a[i], a[i], d[2 * i + 1])
     return d
+
+
+def mulwide_n(pg, a, b):
+    """len(a) == len(b) == n (even): returns 2n registers holding a * b as a plain integer, n^2 wide multiply-adds on the
+    EV/OD split of gen_mulwide plus one merging addition."""
+    n = len(a)
+    ev = [pg.new("e") for _ in range(2 * n)]
+    od = [pg.new("o") for _ in range(2 * n)]
+    for k in range(n // 2):
+        pg.emit("mul.wide", (ev[2 * k], ev[2 * k + 1]), a[2 * k], b[0])
+        pg.emit("mul.wide", (od[2 * k], od[2 * k + 1]), a[2 * k + 1], b[0])
+    for k in range(n, 2 * n):
+        pg.emit("mov", ev[k], 0)
+        pg.emit("mov", od[k], 0)
+
+    def chain(acc, start, mults, bi):
+        for k, aj in enumerate(mults):
+            pg.emit("mad.lo.cc" if k == 0 else "madc.lo.cc", acc[start + 2 * k], aj, bi, acc[start + 2 * k])
+            pg.emit("madc.hi.cc", acc[start + 2 * k + 1], aj, bi, acc[start + 2 * k + 1])
+        if start + n <= 2 * n - 1:
+            pg.emit("addc", acc[start + n], acc[start + n], 0)
+
+    even_a, odd_a = a[0::2], a[1::2]
+    for i in range(1, n):
+        if i % 2 == 0:
+            chain(ev, i, even_a, b[i])
+            chain(od, i, odd_a, b[i])
+        else:
+            chain(ev, i + 1, odd_a, b[i])
+            chain(od, i - 1, even_a, b[i])
+    r = [ev[0]] + [pg.new("p") for _ in range(2 * n - 1)]
+    for k in range(1, 2 * n):
+        pg.emit("add.cc" if k == 1 else ("addc.cc" if k < 2 * n - 1 else "addc"), r[k], ev[k], od[k - 1])
+    return r
+
+
+def abs_diff(pg, x, y):
+    """(|x - y| as len(x) registers, mask register: 0xffffffff when x < y else 0)"""
+    n = len(x)
+    d = [pg.new("d") for _ in range(n)]
+    for k in range(n):
+        pg.emit("sub.cc" if k == 0 else "subc.cc", d[k], x[k], y[k])
+    m = pg.new("w")
+    pg.emit("subc", m, 0, 0)
+    out = [pg.new("d") for _ in range(n)]
+    for k in range(n):
+        pg.emit("xor", d[k], d[k], m)
+    for k in range(n):  # (d ^ m) - m: adds one when m is all ones
+        pg.emit("sub.cc" if k == 0 else ("subc.cc" if k < n - 1 else "subc"), out[k], d[k], m)
+    return out, m
+
+
+def karatsuba_wide(pg, a, b):
+    """a * b (8 x 8 limbs -> 16) with three 4 x 4 products (48 wide multiply-adds instead of 64):
+    a*b = z0 + (z0 + z2 + (a0 - a1)(b1 - b0)) 2^128 + z2 2^256,  z0 = a0 b0, z2 = a1 b1; the middle product is taken on
+    absolute values and added or subtracted by sign (two's complement on 9 limbs)."""
+    a0, a1, b0, b1 = a[0:4], a[4:8], b[0:4], b[4:8]
+    z0 = mulwide_n(pg, a0, b0)
+    z2 = mulwide_n(pg, a1, b1)
+    da, sa = abs_diff(pg, a0, a1)
+    db, sb = abs_diff(pg, b1, b0)
+    z1 = mulwide_n(pg, da, db)
+    s = pg.new("w")
+    pg.emit("xor", s, sa, sb)  # all ones: the middle product is negative
+    mid = [pg.new("m") for _ in range(9)]
+    for k in range(8):
+        pg.emit("add.cc" if k == 0 else "addc.cc", mid[k], z0[k], z2[k])
+    pg.emit("addc", mid[8], 0, 0)
+    x = [pg.new("x") for _ in range(8)]
+    for k in range(8):
+        pg.emit("xor", x[k], z1[k], s)
+    cy = pg.new("x")
+    pg.emit("add.cc", cy, s, 1)  # carry = 1 exactly when s is all ones: the +1 of the two's complement
+    for k in range(8):
+        pg.emit("addc.cc", mid[k], mid[k], x[k])
+    pg.emit("addc.wrap", mid[8], mid[8], s)
+    hi = z0[4:8] + z2[0:8]
+    t = list(z0[0:4]) + [pg.new("t") for _ in range(12)]
+    for k in range(12):
+        op = "add.cc" if k == 0 else ("addc.cc" if k < 11 else "addc")
+        pg.emit(op, t[4 + k], hi[k], mid[k] if k < 9 else 0)
+    return t
+
+
+def gen_mul_karatsuba(mod):
+    """r = a*b/2^256 mod `mod`: Karatsuba product (48) + separate Montgomery reduction (72) = 120 multiply-adds.
+    EXPERIMENT, not emitted: measured on B200 at 64.2 G products/s against 66.5 G/s for gen_mul (136 multiply-adds) -
+    the ~90 extra additions and the longer dependency chains cost more than the 16 multiply-adds they save, and the
+    mixed addition built on it spills at 128 registers (4.3 against 5.6 G additions/s)."""
+    pg = Prog()
+    a = ["a%d" % k for k in range(8)]
+    b = ["b%d" % k for k in range(8)]
+    t = karatsuba_wide(pg, a, b)
+    redc_tail(pg, t, mod, ["r%d" % k for k in range(8)])
+    return pg
 
 
 def gen_sqr_sos(mod):
@@ -401,6 +579,21 @@ def self_check(trials=300, seed=1):
             assert run_binop(ps, x, 0) == x * x * Rinv[mod] % mod, ("sqr", hex(x))
             assert run_binop(pa, x, y) == (x + y) % mod, ("add", hex(x), hex(y))
             assert run_binop(pb, x, y) == (x - y) % mod, ("sub", hex(x), hex(y))
+        pk = gen_mul_karatsuba(mod)
+        half = [(1 << 128) - 1, 1 << 128, (1 << 128) + 1, ((1 << 125) - 1) << 128 | ((1 << 128) - 1), ((1 << 128) - 1) << 64]
+        kvals = vals + [h % mod for h in half]
+        for i, x in enumerate(kvals):
+            y = kvals[(i * 7 + 3) % len(kvals)]
+            assert run_binop(pk, x, y) == x * y * Rinv[mod] % mod, ("mulk", hex(x), hex(y))
+        for x in half:
+            for y in half:
+                assert run_binop(pk, x % mod, y % mod) == (x % mod) * (y % mod) * Rinv[mod] % mod
+        p2 = gen_mul2(mod)
+        for i, x in enumerate(vals):
+            y, z, w = vals[(i * 7 + 3) % len(vals)], vals[(i * 11 + 5) % len(vals)], vals[(i * 13 + 1) % len(vals)]
+            assert run_quadop(p2, x, y, z, w) == (x * y + z * w) * Rinv[mod] % mod, ("mul2", hex(x), hex(y), hex(z), hex(w))
+        for x in edge[3:5]:  # both products at their maximum
+            assert run_quadop(p2, x, x, x, x) == 2 * x * x * Rinv[mod] % mod
     pw = gen_mulwide()
     full = (1 << 256) - 1
     wvals = [0, 1, full, full - 1, 1 << 255, M32, (1 << 224) - 1, R - 1, P - 1] + [rnd.randrange(1 << 256) for _ in range(trials)]
@@ -420,17 +613,18 @@ def emit_fn(name, pg, nin):
     for k in range(8):
         names["a%d" % k] = "%%%d" % idx
         idx += 1
-    if nin == 2:
+    for pre in {1: "", 2: "b", 4: "bcd"}[nin]:
         for k in range(8):
-            names["b%d" % k] = "%%%d" % idx
+            names["%s%d" % (pre, k)] = "%%%d" % idx
             idx += 1
     lines = pg.ptx(names)
     body = "\n".join('        "%s\\n\\t"' % ln for ln in lines)
     outs = ", ".join('"=r"(r[%d])' % k for k in range(8))
     ins = ", ".join('"r"(a[%d])' % k for k in range(8))
-    if nin == 2:
-        ins += ", " + ", ".join('"r"(b[%d])' % k for k in range(8))
-    sig = "const uint32_t (&a)[8]" + (", const uint32_t (&b)[8]" if nin == 2 else "")
+    sig = "const uint32_t (&a)[8]"
+    for pre in {1: "", 2: "b", 4: "bcd"}[nin]:
+        ins += ", " + ", ".join('"r"(%s[%d])' % (pre, k) for k in range(8))
+        sig += ", const uint32_t (&%s)[8]" % pre
     nmul = sum(1 for i in pg.ins if i[0].startswith(("mul", "mad")))
     return ("// %d multiply(-add) PTX instructions; lo/hi pairs fuse into IMAD.WIDE.U32\n"
             "__device__ __forceinline__ void %s(uint32_t (&r)[8], %s) {\n    asm(\n%s\n        : %s\n        : %s);\n}\n"
@@ -467,6 +661,7 @@ def main():
              "// Every function returns a fully reduced value in [0, modulus).\n"]
     parts.append(emit_fn("fq_mul_ptx", gen_mul(P), 2))
     parts.append(emit_fn("fq_sqr_ptx", gen_sqr_sos(P), 1))
+    parts.append(emit_fn("fq_mul2_ptx", gen_mul2(P), 4))
     parts.append(emit_fn("fq_add_ptx", gen_add(P), 2))
     parts.append(emit_fn("fq_sub_ptx", gen_sub(P), 2))
     parts.append(emit_fn("fr_mul_ptx", gen_mul(R), 2))
