@@ -36,9 +36,9 @@ Device::~Device() {
 __global__ void __launch_bounds__(256) k_decompose(DecomposeArgs A) {
     decompose_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
-template <int L, bool LEVEL1>
+template <bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
-    accumulate_body<L, LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+    accumulate_body<LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
 __global__ void __launch_bounds__(128, 3) k_merge(MergeArgs A) {
     merge_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
@@ -76,7 +76,7 @@ __device__ __forceinline__ xyzz sh_load(const ShPoints& s, int t) {
 
 // Accumulate levels >= 2: block b owns partial slots [b*ACC_TILE, (b+1)*ACC_TILE).  Segmented inclusive scan by key
 // (keys are sorted, runs are contiguous), after which the last slot of every run holds the run's sum inside the tile.
-// Output contract = accumulate_body<ACC_TILE, false> run by ONE thread over the same tile (that body is the host
+// Output contract = accumulate_body<false> with L = ACC_TILE run by ONE thread over the same tile (that body is the host
 // reference in tests/emul): closed runs go to their bucket, the at most two runs that cross the tile edge become the
 // two partial slots of this block.
 __global__ void __launch_bounds__(ACC_TILE) k_segscan(AccumulateArgs A) {
@@ -237,9 +237,10 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
                          lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
                          bucket_dst,
                          pk_out.as<uint32_t>(),
-                         pp_out.as<xyzz>()};
-        if (lvl == 0) k_accumulate<ACC_L, true><<<grid_for(T, 128), 128, 0, st>>>(A);
-        else if (tile == ACC_L) k_accumulate<ACC_L, false><<<grid_for(T, 128), 128, 0, st>>>(A);
+                         pp_out.as<xyzz>(),
+                         (uint32_t)tile};
+        if (lvl == 0) k_accumulate<true><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else if (tile == ACC_L) k_accumulate<false><<<grid_for(T, 128), 128, 0, st>>>(A);
         else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
@@ -710,6 +711,7 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
             return COZK_ERR_NO_DEVICE;
         }
         D->sm_count = prop.multiProcessorCount;
+        g_acc_resident_threads = (size_t)D->sm_count * 512;  // k_accumulate: 4 blocks of 128 threads per SM
         {
             // keep freed stream-ordered allocations (device-resident polynomials, rep3poly.cu) in the pool
             cudaMemPool_t pool;
@@ -875,6 +877,10 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
             return COZK_ERR_INVALID_ARG;
         }
         ctx->opt_window = value;
+    } else if (!strcmp(name, "acc_chunk")) {
+        // pairs per thread at level 1 of the accumulate stage: 0 = choose per call (fill the last wave of threads)
+        if (value != 0 && (value < 4 || value > 256)) return COZK_ERR_INVALID_ARG;
+        g_acc_force_l = (int)value;
     } else if (!strcmp(name, "group_pairs")) {
         if (value < 1) return COZK_ERR_INVALID_ARG;
         ctx->opt_group_pairs = value;

@@ -173,6 +173,7 @@ struct AccumulateArgs {
     xyzz* buckets;            // [g*W*B]
     uint32_t* pkeys;          // [2*T] partial keys out, T = ceil(m/L)
     xyzz* ppts;               // [2*T] partial sums out
+    uint32_t L;               // entries per thread (chosen per call at level 1: MsmPlan::acc_tile)
 };
 
 COZK_HD void emit_bucket(const AccumulateArgs& A, uint32_t key, const xyzz& sum) { store_xyzz(&A.buckets[key], sum); }
@@ -193,11 +194,11 @@ COZK_HD void merge_body(size_t b, const MergeArgs& A) {
     store_xyzz(&A.buckets[b], xyzz_add(load_xyzz(&A.buckets[b]), s));
 }
 
-template <int L, bool LEVEL1>
+template <bool LEVEL1>
 COZK_HD void accumulate_body(size_t t, const AccumulateArgs& A) {
-    size_t start = t * (size_t)L;
+    size_t start = t * (size_t)A.L;
     if (start >= A.m) return;
-    size_t end = start + L < A.m ? start + L : A.m;
+    size_t end = start + A.L < A.m ? start + A.L : A.m;
     uint32_t cur = A.keys[start] & KEY_MASK;  // sentinel -> KEY_MASK, never a real key
     bool left_open = start > 0 && cur != KEY_MASK && (A.keys[start - 1] & KEY_MASK) == cur;
     bool first_run = true;

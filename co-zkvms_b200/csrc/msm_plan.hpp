@@ -7,7 +7,8 @@
 
 namespace cozk {
 
-constexpr int ACC_L = 32;          // pairs per thread at level 1 of the accumulate stage
+constexpr int ACC_L = 32;          // entries per thread of the serial accumulate body (level 1: the default, see choose_acc_l)
+constexpr int ACC_L_MIN = 16, ACC_L_MAX = 40;
 constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at small levels >= 2 (block-cooperative segmented scan)
 constexpr size_t ACC_SCAN_MAX = 65536;  // levels with more slots than this stay on the serial, work-efficient body
 constexpr uint32_t SUM_CHUNK = 1024;  // groups per thread block in the first level of the bucket-reduce sums
@@ -15,6 +16,45 @@ constexpr uint32_t GROUP_L = 8;    // buckets per thread in the group step of th
 constexpr uint32_t HOST_FINISH_MAX = 4;  // up to this many vectors the final Horner + inversion run on the host
 constexpr uint32_t C_MIN = 2, C_MAX = 22;
 
+
+// Threads of the level-1 accumulate kernel that are resident on the device at once (SMs x 512); 0 = unknown, keep ACC_L.
+// Set once by the engine at start-up (and by the host emulation, to a small number, so that odd chunk lengths are tested).
+inline size_t g_acc_resident_threads = 0;
+inline int g_acc_force_l = 0;  // option "acc_chunk": fixed chunk length (experiments, tests); 0 = choose_acc_l
+
+// Every level-1 thread does the same work (L mixed additions of 10 multiplications), so the kernel runs in WAVES of
+// `resident` threads and its time is waves * L: 2^20 points at L = 32 are 6.49 waves and pay for 7.  Pick the chunk
+// length whose last wave is fullest.  The second term is the level above: one full addition (14 multiplications) per
+// chunk, T/16 threads of 16 additions each; a wave that is mostly empty still costs about a third of a full one (latency).
+inline int choose_acc_l(size_t m, size_t resident) {
+    if (g_acc_force_l) return g_acc_force_l;
+    if (resident == 0 || m == 0) return ACC_L;
+    auto cost = [&](int L) {
+        size_t T = (m + L - 1) / L;
+        double c = (double)((T + resident - 1) / resident) * L * 10.0;
+        size_t slots = 2 * T;
+        if (slots > ACC_SCAN_MAX) {
+            double w2 = (double)((slots + ACC_L - 1) / ACC_L) / (double)resident;
+            c += (w2 <= 1.0 ? (w2 < 0.35 ? 0.35 : w2) : (double)(size_t)(w2 + 0.999999)) * (ACC_L / 2) * 14.0;
+        } else {
+            c += 8.0 * 14.0;
+        }
+        return c;
+    };
+    int best = ACC_L;
+    double best_cost = cost(ACC_L);
+    for (int d = 1; d <= ACC_L - ACC_L_MIN; ++d) {  // nearest to the default first; switch only for a clear gain
+        for (int L : {ACC_L + d, ACC_L - d}) {
+            if (L < ACC_L_MIN || L > ACC_L_MAX) continue;
+            double c = cost(L);
+            if (c < best_cost * 0.99) {
+                best_cost = c;
+                best = L;
+            }
+        }
+    }
+    return best;
+}
 
 struct MsmPlan {
     size_t n = 0;        // points per vector
@@ -118,12 +158,13 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     p.sort_bits = sb;
     size_t e = p.m;
     p.acc_entries.push_back(e);
-    // Level 1: one thread per ACC_L pairs.  Levels >= 2 reduce the partial slots: big levels with the same serial body
+    // Level 1: one thread per l1 pairs (ACC_L unless another chunk length fills the last wave of threads better).  Levels >= 2 reduce the partial slots: big levels with the same serial body
     // (one addition per live slot: work-efficient, 16 additions deep), small ones with the block-cooperative segmented
     // scan (log2(ACC_TILE) additions deep, but up to that many additions per slot).  Every thread / block emits two
     // slots; a level that ran as a single thread / block has seen everything and leaves no open run.
-    p.acc_tile.push_back(ACC_L);
-    for (size_t t = (e + ACC_L - 1) / ACC_L; t > 1;) {
+    const int l1 = choose_acc_l(e, g_acc_resident_threads);
+    p.acc_tile.push_back(l1);
+    for (size_t t = (e + l1 - 1) / l1; t > 1;) {
         e = 2 * t;
         int tile = e > ACC_SCAN_MAX ? ACC_L : ACC_TILE;
         p.acc_entries.push_back(e);

@@ -23,6 +23,8 @@ def lib():
         L = ctypes.CDLL(LIB)
         vp, sz, u32, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
         L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp, u32, sz, sz, u32]
+        L.emul_set_acc_chunk.argtypes = [sz, ci]
+        L.emul_set_acc_chunk.restype = None
         L.emul_field_op.argtypes = [ci, vp, vp, vp, sz]
         L.emul_g1_op.argtypes = [ci, vp, vp, vp, sz]
         L.emul_ingest.argtypes = [vp, sz, vp]
@@ -37,6 +39,12 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def set_acc_chunk(resident=0, force_l=0):
+    """Level-1 chunk length of the accumulate stage: `resident` threads per wave (the plan then picks the length that
+    fills the last wave, as the engine does with SMs x 512), or a fixed `force_l`; (0, 0) = the default of 32."""
+    lib().emul_set_acc_chunk(resident, force_l)
 
 
 def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None, table_c=0, n=None, base_offset=0,

@@ -20,6 +20,13 @@ using namespace cozk;
 
 extern "C" {
 
+// level-1 chunk length of the accumulate stage: resident != 0 lets the plan choose it as the engine does (wave filling),
+// force_l != 0 fixes it
+void emul_set_acc_chunk(size_t resident, int force_l) {
+    g_acc_resident_threads = resident;
+    g_acc_force_l = force_l;
+}
+
 // bases: n x 64 B; scalars: g vectors, vector v at scalars + v*vector_stride, element i at + i*stride; out: g x 72 B
 int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vector_stride, size_t stride, int form,
              uint32_t g, uint32_t max_bits, uint32_t force_c, const uint8_t* infinity, uint8_t* out, uint32_t* stats,
@@ -82,13 +89,13 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             pk_out.assign(2 * T, 0xDEADBEEFu);
             pp_out.assign(2 * T, xyzz_identity());
             AccumulateArgs A{m, lvl == 0 ? sk.data() : pk_in.data(), sv.data(), chunk_bases,
-                             pp_in.data(), ci > 0 ? scratch.data() : buckets.data(), pk_out.data(), pp_out.data()};
+                             pp_in.data(), ci > 0 ? scratch.data() : buckets.data(), pk_out.data(), pp_out.data(),
+                             (uint32_t)tile};
             for (size_t t = 0; t < T; ++t) {
                 // levels >= 2 run on the GPU as the block-cooperative k_segscan, whose output contract is this body with
                 // one "thread" per tile of ACC_TILE slots
-                if (lvl == 0) accumulate_body<ACC_L, true>(t, A);
-                else if (tile == ACC_L) accumulate_body<ACC_L, false>(t, A);
-                else accumulate_body<ACC_TILE, false>(t, A);
+                if (lvl == 0) accumulate_body<true>(t, A);
+                else accumulate_body<false>(t, A);
             }
             pk_in.swap(pk_out);
             pp_in.swap(pp_out);

@@ -81,6 +81,28 @@ def test_msm_batch_strides_bits_infinity(orc):
     assert (got[0] == orc.msm(bases, masked)).all()
 
 
+def test_accumulate_chunk_lengths(orc):
+    """The level-1 chunk length is chosen per call so that the last wave of threads is full: every length gives the same
+    point, for runs much longer and much shorter than a chunk."""
+    n = 3000
+    bases = orc.gen_bases(4, n)
+    vecs = [orc.gen_scalars(d, 40 + i, n) for i, d in enumerate(("uniform", "const", "wminus", "zero_half"))]
+    want = [orc.msm(bases, v) for v in vecs]
+    try:
+        for force_l in (4, 16, 17, 29, 35, 40, 256):
+            emul.set_acc_chunk(0, force_l)
+            for v, w in zip(vecs, want):
+                for kw in ({"c": 5}, {"table_c": 9}):
+                    got, _ = emul.msm(bases, v, **kw)
+                    assert (got[0] == w).all(), (force_l, kw)
+        for resident in (64, 1000, 75776):
+            emul.set_acc_chunk(resident, 0)
+            got, _ = emul.msm(bases, vecs[0], c=7)
+            assert (got[0] == want[0]).all(), resident
+    finally:
+        emul.set_acc_chunk(0, 0)
+
+
 def test_degenerate_many_levels(orc):
     """All points in one bucket per window (co-jolt party 0/1 shares): the open-run / partial-merge path, 3 levels deep."""
     n = 20000
