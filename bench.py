@@ -35,26 +35,51 @@ if ROOT not in sys.path:
 METRIC = "BN254 G1 MSM Mpoints/s"
 CANON_MULTS_PER_POINT = 160          # c = 16, W = 16, 10 field mults per mixed add
 LIMB_PRODUCTS_PER_MULT = 136         # 8x8 + 8x8 + 8 32-bit limb products per Montgomery multiplication
+# what the kernels actually issue per group addition (SASS-verified counts, tests/test_field_ptx.py): a mixed addition is
+# 6 multiplications (136) + 2 squarings (108) + 1 fused product pair (200); a full addition 10 x 136 + 2 x 108 + 200
+LIMB_PRODUCTS_PER_MADD = 6 * 136 + 2 * 108 + 200
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clock and throttle reasons during the timed region: NVML (sub-millisecond per query, so that even a
+    35 ms timed region gets dozens of samples), nvidia-smi as the fallback."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        return [str(sm), str(self.max_mhz), "0"] + ["Active" if f else "Not Active" for f in flags]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
-                pass
+                self.nvml = None
             time.sleep(0.02)  # an nvidia-smi query takes ~30-50 ms itself: about 15 samples per second
 
     def summary(self):
@@ -63,7 +88,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_run(log2n, dist, steps, warmup, threads):
@@ -223,7 +248,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f)["k_accumulate<32,1>"].get("log2n=%d,dist=%s,window=%d" % (args.log2n, args.dist, int(st["window"])))
+                traffic = json.load(f)["k_accumulate<true>"].get("log2n=%d,dist=%s,window=%d" % (args.log2n, args.dist, int(st["window"])))
         except Exception:
             traffic = None
         line = {"metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
@@ -239,8 +264,8 @@ def main():
                 "roofline": {"bound": "imad", "kernel": "k_accumulate (bucket accumulation, all levels)",
                              "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "G limb-products/s (IMAD.WIDE.U32 lane-ops)",
                              "frac": achieved / imad_peak, "traffic": traffic,
-                             "traffic_note": "DRAM bytes per launch of k_accumulate<32,1> from the committed ncu --set full capture "
-                                             "(profiles/r1_accumulate_ncu.md); algorithmic bytes = pairs x 72",
+                             "traffic_note": "DRAM bytes per launch of k_accumulate<true> (level 1) from the committed ncu --set full capture "
+                                             "(profiles/r3_accumulate_ncu.md); algorithmic bytes = pairs x 72",
                              "peak_source": "self-measured in this run: max(carry-chained IMAD.WIDE.U32.X microbenchmark, "
                                             "fq_mul microbenchmark x 136); MEASURED_PEAKS.json has no integer figure; "
                                             "nominal 148 SM x 32 lanes/clk x 1.965 GHz = 9309 G/s",
@@ -249,6 +274,13 @@ def main():
                              "kernel_ms": acc_ms,
                              "pipeline_frac": limb_products / (ms_per_step * 1e-3) / imad_peak,
                              "actual_field_mults_per_point": plan_mults / n,
+                             "actual_limb_products_per_mixed_add": LIMB_PRODUCTS_PER_MADD,
+                             "frac_actual_work": (st["pairs"] * LIMB_PRODUCTS_PER_MADD
+                                                  + (plan_mults - 10.0 * st["pairs"]) * LIMB_PRODUCTS_PER_MULT)
+                                                 / (ms_per_step * 1e-3) / imad_peak,
+                             "frac_actual_work_note": "limb products the whole call really issues (dedicated squaring and the fused "
+                                                      "product pair need fewer than the canonical 10 x 136 per mixed addition) / call "
+                                                      "time / peak",
                              "window_bits": int(st["window"]), "windows": int(st["windows"]),
                              "fq_mul_per_s_measured": fqmul_rate, "fq_mul_frac_of_imad_peak": fqmul_rate * LIMB_PRODUCTS_PER_MULT / imad_peak,
                              "madd_per_s_measured": madd_rate, "madd_frac_of_imad_peak": madd_rate * 10 * LIMB_PRODUCTS_PER_MULT / imad_peak,

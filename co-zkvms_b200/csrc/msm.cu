@@ -598,7 +598,13 @@ static void srs_table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t
     if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
     uint32_t tc = ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
     uint32_t tw = windows_for(254, tc);
-    if ((double)tw * (double)n * sizeof(affine) > (double)ctx->opt_table_max_bytes) return;
+    const double table_bytes = (double)tw * (double)n * sizeof(affine);
+    if (table_bytes > (double)ctx->opt_table_max_bytes) return;
+    // never more than half of what is free on the device now (sort buffers, buckets and resident polynomials need the rest)
+    size_t free_b = 0, total_b = 0;
+    if (!ctx->devs.empty() && cudaSetDevice(ctx->devs[0]->id) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+        table_bytes > 0.5 * (double)free_b)
+        return;
     if ((double)tw * (double)n >= 2147483647.0) return;  // table indices share 31 bits with the point index; all-ones is the skip mark
     *c = tc;
     *W = tw;

@@ -8,7 +8,7 @@
 namespace cozk {
 
 constexpr int ACC_L = 32;          // entries per thread of the serial accumulate body (level 1: the default, see choose_acc_l)
-constexpr int ACC_L_MIN = 16, ACC_L_MAX = 40;
+constexpr int ACC_L_MIN = 16;
 constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at small levels >= 2 (block-cooperative segmented scan)
 constexpr size_t ACC_SCAN_MAX = 65536;  // levels with more slots than this stay on the serial, work-efficient body
 constexpr uint32_t SUM_CHUNK = 1024;  // groups per thread block in the first level of the bucket-reduce sums
@@ -22,38 +22,20 @@ constexpr uint32_t C_MIN = 2, C_MAX = 22;
 inline size_t g_acc_resident_threads = 0;
 inline int g_acc_force_l = 0;  // option "acc_chunk": fixed chunk length (experiments, tests); 0 = choose_acc_l
 
-// Every level-1 thread does the same work (L mixed additions of 10 multiplications), so the kernel runs in WAVES of
-// `resident` threads and its time is waves * L: 2^20 points at L = 32 are 6.49 waves and pay for 7.  Pick the chunk
-// length whose last wave is fullest.  The second term is the level above: one full addition (14 multiplications) per
-// chunk, T/16 threads of 16 additions each; a wave that is mostly empty still costs about a third of a full one (latency).
+// Level-1 chunk length.  32 pairs per thread is the measured optimum once the kernel fills the device (2^20 points:
+// accumulate stage 2.73 / 2.64 / 2.62 / 2.68 / 2.65 ms at 28 / 30 / 32 / 34 / 36 - a chunk of 32 keys is one 128-byte line,
+// and the blocks do not run in lock-step waves, so "filling the last wave" buys nothing).  A small MSM that cannot fill
+// the device with chunks of 32 gets shorter chunks, down to 16: more threads, a shorter serial chain per thread
+// (2^16 points: 0.48 -> 0.40 ms).
 inline int choose_acc_l(size_t m, size_t resident) {
     if (g_acc_force_l) return g_acc_force_l;
     if (resident == 0 || m == 0) return ACC_L;
-    auto cost = [&](int L) {
-        size_t T = (m + L - 1) / L;
-        double c = (double)((T + resident - 1) / resident) * L * 10.0;
-        size_t slots = 2 * T;
-        if (slots > ACC_SCAN_MAX) {
-            double w2 = (double)((slots + ACC_L - 1) / ACC_L) / (double)resident;
-            c += (w2 <= 1.0 ? (w2 < 0.35 ? 0.35 : w2) : (double)(size_t)(w2 + 0.999999)) * (ACC_L / 2) * 14.0;
-        } else {
-            c += 8.0 * 14.0;
-        }
-        return c;
-    };
-    int best = ACC_L;
-    double best_cost = cost(ACC_L);
-    for (int d = 1; d <= ACC_L - ACC_L_MIN; ++d) {  // nearest to the default first; switch only for a clear gain
-        for (int L : {ACC_L + d, ACC_L - d}) {
-            if (L < ACC_L_MIN || L > ACC_L_MAX) continue;
-            double c = cost(L);
-            if (c < best_cost * 0.99) {
-                best_cost = c;
-                best = L;
-            }
-        }
-    }
-    return best;
+    if ((m + ACC_L - 1) / ACC_L >= resident) return ACC_L;
+    size_t L = (m + resident - 1) / resident;   // the chunk length at which the threads just fill the device
+    L = (L + 3) & ~(size_t)3;
+    if (L < (size_t)ACC_L_MIN) L = ACC_L_MIN;
+    if (L > (size_t)ACC_L) L = ACC_L;
+    return (int)L;
 }
 
 struct MsmPlan {
@@ -158,7 +140,7 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     p.sort_bits = sb;
     size_t e = p.m;
     p.acc_entries.push_back(e);
-    // Level 1: one thread per l1 pairs (ACC_L unless another chunk length fills the last wave of threads better).  Levels >= 2 reduce the partial slots: big levels with the same serial body
+    // Level 1: one thread per l1 pairs (ACC_L; shorter for an MSM too small to fill the device).  Levels >= 2 reduce the partial slots: big levels with the same serial body
     // (one addition per live slot: work-efficient, 16 additions deep), small ones with the block-cooperative segmented
     // scan (log2(ACC_TILE) additions deep, but up to that many additions per slot).  Every thread / block emits two
     // slots; a level that ran as a single thread / block has seen everything and leaves no open run.

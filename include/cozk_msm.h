@@ -96,7 +96,8 @@ int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, const void* sca
 
 /* Tuning / introspection. */
 /* "window" (0 = auto; a forced window also bypasses the SRS table), "group_pairs", "table_max_mib": memory an SRS
- * registered afterwards may spend on its precomputed table of 2^(c*w) * P rows (default 16384; 0 = none).  With a table
+ * registered afterwards may spend on its precomputed table of 2^(c*w) * P rows (default 65536, and never more than half
+ * of the free device memory; 0 = none).  With a table
  * all windows of a scalar share one bucket set, which removes the per-window bucket reduction and the 254 doublings of
  * the final combine; the table is built once at registration, like the reference's SRS in PST13::setup. */
 int cozk_set_option(cozk_ctx* ctx, const char* name, long value);

@@ -225,7 +225,7 @@ def test_precomputed_table_matches_plain_path(cozk, orc):
         with_table = c2.srs_register(bases)
         c2.set_option("table_max_mib", 0)
         plain = c2.srs_register(bases)
-        c2.set_option("table_max_mib", 16384)
+        c2.set_option("table_max_mib", 65536)
         vecs = [orc.gen_scalars(d, 70 + i, n, stride=64) for i, d in enumerate(("uniform", "const", "wminus", "dup"))]
         a = c2.msm_batch(with_table, vecs, n=n, stride=64)
         wa = c2.last_stats()["windows"]
