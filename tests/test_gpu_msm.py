@@ -155,18 +155,20 @@ def test_device_resident_scalars(ctx, orc):
     ctx.srs_release(srs)
 
 
-def test_properties_at_2pow22(ctx):
-    """Size-independent checks at a size the oracle is not run at: split = sum of parts, linearity in the scalars,
-    constant vector = c * sum(P_i), all computed on the device and compared bit for bit."""
+@pytest.mark.parametrize("log2n", [22, 24])
+def test_properties_at_full_size(ctx, log2n):
+    """Size-independent checks at sizes the oracle is not run at (2^22: BASELINE.json configs[2] and [4]; 2^24: the low
+    end of configs[3] on one GPU): split = sum of parts, window-size independence, constant vector = c * sum(P_i), all
+    computed on the device and compared bit for bit."""
     import importlib
     cozk = importlib.import_module("co-zkvms_b200")
-    n = 1 << 22
+    n = 1 << log2n
     dbases = ctx.testgen_bases(1, n)
     srs = ctx.srs_register_device(dbases, n)
     s = ctx.testgen_scalars("uniform", 2, n, form=1)
     full = ctx.msm_batch_ptrs(srs, [s.ptr], n, form=1, device=0)[0]
     # split at an odd boundary
-    cut = 1234567
+    cut = 1234567 if log2n == 22 else 9876543
     a = ctx.msm_batch_ptrs(srs, [s.ptr], cut, form=1, device=0)[0]
     b = ctx.msm_batch_ptrs(srs, [s.ptr + 32 * cut], n - cut, base_offset=cut, form=1, device=0)[0]
     assert (cozk.g1_sum(np.stack([a, b])) == full).all()
