@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "cozk_poly_upload", "cozk_poly_from_device", "cozk_poly_from_wire", "cozk_poly_release", "cozk_poly_info", "cozk_poly_download",
     "cozk_pst13_batch_commit_polys", "cozk_rep3_linear_combination", "cozk_rep3_evaluate_at_chi", "cozk_srs_pair_sums",
     "cozk_pst13_open_key_create", "cozk_pst13_open_key_release", "cozk_pst13_open_poly", "cozk_pst13_open_keyed",
-    "cozk_rep3_last_stats",
+    "cozk_rep3_last_stats", "cozk_rep3_evaluate_at_chi_poly", "cozk_eq_evals", "cozk_spartan_batch_open_worker",
 ]
 
 
@@ -128,6 +128,9 @@ def lib():
     L.cozk_pst13_open_poly.argtypes = [vp, pu64, sz, u64, u64, vp, vp, vp]
     L.cozk_pst13_open_keyed.argtypes = [vp, u64, vp, sz, vp, ci, vp, vp]
     L.cozk_rep3_last_stats.argtypes = [vp, cd]
+    L.cozk_rep3_evaluate_at_chi_poly.argtypes = [vp, pu64, sz, u64, vp]
+    L.cozk_eq_evals.argtypes = [vp, ci, vp, sz, ci, pu64]
+    L.cozk_spartan_batch_open_worker.argtypes = [vp, u64, pu64, sz, pu64, sz, sz, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -358,5 +361,6 @@ def g1_sum(points72):
     return out
 
 
+from . import spartan  # noqa: E402,F401  (co-spartan's worker-side commitment functions over the same entry points)
 from . import pst13  # noqa: E402  (host-side mirror of the reference's PST13 / MultilinearPC interface)
 from . import rep3  # noqa: E402  (device-resident Rep3 polynomials: include/cozk_rep3.h)

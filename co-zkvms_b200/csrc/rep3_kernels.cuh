@@ -14,6 +14,14 @@
 //   N1  pair sums      S[b] = P[2b] + P[2b+1]: open() feeds every quotient scalar to two adjacent bases
 //                      (co-jolt/src/poly/commitment/pst13.rs:459), so its MSM equals a half-size MSM over pair sums.
 //
+//   eq table           chi[b] = prod_i (bit_i(b) ? t_i : 1 - t_i): the table a multilinear evaluation is a dot product with.
+//                      co-spartan evaluates every opened polynomial at the opening point
+//                      (`p.evaluate(point)` in distributed_batch_open_poly_worker,
+//                      co-noir-spartan/co-spartan/src/worker.rs:761-764: ark-poly fixes variable i = bit i of the index
+//                      with point[i]); co-jolt builds the same table with the point reversed (EqPolynomial::evals of
+//                      jolt-core, the `chis` of evaluate_at_chi).  Built on the device, so the chi table is no longer an
+//                      H2D copy of 32 B per coefficient.
+//
 // Like msm_kernels.cuh, every body is a pure function of its thread index and compiles for the host emulation tier.
 //
 // Lazy reduction: a sum of products is accumulated as a plain 576-bit integer (64 limb products per term instead of
@@ -49,6 +57,12 @@ COZK_HD fr fr_mont_from_canon(const fr& a) {
     return fr_mul(a, fr_const(r2));
 }
 COZK_HD fr fr_neg(const fr& a) { return fr_sub(fq_zero(), a); }
+// R mod r (Montgomery one)
+#define COZK_FR_ONE {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}
+COZK_HD fr fr_one() {
+    const uint32_t one[8] = COZK_FR_ONE;
+    return fr_const(one);
+}
 
 // ------------------------------------------------------------------------------------------------ lazy accumulator
 struct fr_wide {
@@ -330,6 +344,39 @@ COZK_HD void pair_sum_body(size_t b, const PairSumArgs& A) {
     store_fq(&A.out[b].x, r.x);
     store_fq(&A.out[b].y, r.y);
     A.out_inf[b] = w[64];
+}
+
+// ------------------------------------------------------------------------------------------------ eq table
+// chi[b] = prod_{i < nv} f_i(bit_i(b)),  f_i(1) = t_i, f_i(0) = 1 - t_i,  t_i = point[i] (LSB first) or point[nv-1-i]
+// (MSB first).  Two small tables over the low lo_bits and the remaining high bits (one thread per entry, at most nv
+// multiplications each), then ONE multiplication per element: chi[b] = hi[b >> lo_bits] * lo[b & mask].  All Montgomery.
+struct EqArgs {
+    const fr* point;   // nv values, Montgomery
+    uint32_t nv, lo_bits;
+    int msb_first;
+    fr* lo_tab;        // [2^lo_bits]
+    fr* hi_tab;        // [2^(nv - lo_bits)]
+    fr* out;           // [2^nv]
+};
+COZK_HD fr eq_factor(const EqArgs& A, uint32_t i, uint32_t bit) {
+    fr t = load_fq(&A.point[A.msb_first ? A.nv - 1 - i : i]);
+    return bit ? t : fr_sub(fr_one(), t);
+}
+// threads [0, 2^lo_bits) fill lo_tab, the next 2^(nv - lo_bits) fill hi_tab
+COZK_HD void eq_small_body(size_t tid, const EqArgs& A) {
+    const size_t nlo = (size_t)1 << A.lo_bits, nhi = (size_t)1 << (A.nv - A.lo_bits);
+    if (tid >= nlo + nhi) return;
+    const bool hi = tid >= nlo;
+    const size_t x = hi ? tid - nlo : tid;
+    const uint32_t first = hi ? A.lo_bits : 0, count = hi ? A.nv - A.lo_bits : A.lo_bits;
+    fr acc = fr_one();
+    for (uint32_t i = 0; i < count; ++i) acc = fr_mul(acc, eq_factor(A, first + i, (uint32_t)(x >> i) & 1u));
+    store_fq(hi ? &A.hi_tab[x] : &A.lo_tab[x], acc);
+}
+COZK_HD void eq_expand_body(size_t b, const EqArgs& A) {
+    if (b >= ((size_t)1 << A.nv)) return;
+    const size_t mask = ((size_t)1 << A.lo_bits) - 1;
+    store_fq(&A.out[b], fr_mul(load_fq(&A.hi_tab[b >> A.lo_bits]), load_fq(&A.lo_tab[b & mask])));
 }
 
 }  // namespace cozk

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(128, 4) k_lincomb(LincombArgs A, int staged) {
 }
 __global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void k_chi_reduce(ChiReduceArgs A) { chi_reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(128) k_eq_small(EqArgs A) { eq_small_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(256) k_eq_expand(EqArgs A) { eq_expand_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(128) k_pair_sum(PairSumArgs A) { pair_sum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 // Polynomials come and go by the hundred (138 trace polynomials per proof): allocate them stream-ordered from the device's
 // memory pool, whose release threshold cozk_init lifts, so that a freed polynomial's memory is reused instead of being
@@ -524,8 +526,10 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
     return COZK_OK;
 }
 
-int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, const void* chis, size_t n, void* out_evals) {
-    if (!ctx || !polys || !chis || !out_evals || k == 0 || k > 0xFFFFFFFFu) {
+// chis: n Fr values, Montgomery, in host memory (h_chis) or already on the polynomials' device (d_chis_in)
+static int evaluate_at_chi_core(cozk_ctx* ctx, const cozk_poly* polys, size_t k, const void* h_chis, const fr* d_chis_in,
+                                int chis_dev, size_t n, void* out_evals) {
+    if (!ctx || !polys || (!h_chis && !d_chis_in) || !out_evals || k == 0 || k > 0xFFFFFFFFu) {
         set_error("null pointer or k == 0");
         return COZK_ERR_INVALID_ARG;
     }
@@ -542,6 +546,10 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
             return COZK_ERR_INVALID_ARG;
         }
     }
+    if (d_chis_in && chis_dev != E[0].dev) {
+        set_error("evaluate_at_chi: the chi table must live on the polynomials' device");
+        return COZK_ERR_INVALID_ARG;
+    }
     Device& D = *ctx->devs[E[0].dev];
     std::vector<PolyDesc> hd(k);
     for (size_t j = 0; j < k; ++j) hd[j] = PolyDesc{E[j].chunk(), E[j].len, E[j].kind, 0};
@@ -554,15 +562,15 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
     fr *d_chis = nullptr, *d_part = nullptr, *d_mid = nullptr, *d_res = nullptr;
     const uint32_t Tmid = T < 64 ? T : 64;
     cudaError_t e = pool_alloc(D, &d_desc, k * sizeof(PolyDesc));
-    if (e == cudaSuccess) e = pool_alloc(D, &d_chis, std::max<size_t>(n, 1) * sizeof(fr));
+    if (e == cudaSuccess && !d_chis_in) e = pool_alloc(D, &d_chis, std::max<size_t>(n, 1) * sizeof(fr));
     if (e == cudaSuccess) e = pool_alloc(D, &d_part, k * (size_t)T * sizeof(fr));
     if (e == cudaSuccess) e = pool_alloc(D, &d_mid, k * (size_t)Tmid * sizeof(fr));
     if (e == cudaSuccess) e = pool_alloc(D, &d_res, k * sizeof(fr));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), k * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_chis, chis, n * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
+    if (e == cudaSuccess && !d_chis_in) e = cudaMemcpyAsync(d_chis, h_chis, n * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
     double ms = 0;
     if (e == cudaSuccess) {
-        ChiArgs A{d_desc, (uint32_t)k, d_chis, n, T, d_part};
+        ChiArgs A{d_desc, (uint32_t)k, d_chis_in ? d_chis_in : d_chis, n, T, d_part};
         StageTimer St(D);
         St.start();
         k_chi_partial<<<blocks_for(k * (size_t)T, 128), 128, 0, D.stream>>>(A);
@@ -582,6 +590,114 @@ int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, c
     }
     ctx->rep3_stats[3] = ms;
     return COZK_OK;
+}
+
+int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, const void* chis, size_t n, void* out_evals) {
+    if (!chis) {
+        set_error("null pointer or k == 0");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return evaluate_at_chi_core(ctx, polys, k, chis, nullptr, 0, n, out_evals);
+}
+
+int cozk_rep3_evaluate_at_chi_poly(cozk_ctx* ctx, const cozk_poly* polys, size_t k, cozk_poly chi, void* out_evals) {
+    if (!ctx) {
+        set_error("null context");
+        return COZK_ERR_INVALID_ARG;
+    }
+    PolyEntry C;
+    int rc = lookup(ctx, chi, &C);
+    if (rc) return rc;
+    if (C.kind != POLY_MONT) {
+        set_error("evaluate_at_chi: the chi table must be a public polynomial of field elements");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return evaluate_at_chi_core(ctx, polys, k, nullptr, reinterpret_cast<const fr*>(C.chunk()), C.dev, C.len, out_evals);
+}
+
+int cozk_eq_evals(cozk_ctx* ctx, int device_index, const void* point, size_t nv, int msb_first, cozk_poly* out) {
+    int rc = check_device(ctx, device_index);
+    if (rc) return rc;
+    if (!point || !out || nv == 0 || nv > 30) {
+        set_error("eq_evals: null pointer or nv outside 1..30");
+        return COZK_ERR_INVALID_ARG;
+    }
+    Device& D = *ctx->devs[device_index];
+    const size_t n = (size_t)1 << nv;
+    const uint32_t lo_bits = (uint32_t)(nv / 2);
+    fr *d_point = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_out = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(D.mu);
+        COZK_CUDA(cudaSetDevice(D.id));
+        cudaError_t e = pool_alloc(D, &d_point, nv * sizeof(fr));
+        if (e == cudaSuccess) e = pool_alloc(D, &d_lo, ((size_t)1 << lo_bits) * sizeof(fr));
+        if (e == cudaSuccess) e = pool_alloc(D, &d_hi, ((size_t)1 << (nv - lo_bits)) * sizeof(fr));
+        if (e == cudaSuccess) e = pool_alloc(D, &d_out, n * sizeof(fr));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_point, point, nv * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
+        if (e == cudaSuccess) {
+            EqArgs A{d_point, (uint32_t)nv, lo_bits, msb_first ? 1 : 0, d_lo, d_hi, d_out};
+            k_eq_small<<<blocks_for(((size_t)1 << lo_bits) + ((size_t)1 << (nv - lo_bits)), 128), 128, 0, D.stream>>>(A);
+            k_eq_expand<<<blocks_for(n, 256), 256, 0, D.stream>>>(A);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);  // `point` is the caller's buffer
+        for (void* p : {(void*)d_point, (void*)d_lo, (void*)d_hi})
+            if (p) pool_free(D, p);
+        if (e != cudaSuccess) {
+            if (d_out) pool_free(D, d_out);
+            set_error(std::string("eq_evals failed: ") + cudaGetErrorString(e));
+            return COZK_ERR_CUDA;
+        }
+    }
+    PolyEntry E;
+    E.dev = device_index;
+    E.kind = POLY_MONT;
+    E.user_kind = COZK_POLY_PUBLIC;
+    E.bits = 0;
+    E.d_data = reinterpret_cast<uint8_t*>(d_out);
+    E.total = n;
+    E.lo = 0;
+    E.len = n;
+    *out = publish(ctx, E);
+    return COZK_OK;
+}
+
+// distributed_batch_open_poly_worker (co-noir-spartan/co-spartan/src/worker.rs:745-772) without the network send:
+//   agg   = aggregate_poly(eta, polys[0..num_comms])      sum_j eta^j * polys[j]          (co-spartan/src/utils.rs:85-107)
+//   (pf, r) = distributed_open(ck, agg, point)            nv folds + nv MSMs               (worker.rs:774-809)
+//   evals = polys.map(|p| p.evaluate(point))              every polynomial, not only the first num_comms   (:761-764)
+// All three on device 0, from device-resident polynomials: the only traffic is the point in and nv + 1 + k values out.
+int cozk_spartan_batch_open_worker(cozk_ctx* ctx, cozk_open_key key, const cozk_srs* level_srs, size_t nv, const cozk_poly* polys,
+                                   size_t k, size_t num_comms, const void* point, const void* eta, void* out_proofs,
+                                   void* out_val, void* out_evals) {
+    if (!ctx || !polys || !point || !eta || !out_proofs || !out_val || !out_evals || k == 0 || num_comms == 0 || num_comms > k) {
+        set_error("batch_open_worker: null pointer, no polynomial, or num_comms outside 1..k");  // polys[0..num_comms] panics
+        return COZK_ERR_INVALID_ARG;
+    }
+    if (key) {
+        OpenKey K;
+        int rc = open_key_lookup(ctx, key, &K);
+        if (rc) return rc;
+        nv = K.nv;
+    }
+    if (nv == 0 || nv > 30) {
+        set_error("bad nv");
+        return COZK_ERR_INVALID_ARG;
+    }
+    // eta^j, Montgomery (host: num_comms - 1 multiplications)
+    std::vector<fr> powers(num_comms);
+    powers[0] = fr_one();
+    fr e1;
+    memcpy(e1.v, eta, 32);
+    for (size_t j = 1; j < num_comms; ++j) powers[j] = fr_mul(powers[j - 1], e1);
+    cozk_poly agg = 0, chi = 0;
+    int rc = cozk_rep3_linear_combination(ctx, polys, powers.data(), num_comms, 0, &agg);
+    if (!rc) rc = cozk_pst13_open_poly(ctx, level_srs, nv, key, agg, point, out_proofs, out_val);
+    if (!rc) rc = cozk_eq_evals(ctx, 0, point, nv, 0, &chi);
+    if (!rc) rc = cozk_rep3_evaluate_at_chi_poly(ctx, polys, k, chi, out_evals);
+    if (agg) cozk_poly_release(ctx, agg);
+    if (chi) cozk_poly_release(ctx, chi);
+    return rc;
 }
 
 int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {

@@ -3,7 +3,8 @@
 Names follow the reference so that the parity tests read like its code:
   Rep3DensePolynomial            co-jolt/src/poly/dense_mlpoly.rs:23-32 (from_wire = receive_request + deserialize)
   linear_combination             co-jolt/src/poly/multilinear_polynomial.rs:196-296
-  evaluate_at_chi/batch_evaluate co-jolt/src/poly/dense_mlpoly.rs:160-194 (chis supplied by the caller)
+  evaluate_at_chi/batch_evaluate co-jolt/src/poly/dense_mlpoly.rs:160-194 (chis from the caller, or eq_evals on the device)
+  eq_evals                       jolt-core EqPolynomial::evals order (msb_first) / ark-poly evaluate order (lsb first)
   batch_commit_rep3              co-jolt/src/poly/commitment/pst13.rs:165-229 over resident polynomials
   prove_rep3                     pst13.rs:125-137 (opening point reversed, share a opened)
 Field elements are 32-byte little-endian Montgomery values unless stated otherwise.
@@ -111,12 +112,26 @@ def linear_combination(polynomials, coefficients, party_id):
 
 
 def batch_evaluate_at_chi(polys, chis):
-    """[poly.evaluate_at_chi(chis) for poly in polys] (batch_evaluate with the eq table supplied): (k, 32) uint8."""
+    """[poly.evaluate_at_chi(chis) for poly in polys] (batch_evaluate with the eq table supplied): (k, 32) uint8.
+    chis: host array of n Montgomery values, or a device-resident public polynomial (eq_evals)."""
     ctx = polys[0].ctx
-    chis = np.ascontiguousarray(chis, dtype=np.uint8).reshape(-1, 32)
     out = np.zeros((len(polys), 32), dtype=np.uint8)
+    if isinstance(chis, Rep3DensePolynomial):
+        _check(_lib().cozk_rep3_evaluate_at_chi_poly(ctx.handle, _handles(polys), len(polys), chis.handle, _vp(out)))
+        return out
+    chis = np.ascontiguousarray(chis, dtype=np.uint8).reshape(-1, 32)
     _check(_lib().cozk_rep3_evaluate_at_chi(ctx.handle, _handles(polys), len(polys), _vp(chis), chis.shape[0], _vp(out)))
     return out
+
+
+def eq_evals(ctx, point, msb_first=True, device=0):
+    """The eq table of `point` ((nv, 32) Montgomery) as a device-resident public polynomial of 2^nv values.
+    msb_first=True: jolt-core's EqPolynomial::evals(r) (point[0] pairs with the top index bit) - the chis of
+    evaluate_at_chi; False: the order ark-poly's evaluate / open() use (point[i] pairs with index bit i)."""
+    point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
+    h = ctypes.c_uint64()
+    _check(_lib().cozk_eq_evals(ctx.handle, device, _vp(point), point.shape[0], 1 if msb_first else 0, ctypes.byref(h)))
+    return Rep3DensePolynomial(ctx, h.value)
 
 
 def batch_commit_rep3(setup, polys, commit_to_public):

@@ -13,6 +13,10 @@
  *   cozk_rep3_linear_combination Rep3MultilinearPolynomial::linear_combination
  *                                          co-jolt/src/poly/multilinear_polynomial.rs:196-296 (call site opening_proof.rs:274-278)
  *   cozk_rep3_evaluate_at_chi    Rep3DensePolynomial::evaluate_at_chi / batch_evaluate  co-jolt/src/poly/dense_mlpoly.rs:160-194
+ *   cozk_eq_evals                the eq table those dot products need, built on the device (jolt-core EqPolynomial::evals
+ *                                          order, or ark-poly's evaluate / fix_variables order)
+ *   cozk_spartan_batch_open_worker  distributed_batch_open_poly_worker  co-noir-spartan/co-spartan/src/worker.rs:745-772
+ *                                          (aggregate_poly + distributed_open + per-polynomial evaluate)
  *   cozk_pst13_open_key_create + cozk_pst13_open_poly   open() behind PST13::prove_rep3 (pst13.rs:125-137, :428-474) on the
  *                                          device-resident joint polynomial; every quotient scalar multiplies two adjacent
  *                                          bases (pst13.rs:459), so level i runs as a half-size MSM over P[2b] + P[2b+1]
@@ -82,6 +86,17 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
  * every polynomial's length (zip_eq).  out: k x 32 B, Montgomery. */
 int cozk_rep3_evaluate_at_chi(cozk_ctx* ctx, const cozk_poly* polys, size_t k, const void* chis, size_t n, void* out_evals);
 
+/* The same with the chi table already on the device (a public polynomial handle, e.g. from cozk_eq_evals). */
+int cozk_rep3_evaluate_at_chi_poly(cozk_ctx* ctx, const cozk_poly* polys, size_t k, cozk_poly chi, void* out_evals);
+
+/* eq table of a point as a device-resident public polynomial of 2^nv values:
+ *   chi[b] = prod_i (bit_i(b) ? t_i : 1 - t_i),  t_i = point[i] (msb_first == 0) or point[nv-1-i] (msb_first != 0).
+ * msb_first == 0 is the order in which ark-poly's DenseMultilinearExtension::evaluate / fix_variables and open()
+ * (pst13.rs:454-458, worker.rs:793-798) consume the point: sum_b poly[b] * chi[b] == poly.evaluate(point).
+ * msb_first != 0 is jolt-core's EqPolynomial::evals(r), the `chis` of Rep3DensePolynomial::evaluate_at_chi
+ * (co-jolt/src/poly/dense_mlpoly.rs:160-181).  point: nv Fr values, Montgomery, host memory. */
+int cozk_eq_evals(cozk_ctx* ctx, int device_index, const void* point, size_t nv, int msb_first, cozk_poly* out);
+
 /* out = SRS of n/2 points S[b] = P[2b] + P[2b+1] (n even).  Setup-time work, like the SRS itself. */
 int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out);
 
@@ -103,6 +118,17 @@ int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, co
 /* cozk_pst13_open with a key: host evaluations as in cozk_pst13_open. */
 int cozk_pst13_open_keyed(cozk_ctx* ctx, cozk_open_key key, const void* evals, size_t stride_bytes, const void* point,
                           int form, void* out_proofs, void* out_eval);
+
+/* co-spartan's distributed_batch_open_poly_worker (co-noir-spartan/co-spartan/src/worker.rs:745-772) without the network
+ * send, on device 0 from device-resident polynomials (the party's share_0 evaluations, COZK_POLY_PUBLIC images):
+ *   agg = aggregate_poly(eta, polys[0..num_comms]) (co-spartan/src/utils.rs:85-107); (proofs, val) = distributed_open(ck,
+ *   agg, point) (worker.rs:774-809); evals[j] = polys[j].evaluate(point) for ALL k polynomials (:761-764).
+ * key != 0: the keyed opening schedule (level_srs / nv taken from the key); else level_srs[i] = ck.powers_of_g[i].
+ * point: nv Fr, eta: one Fr (Montgomery).  out_proofs: nv x 72 B; out_val: 32 B; out_evals: k x 32 B (Montgomery).
+ * Every polynomial must have 2^nv evaluations (evaluate asserts the point length; COZK_ERR_INVALID_ARG / KEY_LENGTH). */
+int cozk_spartan_batch_open_worker(cozk_ctx* ctx, cozk_open_key key, const cozk_srs* level_srs, size_t nv, const cozk_poly* polys,
+                                   size_t k, size_t num_comms, const void* point, const void* eta, void* out_proofs,
+                                   void* out_val, void* out_evals);
 
 /* Timings (ms, CUDA events on the engine's stream) of the last call on this thread's context:
  * [0] cozk_poly_from_wire / upload: H2D  [1] ingest kernel  [2] linear combination kernel  [3] chi kernels  [4] bytes moved by [2] */

@@ -20,6 +20,14 @@ restated, each from the in-tree source it follows:
                         (mpc-types/src/protocols/rep3/arithmetic/types.rs:76-81): (a + b) * TWO_INV, TWO_INV = (r+1)/2
                         (snarks-core/src/field.rs:6).
   pair sums / open      co-jolt/src/poly/commitment/pst13.rs:428-474; scalars[x] = q[x >> 1] (:459).
+  eq tables             chi[b] = prod_i (bit_i(b) ? t_i : 1 - t_i).  ark-poly's DenseMultilinearExtension::evaluate (third
+                        party) fixes variable i = bit i of the index with point[i] - the same recursion the in-tree
+                        distributed_open writes out (co-noir-spartan/co-spartan/src/worker.rs:793-798:
+                        r[k-1][b] = r[k][2b] (1 - point_i) + r[k][2b+1] point_i), which is what dmle_evaluate follows;
+                        jolt-core's EqPolynomial::evals (third party) pairs point[0] with the TOP index bit.
+  co-spartan worker     aggregate_poly co-noir-spartan/co-spartan/src/utils.rs:85-107; distributed_batch_open_poly_worker
+                        co-noir-spartan/co-spartan/src/worker.rs:745-772 (aggregate the first num_comms polynomials, open
+                        the aggregate, evaluate EVERY polynomial at the point).
 """
 import struct
 
@@ -160,3 +168,44 @@ def open_quotients(evals, point):
         qs.append([(r[2 * b + 1] - r[2 * b]) % R for b in range(half)])
         r = [(r[2 * b] * (1 - t) + r[2 * b + 1] * t) % R for b in range(half)]
     return qs, r[0]
+
+
+# ---------------------------------------------------------------- eq tables, co-spartan's batched opening worker
+
+def eq_evals(point, msb_first=False):
+    """chi[b] = prod_i (bit_i(b) ? t_i : 1 - t_i) with t_i = point[i] (lsb first) or point[nv - 1 - i] (msb first)."""
+    nv = len(point)
+    ts = [point[nv - 1 - i] if msb_first else point[i] for i in range(nv)]
+    chi = [1]
+    for t in ts:  # variable i doubles the table: index bit i is the new top bit
+        chi = [c * (1 - t) % R for c in chi] + [c * t % R for c in chi]
+    return chi
+
+
+def dmle_evaluate(evals, point):
+    """DenseMultilinearExtension::evaluate(point): fix variable i (index bit i) to point[i], as worker.rs:793-798 folds."""
+    r = [e % R for e in evals]
+    if len(r) != 1 << len(point):
+        raise ValueError("invalid size of partial point")
+    for t in point:
+        r = [(r[2 * b] * (1 - t) + r[2 * b + 1] * t) % R for b in range(len(r) // 2)]
+    return r[0]
+
+
+def aggregate_poly(eta, polys):
+    """utils.rs:85-107: evals[i] += x * p[i] for the polynomials in turn, x *= eta; zip stops at the shorter vector."""
+    n = 1 << max(max(len(p), 1).bit_length() - 1 for p in polys)
+    out = [0] * n
+    x = 1
+    for p in polys:
+        for i, v in enumerate(p[:n]):
+            out[i] = (out[i] + x * v) % R
+        x = x * eta % R
+    return out
+
+
+def distributed_batch_open_poly_worker(polys, point, eta, num_comms):
+    """worker.rs:745-772 without the group side: (quotient vectors per level - NOT duplicated -, val, evals)."""
+    agg = aggregate_poly(eta, polys[:num_comms])
+    qs, val = open_quotients(agg, point)
+    return qs, val, [dmle_evaluate(p, point) for p in polys]

@@ -32,6 +32,7 @@ def lib():
         L.emul_lincomb.argtypes = [vp, vp, vp, u32, vp, u32, u32, sz, vp]
         L.emul_chi.argtypes = [vp, vp, vp, u32, vp, sz, u32, vp]
         L.emul_pair_sum.argtypes = [vp, vp, sz, vp, vp]
+        L.emul_eq.argtypes = [vp, u32, u32, ci, vp]
         L.emul_wide_dot.argtypes = [vp, vp, sz, u32, vp]
         _lib = L
     return _lib
@@ -143,4 +144,14 @@ def wide_dot(a, b, repeat=1):
     b = np.ascontiguousarray(b, dtype=np.uint8)
     out = np.zeros(32, np.uint8)
     lib().emul_wide_dot(_p(a), _p(b), a.shape[0], repeat, _p(out))
+    return out
+
+
+def eq(point, msb_first=False, lo_bits=None):
+    """point: (nv, 32) Montgomery -> (2^nv, 32) eq table through the two thread bodies of cozk_eq_evals."""
+    point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
+    nv = point.shape[0]
+    lo_bits = nv // 2 if lo_bits is None else lo_bits
+    out = np.zeros((1 << nv, 32), np.uint8)
+    lib().emul_eq(_p(point), nv, lo_bits, 1 if msb_first else 0, _p(out))
     return out

@@ -240,6 +240,13 @@ void emul_chi(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* 
     for (size_t t = 0; t < (size_t)k * Tmid; ++t) chi_reduce_body(t, R1);
     for (size_t j = 0; j < k; ++j) chi_reduce_body(j, R2);
 }
+// eq table (both kernels of cozk_eq_evals): point nv x 32 B Montgomery -> out 2^nv x 32 B
+void emul_eq(const uint8_t* point, uint32_t nv, uint32_t lo_bits, int msb_first, uint8_t* out) {
+    std::vector<fr> lo((size_t)1 << lo_bits), hi((size_t)1 << (nv - lo_bits));
+    EqArgs A{reinterpret_cast<const fr*>(point), nv, lo_bits, msb_first, lo.data(), hi.data(), reinterpret_cast<fr*>(out)};
+    for (size_t t = 0; t < lo.size() + hi.size(); ++t) eq_small_body(t, A);
+    for (size_t b = 0; b < ((size_t)1 << nv); ++b) eq_expand_body(b, A);
+}
 void emul_pair_sum(const uint8_t* bases, const uint8_t* infinity, size_t half, uint8_t* out, uint8_t* out_inf) {
     PairSumArgs A{reinterpret_cast<const affine*>(bases), infinity, half, reinterpret_cast<affine*>(out), out_inf};
     for (size_t b = 0; b < half; ++b) pair_sum_body(b, A);

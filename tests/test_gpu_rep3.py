@@ -323,3 +323,73 @@ def test_three_party_flow_commit_combine_open(cozk, ctx, orc):
     assert (pst.coordinate_prove(party_proofs) == want_proofs).all()
     rep3.release_open_key(setup)
     setup.release()
+
+
+@pytest.mark.parametrize("nv", [1, 2, 9, 14])
+def test_eq_evals_on_device(cozk, ctx, nv):
+    """cozk_eq_evals against the restated eq table, both index orders; the table then serves evaluate_at_chi from HBM
+    (no H2D of the chis) and reproduces DenseMultilinearExtension::evaluate as a dot product."""
+    rep3 = cozk.rep3
+    point = _rand_fr(80 + nv, nv)
+    n = 1 << nv
+    for msb in (False, True):
+        chi = rep3.eq_evals(ctx, H.scalars_wire(point), msb_first=msb)
+        assert len(chi) == n and chi.kind == rep3.PUBLIC
+        assert _from_dense(chi.download()) == rep3ref.eq_evals(point, msb_first=msb), (nv, msb)
+        chi.release()
+    a, b, pub = _rand_fr(81, n), _rand_fr(82, n), _rand_fr(83, n)
+    polys = [rep3.Rep3DensePolynomial.upload(ctx, _shared_mont(list(zip(a, b)))),
+             rep3.Rep3DensePolynomial.upload(ctx, H.scalars_wire(pub), rep3.PUBLIC)]
+    chi = rep3.eq_evals(ctx, H.scalars_wire(point), msb_first=False)
+    got = _from_dense(rep3.batch_evaluate_at_chi(polys, chi))
+    assert got[1] == rep3ref.dmle_evaluate(pub, point)
+    assert got[0] == rep3ref.evaluate_at_chi(("shared", list(zip(a, b))), rep3ref.eq_evals(point))
+    # the host-table entry point gives the same bytes
+    assert got == _from_dense(rep3.batch_evaluate_at_chi(polys, H.scalars_wire(rep3ref.eq_evals(point))))
+    short = rep3.eq_evals(ctx, H.scalars_wire(point[:-1] if nv > 1 else point + point))
+    with pytest.raises(cozk.CozkError):  # zip_eq: lengths differ
+        rep3.batch_evaluate_at_chi(polys, short)
+    with pytest.raises(cozk.CozkError):  # the table must be a polynomial of field elements
+        rep3.batch_evaluate_at_chi(polys, polys[0])
+    for p in polys + [chi, short]:
+        p.release()
+
+
+@pytest.mark.parametrize("nv,k,num_comms", [(3, 2, 2), (10, 5, 3), (13, 4, 4)])
+def test_spartan_batch_open_worker(cozk, ctx, orc, nv, k, num_comms):
+    """co-spartan's distributed_batch_open_poly_worker (worker.rs:745-772) in one call over resident polynomials, against
+    its restatement: proofs[i] = MSM(ck.powers_of_g[i], q_i duplicated), val = the aggregate at the point, evals = every
+    polynomial at the point; keyed and reference opening schedules; and the pieces under the reference's names."""
+    rep3, pst, spartan = cozk.rep3, cozk.pst13, cozk.spartan
+    levels = _levels(orc, nv, seed=11)
+    ck = rep3.create_open_key(pst.PST13Setup(ctx, levels))
+    n = 1 << nv
+    evals = [_rand_fr(90 + j, n) for j in range(k)]
+    point, eta = _rand_fr(97, nv), _rand_fr(98, 1)[0]
+    qs, want_val, want_evals = rep3ref.distributed_batch_open_poly_worker(evals, point, eta, num_comms)
+    want_proofs = np.stack([orc.msm(levels[i], np.repeat(H.scalars_wire(qs[i]), 2, axis=0)) for i in range(nv)])
+    polys = [spartan.upload_evaluations(ctx, H.scalars_wire(e)) for e in evals]
+    for keyed in (True, False):
+        pf = spartan.distributed_batch_open_poly_worker(polys, ck, H.scalars_wire(point), H.scalars_wire([eta])[0], num_comms, keyed=keyed)
+        assert (pf["proofs"] == want_proofs).all(), keyed
+        assert pyref.from_mont(H.to_int(pf["val"]), R) == want_val
+        assert _from_dense(pf["evals"]) == want_evals
+    # the same from the pieces
+    agg = spartan.aggregate_poly(H.scalars_wire([eta])[0], polys[:num_comms])
+    assert _from_dense(agg.download()) == rep3ref.aggregate_poly(eta, evals[:num_comms])
+    proofs, val = spartan.distributed_open(ck, agg, H.scalars_wire(point))
+    assert (proofs == want_proofs).all() and pyref.from_mont(H.to_int(val), R) == want_val
+    comms = spartan.poly_commit_worker(ck, polys)
+    for c, e in zip(comms, evals):
+        assert c.nv == nv and (c.g_product == orc.msm(levels[0], H.scalars_wire(e))).all()
+    # polys[0..num_comms] out of range panics in the reference
+    with pytest.raises(cozk.CozkError):
+        spartan.distributed_batch_open_poly_worker(polys, ck, H.scalars_wire(point), H.scalars_wire([eta])[0], k + 1)
+    # a polynomial of another size: evaluate() asserts the point length
+    odd = spartan.upload_evaluations(ctx, H.scalars_wire(evals[0] + evals[0]))
+    with pytest.raises(cozk.CozkError):
+        spartan.distributed_batch_open_poly_worker(polys + [odd], ck, H.scalars_wire(point), H.scalars_wire([eta])[0], num_comms)
+    for p in polys + [agg, odd]:
+        p.release()
+    rep3.release_open_key(ck)
+    ck.release()

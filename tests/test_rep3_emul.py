@@ -170,3 +170,29 @@ def test_pair_sum_body_and_open_identity(orc):
     for s, p in zip(q, want):
         acc2 = pyref.add(acc2, pyref.mul(s, p) if p is not None else None)
     assert acc == acc2 and lhs is None
+
+
+def test_eq_table_bodies_and_spartan_worker_restatement():
+    """The two thread bodies behind cozk_eq_evals against the Python restatement, both index orders and every split of the
+    index bits; and the restated identities they rest on: sum_b p[b] * chi[b] = p.evaluate(point) (what lets co-spartan's
+    per-polynomial `evaluate` run as a dot product), msb-first = lsb-first of the reversed point, and the final value of
+    the opening fold = the evaluation of the aggregate."""
+    for nv in (1, 4, 7):
+        point = _rand_fr(40 + nv, nv)
+        pm = np.stack([H.fr_mont(t) for t in point])
+        for msb in (False, True):
+            want = rep3ref.eq_evals(point, msb_first=msb)
+            for lo_bits in sorted({0, nv // 2, nv}):
+                got = emul.eq(pm, msb_first=msb, lo_bits=lo_bits)
+                assert [pyref.from_mont(H.to_int(row), R) for row in got] == want, (nv, msb, lo_bits)
+        assert rep3ref.eq_evals(point, msb_first=True) == rep3ref.eq_evals(point[::-1], msb_first=False)
+        poly = _rand_fr(50 + nv, 1 << nv)
+        chi = rep3ref.eq_evals(point)
+        assert sum(p * c for p, c in zip(poly, chi)) % R == rep3ref.dmle_evaluate(poly, point)
+    nv, k, num_comms = 5, 4, 3
+    polys = [_rand_fr(60 + j, 1 << nv) for j in range(k)]
+    point, eta = _rand_fr(70, nv), _rand_fr(71, 1)[0]
+    qs, val, evals = rep3ref.distributed_batch_open_poly_worker(polys, point, eta, num_comms)
+    assert [len(q) for q in qs] == [1 << (nv - 1 - i) for i in range(nv)]
+    assert val == sum(pow(eta, j, R) * evals[j] for j in range(num_comms)) % R   # evaluation is linear in the polynomial
+    assert rep3ref.aggregate_poly(eta, [polys[0][:8], polys[1]])[8:] == [eta * v % R for v in polys[1][8:]]  # zip stops at the shorter

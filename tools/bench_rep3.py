@@ -113,6 +113,24 @@ def main():
     print(json.dumps({"experiment": "chi", "log2n": args.log2n, "k": args.k, "ms": chi_ms, "gbs": chi_bytes / chi_ms / 1e6,
                       "frac_of_hbm": chi_bytes / chi_ms / 1e6 / peak,
                       "frac_of_imad": 64.0 * args.k * n / (chi_ms * 1e-3) / imad_peak}))
+    # the eq table built on the device instead of copied in: wall clock of the two ways to get evaluate_at_chi's input
+    pt = ctx.testgen_scalars("uniform", 13, args.log2n).download().reshape(args.log2n, 32)
+    w_host, w_dev, w_eq = [], [], []
+    for _ in range(args.reps + 1):
+        t0 = time.perf_counter()
+        rep3.batch_evaluate_at_chi(polys, chis)
+        w_host.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        chi = rep3.eq_evals(ctx, pt, msb_first=True)
+        w_eq.append(time.perf_counter() - t0)
+        rep3.batch_evaluate_at_chi(polys, chi)
+        w_dev.append(time.perf_counter() - t0)
+        chi.release()
+    print(json.dumps({"experiment": "eq_evals", "log2n": args.log2n, "k": args.k,
+                      "eq_evals_wall_ms": 1e3 * float(np.median(w_eq[1:])),
+                      "eq_table_gbs": 32 * n / float(np.median(w_eq[1:])) / 1e9,
+                      "chi_with_host_table_wall_ms": 1e3 * float(np.median(w_host[1:])),
+                      "chi_with_device_eq_table_wall_ms": 1e3 * float(np.median(w_dev[1:]))}))
     for p in polys:
         p.release()
 
@@ -153,6 +171,24 @@ def main():
         print(json.dumps({"experiment": "open", "nv": nv, "open_small_log2": small, "reference_schedule_ms": ref_ms,
                           "keyed_ms": key_ms, "speedup": ref_ms / key_ms, "open_key_setup_s": key_s,
                           "identical_proofs": bool((ref_proofs == key_proofs).all())}))
+        if small == [int(x) for x in args.small.split(",")][-1]:
+            # co-spartan's distributed_batch_open_poly_worker on resident share_0 polynomials: aggregate + open + evaluate
+            spartan = cozk.spartan
+            sp = []
+            for j in range(4):
+                t = ctx.testgen_scalars("uniform", 30 + j, m)
+                sp.append(rep3.Rep3DensePolynomial.from_device(ctx, t, m, kind=rep3.PUBLIC))
+                t.free()
+            eta = ctx.testgen_scalars("uniform", 14, 1).download().reshape(32)
+            ts = []
+            for _ in range(args.reps + 1):
+                t0 = time.perf_counter()
+                spartan.distributed_batch_open_poly_worker(sp, setup, point, eta, 3)
+                ts.append(time.perf_counter() - t0)
+            print(json.dumps({"experiment": "spartan_batch_open_worker", "nv": nv, "polys": 4, "num_comms": 3,
+                              "wall_ms": 1e3 * float(np.median(ts[1:])), "keyed_open_alone_ms": key_ms}))
+            for q in sp:
+                q.release()
         rep3.release_open_key(setup)
     ctx.close()
 
