@@ -134,6 +134,7 @@ struct cozk_ctx {
     long opt_open_small_log2 = 14;   // opening levels with at most 2^this quotient values share one batched MSM (measured: 10..14 -> 19.4 .. 18.1 ms at nv = 22)
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;
+    long opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
     long opt_stream_min_points = 1L << 23;  // host-resident single vectors this long are streamed in chunks (0 = never)

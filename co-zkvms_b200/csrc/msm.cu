@@ -887,6 +887,10 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // pairs per thread at level 1 of the accumulate stage: 0 = choose per call (fill the last wave of threads)
         if (value != 0 && (value < 4 || value > 256)) return COZK_ERR_INVALID_ARG;
         g_acc_force_l = (int)value;
+    } else if (!strcmp(name, "peer_direct")) {
+        // multi-device linear combination: 1 = the summing kernel reads remote partials over peer mappings, 0 = staged copies
+        if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;
+        ctx->opt_peer_direct = value;
     } else if (!strcmp(name, "group_pairs")) {
         if (value < 1) return COZK_ERR_INVALID_ARG;
         ctx->opt_group_pairs = value;

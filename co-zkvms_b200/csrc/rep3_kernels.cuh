@@ -346,6 +346,43 @@ COZK_HD void pair_sum_body(size_t b, const PairSumArgs& A) {
     A.out_inf[b] = w[64];
 }
 
+// ------------------------------------------------------------------------------------------------ partial joint polynomials
+// A party's polynomials spread over several GPUs (one batch-commit shard per device): each device forms the linear
+// combination of ITS polynomials, and the device that opens adds the partial results - the one exchange step of the
+// commitment path.  Thread i reads element i of every partial (over NVLink peer mappings for the remote ones) and
+// writes the joint element: transfer and addition are one kernel, nothing is staged.  Partials are lincomb outputs:
+// shared (64 B) or public Montgomery (32 B); a public partial follows rep3 add_public like a public term.
+struct SumPartialsArgs {
+    const PolyDesc* parts;  // g descriptors; data may point into a peer device's memory
+    uint32_t g;
+    uint32_t party;
+    uint32_t shared_out;
+    size_t n;
+    uint8_t* out;
+};
+COZK_HD void sum_partials_body(size_t i, const SumPartialsArgs& A) {
+    if (i >= A.n) return;
+    fr a = fq_zero(), b = fq_zero(), p = fq_zero();
+    for (uint32_t j = 0; j < A.g; ++j) {
+        const PolyDesc d = A.parts[j];
+        if (i >= d.len) continue;
+        if (d.kind == POLY_SHARED) {
+            a = fr_add(a, load_fq(d.data + 64 * i));
+            b = fr_add(b, load_fq(d.data + 64 * i + 32));
+        } else {
+            p = fr_add(p, load_fq(d.data + 32 * i));
+        }
+    }
+    if (!A.shared_out) {
+        store_fq(A.out + 32 * i, p);
+        return;
+    }
+    if (A.party == 0) a = fr_add(a, p);
+    if (A.party == 1) b = fr_add(b, p);
+    store_fq(A.out + 64 * i, a);
+    store_fq(A.out + 64 * i + 32, b);
+}
+
 // ------------------------------------------------------------------------------------------------ eq table
 // chi[b] = prod_{i < nv} f_i(bit_i(b)),  f_i(1) = t_i, f_i(0) = 1 - t_i,  t_i = point[i] (LSB first) or point[nv-1-i]
 // (MSB first).  Two small tables over the low lo_bits and the remaining high bits (one thread per entry, at most nv

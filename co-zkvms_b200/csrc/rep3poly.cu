@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include "engine.hpp"
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(128, 4) k_lincomb(LincombArgs A, int staged) {
 }
 __global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void k_chi_reduce(ChiReduceArgs A) { chi_reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(256) k_sum_partials(SumPartialsArgs A) { sum_partials_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(128) k_eq_small(EqArgs A) { eq_small_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(256) k_eq_expand(EqArgs A) { eq_expand_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(128) k_pair_sum(PairSumArgs A) { pair_sum_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
@@ -426,68 +428,71 @@ int cozk_pst13_batch_commit_polys(cozk_ctx* ctx, cozk_srs srs, const cozk_poly* 
         if (present[j]) groups[Key{E[j].dev, E[j].kind, E[j].bits}].push_back(j);
     }
     uint64_t nv64 = nv;
-    for (auto& kv : groups) {
-        std::vector<const void*> ptrs;
-        for (size_t j : kv.second) ptrs.push_back(E[j].chunk());
-        std::vector<uint8_t> pts(ptrs.size() * 72);
-        size_t stride = kv.first.kind == POLY_SHARED ? 64 : 32;
-        int form = kv.first.kind == POLY_CANON ? COZK_CANON : COZK_MONT;
-        int rc = msm_dispatch(ctx, kv.first.dev, srs, 0, n, nullptr, ptrs.data(), ptrs.size(), stride, form, kv.first.bits, pts.data());
-        if (rc) return rc;
-        for (size_t i = 0; i < kv.second.size(); ++i) {
-            uint8_t* o = out + COZK_COMMITMENT_BYTES * kv.second[i];
-            memcpy(o, &nv64, 8);
-            memcpy(o + 8, &pts[72 * i], 72);
+    // the groups of one device run one after the other, the devices side by side (one host thread each)
+    std::map<int, std::vector<const Key*>> per_dev;
+    for (auto& kv : groups) per_dev[kv.first.dev].push_back(&kv.first);
+    std::vector<int> rcs(per_dev.size(), COZK_OK);
+    std::vector<std::string> errs(per_dev.size());
+    auto run_device = [&](size_t slot, const std::vector<const Key*>& keys) {
+        for (const Key* key : keys) {
+            const std::vector<size_t>& members = groups[*key];
+            std::vector<const void*> ptrs;
+            for (size_t j : members) ptrs.push_back(E[j].chunk());
+            std::vector<uint8_t> pts(ptrs.size() * 72);
+            size_t stride = key->kind == POLY_SHARED ? 64 : 32;
+            int form = key->kind == POLY_CANON ? COZK_CANON : COZK_MONT;
+            int rc = msm_dispatch(ctx, key->dev, srs, 0, n, nullptr, ptrs.data(), ptrs.size(), stride, form, key->bits, pts.data());
+            if (rc) {
+                rcs[slot] = rc;
+                errs[slot] = cozk_last_error();
+                return;
+            }
+            for (size_t i = 0; i < members.size(); ++i) {
+                uint8_t* o = out + COZK_COMMITMENT_BYTES * members[i];
+                memcpy(o, &nv64, 8);
+                memcpy(o + 8, &pts[72 * i], 72);
+            }
+        }
+    };
+    if (per_dev.size() == 1) {
+        run_device(0, per_dev.begin()->second);
+    } else {
+        std::vector<std::thread> th;
+        size_t slot = 0;
+        for (auto& kv : per_dev) th.emplace_back(run_device, slot++, std::cref(kv.second));
+        for (auto& t : th) t.join();
+    }
+    for (size_t i = 0; i < rcs.size(); ++i) {
+        if (rcs[i]) {
+            set_error(errs[i]);
+            return rcs[i];
         }
     }
     return COZK_OK;
 }
 
-int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const void* coeffs, size_t k, int party_id,
-                                 cozk_poly* out) {
-    if (!ctx || !polys || !coeffs || !out || k == 0 || k > 0xFFFFFFFFu || party_id < 0 || party_id > 2) {
-        set_error("null pointer, k == 0 or party id outside 0..2");
-        return COZK_ERR_INVALID_ARG;
-    }
-    std::vector<PolyEntry> E(k);
-    size_t max_len = 0, max_shared = 0;
-    bool any_shared = false;
-    for (size_t j = 0; j < k; ++j) {
-        int rc = lookup(ctx, polys[j], &E[j]);
-        if (rc) return rc;
-        if (E[j].dev != E[0].dev) {
-            set_error("linear_combination: all polynomials must live on one device");
-            return COZK_ERR_INVALID_ARG;
-        }
-        max_len = std::max(max_len, E[j].len);
-        if (E[j].kind == POLY_SHARED) {
-            any_shared = true;
-            max_shared = std::max(max_shared, E[j].len);
-        }
-    }
-    if (any_shared && max_shared < max_len) {
-        // the reference leaves such an index as SharedOrPublic::Public and panics in as_shared() ("Not an arithmetic share")
-        set_error("linear_combination: a public polynomial is longer than every shared one");
-        return COZK_ERR_INVALID_ARG;
-    }
-    Device& D = *ctx->devs[E[0].dev];
+// Linear combination of polynomials that all live on ctx->devs[dev]; coeffs: one Montgomery value per polynomial.
+// shared_out: the result is an array of shares (public terms follow add_public) / a dense public polynomial.
+static int lincomb_on_device(cozk_ctx* ctx, int dev, const std::vector<PolyEntry>& E, const std::vector<fr>& coeffs, int party_id,
+                             bool shared_out, PolyEntry* out, double* ms_out, double* bytes_out) {
+    const size_t k = E.size();
+    Device& D = *ctx->devs[dev];
+    size_t max_len = 0;
     // coefficient pairs: [2j] = c_j (Montgomery), [2j+1] = c_j * R for terms whose values are canonical integers
     std::vector<fr> hc(2 * k);
-    const uint8_t* cb = reinterpret_cast<const uint8_t*>(coeffs);
-    for (size_t j = 0; j < k; ++j) {
-        memcpy(hc[2 * j].v, cb + 32 * j, 32);
-        hc[2 * j + 1] = fr_mont_from_canon(hc[2 * j]);
-    }
     std::vector<PolyDesc> hd(k);
     double bytes = 0;
     for (size_t j = 0; j < k; ++j) {
+        hc[2 * j] = coeffs[j];
+        hc[2 * j + 1] = fr_mont_from_canon(coeffs[j]);
         hd[j] = PolyDesc{E[j].chunk(), E[j].len, E[j].kind, 0};
         bytes += (double)E[j].len * E[j].elem_bytes();
+        max_len = std::max(max_len, E[j].len);
     }
     PolyEntry O;
-    O.dev = E[0].dev;
-    O.kind = any_shared ? POLY_SHARED : POLY_MONT;
-    O.user_kind = any_shared ? COZK_POLY_SHARED : COZK_POLY_PUBLIC;
+    O.dev = dev;
+    O.kind = shared_out ? POLY_SHARED : POLY_MONT;
+    O.user_kind = shared_out ? COZK_POLY_SHARED : COZK_POLY_PUBLIC;
     O.total = O.len = max_len;
     bytes += (double)max_len * O.elem_bytes();
     std::lock_guard<std::mutex> lock(D.mu);
@@ -502,7 +507,7 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_coef, hc.data(), 2 * k * sizeof(fr), cudaMemcpyHostToDevice, D.stream);
     double ms = 0;
     if (e == cudaSuccess && max_len) {
-        LincombArgs A{d_desc, d_coef, (uint32_t)k, (uint32_t)party_id, any_shared ? 1u : 0u, max_len, d_out};
+        LincombArgs A{d_desc, d_coef, (uint32_t)k, (uint32_t)party_id, shared_out ? 1u : 0u, max_len, d_out};
         StageTimer T(D);
         T.start();
         size_t smem = (((size_t)k * sizeof(PolyDesc) + 15) & ~(size_t)15) + 2 * k * sizeof(fr);
@@ -520,8 +525,200 @@ int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const vo
         return COZK_ERR_CUDA;
     }
     O.d_data = d_out;
-    ctx->rep3_stats[2] = ms;
+    *out = O;
+    *ms_out = ms;
+    *bytes_out = bytes;
+    return COZK_OK;
+}
+
+static void free_entry(cozk_ctx* ctx, const PolyEntry& E) {
+    if (!E.d_data) return;
+    Device& D = *ctx->devs[E.dev];
+    std::lock_guard<std::mutex> lock(D.mu);
+    cudaSetDevice(D.id);
+    pool_free(D, E.d_data);
+}
+
+// Device `to` may read stream-ordered pool allocations of device `from` through a peer mapping (NVLink / NVSwitch on the
+// 8 x B200 box).  False when the two devices have no peer path: the caller then stages a copy instead.
+static bool peer_readable(cozk_ctx* ctx, int from, int to) {
+    if (ctx->opt_peer_direct == 0) return false;
+    const int from_id = ctx->devs[from]->id, to_id = ctx->devs[to]->id;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, to_id, from_id) != cudaSuccess || !can) return false;
+    if (cudaSetDevice(to_id) != cudaSuccess) return false;
+    cudaError_t e = cudaDeviceEnablePeerAccess(from_id, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, from_id) != cudaSuccess) return false;
+    cudaMemAccessDesc desc = {};
+    desc.location.type = cudaMemLocationTypeDevice;
+    desc.location.id = to_id;
+    desc.flags = cudaMemAccessFlagsProtReadWrite;
+    if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
+int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const void* coeffs, size_t k, int party_id,
+                                 cozk_poly* out) {
+    if (!ctx || !polys || !coeffs || !out || k == 0 || k > 0xFFFFFFFFu || party_id < 0 || party_id > 2) {
+        set_error("null pointer, k == 0 or party id outside 0..2");
+        return COZK_ERR_INVALID_ARG;
+    }
+    std::vector<PolyEntry> E(k);
+    size_t max_len = 0, max_shared = 0;
+    bool any_shared = false;
+    std::map<int, std::vector<size_t>> by_dev;
+    for (size_t j = 0; j < k; ++j) {
+        int rc = lookup(ctx, polys[j], &E[j]);
+        if (rc) return rc;
+        by_dev[E[j].dev].push_back(j);
+        max_len = std::max(max_len, E[j].len);
+        if (E[j].kind == POLY_SHARED) {
+            any_shared = true;
+            max_shared = std::max(max_shared, E[j].len);
+        }
+    }
+    if (any_shared && max_shared < max_len) {
+        // the reference leaves such an index as SharedOrPublic::Public and panics in as_shared() ("Not an arithmetic share")
+        set_error("linear_combination: a public polynomial is longer than every shared one");
+        return COZK_ERR_INVALID_ARG;
+    }
+    std::vector<fr> hc(k);
+    const uint8_t* cb = reinterpret_cast<const uint8_t*>(coeffs);
+    for (size_t j = 0; j < k; ++j) memcpy(hc[j].v, cb + 32 * j, 32);
+
+    if (by_dev.size() == 1) {
+        PolyEntry O;
+        double ms = 0, bytes = 0;
+        int rc = lincomb_on_device(ctx, E[0].dev, E, hc, party_id, any_shared, &O, &ms, &bytes);
+        if (rc) return rc;
+        ctx->rep3_stats[2] = ms;
+        ctx->rep3_stats[4] = bytes;
+        ctx->rep3_stats[5] = 0;
+        *out = publish(ctx, O);
+        return COZK_OK;
+    }
+
+    // ---- polynomials on several devices: one partial joint polynomial per device (concurrently), then ONE kernel on
+    // device 0 - where the opening runs - adds them, reading the remote partials through NVLink peer mappings.
+    const size_t G = by_dev.size();
+    std::vector<int> devs;
+    for (auto& kv : by_dev) devs.push_back(kv.first);
+    std::vector<PolyEntry> part(G);
+    std::vector<int> rcs(G, COZK_OK);
+    std::vector<std::string> errs(G);
+    std::vector<double> mss(G, 0), bys(G, 0);
+    {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) {
+            th.emplace_back([&, g]() {
+                const std::vector<size_t>& idx = by_dev[devs[g]];
+                std::vector<PolyEntry> Eg;
+                std::vector<fr> cg;
+                bool shared_g = false;
+                for (size_t j : idx) {
+                    Eg.push_back(E[j]);
+                    cg.push_back(hc[j]);
+                    shared_g = shared_g || E[j].kind == POLY_SHARED;
+                }
+                // party 2 adds public terms to neither share; inside a partial the rule is the same, so it is applied
+                // once per term whichever device holds it
+                rcs[g] = lincomb_on_device(ctx, devs[g], Eg, cg, party_id, shared_g, &part[g], &mss[g], &bys[g]);
+                if (rcs[g]) errs[g] = cozk_last_error();
+            });
+        }
+        for (auto& t : th) t.join();
+    }
+    auto drop_partials = [&]() {
+        for (size_t g = 0; g < G; ++g) free_entry(ctx, part[g]);
+    };
+    for (size_t g = 0; g < G; ++g) {
+        if (rcs[g]) {
+            drop_partials();
+            set_error(errs[g]);
+            return rcs[g];
+        }
+    }
+    const int odev = 0;
+    Device& D = *ctx->devs[odev];
+    // remote partials: peer-mapped where the devices have a peer path, staged by a peer copy otherwise
+    std::vector<PolyDesc> hd(G);
+    std::vector<uint8_t*> staged;
+    PolyEntry O;
+    O.dev = odev;
+    O.kind = any_shared ? POLY_SHARED : POLY_MONT;
+    O.user_kind = any_shared ? COZK_POLY_SHARED : COZK_POLY_PUBLIC;
+    O.total = O.len = max_len;
+    double peer_bytes = 0;
+    std::vector<bool> direct(G, true);
+    for (size_t g = 0; g < G; ++g)
+        if (part[g].dev != odev) direct[g] = peer_readable(ctx, part[g].dev, odev);
+    std::lock_guard<std::mutex> lock(D.mu);
+    cudaError_t e = cudaSetDevice(D.id);
+    PolyDesc* d_desc = nullptr;
+    uint8_t* d_out = nullptr;
+    for (size_t g = 0; g < G && e == cudaSuccess; ++g) {
+        const uint8_t* src = part[g].d_data;
+        const size_t nbytes = part[g].len * part[g].elem_bytes();
+        if (part[g].dev != odev) {
+            peer_bytes += (double)nbytes;
+            if (!direct[g]) {
+                uint8_t* tmp = nullptr;
+                e = pool_alloc(D, &tmp, std::max<size_t>(nbytes, 16));
+                if (e == cudaSuccess) {
+                    staged.push_back(tmp);
+                    e = cudaMemcpyPeerAsync(tmp, D.id, src, ctx->devs[part[g].dev]->id, nbytes, D.stream);
+                    src = tmp;
+                }
+            }
+        }
+        hd[g] = PolyDesc{src, part[g].len, part[g].kind, 0};
+    }
+    if (e == cudaSuccess) e = pool_alloc(D, &d_desc, G * sizeof(PolyDesc));
+    if (e == cudaSuccess) e = pool_alloc(D, &d_out, std::max<size_t>(max_len, 1) * O.elem_bytes());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_desc, hd.data(), G * sizeof(PolyDesc), cudaMemcpyHostToDevice, D.stream);
+    double sum_ms = 0;
+    if (e == cudaSuccess && max_len) {
+        SumPartialsArgs A{d_desc, (uint32_t)G, (uint32_t)party_id, any_shared ? 1u : 0u, max_len, d_out};
+        StageTimer T(D);
+        T.start();
+        k_sum_partials<<<blocks_for(max_len, 256), 256, 0, D.stream>>>(A);
+        e = cudaGetLastError();
+        sum_ms = T.stop();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+    if (d_desc) pool_free(D, d_desc);
+    for (uint8_t* t : staged) pool_free(D, t);
+    if (e != cudaSuccess) {
+        if (d_out) pool_free(D, d_out);
+        set_error(std::string("linear_combination (partial sums) failed: ") + cudaGetErrorString(e));
+    }
+    // the partials live on other devices (and on this one): release them without holding this device's lock twice
+    for (size_t g = 0; g < G; ++g) {
+        if (part[g].dev == odev) pool_free(D, part[g].d_data);
+    }
+    for (size_t g = 0; g < G; ++g) {
+        if (part[g].dev != odev) free_entry(ctx, part[g]);
+    }
+    if (e != cudaSuccess) return COZK_ERR_CUDA;
+    O.d_data = d_out;
+    double ms_max = 0, bytes = 0;
+    for (size_t g = 0; g < G; ++g) {
+        ms_max = std::max(ms_max, mss[g]);
+        bytes += bys[g];
+    }
+    ctx->rep3_stats[2] = ms_max;  // the partial combinations run concurrently: the slowest device
     ctx->rep3_stats[4] = bytes;
+    ctx->rep3_stats[5] = sum_ms;  // the exchange step
+    ctx->rep3_stats[6] = peer_bytes;
     *out = publish(ctx, O);
     return COZK_OK;
 }

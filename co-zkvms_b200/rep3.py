@@ -201,4 +201,5 @@ def open_keyed(setup, evals, point, stride=32):
 def last_stats(ctx):
     s = (ctypes.c_double * 8)()
     _check(_lib().cozk_rep3_last_stats(ctx.handle, s))
-    return {"h2d_ms": s[0], "ingest_ms": s[1], "lincomb_ms": s[2], "chi_ms": s[3], "lincomb_bytes": s[4]}
+    return {"h2d_ms": s[0], "ingest_ms": s[1], "lincomb_ms": s[2], "chi_ms": s[3], "lincomb_bytes": s[4],
+            "partial_sum_ms": s[5], "peer_bytes": s[6]}

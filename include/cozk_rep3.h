@@ -77,7 +77,11 @@ int cozk_pst13_batch_commit_polys(cozk_ctx* ctx, cozk_srs srs, const cozk_poly* 
  * With at least one shared input the result is shared: public terms join share a on party 0, share b on party 1 and
  * neither on party 2 (rep3 add_public); every index must then be covered by a shared polynomial (the reference panics in
  * `as_shared()` otherwise) -> COZK_ERR_INVALID_ARG.  With public inputs only the result is a public polynomial.
- * All inputs must live on one device; the result lives there too. */
+ * Inputs on one device: the result lives there too.  Inputs spread over several devices of the context (a party's
+ * polynomials dealt over the GPUs of a box, each device committing its own): every device forms the combination of ITS
+ * polynomials, and one kernel on device 0 - where the opening runs - adds the partial results, reading the remote ones
+ * through NVLink peer mappings (staged peer copies when two devices have no peer path, or with option "peer_direct" = 0);
+ * the result lives on device 0. */
 int cozk_rep3_linear_combination(cozk_ctx* ctx, const cozk_poly* polys, const void* coeffs, size_t k, int party_id,
                                  cozk_poly* out);
 

@@ -31,6 +31,7 @@ def lib():
         L.emul_widen.argtypes = [vp, u32, u32, sz, vp]
         L.emul_lincomb.argtypes = [vp, vp, vp, u32, vp, u32, u32, sz, vp]
         L.emul_chi.argtypes = [vp, vp, vp, u32, vp, sz, u32, vp]
+        L.emul_sum_partials.argtypes = [vp, vp, vp, u32, u32, u32, sz, vp]
         L.emul_pair_sum.argtypes = [vp, vp, sz, vp, vp]
         L.emul_eq.argtypes = [vp, u32, u32, ci, vp]
         L.emul_wide_dot.argtypes = [vp, vp, sz, u32, vp]
@@ -119,6 +120,25 @@ def lincomb(polys, coeffs, party):
     coeffs = np.ascontiguousarray(coeffs, dtype=np.uint8)
     out = np.zeros((n, 64 if shared_out else 32), np.uint8)
     lib().emul_lincomb(ptrs, _p(lens), _p(kinds), len(arrs), _p(coeffs), party, shared_out, n, _p(out))
+    return out
+
+
+def lincomb_by_device(polys, coeffs, party, device_of):
+    """The multi-device linear combination as the engine runs it: one partial combination per device (a partial is
+    shared when its device holds a shared polynomial, public otherwise), then the summing body.  device_of[j]: device of
+    polynomial j."""
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint8).reshape(len(polys), 32)
+    any_shared = any(k == "shared" for k, _ in polys)
+    parts = []
+    for dev in sorted(set(device_of)):
+        idx = [j for j, d in enumerate(device_of) if d == dev]
+        sub = [polys[j] for j in idx]
+        out = lincomb(sub, coeffs[idx], party)
+        parts.append(("shared" if any(k == "shared" for k, _ in sub) else "mont", out))
+    arrs, ptrs, lens, kinds = _descs(parts)
+    n = int(lens.max())
+    out = np.zeros((n, 64 if any_shared else 32), np.uint8)
+    lib().emul_sum_partials(ptrs, _p(lens), _p(kinds), len(arrs), party, 1 if any_shared else 0, n, _p(out))
     return out
 
 

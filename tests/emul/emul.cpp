@@ -228,6 +228,13 @@ void emul_lincomb(const uint8_t* const* ptrs, const uint64_t* lens, const uint32
     LincombArgs A{d.data(), c.data(), k, party, shared_out, n, out};
     for (size_t i = 0; i < n; ++i) lincomb_body(i, A);
 }
+// the exchange step of a multi-device linear combination: partial joint polynomials (lincomb outputs) -> their sum
+void emul_sum_partials(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* kinds, uint32_t g, uint32_t party,
+                       uint32_t shared_out, size_t n, uint8_t* out) {
+    std::vector<PolyDesc> d = make_descs(ptrs, lens, kinds, g);
+    SumPartialsArgs A{d.data(), g, party, shared_out, n, out};
+    for (size_t i = 0; i < n; ++i) sum_partials_body(i, A);
+}
 void emul_chi(const uint8_t* const* ptrs, const uint64_t* lens, const uint32_t* kinds, uint32_t k, const uint8_t* chis, size_t n,
               uint32_t T, uint8_t* out) {
     std::vector<PolyDesc> d = make_descs(ptrs, lens, kinds, k);

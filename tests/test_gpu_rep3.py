@@ -393,3 +393,74 @@ def test_spartan_batch_open_worker(cozk, ctx, orc, nv, k, num_comms):
         p.release()
     rep3.release_open_key(ck)
     ck.release()
+
+
+def test_multi_device_resident_flow(cozk, orc):
+    """A party's polynomials dealt over several GPUs of one process: every device commits its own (side by side), the
+    linear combination is formed per device and summed on device 0 by the kernel that reads the remote partials over
+    peer mappings (and by the staged-copy fallback), and the joint polynomial opens there.  Same bytes as the
+    one-device flow and the restatement.  Skipped on a single-GPU box."""
+    import torch
+    ndev = min(torch.cuda.device_count(), 4)
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rep3, pst = cozk.rep3, cozk.pst13
+    nv = 10
+    n = 1 << nv
+    with cozk.Context(devices=list(range(ndev))) as mctx:
+        levels = _levels(orc, nv, seed=13)
+        setup = rep3.create_open_key(pst.PST13Setup(mctx, levels))
+        shared = [list(zip(_rand_fr(100 + 2 * j, n), _rand_fr(101 + 2 * j, n))) for j in range(5)]
+        shared[4] = shared[4][: n // 2]                       # a shorter shared polynomial
+        pub = _rand_fr(120, n)
+        small = [pyref.limb(121, i, 0) & 0xFFFF for i in range(n)]
+        coeffs = _rand_fr(122, 7)
+        ref_polys = [("shared", s_) for s_ in shared] + [("public", pub), ("public", small)]
+
+        def upload(placement):
+            out = [rep3.Rep3DensePolynomial.upload(mctx, _shared_mont(s_), device=placement[j]) for j, s_ in enumerate(shared)]
+            out.append(rep3.Rep3DensePolynomial.upload(mctx, H.scalars_wire(pub), rep3.PUBLIC, device=placement[5]))
+            out.append(rep3.Rep3DensePolynomial.upload(mctx, np.array(small, np.uint16), rep3.U16, device=placement[6]))
+            return out
+
+        last = ndev - 1
+        placements = [[j % ndev for j in range(7)],           # round-robin
+                      [0, 0, 0, 0, 0, last, last],            # a device that holds public polynomials only
+                      [last] * 7]                             # all on one device: the result stays there
+        point = _rand_fr(123, nv)
+        for party in (0, 1, 2):
+            _, want = rep3ref.linear_combination(ref_polys, coeffs, party)
+            for placement in placements:
+                polys = upload(placement)
+                for direct in (1, 0):
+                    mctx.set_option("peer_direct", direct)
+                    joint = rep3.linear_combination(polys, H.scalars_wire(coeffs), party)
+                    assert joint.info() == (n, rep3.SHARED, 0 if len(set(placement)) > 1 else placement[0])
+                    assert _from_shared(joint.download()) == want, (party, placement, direct)
+                    if party == 0 and direct == 1 and joint.info()[2] == 0:
+                        want_proofs, want_ev = _open_reference(orc, levels, [a for a, _ in want], point)
+                        proofs, ev = rep3.open_poly(setup, joint, H.scalars_wire(point))
+                        assert (proofs == want_proofs).all() and pyref.from_mont(H.to_int(ev), R) == want_ev
+                    joint.release()
+                mctx.set_option("peer_direct", 1)
+                if party == 0:
+                    # commitments of full-length polynomials spread over the devices
+                    full = [polys[j] for j in (0, 1, 2, 3, 5, 6)]
+                    comms = rep3.batch_commit_rep3(setup, full, commit_to_public=True)
+                    vecs = [H.scalars_wire([a for a, _ in shared[j]]) for j in range(4)] + [H.scalars_wire(pub), H.scalars_wire(small)]
+                    for c, v in zip(comms, vecs):
+                        assert (c.g_product == orc.msm(levels[0], v)).all()
+                for p in polys:
+                    p.release()
+        # public polynomials only, on different devices: the result is public
+        pp = [rep3.Rep3DensePolynomial.upload(mctx, H.scalars_wire(pub), rep3.PUBLIC, device=0),
+              rep3.Rep3DensePolynomial.upload(mctx, np.array(small, np.uint16), rep3.U16, device=last)]
+        joint = rep3.linear_combination(pp, H.scalars_wire(coeffs[:2]), 1)
+        _, wantp = rep3ref.linear_combination(ref_polys[5:], coeffs[:2], 1)
+        assert joint.kind == rep3.PUBLIC and _from_dense(joint.download()) == wantp
+        st = rep3.last_stats(mctx)
+        assert st["peer_bytes"] == 32 * n and st["partial_sum_ms"] > 0
+        for p in pp + [joint]:
+            p.release()
+        rep3.release_open_key(setup)
+        setup.release()

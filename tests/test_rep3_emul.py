@@ -98,6 +98,31 @@ def test_lincomb_body(party):
     assert _from_shared(got) == want
 
 
+@pytest.mark.parametrize("party", [0, 1, 2])
+def test_lincomb_split_over_devices(party):
+    """The multi-device form: one partial combination per device, then the summing body (the kernel that reads the
+    remote partials over NVLink).  Any placement gives the reference's joint polynomial - a device that holds public
+    polynomials only contributes a PUBLIC partial, which must follow add_public exactly once."""
+    n = 16
+    sh1 = list(zip(_rand_fr(10, n), _rand_fr(11, n)))
+    sh2 = list(zip(_rand_fr(12, n // 2), _rand_fr(13, n // 2)))
+    pub = _rand_fr(14, n)
+    small = [pyref.limb(15, i, 0) & 0xFFFF for i in range(n // 4)]
+    neg = [(-(pyref.limb(16, i, 0) & 0xFFFFFFFF)) % R for i in range(n)]
+    coeffs = _rand_fr(17, 5)
+    polys_ref = [("shared", sh1), ("shared", sh2), ("public", pub), ("public", small), ("public", neg)]
+    _, want = rep3ref.linear_combination(polys_ref, coeffs, party)
+    polys = [("shared", _shared_mont(sh1)), ("shared", _shared_mont(sh2)), ("mont", H.scalars_wire(pub)),
+             ("canon", H.scalars_wire(small, form=1)), ("canon", H.scalars_wire(neg, form=1))]
+    for placement in ([0, 1, 0, 1, 0], [0, 0, 1, 1, 1], [3, 1, 2, 0, 2], [1, 0, 0, 0, 0]):
+        got = emul.lincomb_by_device(polys, H.scalars_wire(coeffs), party, placement)
+        assert _from_shared(got) == want, placement
+    # public polynomials only: the result stays public whatever the placement
+    _, wantp = rep3ref.linear_combination(polys_ref[2:], coeffs[2:], party)
+    got = emul.lincomb_by_device(polys[2:], H.scalars_wire(coeffs[2:]), party, [0, 1, 2])
+    assert [pyref.from_mont(H.to_int(row), R) for row in got] == wantp
+
+
 def test_lincomb_public_only_and_degenerate():
     n = 8
     pub = _rand_fr(20, n)

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Replay of one co-jolt party's commitment path with the share kept in HBM from arrival to opening proof (one GPU).
+"""Replay of one co-jolt party's commitment path with the share kept in HBM from arrival to opening proof (one process,
+--gpus N devices: the polynomials are dealt round-robin to the devices as they arrive, every device commits its own, the
+joint polynomial is formed per device and summed on device 0 over NVLink peer mappings, device 0 opens).
 
 What `JoltRep3Prover::init` + `prove` ask of the commitment scheme, through the
 resident-polynomial entry points (include/cozk_rep3.h):
@@ -54,8 +56,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2t", default="16")
     ap.add_argument("--parties", default="0,2")
+    ap.add_argument("--gpus", type=int, default=1)
     args = ap.parse_args()
-    ctx = cozk.Context()
+    G = args.gpus
+    ctx = cozk.Context(devices=list(range(G)))
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(G)
+
+    def receive(image, count):
+        """`count` polynomials from one wire image, dealt round-robin; one host thread per device (ctypes drops the GIL)."""
+        def on_device(d):
+            return [rep3.Rep3DensePolynomial.from_wire(ctx, image.array, device=d)[0] for _ in range(d, count, G)]
+        return [p for part in pool.map(on_device, range(G)) for p in part]
+
     dist_of_party = {0: "const", 1: "const", 2: "wminus"}
     for lt in [int(x) for x in args.log2t.split(",")]:
         T = 1 << lt
@@ -84,8 +97,8 @@ def main():
             times = {}
             for rep in range(2):  # pass 0 warms the engine's scratch buffers up to their final size
                 t0 = time.perf_counter()
-                polys = [rep3.Rep3DensePolynomial.from_wire(ctx, img.array)[0] for _ in range(N_SHARED)]
-                finals = [rep3.Rep3DensePolynomial.from_wire(ctx, img16.array)[0] for _ in range(N_FINAL)]
+                polys = receive(img, N_SHARED)
+                finals = receive(img16, N_FINAL)
                 times["receive_s"] = time.perf_counter() - t0
                 t0 = time.perf_counter()
                 comms = rep3.batch_commit_rep3(setup, polys, commit_to_public=False)
@@ -96,6 +109,7 @@ def main():
                 t0 = time.perf_counter()
                 joint = rep3.linear_combination(polys + finals, coeffs, party)
                 times["linear_combination_s"] = time.perf_counter() - t0
+                lin_stats = rep3.last_stats(ctx)
                 t0 = time.perf_counter()
                 proofs, _ = rep3.prove_rep3(setup, joint, point)
                 times["prove_rep3_s"] = time.perf_counter() - t0
@@ -104,7 +118,8 @@ def main():
             total = sum(times.values())
             wire_bytes = N_SHARED * img.nbytes + N_FINAL * img16.nbytes
             line = {"config": "co-jolt party commitment path, share resident in HBM", "log2_T": lt, "party": party,
-                    "share_dist": dist_of_party[party], "gpus": 1, "gpu_seconds": {k: round(v, 4) for k, v in times.items()},
+                    "share_dist": dist_of_party[party], "gpus": G,
+                    "partial_sum_kernel_ms": round(lin_stats["partial_sum_ms"], 3), "peer_gbytes": round(lin_stats["peer_bytes"] / 1e9, 3), "gpu_seconds": {k: round(v, 4) for k, v in times.items()},
                     "total_s": round(total, 4), "wire_gbytes": round(wire_bytes / 1e9, 3),
                     "receive_gbytes_per_s": round(wire_bytes / times["receive_s"] / 1e9, 1),
                     "commit_Mpoints_per_s": round(N_SHARED * T / times["commit_trace_polys_s"] / 1e6, 1),
