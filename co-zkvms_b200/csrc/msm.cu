@@ -609,12 +609,20 @@ static void srs_table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t
     *c = tc;
     *W = tw;
 }
+// Launches the table build on the device's stream and returns: with several devices the tables are built side by side
+// (the current device must be D's); srs_wait_tables waits for all of them.
 static int srs_build_table(Device& D, affine* d_table, size_t n, uint32_t c, uint32_t W) {
     if (W <= 1 || n == 0) return COZK_OK;
     TableArgs A{d_table, n, c, W};
     k_build_table<<<grid_for(n, 128), 128, 0, D.stream>>>(A);
     COZK_CUDA(cudaGetLastError());
-    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    return COZK_OK;
+}
+static int srs_wait_tables(cozk_ctx* ctx, size_t n_devices) {
+    for (size_t j = 0; j < n_devices; ++j) {
+        COZK_CUDA(cudaSetDevice(ctx->devs[j]->id));
+        COZK_CUDA(cudaStreamSynchronize(ctx->devs[j]->stream));
+    }
     return COZK_OK;
 }
 
@@ -671,6 +679,11 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
         }
         S.d_bases.push_back(d);
         S.d_inf.push_back(dinf);
+    }
+    int wrc = srs_wait_tables(ctx, S.d_bases.size());
+    if (wrc) {
+        undo();
+        return wrc;
     }
     std::lock_guard<std::mutex> lock(ctx->mu);
     *out = ctx->next_handle++;
@@ -801,6 +814,15 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
             }
             return rc;
         }
+    }
+    int wrc = srs_wait_tables(ctx, S.d_bases.size());
+    if (wrc) {
+        for (size_t j = 0; j < S.d_bases.size(); ++j) {
+            cudaSetDevice(ctx->devs[j]->id);
+            cudaFree(S.d_bases[j]);
+            if (S.d_inf[j]) cudaFree(S.d_inf[j]);
+        }
+        return wrc;
     }
     std::lock_guard<std::mutex> lock(ctx->mu);
     *out = ctx->next_handle++;
