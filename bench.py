@@ -293,7 +293,9 @@ def main():
             log2c = min(args.log2n, 20 if cores >= 8 else 18)
             v, ms_c, sample = cpu_reference_run(log2c, args.dist, 2, 1, cores)
             line["cpu_baseline"] = {"value": v, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample,
-                                    "ms_per_msm": ms_c}
+                                    "ms_per_msm": ms_c, "per_core": v / cores,
+                                    "anchor": "the reference's own traces give 0.12-0.13 Mpoints/s per vCPU for arkworks / jolt-core "
+                                              "(SURVEY.md section 6): the port is not a straw man"}
             if log2c == args.log2n:
                 # the CPU baseline doubles as a parity check of the timed MSM
                 from oracle import orc as _o
