@@ -138,7 +138,7 @@ struct cozk_ctx {
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
     long opt_stream_min_points = 1L << 23;  // host-resident single vectors this long are streamed in chunks (0 = never)
-    long opt_stream_chunks = 2;              // measured: 2 chunks give +5-7 % end to end at 2^24-2^25, 4 chunks lose it again to the merge passes
+    long opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
     long opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     long opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables
 };
