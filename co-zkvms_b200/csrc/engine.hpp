@@ -131,7 +131,7 @@ struct cozk_ctx {
     std::map<uint64_t, cozk::SrsEntry> srs;
     std::map<uint64_t, cozk::PolyEntry> polys;
     std::map<uint64_t, cozk::OpenKey> open_keys;
-    long opt_open_small_log2 = 14;   // opening levels with at most 2^this quotient values share one batched MSM (measured: 10..14 -> 19.4 .. 18.1 ms at nv = 22)
+    long opt_open_small_log2 = 15;   // opening levels with at most 2^this quotient values share one batched MSM (measured at nv = 22 / 18: 13: 17.5 ms, 14: 17.2 / 4.13, 15: 17.0 / 3.91, 16: 17.5 / 4.42, 17: 18.0)
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;
     long opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first

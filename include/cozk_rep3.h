@@ -105,7 +105,7 @@ int cozk_eq_evals(cozk_ctx* ctx, int device_index, const void* point, size_t nv,
 int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out);
 
 /* Setup-time key of the PST13 opening: the pair sums of every level (each MSM halves), with the levels that hold at most
- * 2^14 quotient scalars (option "open_small_log2") concatenated into one SRS so that ONE batched MSM opens all of them -
+ * 2^15 quotient scalars (option "open_small_log2") concatenated into one SRS so that ONE batched MSM opens all of them -
  * an MSM of a few thousand points is latency-bound, a dozen of them in a row dominate the reference's schedule.
  * level_srs[i] = ck.powers_of_g[i] (2^(nv-i) points) stay owned by the caller and must outlive the key. */
 typedef uint64_t cozk_open_key;

@@ -219,7 +219,7 @@ def test_open_resident_polynomial_with_key(cozk, ctx, orc, nv, small):
     try:
         setup = rep3.create_open_key(pst.PST13Setup(ctx, levels))
     finally:
-        ctx.set_option("open_small_log2", 14)
+        ctx.set_option("open_small_log2", 15)
     n = 1 << nv
     a, b = _rand_fr(60, n), _rand_fr(62, n)
     point = _rand_fr(61, nv)
