@@ -60,3 +60,29 @@ def test_two_rank_gather_and_combine():
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res), res
     assert all(r[2] == (2, 2, 72) for r in res)
+
+
+def test_spartan_mirror_eta_powers():
+    """co-zkvms_b200/spartan.py: the `x *= eta` sequence of aggregate_poly (co-spartan/src/utils.rs:96-102) as Montgomery
+    coefficients for the device-side linear combination."""
+    from oracle import pyref
+    from tests import helpers as H
+    sp = importlib.import_module("co-zkvms_b200.spartan")
+    eta = pyref.scalar_uniform(5, 0)
+    got = sp._fr_powers(H.fr_mont(eta), 6)
+    assert [pyref.from_mont(H.to_int(row), H.R) for row in got] == [pow(eta, j, H.R) for j in range(6)]
+    assert sp._fr_powers(H.fr_mont(0), 3).tolist() == [list(H.fr_mont(1)), list(H.fr_mont(0)), list(H.fr_mont(0))]
+
+
+def test_bench_reference_arm_line():
+    """bench.py --impl reference runs the CPU restatement only (no GPU, no engine) and prints the contract's JSON line."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--log2n", "14", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpoints/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["config"]["log2_points_per_gpu"] == 14
