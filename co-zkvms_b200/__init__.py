@@ -18,8 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # COZK_LIB: load another build of the same library (kernel experiments measured side by side with tools/sweep.py)
 LIB_PATH = os.environ.get("COZK_LIB") or os.path.join(HERE, "libcozk_msm.so")
-SOURCES = ["msm.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
-HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "rep3_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp"]
+SOURCES = ["msm.cu", "depth_kernels.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
+HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "rep3_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp",
+           "depth_kernels.hpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

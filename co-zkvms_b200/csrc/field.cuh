@@ -39,6 +39,31 @@ typedef fq fr;  // same layout, different modulus; only mul-by-one (from Montgom
 
 #if defined(__CUDA_ARCH__)
 #include "field_ptx.inc"
+#if defined(COZK_FIELD_CALLS)
+// The three multiplication forms as real functions (register ABI: arguments and result travel in registers, no stack
+// frame).  A translation unit defines COZK_FIELD_CALLS before its first include when its kernels are bound by depth on a
+// few warps and should stay small (depth_kernels.cu); everywhere else the operations expand inline.
+namespace cozk_calls {
+struct f8 {
+    uint32_t v[8];
+};
+static __device__ __noinline__ f8 mul(f8 a, f8 b) {
+    f8 r;
+    fq_mul_ptx(r.v, a.v, b.v);
+    return r;
+}
+static __device__ __noinline__ f8 sqr(f8 a) {
+    f8 r;
+    fq_sqr_ptx(r.v, a.v);
+    return r;
+}
+static __device__ __noinline__ f8 mul2(f8 a, f8 b, f8 c, f8 d) {
+    f8 r;
+    fq_mul2_ptx(r.v, a.v, b.v, c.v, d.v);
+    return r;
+}
+}  // namespace cozk_calls
+#endif
 #endif
 
 // ------------------------------------------------------------------ portable (host) bodies
@@ -154,7 +179,17 @@ inline void sub_mod(uint32_t* r, const uint32_t* a, const uint32_t* b, const uin
 // ------------------------------------------------------------------ Fq operations (fully reduced in, fully reduced out)
 COZK_HD fq fq_mul(const fq& a, const fq& b) {
     fq r;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(COZK_FIELD_CALLS)
+    cozk_calls::f8 x, y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x.v[i] = a.v[i];
+        y.v[i] = b.v[i];
+    }
+    const cozk_calls::f8 z = cozk_calls::mul(x, y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = z.v[i];
+#elif defined(__CUDA_ARCH__)
     fq_mul_ptx(r.v, a.v, b.v);
 #else
     const uint32_t mod[8] = COZK_FQ_MOD;
@@ -164,7 +199,14 @@ COZK_HD fq fq_mul(const fq& a, const fq& b) {
 }
 COZK_HD fq fq_sqr(const fq& a) {
     fq r;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(COZK_FIELD_CALLS)
+    cozk_calls::f8 x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x.v[i] = a.v[i];
+    const cozk_calls::f8 z = cozk_calls::sqr(x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = z.v[i];
+#elif defined(__CUDA_ARCH__)
     fq_sqr_ptx(r.v, a.v);
 #else
     const uint32_t mod[8] = COZK_FQ_MOD;
@@ -176,7 +218,21 @@ COZK_HD fq fq_add(const fq& a, const fq& b);
 // a*b + c*d with ONE Montgomery reduction (200 multiply-adds instead of 272); same fully reduced value as
 // fq_add(fq_mul(a, b), fq_mul(c, d)), which is what the host build computes
 COZK_HD fq fq_mul2(const fq& a, const fq& b, const fq& c, const fq& d) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(COZK_FIELD_CALLS)
+    cozk_calls::f8 x, y, z, w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x.v[i] = a.v[i];
+        y.v[i] = b.v[i];
+        z.v[i] = c.v[i];
+        w.v[i] = d.v[i];
+    }
+    const cozk_calls::f8 o = cozk_calls::mul2(x, y, z, w);
+    fq r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = o.v[i];
+    return r;
+#elif defined(__CUDA_ARCH__)
     fq r;
     fq_mul2_ptx(r.v, a.v, b.v, c.v, d.v);
     return r;

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <thread>
 
+#include "depth_kernels.hpp"
 #include "engine.hpp"
 #include "msm_kernels.cuh"
 #include "msm_plan.hpp"
@@ -40,40 +41,6 @@ template <bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
-__global__ void __launch_bounds__(128, 3) k_merge(MergeArgs A) {
-    merge_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
-}
-__global__ void __launch_bounds__(128, 3) k_group(GroupArgs A) {
-    group_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
-}
-
-// ---- block-cooperative kernels for the shallow stages.  A single thread needs ~7 us per group addition, so the stages
-// that follow level 1 are bound by DEPTH: a block of ACC_TILE threads holds one partial sum per thread in shared memory
-// (structure of arrays: word k of thread t at w[k][t], conflict-free) and combines them in log2(ACC_TILE) steps.
-struct ShPoints {
-    uint32_t w[32][ACC_TILE];
-};
-__device__ __forceinline__ void sh_store(ShPoints& s, int t, const xyzz& p) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        s.w[k][t] = p.X.v[k];
-        s.w[8 + k][t] = p.Y.v[k];
-        s.w[16 + k][t] = p.ZZ.v[k];
-        s.w[24 + k][t] = p.ZZZ.v[k];
-    }
-}
-__device__ __forceinline__ xyzz sh_load(const ShPoints& s, int t) {
-    xyzz p;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        p.X.v[k] = s.w[k][t];
-        p.Y.v[k] = s.w[8 + k][t];
-        p.ZZ.v[k] = s.w[16 + k][t];
-        p.ZZZ.v[k] = s.w[24 + k][t];
-    }
-    return p;
-}
-
 // Accumulate levels >= 2: block b owns partial slots [b*ACC_TILE, (b+1)*ACC_TILE).  Segmented inclusive scan by key
 // (keys are sorted, runs are contiguous), after which the last slot of every run holds the run's sum inside the tile.
 // Output contract = accumulate_body<false> with L = ACC_TILE run by ONE thread over the same tile (that body is the host
@@ -125,48 +92,9 @@ __global__ void __launch_bounds__(ACC_TILE) k_segscan(AccumulateArgs A) {
     if (t < 2) A.pkeys[2 * (size_t)blockIdx.x + t] = okey[t];
 }
 
-// Bucket-reduce sums: block (q, id, win) adds the groups of chunk q that belong to sum `id` of window `win`
-// (id 0: all W_g, id 1: all S_g, id 2+j: the S_g whose index has bit j set; plain = no masks, one source array).
-// Output contract = bitsum_body with f = chunk (masked) / plainsum_body with f = chunk (plain).
-struct TreeSumArgs {
-    const xyzz* s;
-    const xyzz* w;
-    xyzz* out;        // [(win*NS + id)*chunks + q]
-    uint32_t G;       // entries per (window[, id]) array
-    uint32_t NS;
-    uint32_t chunk;   // entries per block
-    uint32_t chunks;  // G / chunk
-    int masked;       // 1: sources are s / w with [win*G + e] and the bit masks; 0: source is s with [(win*NS + id)*G + e]
-};
-__global__ void __launch_bounds__(ACC_TILE) k_treesum(TreeSumArgs A) {
-    __shared__ ShPoints sp;
-    const int t = threadIdx.x;
-    // blockIdx.x = (win * NS + id) * chunks + q   (one-dimensional: windows can exceed the 65,535 limit of grid.y/z)
-    const uint32_t q = blockIdx.x % A.chunks;
-    const size_t rest = blockIdx.x / A.chunks;
-    const uint32_t id = (uint32_t)(rest % A.NS);
-    const size_t win = rest / A.NS;
-    const xyzz* src = A.masked ? ((id == 0 ? A.w : A.s) + win * A.G) : (A.s + (win * A.NS + id) * (size_t)A.G);
-    xyzz acc = xyzz_identity();
-    for (uint32_t e = q * A.chunk + t; e < (q + 1) * A.chunk; e += ACC_TILE) {
-        if (A.masked && id >= 2 && !((e >> (id - 2)) & 1u)) continue;
-        acc = xyzz_add(acc, load_xyzz(&src[e]));
-    }
-    sh_store(sp, t, acc);
-    __syncthreads();
-    for (int d = ACC_TILE / 2; d > 0; d >>= 1) {
-        if (t < d) {
-            acc = xyzz_add(acc, sh_load(sp, t + d));
-            sh_store(sp, t, acc);
-        }
-        __syncthreads();
-    }
-    if (t == 0) store_xyzz(&A.out[(win * A.NS + id) * (size_t)A.chunks + q], acc);
-}
-__global__ void __launch_bounds__(32) k_finish(FinishArgs A) {
-    finish_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
-}
-
+// The stages behind the accumulate levels (bucket merge, bucket reduce, finish) live in depth_kernels.cu: they are bound
+// by DEPTH (a chain of a few dozen group additions on a handful of warps) and are compiled with the field operations as
+// calls instead of inline expansions (see there).
 __global__ void __launch_bounds__(128) k_build_table(TableArgs A) {
     table_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
@@ -247,7 +175,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     }
     if (merge) {
         MergeArgs MA{D.buckets.as<xyzz>(), bucket_dst, P.total_buckets};
-        k_merge<<<grid_for(P.total_buckets, 128), 128, 0, st>>>(MA);
+        launch_merge(MA, grid_for(P.total_buckets, 128), st);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
     }
@@ -261,20 +189,20 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     if ((rc = D.rs[0].ensure(groups * sizeof(xyzz)))) return rc;
     if ((rc = D.rw[0].ensure(groups * sizeof(xyzz)))) return rc;
     GroupArgs GA{D.buckets.as<xyzz>(), D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), P.group_l, groups};
-    k_group<<<grid_for(groups, 64), 64, 0, st>>>(GA);
+    launch_group(GA, grid_for(groups, 64), st);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
     size_t nsums = windows * P.NS;
     if ((rc = D.rs[1].ensure(nsums * P.sum_chunks * sizeof(xyzz)))) return rc;
     if ((rc = D.rw[1].ensure(nsums * sizeof(xyzz)))) return rc;
     TreeSumArgs TA{D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.G, P.NS, P.sum_chunk, P.sum_chunks, 1};
-    k_treesum<<<(unsigned)(windows * P.NS * P.sum_chunks), ACC_TILE, 0, st>>>(TA);
+    launch_treesum(TA, (unsigned)(windows * P.NS * P.sum_chunks), st);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
     xyzz* cur = D.rs[1].as<xyzz>();
     if (P.sum_chunks > 1) {
         TreeSumArgs TB{cur, nullptr, D.rw[1].as<xyzz>(), P.sum_chunks, P.NS, P.sum_chunks, 1, 0};
-        k_treesum<<<(unsigned)(windows * P.NS), ACC_TILE, 0, st>>>(TB);
+        launch_treesum(TB, (unsigned)(windows * P.NS), st);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
         cur = D.rw[1].as<xyzz>();
@@ -289,7 +217,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         D.finish_on_host = true;
     } else {
         FinishArgs F{cur, P.g, P.Wb, P.c, P.NS, P.log_l, D.out.as<uint8_t>()};
-        k_finish<<<grid_for(P.g, 32), 32, 0, st>>>(F);
+        launch_finish(F, grid_for(P.g, 32), st);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
         D.finish_on_host = false;
