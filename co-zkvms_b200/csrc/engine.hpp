@@ -59,6 +59,11 @@ struct Device {
     DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2, pk[2], pp[2], rs[2], rw[2], out, flush;
     std::mutex open_mu;  // one PST13 opening at a time per device: it owns the four buffers below across its MSM calls
     DevBuf open_in, open_r[2], open_q, open_qs;
+    // dominant-digit analysis (msm_kernels.cuh, DomArgs): per-segment candidate digits, counters, modes, offsets, cursors
+    DevBuf dom_cand, dom_counts, dom_mode, dom_off, dom_len, dom_cursor;
+    std::vector<int32_t> h_dom_cand;
+    std::vector<uint32_t> h_dom_counts, h_dom_mode;
+    std::vector<uint64_t> h_dom_off, h_dom_len;
     cudaEvent_t ev[8] = {};
     cudaEvent_t copy_done[2] = {};
     double stats[12] = {};
@@ -73,6 +78,7 @@ struct SrsEntry {
     std::vector<uint8_t*> d_inf;     // per device, may be null
     uint32_t table_c = 0;            // window size the table rows were built for; 0 = no table
     uint32_t table_W = 1;            // rows
+    bool has_totals = false;         // entry table_W * n + w of d_bases holds the sum of row w (dominant-digit mode)
 };
 
 // A device-resident polynomial (include/cozk_rep3.h).  d_data holds `total` coefficients; the handle covers
@@ -134,6 +140,8 @@ struct cozk_ctx {
     long opt_open_small_log2 = 15;   // opening levels with at most 2^this quotient values share one batched MSM (measured at nv = 22 / 18: 13: 17.5 ms, 14: 17.2 / 4.13, 15: 17.0 / 3.91, 16: 17.5 / 4.42, 17: 18.0)
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;
+    long opt_dominant = 1;           // 1: whole-SRS calls look for windows dominated by one digit (constant co-jolt shares) and use the row totals
+    long opt_dominant_min_points = 1L << 21;  // ... when the call has at least this many (vector, point) pairs: the look costs ~35 us
     long opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)

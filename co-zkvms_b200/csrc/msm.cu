@@ -37,6 +37,8 @@ Device::~Device() {
 __global__ void __launch_bounds__(256) k_decompose(DecomposeArgs A) {
     decompose_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
+__global__ void __launch_bounds__(32) k_dom_cand(DomArgs A) { dom_cand_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+__global__ void __launch_bounds__(256) k_dom_count(DomArgs A) { dom_count_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 template <bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
@@ -105,7 +107,8 @@ static inline unsigned grid_for(size_t threads, unsigned block) { return (unsign
 // Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
 static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
                      const uint8_t* const* d_vec_ptrs, size_t vector_stride, size_t stride, int form, size_t table_stride,
-                     size_t val_offset, double* launches, int phases = 3, bool merge = false) {
+                     size_t val_offset, double* launches, int phases = 3, bool merge = false, const DecomposeArgs* dom = nullptr) {
+    // dom: dominant-digit layout of this group (only its dom_* / seg_* / totals_index fields are read), or null
     // phases: bit 0 = decompose + sort + accumulate into the buckets, bit 1 = bucket reduce + finish.  A streamed MSM
     // (one vector fed in point chunks while the next chunk is still on the PCIe bus) runs bit 0 once per chunk, with
     // merge = true from the second chunk on, and bit 1 once at the end.
@@ -123,6 +126,14 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     // 1 decompose
     DecomposeArgs DA{d_scalars, d_vec_ptrs, vector_stride, stride, form, P.n, P.g, P.c, P.W, d_inf,
                      D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>(), P.Wb, table_stride, val_offset};
+    if (dom) {
+        DA.dom_mode = dom->dom_mode;
+        DA.dom_cand = dom->dom_cand;
+        DA.seg_off = dom->seg_off;
+        DA.seg_cursor = dom->seg_cursor;
+        DA.seg_len = dom->seg_len;
+        DA.totals_index = dom->totals_index;
+    }
     k_decompose<<<grid_for((size_t)P.g * P.n, 256), 256, 0, st>>>(DA);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
@@ -240,6 +251,59 @@ static void host_sum(const uint8_t* pts, size_t count, uint8_t* out) {
 }
 
 constexpr size_t MAX_POINTS_PER_PASS = (size_t)1 << 26;
+
+// Dominant-digit analysis of one group (scalars already on the device): candidate digits from every vector's first
+// scalar, a look at the first 1024 scalars of every vector, and - only if that sample shows a dominated window - the full
+// count.  Fills `dom` and shrinks the plan's pair count when at least one segment is special; returns false otherwise.
+static int analyse_dominant(Device& D, MsmPlan& P, const uint8_t* d_scalars, const uint8_t* const* d_vec_ptrs, size_t vector_stride,
+                            size_t stride, int form, size_t totals_index, DecomposeArgs* dom, bool* use, double* launches) {
+    *use = false;
+    const size_t segs = (size_t)P.g * P.W;
+    int rc;
+    if ((rc = D.dom_cand.ensure(segs * 4))) return rc;
+    if ((rc = D.dom_counts.ensure(2 * segs * 4))) return rc;
+    DomArgs A{{d_scalars, d_vec_ptrs, vector_stride, stride, form, P.n, P.g, P.c, P.W, nullptr, nullptr, nullptr, P.Wb, 0, 0},
+              D.dom_cand.as<int32_t>(), D.dom_counts.as<uint32_t>(), D.dom_counts.as<uint32_t>() + segs, 0};
+    cudaStream_t st = D.stream;
+    k_dom_cand<<<grid_for(P.g, 32), 32, 0, st>>>(A);
+    COZK_CUDA(cudaGetLastError());
+    D.h_dom_cand.resize(segs);
+    D.h_dom_counts.resize(2 * segs);
+    const size_t sample = std::min<size_t>(P.n, 1024);
+    for (int round = 0; round < 2; ++round) {
+        A.count_n = round == 0 ? sample : P.n;
+        COZK_CUDA(cudaMemsetAsync(D.dom_counts.p, 0, 2 * segs * 4, st));
+        k_dom_count<<<grid_for((size_t)P.g * A.count_n, 256), 256, 0, st>>>(A);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+        COZK_CUDA(cudaMemcpyAsync(D.h_dom_counts.data(), D.dom_counts.p, 2 * segs * 4, cudaMemcpyDeviceToHost, st));
+        if (round == 0) COZK_CUDA(cudaMemcpyAsync(D.h_dom_cand.data(), D.dom_cand.p, segs * 4, cudaMemcpyDeviceToHost, st));
+        COZK_CUDA(cudaStreamSynchronize(st));
+        size_t m = dom_layout(D.h_dom_cand.data(), D.h_dom_counts.data(), D.h_dom_counts.data() + segs, segs, A.count_n, D.h_dom_mode,
+                              D.h_dom_off, D.h_dom_len);
+        if (m == 0) return COZK_OK;            // nothing dominated (in the sample, or in the whole vectors)
+        if (A.count_n == P.n) {
+            plan_set_pairs(P, m);
+            break;
+        }
+    }
+    if ((rc = D.dom_mode.ensure(segs * 4))) return rc;
+    if ((rc = D.dom_off.ensure(segs * 8))) return rc;
+    if ((rc = D.dom_len.ensure(segs * 8))) return rc;
+    if ((rc = D.dom_cursor.ensure(segs * 4))) return rc;
+    COZK_CUDA(cudaMemcpyAsync(D.dom_mode.p, D.h_dom_mode.data(), segs * 4, cudaMemcpyHostToDevice, st));
+    COZK_CUDA(cudaMemcpyAsync(D.dom_off.p, D.h_dom_off.data(), segs * 8, cudaMemcpyHostToDevice, st));
+    COZK_CUDA(cudaMemcpyAsync(D.dom_len.p, D.h_dom_len.data(), segs * 8, cudaMemcpyHostToDevice, st));
+    COZK_CUDA(cudaMemsetAsync(D.dom_cursor.p, 0, segs * 4, st));
+    dom->dom_mode = D.dom_mode.as<uint32_t>();
+    dom->dom_cand = D.dom_cand.as<int32_t>();
+    dom->seg_off = D.dom_off.as<uint64_t>();
+    dom->seg_cursor = D.dom_cursor.as<uint32_t>();
+    dom->seg_len = D.dom_len.as<uint64_t>();
+    dom->totals_index = totals_index;
+    *use = true;
+    return COZK_OK;
+}
 
 // All k vectors over bases [offset, offset+n) on ONE device.  host_scalars xor dev_scalars.
 static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t offset, size_t n,
@@ -369,8 +433,6 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             size_t v0 = gi * gmax, g = std::min(gmax, k - v0);
             int slot = (int)(gi & 1);
             MsmPlan P = make_plan(pn, (uint32_t)g, bits, max_buckets, (uint32_t)ctx->opt_window, table_c);
-            plan_mults += P.field_mults();
-            plan_pairs += (double)P.m;
             last_c = P.c;
             last_W = P.W;
             COZK_CUDA(cudaStreamWaitEvent(D.stream, D.copy_done[slot], 0));
@@ -378,9 +440,19 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                 // the other staging slot was last read by group gi-1, which has been synchronised below
                 if ((rc = stage(gi + 1))) return rc;
             }
-            rc = run_group(D, P, d_bases, d_inf, host_scalars ? D.scalars[slot].as<uint8_t>() : nullptr,
-                           host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096, vstride, stride, form,
-                           table_stride, val_offset, &launches);
+            const uint8_t* g_scalars = host_scalars ? D.scalars[slot].as<uint8_t>() : nullptr;
+            const uint8_t* const* g_ptrs = host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096;
+            DecomposeArgs dom = {};
+            bool use_dom = false;
+            if (ctx->opt_dominant && S.has_totals && !d_inf && passes == 1 && offset == 0 && pn == S.n &&
+                (double)g * (double)pn >= (double)ctx->opt_dominant_min_points) {
+                rc = analyse_dominant(D, P, g_scalars, g_ptrs, vstride, stride, form, (size_t)S.table_W * S.n, &dom, &use_dom, &launches);
+                if (rc) return rc;
+            }
+            plan_mults += P.field_mults();  // after the analysis: the statistics report the pairs really made
+            plan_pairs += (double)P.m;
+            rc = run_group(D, P, d_bases, d_inf, g_scalars, g_ptrs, vstride, stride, form, table_stride, val_offset, &launches, 3,
+                           false, use_dom ? &dom : nullptr);
             if (rc) return rc;
             if (!D.finish_on_host)
                 COZK_CUDA(cudaMemcpyAsync(pass_out + v0 * 72, D.out.p, g * 72, cudaMemcpyDeviceToHost, D.stream));
@@ -557,6 +629,52 @@ static int srs_wait_tables(cozk_ctx* ctx, size_t n_devices) {
     return COZK_OK;
 }
 
+// The sum of every table row, stored behind the table (entry table_W * n + w): what the dominant-digit mode of the
+// decompose pass needs (msm_kernels.cuh).  Each sum is an n-point MSM whose scalars are all 1 - one window, one bucket - run
+// through the engine's own pipeline on a view of the row.  Setup-time work (2^20 points, 15 rows: ~15 ms).
+static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
+    S.has_totals = false;
+    if (S.n < 1024) return COZK_OK;
+    for (uint8_t* f : S.d_inf)
+        if (f) return COZK_OK;  // bases at infinity: the totals would have to leave them out; not worth a second code path
+    const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    bool ok = true;
+    for (size_t di = 0; di < S.d_bases.size() && ok; ++di) {
+        Device& D = *ctx->devs[di];
+        uint32_t* d_one = nullptr;
+        COZK_CUDA(cudaSetDevice(D.id));
+        COZK_CUDA(cudaMalloc(&d_one, 32));
+        cudaError_t e = cudaMemcpy(d_one, one, 32, cudaMemcpyHostToDevice);
+        int rc = e == cudaSuccess ? COZK_OK : COZK_ERR_CUDA;
+        for (uint32_t r = 0; r < S.table_W && ok && !rc; ++r) {
+            SrsEntry V;
+            V.n = S.n;
+            V.d_bases.assign(S.d_bases.size(), nullptr);
+            V.d_inf.assign(S.d_bases.size(), nullptr);
+            V.d_bases[di] = S.d_bases[di] + (size_t)r * S.n;
+            const void* ptr = d_one;
+            uint8_t out[72];
+            rc = run_on_device(ctx, (int)di, V, 0, S.n, nullptr, &ptr, 1, 0, COZK_CANON, 1, out);
+            if (rc) break;
+            if (out[64]) {
+                ok = false;  // a row that sums to the identity has no affine form: keep the plain path for this SRS
+                break;
+            }
+            COZK_CUDA(cudaSetDevice(D.id));
+            e = cudaMemcpy(S.d_bases[di] + (size_t)S.table_W * S.n + r, out, 64, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = COZK_ERR_CUDA;
+        }
+        cudaSetDevice(D.id);
+        cudaFree(d_one);
+        if (rc) {
+            if (rc == COZK_ERR_CUDA) set_error("SRS registration: row totals failed");
+            return rc;
+        }
+    }
+    S.has_totals = ok;
+    return COZK_OK;
+}
+
 // Bases (and optional infinity flags) that already live on one device of the context: copied device-to-device, every
 // other device gets a peer copy; the precomputed table is built on each.
 int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out) {
@@ -588,7 +706,7 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
         affine* d = nullptr;
         uint8_t* dinf = nullptr;
         cudaError_t e = cudaSetDevice(D.id);
-        if (e == cudaSuccess) e = cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine));
+        if (e == cudaSuccess) e = cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + S.table_W) * sizeof(affine));
         // on the destination device's own stream and synchronised there: nothing in this library relies on the legacy
         // default stream, which its non-blocking streams do not wait for (the source is complete: callers synchronise)
         if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine), D.stream);
@@ -612,6 +730,7 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
         S.d_inf.push_back(dinf);
     }
     int wrc = srs_wait_tables(ctx, S.d_bases.size());
+    if (!wrc) wrc = srs_compute_totals(ctx, S);
     if (wrc) {
         undo();
         return wrc;
@@ -719,7 +838,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         COZK_CUDA(cudaSetDevice(D->id));
         affine* d = nullptr;
         uint8_t* di = nullptr;
-        COZK_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * S.table_W * sizeof(affine)));
+        COZK_CUDA(cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + S.table_W) * sizeof(affine)));
         // Copies go through the engine's own stream and are synchronised there.  A plain cudaMemcpy from pageable memory
         // returns once the data is STAGED - its DMA runs on the legacy default stream, which the engine's non-blocking
         // streams do not wait for, so the table build could read row 0 before the tail of the copy had landed.
@@ -747,6 +866,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         }
     }
     int wrc = srs_wait_tables(ctx, S.d_bases.size());
+    if (!wrc) wrc = srs_compute_totals(ctx, S);
     if (wrc) {
         for (size_t j = 0; j < S.d_bases.size(); ++j) {
             cudaSetDevice(ctx->devs[j]->id);
@@ -840,6 +960,13 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // pairs per thread at level 1 of the accumulate stage: 0 = choose per call (fill the last wave of threads)
         if (value != 0 && (value < 4 || value > 256)) return COZK_ERR_INVALID_ARG;
         g_acc_force_l = (int)value;
+    } else if (!strcmp(name, "dominant")) {
+        // 1: whole-SRS calls look for windows dominated by one digit and use the row totals; 0: always the plain layout
+        if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;
+        ctx->opt_dominant = value;
+    } else if (!strcmp(name, "dominant_min_points")) {
+        if (value < 0) return COZK_ERR_INVALID_ARG;
+        ctx->opt_dominant_min_points = value;
     } else if (!strcmp(name, "peer_direct")) {
         // multi-device linear combination: 1 = the summing kernel reads remote partials over peer mappings, 0 = staged copies
         if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;

@@ -95,6 +95,21 @@ struct DecomposeArgs {
     uint32_t bucket_windows;   // W normally, 1 in table mode
     size_t table_stride;       // points per table row (the registered SRS length), 0 = no table
     size_t val_offset;         // base_offset of this call inside a table row (0 without table: bases are pre-offset)
+    // Dominant-digit mode (dom_mode != null; the call covers the WHOLE registered SRS, which carries the sum of every table
+    // row).  Real co-jolt shares are constant or nearly constant vectors: in most windows nearly every
+    // scalar has the SAME digit c.  With S = sum_i T_w[i] precomputed,
+    //     sum_i d_i T_w[i] = sum_{i: d_i != c} d_i T_w[i]  +  c * (S - sum_{i: d_i != c} T_w[i]),
+    // so a window whose dominant digit covers a fraction f of the scalars needs 2 (1 - f) n + 1 pairs instead of n: every
+    // other scalar contributes its own pair plus one pair that takes its point OUT of bucket |c|, and one pair puts S in.
+    // Segment (v, w) of the pair list starts at seg_off[v*W + w]; its mode is 0 (as above: pair i at offset i), 1 (dominant
+    // digit dom_cand[v*W + w] != 0) or 2 (zero digits dropped, nothing to compensate); slots of modes 1 / 2 come from the
+    // cursor seg_cursor[v*W + w].
+    const uint32_t* dom_mode;
+    const int32_t* dom_cand;
+    const uint64_t* seg_off;
+    uint32_t* seg_cursor;
+    const uint64_t* seg_len;   // pairs of the segment (mode 1: its last pair is the total S)
+    size_t totals_index;       // index (into the base table) of the total of table row 0; row w: + w (table mode)
 };
 
 // bits [off, off+c) of a 256-bit little-endian integer, c <= 24
@@ -106,33 +121,142 @@ COZK_HD uint32_t extract_bits(const fr& s, uint32_t off, uint32_t c) {
     return (uint32_t)x & ((1u << c) - 1u);
 }
 
+// window w of a canonical scalar as a signed digit: magnitude in [0, B], sign, carry into the next window
+COZK_HD uint32_t signed_digit(const fr& s, uint32_t w, uint32_t c, uint32_t& carry, uint32_t& neg) {
+    const uint32_t B = 1u << (c - 1);
+    uint32_t d = extract_bits(s, w * c, c) + carry;
+    neg = 0;
+    carry = 0;
+    if (d > B) {  // digit in [-B+1, B]; the top window never carries because W*c >= bits + 1
+        d = (1u << c) - d;
+        neg = VAL_NEG;
+        carry = 1;
+    }
+    return d;
+}
+COZK_HD fr decompose_load(size_t tid, const DecomposeArgs& A, uint32_t& v, size_t& i) {
+    v = (uint32_t)(tid / A.n);
+    i = tid - (size_t)v * A.n;
+    const uint8_t* vec = A.vec_ptrs ? A.vec_ptrs[v] : A.scalars + (size_t)v * A.vector_stride;
+    fr s = load_fq(vec + i * A.stride);
+    return A.form == SCALAR_MONT ? fr_from_mont(s) : fr_reduce_canon(s);
+}
+// one slot counter per segment; on the device the lanes of a warp that ask for the same counter share one atomic
+COZK_HD uint32_t seg_take(uint32_t* cursor, uint32_t seg, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    const unsigned peers = __match_any_sync(__activemask(), seg);
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == (unsigned)leader) base = atomicAdd(&cursor[seg], n * (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + n * (uint32_t)__popc(peers & ((1u << lane) - 1u));
+#else
+    uint32_t base = cursor[seg];
+    cursor[seg] += n;
+    return base;
+#endif
+}
+
 // thread tid = v*n + i
 COZK_HD void decompose_body(size_t tid, const DecomposeArgs& A) {
     if (tid >= (size_t)A.g * A.n) return;
-    uint32_t v = (uint32_t)(tid / A.n);
-    size_t i = tid - (size_t)v * A.n;
-    const uint8_t* vec = A.vec_ptrs ? A.vec_ptrs[v] : A.scalars + (size_t)v * A.vector_stride;
-    fr s = load_fq(vec + i * A.stride);
-    if (A.form == SCALAR_MONT) s = fr_from_mont(s); else s = fr_reduce_canon(s);
+    uint32_t v;
+    size_t i;
+    const fr s = decompose_load(tid, A, v, i);
     bool skip = A.infinity && A.infinity[i];
     const uint32_t B = 1u << (A.c - 1);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < A.W; ++w) {
-        uint32_t d = extract_bits(s, w * A.c, A.c) + carry;
-        uint32_t neg = 0;
-        carry = 0;
-        if (d > B) {  // digit in [-B+1, B]; the top window never carries because W*c >= bits + 1
-            d = (1u << A.c) - d;
-            neg = VAL_NEG;
-            carry = 1;
-        }
-        size_t o = ((size_t)v * A.W + w) * A.n + i;
+        uint32_t neg;
+        const uint32_t d = signed_digit(s, w, A.c, carry, neg);
         // A zero digit keeps a valid key (bucket 0 of its window) and is marked in val instead: the sort then needs no
         // extra key bit for a sentinel, which saves a whole radix pass when the bucket index is a multiple of 8 bits.
-        bool zero = (d == 0) || skip;
-        uint32_t bw = A.table_stride ? 0u : w;
-        A.keys[o] = (v * A.bucket_windows + bw) * B + (zero ? 0u : d - 1);
-        A.vals[o] = zero ? VAL_SKIP : ((uint32_t)((size_t)w * A.table_stride + A.val_offset + i) | neg);
+        const bool zero = (d == 0) || skip;
+        const uint32_t bw = A.table_stride ? 0u : w;
+        const uint32_t key0 = (v * A.bucket_windows + bw) * B;
+        const uint32_t point = (uint32_t)((size_t)w * A.table_stride + A.val_offset + i);
+        const uint32_t key = key0 + (zero ? 0u : d - 1);
+        const uint32_t val = zero ? VAL_SKIP : (point | neg);
+        const uint32_t seg = v * A.W + w;
+        const uint32_t mode = A.dom_mode ? A.dom_mode[seg] : 0u;
+        if (mode == 0) {
+            const size_t o = (A.dom_mode ? (size_t)A.seg_off[seg] : (size_t)seg * A.n) + i;
+            A.keys[o] = key;
+            A.vals[o] = val;
+        } else if (mode == 2) {  // zero digits are the dominant ones: they simply do not appear
+            if (zero) continue;
+            const size_t o = (size_t)A.seg_off[seg] + seg_take(A.seg_cursor, seg, 1);
+            A.keys[o] = key;
+            A.vals[o] = val;
+        } else {
+            const int32_t cand = A.dom_cand[seg];
+            const uint32_t cmag = (uint32_t)(cand < 0 ? -cand : cand), cneg = cand < 0 ? VAL_NEG : 0u;
+            if (i == 0) {  // the total of the row enters bucket |c| with the sign of c
+                const size_t o = (size_t)A.seg_off[seg] + (size_t)A.seg_len[seg] - 1;
+                A.keys[o] = key0 + cmag - 1;
+                A.vals[o] = (uint32_t)(A.totals_index + (A.table_stride ? w : 0u)) | cneg;
+            }
+            if (!zero && d == cmag && neg == cneg) continue;  // the dominant digit: covered by the total
+            const size_t o = (size_t)A.seg_off[seg] + seg_take(A.seg_cursor, seg, 2);
+            A.keys[o] = key;
+            A.vals[o] = val;
+            A.keys[o + 1] = key0 + cmag - 1;  // and its point leaves bucket |c|: opposite sign of c
+            A.vals[o + 1] = point | (cneg ^ VAL_NEG);
+        }
+    }
+}
+
+// Dominant-digit analysis.  Candidate per (vector, window): the digit of the vector's FIRST scalar (for a constant or
+// nearly constant share that is the dominant one); then one pass counts, per segment, the scalars with that digit and
+// the scalars with a zero digit.  The host turns the counts into modes and segment offsets.
+struct DomArgs {
+    DecomposeArgs D;       // scalars, form, n, g, c, W as for the decompose pass
+    int32_t* cand;         // [g*W] signed digit of element 0
+    uint32_t* count_cand;  // [g*W]
+    uint32_t* count_zero;  // [g*W]
+    size_t count_n;        // scalars per vector the counting pass looks at; 0 = n.  A sample (count_n < n) is taken half
+                           // from the head and half from the tail of the vector: polynomials are zero-padded at the end
+};
+// thread v
+COZK_HD void dom_cand_body(size_t v, const DomArgs& A) {
+    if (v >= A.D.g) return;
+    uint32_t vv;
+    size_t i;
+    const fr s = decompose_load(v * A.D.n, A.D, vv, i);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < A.D.W; ++w) {
+        uint32_t neg;
+        const uint32_t d = signed_digit(s, w, A.D.c, carry, neg);
+        A.cand[v * A.D.W + w] = neg ? -(int32_t)d : (int32_t)d;
+    }
+}
+COZK_HD void dom_bump(uint32_t* counter, uint32_t seg, bool hit) {
+#if defined(__CUDA_ARCH__)
+    // lanes of one warp nearly always belong to one vector: count per distinct segment with one atomic each
+    const unsigned peers = __match_any_sync(__activemask(), seg);
+    const unsigned hits = __ballot_sync(peers, hit) & peers;
+    if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1) && hits) atomicAdd(&counter[seg], (uint32_t)__popc(hits));
+#else
+    if (hit) counter[seg] += 1;
+#endif
+}
+// thread tid = v*n + i
+COZK_HD void dom_count_body(size_t tid, const DomArgs& A) {
+    const size_t cn = A.count_n ? A.count_n : A.D.n;
+    if (tid >= (size_t)A.D.g * cn) return;
+    uint32_t v = (uint32_t)(tid / cn);
+    size_t i = tid - (size_t)v * cn;
+    if (cn < A.D.n && i >= cn / 2) i += A.D.n - cn;
+    const fr s = decompose_load((size_t)v * A.D.n + i, A.D, v, i);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < A.D.W; ++w) {
+        uint32_t neg;
+        const uint32_t d = signed_digit(s, w, A.D.c, carry, neg);
+        const uint32_t seg = v * A.D.W + w;
+        const int32_t sd = neg ? -(int32_t)d : (int32_t)d;
+        dom_bump(A.count_cand, seg, sd == A.cand[seg]);
+        dom_bump(A.count_zero, seg, d == 0);
     }
 }
 

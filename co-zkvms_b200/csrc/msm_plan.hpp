@@ -123,21 +123,11 @@ inline uint32_t choose_table_window(size_t n) {
     return best;
 }
 
-// table_c != 0: use the SRS's precomputed table (window size fixed at registration, one bucket set per vector)
-inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0, uint32_t table_c = 0) {
-    MsmPlan p;
-    p.n = n;
-    p.g = g;
-    p.bits = bits == 0 || bits > 254 ? 254 : bits;
-    p.c = table_c ? table_c : (force_c ? force_c : choose_window(n, g, p.bits, max_buckets));
-    p.W = windows_for(p.bits, p.c);
-    p.Wb = table_c ? 1 : p.W;
-    p.B = 1u << (p.c - 1);
-    p.m = (size_t)g * p.W * n;
-    p.total_buckets = (size_t)g * p.Wb * p.B;
-    uint32_t sb = 1;
-    while (((uint64_t)1 << sb) < (uint64_t)p.total_buckets) ++sb;  // keys are < total_buckets (no sentinel at level 1)
-    p.sort_bits = sb;
+// level structure of the accumulate stage for m (key, val) pairs (m = g*W*n, or fewer in dominant-digit mode)
+inline void plan_set_pairs(MsmPlan& p, size_t m) {
+    p.m = m;
+    p.acc_entries.clear();
+    p.acc_tile.clear();
     size_t e = p.m;
     p.acc_entries.push_back(e);
     // Level 1: one thread per l1 pairs (ACC_L; shorter for an MSM too small to fill the device).  Levels >= 2 reduce the partial slots: big levels with the same serial body
@@ -153,6 +143,51 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
         p.acc_tile.push_back(tile);
         t = (e + tile - 1) / tile;
     }
+}
+
+// Dominant-digit layout (msm_kernels.cuh, DecomposeArgs): from the per-segment counts of the analysis pass to modes, segment
+// offsets and lengths.  A non-zero dominant digit pays off only when nearly every scalar has it (every other scalar costs
+// two pairs): 90 %.  Dropping zero digits always pays; it is worth a compacted segment from 25 % on.  Returns the total
+// number of pairs, or 0 when no segment is dominant (the caller then keeps the plain layout).
+inline size_t dom_layout(const int32_t* cand, const uint32_t* count_cand, const uint32_t* count_zero, size_t segments, size_t n,
+                         std::vector<uint32_t>& mode, std::vector<uint64_t>& seg_off, std::vector<uint64_t>& seg_len) {
+    mode.assign(segments, 0);
+    seg_off.assign(segments, 0);
+    seg_len.assign(segments, 0);
+    size_t total = 0, special = 0;
+    for (size_t sgm = 0; sgm < segments; ++sgm) {
+        size_t len = n;
+        if (cand[sgm] != 0 && (double)count_cand[sgm] >= 0.9 * (double)n) {
+            mode[sgm] = 1;
+            len = 2 * (n - count_cand[sgm]) + 1;
+        } else if ((double)count_zero[sgm] >= 0.25 * (double)n) {
+            mode[sgm] = 2;
+            len = n - count_zero[sgm];
+        }
+        special += mode[sgm] != 0;
+        seg_off[sgm] = total;
+        seg_len[sgm] = len;
+        total += len;
+    }
+    return special ? total : 0;
+}
+
+// table_c != 0: use the SRS's precomputed table (window size fixed at registration, one bucket set per vector)
+inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0, uint32_t table_c = 0) {
+    MsmPlan p;
+    p.n = n;
+    p.g = g;
+    p.bits = bits == 0 || bits > 254 ? 254 : bits;
+    p.c = table_c ? table_c : (force_c ? force_c : choose_window(n, g, p.bits, max_buckets));
+    p.W = windows_for(p.bits, p.c);
+    p.Wb = table_c ? 1 : p.W;
+    p.B = 1u << (p.c - 1);
+    p.m = (size_t)g * p.W * n;
+    p.total_buckets = (size_t)g * p.Wb * p.B;
+    uint32_t sb = 1;
+    while (((uint64_t)1 << sb) < (uint64_t)p.total_buckets) ++sb;  // keys are < total_buckets (no sentinel at level 1)
+    p.sort_bits = sb;
+    plan_set_pairs(p, p.m);
     // few buckets: shallow groups (depth is what costs); millions of buckets: the stage is throughput bound and the
     // NS masked sums per group dominate, so make groups larger
     uint32_t gl = p.total_buckets <= ((size_t)1 << 20) ? GROUP_L : (p.total_buckets <= ((size_t)1 << 22) ? 2 * GROUP_L : 4 * GROUP_L);

@@ -23,6 +23,8 @@ def lib():
         L = ctypes.CDLL(LIB)
         vp, sz, u32, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
         L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp, u32, sz, sz, u32]
+        L.emul_set_dominant.argtypes = [ci]
+        L.emul_set_dominant.restype = None
         L.emul_set_acc_chunk.argtypes = [sz, ci]
         L.emul_set_acc_chunk.restype = None
         L.emul_field_op.argtypes = [ci, vp, vp, vp, sz]
@@ -43,6 +45,12 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+def set_dominant(on):
+    """1: calls that cover the whole SRS go through the engine's dominant-digit path (analysis pass, compacted segments,
+    row totals); 0: the plain pair layout."""
+    lib().emul_set_dominant(1 if on else 0)
+
+
 def set_acc_chunk(resident=0, force_l=0):
     """Level-1 chunk length of the accumulate stage: `resident` threads per wave (the plan then picks the length that
     fills the last wave, as the engine does with SMs x 512), or a fixed `force_l`; (0, 0) = the default of 32."""
@@ -58,7 +66,7 @@ def msm(bases, scalars, form=0, g=1, bits=0, c=0, stride=32, infinity=None, tabl
     srs_n = bases.shape[0]
     n = srs_n if n is None else n
     out = np.zeros((g, 72), np.uint8)
-    st = np.zeros(4, np.uint32)
+    st = np.zeros(6, np.uint32)  # window, windows, accumulate levels, sum chunks, pairs, dominant-digit path taken
     inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
     rc = lib().emul_msm(_p(bases), n, _p(scalars), n * stride, stride, form, g, bits, c, _p(inf), _p(out), _p(st),
                         table_c, srs_n, base_offset, stream_chunks)

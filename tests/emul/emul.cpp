@@ -18,7 +18,12 @@
 
 using namespace cozk;
 
+static uint32_t g_last_pairs = 0, g_last_dominant = 0;  // of the last chunk of the last emul_msm call (stats[4], stats[5])
+static int g_dominant = 0;  // 1: run the dominant-digit path of the engine (whole-SRS calls)
+
 extern "C" {
+
+void emul_set_dominant(int on) { g_dominant = on; }
 
 // level-1 chunk length of the accumulate stage: resident != 0 lets the plan choose it as the engine does (wave filling),
 // force_l != 0 fixes it
@@ -62,10 +67,68 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     for (size_t ci = 0; ci < chunks; ++ci) {
         size_t clo = ci * cn_max, cn = std::min(cn_max, n - clo);
         MsmPlan Pc = chunks == 1 ? P : make_plan(cn, g, max_bits, (size_t)1 << 24, P.c, table_c);
+        // dominant-digit mode: the call must cover the whole SRS in one piece; the sums of the table rows sit behind the
+        // table (the engine computes them at registration), the analysis pass picks the segments that use them
+        std::vector<affine> with_totals;
+        std::vector<uint32_t> dmode, cursor;
+        std::vector<uint64_t> doff, dlen;
+        std::vector<int32_t> cand;
+        bool dom = false;
+        size_t totals_index = 0;
+        if (g_dominant && chunks == 1 && !infinity && n == srs_n && base_offset == 0) {
+            const size_t rows = table_c ? windows_for(254, table_c) : 1;
+            with_totals.assign(base_ptr, base_ptr + rows * srs_n);
+            bool ok = true;
+            for (size_t r = 0; r < rows && ok; ++r) {
+                xyzz t = xyzz_identity();
+                for (size_t i = 0; i < srs_n; ++i) t = xyzz_madd(t, base_ptr[r * srs_n + i]);
+                uint8_t wire[72];
+                xyzz_to_wire(t, wire);
+                ok = wire[64] == 0;
+                affine a;
+                memcpy(&a, wire, 64);
+                with_totals.push_back(a);
+            }
+            if (ok) {
+                const size_t segs = (size_t)g * Pc.W;
+                cand.assign(segs, 0);
+                std::vector<uint32_t> cc(segs, 0), cz(segs, 0);
+                DomArgs DA{{scalars, nullptr, vector_stride, stride, form, cn, g, Pc.c, Pc.W, nullptr, nullptr, nullptr, Pc.Wb,
+                            table_c ? srs_n : 0, 0},
+                           cand.data(), cc.data(), cz.data()};
+                for (size_t v = 0; v < g; ++v) dom_cand_body(v, DA);
+                // as the engine: a sample (head and tail of every vector) first, the full count only if it shows something
+                size_t m = 0;
+                for (int round = 0; round < 2; ++round) {
+                    DA.count_n = round == 0 ? std::min<size_t>(cn, 64) : cn;
+                    std::fill(cc.begin(), cc.end(), 0u);
+                    std::fill(cz.begin(), cz.end(), 0u);
+                    for (size_t t = 0; t < (size_t)g * DA.count_n; ++t) dom_count_body(t, DA);
+                    m = dom_layout(cand.data(), cc.data(), cz.data(), segs, DA.count_n, dmode, doff, dlen);
+                    if (m == 0) break;
+                }
+                if (m) {
+                    dom = true;
+                    plan_set_pairs(Pc, m);
+                    cursor.assign(segs, 0);
+                    totals_index = rows * srs_n;
+                }
+            }
+        }
+        g_last_pairs = (uint32_t)Pc.m;
+        g_last_dominant = dom ? 1 : 0;
         std::vector<uint32_t> keys(Pc.m), vals(Pc.m);
         DecomposeArgs D{scalars + clo * stride, nullptr, vector_stride, stride, form, cn, g, Pc.c, Pc.W,
                         infinity ? infinity + clo : nullptr, keys.data(), vals.data(),
                         Pc.Wb, table_c ? srs_n : 0, table_c ? base_offset + clo : 0};
+        if (dom) {
+            D.dom_mode = dmode.data();
+            D.dom_cand = cand.data();
+            D.seg_off = doff.data();
+            D.seg_cursor = cursor.data();
+            D.seg_len = dlen.data();
+            D.totals_index = totals_index;
+        }
         for (size_t t = 0; t < (size_t)g * cn; ++t) decompose_body(t, D);
         std::vector<size_t> order(Pc.m);
         std::iota(order.begin(), order.end(), (size_t)0);
@@ -76,7 +139,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             sk[i] = keys[order[i]];
             sv[i] = vals[order[i]];
         }
-        const affine* chunk_bases = table_c ? base_ptr : base_ptr + clo;
+        const affine* chunk_bases = dom ? with_totals.data() : (table_c ? base_ptr : base_ptr + clo);
         std::vector<xyzz> scratch;
         if (ci > 0) {
             scratch.resize(P.total_buckets);
@@ -132,6 +195,8 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         stats[1] = P.W;
         stats[2] = (uint32_t)P.acc_entries.size();
         stats[3] = P.sum_chunks;
+        stats[4] = g_last_pairs;
+        stats[5] = g_last_dominant;
     }
     return 0;
 }

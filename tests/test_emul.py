@@ -103,6 +103,40 @@ def test_accumulate_chunk_lengths(orc):
         emul.set_acc_chunk(0, 0)
 
 
+@pytest.mark.parametrize("dist", ["const", "wminus", "zero_half", "uniform", "dup", "small16"])
+def test_dominant_digit_path(orc, dist):
+    """Windows in which (nearly) every scalar has the same digit - the real co-jolt share shapes - run as
+    sum_{d_i != c} d_i T_i + c (S - sum_{d_i != c} T_i) with the row total S precomputed; zero-dominated windows drop
+    their zero digits.  Same point as the plain layout and the oracle, with the table and with per-window buckets, for a
+    batch, and for vectors in which a few scalars break the pattern."""
+    n = 600
+    bases = orc.gen_bases(5, n)
+    sc = orc.gen_scalars(dist, 50, n)
+    broken = sc.copy()
+    broken[7] = orc.gen_scalars("uniform", 51, 1)[0]      # one scalar off the pattern
+    broken[n - 1] = 0
+    vecs = [sc, broken, orc.gen_scalars("const", 52, n)]
+    want = [orc.msm(bases, v) for v in vecs]
+    try:
+        emul.set_dominant(True)
+        for kw in ({"c": 6}, {"table_c": 7}, {"table_c": 11}, {"c": 13}):
+            for v, w in zip(vecs, want):
+                got, st = emul.msm(bases, v, **kw)
+                assert (got[0] == w).all(), (dist, kw)
+            assert st[5] == 1 and st[4] <= st[1] + 1      # the constant vector: one pair (the row total) per window
+            got, _ = emul.msm(bases, np.concatenate(vecs), g=3, **kw)
+            assert all((got[j] == want[j]).all() for j in range(3)), (dist, kw, "batch")
+        # element 0 itself off the pattern: the candidate is not the dominant digit, the result is still right
+        odd = sc.copy()
+        odd[0] = orc.gen_scalars("uniform", 53, 1)[0]
+        got, _ = emul.msm(bases, odd, table_c=9)
+        assert (got[0] == orc.msm(bases, odd)).all()
+        got, st = emul.msm(bases, orc.gen_scalars("uniform", 54, n), table_c=9)
+        assert st[5] == 0 and st[4] == st[1] * n          # uniform scalars: nothing dominant, the plain layout
+    finally:
+        emul.set_dominant(False)
+
+
 def test_degenerate_many_levels(orc):
     """All points in one bucket per window (co-jolt party 0/1 shares): the open-run / partial-merge path, 3 levels deep."""
     n = 20000

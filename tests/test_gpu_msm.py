@@ -247,6 +247,54 @@ def test_precomputed_table_matches_plain_path(cozk, orc):
         c2.srs_release(plain)
 
 
+def test_dominant_digit_path(cozk, orc):
+    """Whole-SRS calls on vectors whose windows are dominated by one digit (the real co-jolt share shapes: constant
+    vectors, w - c0 - c1, zero padding) use the precomputed row totals: same bytes as the plain layout and the oracle, far
+    fewer (key, val) pairs; uniform vectors keep the plain layout; prefix calls and SRSs with points at infinity too."""
+    n = 1 << 15
+    bases = orc.gen_bases(12, n)
+    dists = ("const", "wminus", "zero_half", "uniform", "dup", "small16")
+    vecs = [orc.gen_scalars(d, 110 + i, n, stride=64) for i, d in enumerate(dists)]
+    broken = vecs[0].copy()
+    broken[5] = vecs[3][5]
+    broken[n - 3] = 0
+    vecs.append(broken)
+    want = np.stack([orc.msm(bases, v) for v in vecs])
+    with cozk.Context() as c2:
+        c2.set_option("dominant_min_points", 0)
+        with_table = c2.srs_register(bases)
+        c2.set_option("table_max_mib", 0)
+        plain = c2.srs_register(bases)
+        for srs in (with_table, plain):
+            pairs = {}
+            for dom in (1, 0):
+                c2.set_option("dominant", dom)
+                for j, v in enumerate(vecs):
+                    assert (c2.msm_batch(srs, [v], stride=64)[0] == want[j]).all(), (srs, dom, j)
+                    pairs[(dom, j)] = c2.last_stats()["pairs"]
+                assert (c2.msm_batch(srs, vecs, stride=64) == want).all(), (srs, dom, "batch")
+            windows = c2.last_stats()["windows"]
+            assert pairs[(1, 0)] <= windows + 1 and pairs[(0, 0)] == windows * n      # constant vector: the row totals only
+            assert pairs[(1, 1)] < 0.6 * pairs[(0, 1)]                                  # w - c0 - c1: the high windows collapse
+            assert pairs[(1, 2)] < 0.6 * pairs[(0, 2)]                                  # half zeros: found through the tail sample
+            assert pairs[(1, 3)] == pairs[(0, 3)]                                       # uniform: plain layout
+            assert pairs[(1, 6)] <= windows * 5 + 1                                     # two scalars off the pattern: 2 pairs each
+            c2.set_option("dominant", 1)
+            # a prefix of the SRS has no totals: plain path, same bytes
+            assert (c2.msm_batch(srs, [vecs[0]], n=n // 2, stride=64)[0] == orc.msm(bases[: n // 2], vecs[0][: n // 2])).all()
+        # canonical form, dense stride
+        can = orc.gen_scalars("const", 130, n, form=1)
+        assert (c2.msm_batch(with_table, can, form=1)[0] == orc.msm(bases, can, form=1)).all()
+        inf = np.zeros(n, np.uint8)
+        inf[::5] = 1
+        srs_inf = c2.srs_register(bases, infinity=inf)
+        masked = vecs[0].copy()
+        masked[::5] = 0
+        assert (c2.msm_batch(srs_inf, [vecs[0]], stride=64)[0] == orc.msm(bases, masked)).all()
+        for h in (with_table, plain, srs_inf):
+            c2.srs_release(h)
+
+
 def test_randomised_shapes(ctx, orc):
     """Seeded random shapes through the C ABI: n, base_offset, batch size, stride, form, distribution, bit hint."""
     rng = np.random.default_rng(20261018)
