@@ -38,7 +38,44 @@ __global__ void __launch_bounds__(256) k_decompose(DecomposeArgs A) {
     decompose_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
 __global__ void __launch_bounds__(32) k_dom_cand(DomArgs A) { dom_cand_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
-__global__ void __launch_bounds__(256) k_dom_count(DomArgs A) { dom_count_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+// Output contract = dom_count_body over all (vector, scalar) pairs.  Block-cooperative: blockIdx.y is the vector, the
+// block's threads stride over its scalars, hits are counted per warp (ballot) into shared counters and flushed with one
+// global atomic per window and block - a constant vector sends EVERY scalar of a window to the same counter.
+__global__ void __launch_bounds__(256) k_dom_count(DomArgs A) {
+    __shared__ uint32_t sc[256];  // [0, W): candidate hits, [128, 128 + W): zero digits (W <= 128)
+    const uint32_t v = blockIdx.y, W = A.D.W;
+    const size_t n = A.D.n, cn = A.count_n ? A.count_n : n;
+    sc[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < cn; base += (size_t)gridDim.x * blockDim.x) {
+        size_t i = base + lane;
+        const bool valid = i < cn;
+        if (cn < n && i >= cn / 2) i += n - cn;
+        fr s = fq_zero();
+        if (valid) {
+            uint32_t vv;
+            size_t ii;
+            s = decompose_load((size_t)v * n + i, A.D, vv, ii);
+        }
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < W; ++w) {
+            uint32_t neg;
+            const uint32_t d = signed_digit(s, w, A.D.c, carry, neg);
+            const int32_t sd = neg ? -(int32_t)d : (int32_t)d;
+            const unsigned hc = __ballot_sync(0xFFFFFFFFu, valid && sd == A.cand[v * W + w]);
+            const unsigned hz = __ballot_sync(0xFFFFFFFFu, valid && d == 0);
+            if (lane == 0) {
+                if (hc) atomicAdd(&sc[w], (uint32_t)__popc(hc));
+                if (hz) atomicAdd(&sc[128 + w], (uint32_t)__popc(hz));
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t t = threadIdx.x;
+    if (t < W && sc[t]) atomicAdd(&A.count_cand[v * W + t], sc[t]);
+    if (t >= 128 && t - 128 < W && sc[t]) atomicAdd(&A.count_zero[v * W + t - 128], sc[t]);
+}
 template <bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
@@ -273,7 +310,11 @@ static int analyse_dominant(Device& D, MsmPlan& P, const uint8_t* d_scalars, con
     for (int round = 0; round < 2; ++round) {
         A.count_n = round == 0 ? sample : P.n;
         COZK_CUDA(cudaMemsetAsync(D.dom_counts.p, 0, 2 * segs * 4, st));
-        k_dom_count<<<grid_for((size_t)P.g * A.count_n, 256), 256, 0, st>>>(A);
+        {
+            // enough blocks to fill the device, never more than the scalars need
+            unsigned per_vec = std::min<unsigned>(grid_for(A.count_n, 256), std::max<unsigned>(1u, (unsigned)(D.sm_count * 8 / P.g) + 1));
+            k_dom_count<<<dim3(per_vec, P.g), 256, 0, st>>>(A);
+        }
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
         COZK_CUDA(cudaMemcpyAsync(D.h_dom_counts.data(), D.dom_counts.p, 2 * segs * 4, cudaMemcpyDeviceToHost, st));
@@ -644,7 +685,10 @@ static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
         uint32_t* d_one = nullptr;
         COZK_CUDA(cudaSetDevice(D.id));
         COZK_CUDA(cudaMalloc(&d_one, 32));
-        cudaError_t e = cudaMemcpy(d_one, one, 32, cudaMemcpyHostToDevice);
+        // on the engine's stream and synchronised there (a pageable cudaMemcpy is only STAGED when it returns, and the
+        // engine's non-blocking streams do not wait for the legacy default stream)
+        cudaError_t e = cudaMemcpyAsync(d_one, one, 32, cudaMemcpyHostToDevice, D.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
         int rc = e == cudaSuccess ? COZK_OK : COZK_ERR_CUDA;
         for (uint32_t r = 0; r < S.table_W && ok && !rc; ++r) {
             SrsEntry V;
@@ -661,7 +705,8 @@ static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
                 break;
             }
             COZK_CUDA(cudaSetDevice(D.id));
-            e = cudaMemcpy(S.d_bases[di] + (size_t)S.table_W * S.n + r, out, 64, cudaMemcpyHostToDevice);
+            e = cudaMemcpyAsync(S.d_bases[di] + (size_t)S.table_W * S.n + r, out, 64, cudaMemcpyHostToDevice, D.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
             if (e != cudaSuccess) rc = COZK_ERR_CUDA;
         }
         cudaSetDevice(D.id);

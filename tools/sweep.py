@@ -24,12 +24,15 @@ ap.add_argument("--stream-min", type=int, default=-1, help="stream_min_points op
 ap.add_argument("--stream-chunks", type=int, default=0)
 ap.add_argument("--table-window", type=int, default=-1, help="-1 auto, 0 no table, else forced table window")
 ap.add_argument("--acc-chunk", type=int, default=0, help="pairs per level-1 accumulate thread (0 = chosen per call)")
+ap.add_argument("--dominant", type=int, default=-1, help="-1 default, 0 off, 1 on (dominant-digit mode of whole-SRS calls)")
 ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
 
 ctx = cozk.Context()
 if args.window:
     ctx.set_option("window", args.window)
+if args.dominant >= 0:
+    ctx.set_option("dominant", args.dominant)
 if args.acc_chunk:
     ctx.set_option("acc_chunk", args.acc_chunk)
 if args.stream_min >= 0:
