@@ -100,6 +100,11 @@ int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, const void* sca
  * of the free device memory; 0 = none).  With a table
  * all windows of a scalar share one bucket set, which removes the per-window bucket reduction and the 254 doublings of
  * the final combine; the table is built once at registration, like the reference's SRS in PST13::setup. */
+/* "dominant" (default 1) / "dominant_min_points" (default 2^21): a call that covers a whole registered SRS and has at least
+ * that many (vector, point) pairs looks for windows in which (nearly) every scalar has the same digit - the constant and
+ * nearly constant share vectors of co-jolt (co-jolt/src/poly/dense_mlpoly.rs:567-585) - and replaces those pairs by the
+ * precomputed sum of the table row.  Same result, far fewer additions; uniform vectors pay one look at a sample.
+ * "acc_chunk", "stream_chunks", "stream_min_points", "table_window", "open_small_log2", "peer_direct": see msm.cu. */
 int cozk_set_option(cozk_ctx* ctx, const char* name, long value);
 /* Timings (ms, CUDA events) of the stages of the last cozk_msm_batch* call on device 0 of the context:
  * [0] h2d  [1] decompose  [2] sort  [3] accumulate  [4] bucket-reduce  [5] finish+d2h  [6] total  [7] kernels launched
