@@ -231,18 +231,9 @@ COZK_HD void dom_cand_body(size_t v, const DomArgs& A) {
         A.cand[v * A.D.W + w] = neg ? -(int32_t)d : (int32_t)d;
     }
 }
-COZK_HD void dom_bump(uint32_t* counter, uint32_t seg, bool hit) {
-#if defined(__CUDA_ARCH__)
-    // lanes of one warp nearly always belong to one vector: count per distinct segment with one atomic each
-    const unsigned peers = __match_any_sync(__activemask(), seg);
-    const unsigned hits = __ballot_sync(peers, hit) & peers;
-    if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1) && hits) atomicAdd(&counter[seg], (uint32_t)__popc(hits));
-#else
-    if (hit) counter[seg] += 1;
-#endif
-}
-// thread tid = v*n + i
-COZK_HD void dom_count_body(size_t tid, const DomArgs& A) {
+// thread tid = v*count_n + i.  SERIAL form (plain increments): the host emulation runs it as it is; on the GPU the
+// block-cooperative k_dom_count (msm.cu) produces the same counters with ballots and shared-memory counters.
+inline void dom_count_body(size_t tid, const DomArgs& A) {
     const size_t cn = A.count_n ? A.count_n : A.D.n;
     if (tid >= (size_t)A.D.g * cn) return;
     uint32_t v = (uint32_t)(tid / cn);
@@ -255,8 +246,8 @@ COZK_HD void dom_count_body(size_t tid, const DomArgs& A) {
         const uint32_t d = signed_digit(s, w, A.D.c, carry, neg);
         const uint32_t seg = v * A.D.W + w;
         const int32_t sd = neg ? -(int32_t)d : (int32_t)d;
-        dom_bump(A.count_cand, seg, sd == A.cand[seg]);
-        dom_bump(A.count_zero, seg, d == 0);
+        if (sd == A.cand[seg]) A.count_cand[seg] += 1;
+        if (d == 0) A.count_zero[seg] += 1;
     }
 }
 
