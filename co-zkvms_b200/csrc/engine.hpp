@@ -78,7 +78,16 @@ struct SrsEntry {
     std::vector<uint8_t*> d_inf;     // per device, may be null
     uint32_t table_c = 0;            // window size the table rows were built for; 0 = no table
     uint32_t table_W = 1;            // rows
-    bool has_totals = false;         // entry table_W * n + w of d_bases holds the sum of row w (dominant-digit mode)
+    // Dominant-digit mode: behind the table, entry table_W * n + j * table_W + w holds the sum of the first n >> j points of
+    // row w, for j = 0 .. total_levels - 1 (n >> j >= 1024): whole-SRS calls and power-of-two prefixes (a 2^16 polynomial
+    // against a 2^22 SRS).  Bit j of total_ok: level j is usable (every row sum is a finite point).
+    uint32_t total_levels = 0;
+    uint64_t total_ok = 0;
+    static uint32_t totals_levels_for(size_t n) {
+        uint32_t l = 0;
+        while (l < 40 && (n >> l) >= 1024) ++l;
+        return l;
+    }
 };
 
 // A device-resident polynomial (include/cozk_rep3.h).  d_data holds `total` coefficients; the handle covers

@@ -485,9 +485,13 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             const uint8_t* const* g_ptrs = host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096;
             DecomposeArgs dom = {};
             bool use_dom = false;
-            if (ctx->opt_dominant && S.has_totals && !d_inf && passes == 1 && offset == 0 && pn == S.n &&
-                (double)g * (double)pn >= (double)ctx->opt_dominant_min_points) {
-                rc = analyse_dominant(D, P, g_scalars, g_ptrs, vstride, stride, form, (size_t)S.table_W * S.n, &dom, &use_dom, &launches);
+            // the whole SRS or a power-of-two prefix of it: the sums of those point ranges were computed at registration
+            uint32_t tl = 0;
+            while (tl < S.total_levels && (S.n >> tl) != pn) ++tl;
+            if (ctx->opt_dominant && tl < S.total_levels && ((S.total_ok >> tl) & 1) && (S.n >> tl << tl) == S.n && !d_inf &&
+                passes == 1 && offset == 0 && (double)g * (double)pn >= (double)ctx->opt_dominant_min_points) {
+                rc = analyse_dominant(D, P, g_scalars, g_ptrs, vstride, stride, form,
+                                      (size_t)S.table_W * S.n + (size_t)tl * S.table_W, &dom, &use_dom, &launches);
                 if (rc) return rc;
             }
             plan_mults += P.field_mults();  // after the analysis: the statistics report the pairs really made
@@ -670,17 +674,20 @@ static int srs_wait_tables(cozk_ctx* ctx, size_t n_devices) {
     return COZK_OK;
 }
 
-// The sum of every table row, stored behind the table (entry table_W * n + w): what the dominant-digit mode of the
-// decompose pass needs (msm_kernels.cuh).  Each sum is an n-point MSM whose scalars are all 1 - one window, one bucket - run
-// through the engine's own pipeline on a view of the row.  Setup-time work (2^20 points, 15 rows: ~15 ms).
+// The sums of every table row over the whole SRS and over its power-of-two prefixes (down to 1024 points), stored behind
+// the table: what the dominant-digit mode of the decompose pass needs (msm_kernels.cuh).  Each sum is an MSM whose scalars
+// are all 1 - one window, one bucket - run through the engine's own pipeline on a view of the row.  Setup-time work
+// (2^20 points, 15 rows: ~30 ms for all prefix lengths together).
 static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
-    S.has_totals = false;
-    if (S.n < 1024) return COZK_OK;
+    S.total_levels = 0;
+    S.total_ok = 0;
+    const uint32_t levels = SrsEntry::totals_levels_for(S.n);
+    if (levels == 0) return COZK_OK;
     for (uint8_t* f : S.d_inf)
         if (f) return COZK_OK;  // bases at infinity: the totals would have to leave them out; not worth a second code path
     const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-    bool ok = true;
-    for (size_t di = 0; di < S.d_bases.size() && ok; ++di) {
+    uint64_t ok = ~(uint64_t)0;
+    for (size_t di = 0; di < S.d_bases.size(); ++di) {
         Device& D = *ctx->devs[di];
         uint32_t* d_one = nullptr;
         COZK_CUDA(cudaSetDevice(D.id));
@@ -690,24 +697,32 @@ static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
         cudaError_t e = cudaMemcpyAsync(d_one, one, 32, cudaMemcpyHostToDevice, D.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
         int rc = e == cudaSuccess ? COZK_OK : COZK_ERR_CUDA;
-        for (uint32_t r = 0; r < S.table_W && ok && !rc; ++r) {
-            SrsEntry V;
-            V.n = S.n;
-            V.d_bases.assign(S.d_bases.size(), nullptr);
-            V.d_inf.assign(S.d_bases.size(), nullptr);
-            V.d_bases[di] = S.d_bases[di] + (size_t)r * S.n;
-            const void* ptr = d_one;
-            uint8_t out[72];
-            rc = run_on_device(ctx, (int)di, V, 0, S.n, nullptr, &ptr, 1, 0, COZK_CANON, 1, out);
-            if (rc) break;
-            if (out[64]) {
-                ok = false;  // a row that sums to the identity has no affine form: keep the plain path for this SRS
-                break;
+        for (uint32_t j = 0; j < levels && !rc; ++j) {
+            const size_t len = S.n >> j;
+            if (len << j != S.n) {  // only exact halvings of the SRS length
+                ok &= ~((uint64_t)1 << j);
+                continue;
             }
-            COZK_CUDA(cudaSetDevice(D.id));
-            e = cudaMemcpyAsync(S.d_bases[di] + (size_t)S.table_W * S.n + r, out, 64, cudaMemcpyHostToDevice, D.stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-            if (e != cudaSuccess) rc = COZK_ERR_CUDA;
+            for (uint32_t r = 0; r < S.table_W && !rc; ++r) {
+                SrsEntry V;
+                V.n = len;
+                V.d_bases.assign(S.d_bases.size(), nullptr);
+                V.d_inf.assign(S.d_bases.size(), nullptr);
+                V.d_bases[di] = S.d_bases[di] + (size_t)r * S.n;
+                const void* ptr = d_one;
+                uint8_t out[72];
+                rc = run_on_device(ctx, (int)di, V, 0, len, nullptr, &ptr, 1, 0, COZK_CANON, 1, out);
+                if (rc) break;
+                if (out[64]) {
+                    ok &= ~((uint64_t)1 << j);  // a sum that is the identity has no affine form: plain path for this length
+                    continue;
+                }
+                COZK_CUDA(cudaSetDevice(D.id));
+                e = cudaMemcpyAsync(S.d_bases[di] + (size_t)S.table_W * S.n + (size_t)j * S.table_W + r, out, 64,
+                                    cudaMemcpyHostToDevice, D.stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+                if (e != cudaSuccess) rc = COZK_ERR_CUDA;
+            }
         }
         cudaSetDevice(D.id);
         cudaFree(d_one);
@@ -716,7 +731,8 @@ static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
             return rc;
         }
     }
-    S.has_totals = ok;
+    S.total_levels = levels;
+    S.total_ok = ok;
     return COZK_OK;
 }
 
@@ -751,7 +767,7 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
         affine* d = nullptr;
         uint8_t* dinf = nullptr;
         cudaError_t e = cudaSetDevice(D.id);
-        if (e == cudaSuccess) e = cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + S.table_W) * sizeof(affine));
+        if (e == cudaSuccess) e = cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + (size_t)S.table_W * (SrsEntry::totals_levels_for(n) + 1)) * sizeof(affine));
         // on the destination device's own stream and synchronised there: nothing in this library relies on the legacy
         // default stream, which its non-blocking streams do not wait for (the source is complete: callers synchronise)
         if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine), D.stream);
@@ -883,7 +899,7 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         COZK_CUDA(cudaSetDevice(D->id));
         affine* d = nullptr;
         uint8_t* di = nullptr;
-        COZK_CUDA(cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + S.table_W) * sizeof(affine)));
+        COZK_CUDA(cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + (size_t)S.table_W * (SrsEntry::totals_levels_for(n) + 1)) * sizeof(affine)));
         // Copies go through the engine's own stream and are synchronised there.  A plain cudaMemcpy from pageable memory
         // returns once the data is STAGED - its DMA runs on the legacy default stream, which the engine's non-blocking
         // streams do not wait for, so the table build could read row 0 before the tail of the copy had landed.

@@ -100,7 +100,8 @@ int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, const void* sca
  * of the free device memory; 0 = none).  With a table
  * all windows of a scalar share one bucket set, which removes the per-window bucket reduction and the 254 doublings of
  * the final combine; the table is built once at registration, like the reference's SRS in PST13::setup. */
-/* "dominant" (default 1) / "dominant_min_points" (default 2^21): a call that covers a whole registered SRS and has at least
+/* "dominant" (default 1) / "dominant_min_points" (default 2^21): a call that covers a whole registered SRS (or an exact
+ * halving of it, down to 1024 points) and has at least
  * that many (vector, point) pairs looks for windows in which (nearly) every scalar has the same digit - the constant and
  * nearly constant share vectors of co-jolt (co-jolt/src/poly/dense_mlpoly.rs:567-585) - and replaces those pairs by the
  * precomputed sum of the table row.  Same result, far fewer additions; uniform vectors pay one look at a sample.

@@ -75,13 +75,15 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         std::vector<int32_t> cand;
         bool dom = false;
         size_t totals_index = 0;
-        if (g_dominant && chunks == 1 && !infinity && n == srs_n && base_offset == 0) {
+        // (the engine keeps such sums for the whole SRS and for its exact halvings down to 1024 points; here they are
+        // computed for whatever prefix the call covers)
+        if (g_dominant && chunks == 1 && !infinity && base_offset == 0) {
             const size_t rows = table_c ? windows_for(254, table_c) : 1;
             with_totals.assign(base_ptr, base_ptr + rows * srs_n);
             bool ok = true;
             for (size_t r = 0; r < rows && ok; ++r) {
                 xyzz t = xyzz_identity();
-                for (size_t i = 0; i < srs_n; ++i) t = xyzz_madd(t, base_ptr[r * srs_n + i]);
+                for (size_t i = 0; i < n; ++i) t = xyzz_madd(t, base_ptr[r * srs_n + i]);
                 uint8_t wire[72];
                 xyzz_to_wire(t, wire);
                 ok = wire[64] == 0;

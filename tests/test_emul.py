@@ -131,6 +131,10 @@ def test_dominant_digit_path(orc, dist):
         odd[0] = orc.gen_scalars("uniform", 53, 1)[0]
         got, _ = emul.msm(bases, odd, table_c=9)
         assert (got[0] == orc.msm(bases, odd)).all()
+        # a prefix of the SRS (a short polynomial against a long SRS), with the table and with per-window buckets
+        for kw in ({"table_c": 8}, {"c": 7}):
+            got, st = emul.msm(bases, vecs[2][: n // 2], n=n // 2, **kw)
+            assert st[5] == 1 and (got[0] == orc.msm(bases[: n // 2], vecs[2][: n // 2])).all(), kw
         got, st = emul.msm(bases, orc.gen_scalars("uniform", 54, n), table_c=9)
         assert st[5] == 0 and st[4] == st[1] * n          # uniform scalars: nothing dominant, the plain layout
     finally:

@@ -280,8 +280,13 @@ def test_dominant_digit_path(cozk, orc):
             assert pairs[(1, 3)] == pairs[(0, 3)]                                       # uniform: plain layout
             assert pairs[(1, 6)] <= windows * 5 + 1                                     # two scalars off the pattern: 2 pairs each
             c2.set_option("dominant", 1)
-            # a prefix of the SRS has no totals: plain path, same bytes
-            assert (c2.msm_batch(srs, [vecs[0]], n=n // 2, stride=64)[0] == orc.msm(bases[: n // 2], vecs[0][: n // 2])).all()
+            # exact halvings of the SRS carry their own totals (a 2^16 polynomial against a 2^22 SRS): dominant path too;
+            # any other prefix and any offset keep the plain layout; same bytes everywhere
+            for m_, off in ((n // 2, 0), (n // 8, 0), (n // 2 + 1, 0), (n // 4, n // 4)):
+                got = c2.msm_batch(srs, [vecs[0]], n=m_, base_offset=off, stride=64)[0]
+                assert (got == orc.msm(bases[off:off + m_], vecs[0][:m_])).all(), (srs, m_, off)
+                made = c2.last_stats()["pairs"]
+                assert (made <= c2.last_stats()["windows"] + 1) == (off == 0 and m_ in (n // 2, n // 8)), (m_, off, made)
         # canonical form, dense stride
         can = orc.gen_scalars("const", 130, n, form=1)
         assert (c2.msm_batch(with_table, can, form=1)[0] == orc.msm(bases, can, form=1)).all()
