@@ -362,6 +362,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     COZK_CUDA(cudaEventRecord(D.ev[0], D.stream));
     double plan_mults = 0, plan_pairs = 0, host_finish_ms = 0;
     uint32_t last_c = 0, last_W = 0;
+    // k_accumulate<true>: 4 blocks of 128 threads per SM are resident
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk};
 
     for (size_t pass = 0; pass < passes; ++pass) {
         size_t lo = pass * MAX_POINTS_PER_PASS;
@@ -408,7 +410,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             for (size_t ci = 0; ci < chunks; ++ci) {
                 int slot = (int)(ci & 1);
                 size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
-                P = make_plan(cn, 1, bits, max_buckets, cfix ? cfix : (uint32_t)ctx->opt_window, table_c);
+                P = make_plan(cn, 1, bits, max_buckets, cfix ? cfix : (uint32_t)ctx->opt_window, table_c, acc_tuning);
                 plan_mults += P.field_mults();
                 plan_pairs += (double)P.m;
                 last_c = P.c;
@@ -473,7 +475,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         for (size_t gi = 0; gi < ngroups; ++gi) {
             size_t v0 = gi * gmax, g = std::min(gmax, k - v0);
             int slot = (int)(gi & 1);
-            MsmPlan P = make_plan(pn, (uint32_t)g, bits, max_buckets, (uint32_t)ctx->opt_window, table_c);
+            MsmPlan P = make_plan(pn, (uint32_t)g, bits, max_buckets, (uint32_t)ctx->opt_window, table_c, acc_tuning);
             last_c = P.c;
             last_W = P.W;
             COZK_CUDA(cudaStreamWaitEvent(D.stream, D.copy_done[slot], 0));
@@ -841,7 +843,6 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
             return COZK_ERR_NO_DEVICE;
         }
         D->sm_count = prop.multiProcessorCount;
-        g_acc_resident_threads = (size_t)D->sm_count * 512;  // k_accumulate: 4 blocks of 128 threads per SM
         {
             // keep freed stream-ordered allocations (device-resident polynomials, rep3poly.cu) in the pool
             cudaMemPool_t pool;
@@ -1020,7 +1021,7 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "acc_chunk")) {
         // pairs per thread at level 1 of the accumulate stage: 0 = choose per call (fill the last wave of threads)
         if (value != 0 && (value < 4 || value > 256)) return COZK_ERR_INVALID_ARG;
-        g_acc_force_l = (int)value;
+        ctx->opt_acc_chunk = value;
     } else if (!strcmp(name, "dominant")) {
         // 1: whole-SRS calls look for windows dominated by one digit and use the row totals; 0: always the plain layout
         if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;

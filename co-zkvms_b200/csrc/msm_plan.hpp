@@ -17,18 +17,22 @@ constexpr uint32_t HOST_FINISH_MAX = 4;  // up to this many vectors the final Ho
 constexpr uint32_t C_MIN = 2, C_MAX = 22;
 
 
-// Threads of the level-1 accumulate kernel that are resident on the device at once (SMs x 512); 0 = unknown, keep ACC_L.
-// Set once by the engine at start-up (and by the host emulation, to a small number, so that odd chunk lengths are tested).
-inline size_t g_acc_resident_threads = 0;
-inline int g_acc_force_l = 0;  // option "acc_chunk": fixed chunk length (experiments, tests); 0 = choose_acc_l
+// Tuning of the level-1 chunk length, carried by the plan: `resident` = threads of the level-1 accumulate kernel that are
+// resident on the device at once (SMs x 512; 0 = unknown, keep ACC_L); `force_l` = option "acc_chunk" (a fixed chunk
+// length for experiments and tests; 0 = choose).
+struct AccTuning {
+    size_t resident = 0;
+    int force_l = 0;
+};
 
 // Level-1 chunk length.  32 pairs per thread is the measured optimum once the kernel fills the device (2^20 points:
 // accumulate stage 2.73 / 2.64 / 2.62 / 2.68 / 2.65 ms at 28 / 30 / 32 / 34 / 36 - a chunk of 32 keys is one 128-byte line,
 // and the blocks do not run in lock-step waves, so "filling the last wave" buys nothing).  A small MSM that cannot fill
 // the device with chunks of 32 gets shorter chunks, down to 16: more threads, a shorter serial chain per thread
 // (2^16 points: 0.48 -> 0.40 ms).
-inline int choose_acc_l(size_t m, size_t resident) {
-    if (g_acc_force_l) return g_acc_force_l;
+inline int choose_acc_l(size_t m, const AccTuning& t) {
+    if (t.force_l) return t.force_l;
+    const size_t resident = t.resident;
     if (resident == 0 || m == 0) return ACC_L;
     if ((m + ACC_L - 1) / ACC_L >= resident) return ACC_L;
     size_t L = (m + resident - 1) / resident;   // the chunk length at which the threads just fill the device
@@ -44,6 +48,7 @@ struct MsmPlan {
     uint32_t bits = 254; // significant scalar bits
     uint32_t c = 0, W = 0, B = 0;
     uint32_t Wb = 0;                 // bucket sets per vector: W, or 1 when a precomputed 2^(c*w)*P table is used
+    AccTuning acc;                   // chunk-length tuning the level structure was (and is re-) built with
     size_t m = 0;                    // g*W*n pairs
     size_t total_buckets = 0;        // g*W*B
     uint32_t sort_bits = 0;          // radix-sort key bits
@@ -134,7 +139,7 @@ inline void plan_set_pairs(MsmPlan& p, size_t m) {
     // (one addition per live slot: work-efficient, 16 additions deep), small ones with the block-cooperative segmented
     // scan (log2(ACC_TILE) additions deep, but up to that many additions per slot).  Every thread / block emits two
     // slots; a level that ran as a single thread / block has seen everything and leaves no open run.
-    const int l1 = choose_acc_l(e, g_acc_resident_threads);
+    const int l1 = choose_acc_l(e, p.acc);
     p.acc_tile.push_back(l1);
     for (size_t t = (e + l1 - 1) / l1; t > 1;) {
         e = 2 * t;
@@ -173,8 +178,10 @@ inline size_t dom_layout(const int32_t* cand, const uint32_t* count_cand, const 
 }
 
 // table_c != 0: use the SRS's precomputed table (window size fixed at registration, one bucket set per vector)
-inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0, uint32_t table_c = 0) {
+inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, uint32_t force_c = 0, uint32_t table_c = 0,
+                         const AccTuning& acc = AccTuning()) {
     MsmPlan p;
+    p.acc = acc;
     p.n = n;
     p.g = g;
     p.bits = bits == 0 || bits > 254 ? 254 : bits;

@@ -18,6 +18,7 @@
 
 using namespace cozk;
 
+static AccTuning g_acc;  // emul_set_acc_chunk
 static uint32_t g_last_pairs = 0, g_last_dominant = 0;  // of the last chunk of the last emul_msm call (stats[4], stats[5])
 static int g_dominant = 0;  // 1: run the dominant-digit path of the engine (whole-SRS calls)
 
@@ -28,8 +29,8 @@ void emul_set_dominant(int on) { g_dominant = on; }
 // level-1 chunk length of the accumulate stage: resident != 0 lets the plan choose it as the engine does (wave filling),
 // force_l != 0 fixes it
 void emul_set_acc_chunk(size_t resident, int force_l) {
-    g_acc_resident_threads = resident;
-    g_acc_force_l = force_l;
+    g_acc.resident = resident;
+    g_acc.force_l = force_l;
 }
 
 // bases: n x 64 B; scalars: g vectors, vector v at scalars + v*vector_stride, element i at + i*stride; out: g x 72 B
@@ -44,7 +45,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         return 0;
     }
     // table mode: `bases` holds the whole registered SRS (srs_n points); the call uses [base_offset, base_offset + n)
-    MsmPlan P = make_plan(n, g, max_bits, (size_t)1 << 24, force_c, table_c);
+    MsmPlan P = make_plan(n, g, max_bits, (size_t)1 << 24, force_c, table_c, g_acc);
     std::vector<affine> table;
     const affine* base_ptr = reinterpret_cast<const affine*>(bases);
     if (table_c) {
@@ -66,7 +67,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
     std::vector<xyzz> pp_in, pp_out;
     for (size_t ci = 0; ci < chunks; ++ci) {
         size_t clo = ci * cn_max, cn = std::min(cn_max, n - clo);
-        MsmPlan Pc = chunks == 1 ? P : make_plan(cn, g, max_bits, (size_t)1 << 24, P.c, table_c);
+        MsmPlan Pc = chunks == 1 ? P : make_plan(cn, g, max_bits, (size_t)1 << 24, P.c, table_c, g_acc);
         // dominant-digit mode: the call must cover the whole SRS in one piece; the sums of the table rows sit behind the
         // table (the engine computes them at registration), the analysis pass picks the segments that use them
         std::vector<affine> with_totals;
