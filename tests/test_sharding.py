@@ -86,3 +86,22 @@ def test_bench_reference_arm_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["config"]["log2_points_per_gpu"] == 14
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The last bench line measured on the B200 (profiles/r3_bench_1gpu.json, copied from the gpurun call) carries every key
+    the driver's contract names; a change of bench.py that drops one shows up here as soon as the line is refreshed."""
+    import json
+    with open(os.path.join(ROOT, "profiles", "r3_bench_1gpu.json")) as f:
+        line = json.loads(f.read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in line, k
+    assert line["config"]["workload"] and "model" not in line["config"]
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["e2e"]["h2d_bytes_per_step"] == 32 << line["config"]["log2_points_per_gpu"] and line["e2e"]["value"] < line["value"]
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-9
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["kind"] == "port"
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and line["clocks"]["samples"] >= 10
+    assert line["gpu_launches"] > 0 and line["parity_vs_oracle"] is True and line["warmup"] >= 3
