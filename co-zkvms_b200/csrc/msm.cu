@@ -490,8 +490,11 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             // the whole SRS or a power-of-two prefix of it: the sums of those point ranges were computed at registration
             uint32_t tl = 0;
             while (tl < S.total_levels && (S.n >> tl) != pn) ++tl;
+            // (a total's index shares the 31 index bits of `val` with the table entries)
+            const bool totals_addressable = (double)S.table_W * (double)S.n + (double)(S.total_levels + 1) * S.table_W < 2147483647.0;
             if (ctx->opt_dominant && tl < S.total_levels && ((S.total_ok >> tl) & 1) && (S.n >> tl << tl) == S.n && !d_inf &&
-                passes == 1 && offset == 0 && (double)g * (double)pn >= (double)ctx->opt_dominant_min_points) {
+                totals_addressable && passes == 1 && offset == 0 &&
+                (double)g * (double)pn >= (double)ctx->opt_dominant_min_points) {
                 rc = analyse_dominant(D, P, g_scalars, g_ptrs, vstride, stride, form,
                                       (size_t)S.table_W * S.n + (size_t)tl * S.table_W, &dom, &use_dom, &launches);
                 if (rc) return rc;
