@@ -18,23 +18,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # COZK_LIB: load another build of the same library (kernel experiments measured side by side with tools/sweep.py)
 LIB_PATH = os.environ.get("COZK_LIB") or os.path.join(HERE, "libcozk_msm.so")
-SOURCES = ["msm.cu", "depth_kernels.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
-HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "rep3_kernels.cuh", "msm_plan.hpp", "engine.hpp", "pst13.hpp",
+SOURCES = ["msm.cu", "sort.cu", "depth_kernels.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
+HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "sort_kernels.cuh", "rep3_kernels.cuh", "msm_plan.hpp", "engine.hpp",
            "depth_kernels.hpp"]
+PUBLIC_HEADERS = ["cozk_msm.h", "cozk_rep3.h", "cozk_pst13.h", "cozk_test.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 MONT, CANON = 0, 1
 OK, ERR_INVALID_ARG, ERR_KEY_LENGTH, ERR_CUDA, ERR_NO_DEVICE, ERR_BAD_HANDLE, ERR_WIRE = 0, -1, -2, -3, -4, -5, -6
 DIST = {"uniform": 0, "const": 1, "wminus": 2, "dup": 3, "small16": 4, "zero_half": 5}
 
-# every symbol include/cozk_msm.h and csrc/pst13.hpp declare (checked by tests/test_abi.py without a GPU)
+# every symbol include/cozk_msm.h, cozk_pst13.h and cozk_test.h declare (checked by tests/test_abi.py without a GPU)
 ABI_SYMBOLS = [
     "cozk_init", "cozk_destroy", "cozk_device_count", "cozk_srs_register", "cozk_srs_release", "cozk_srs_len",
     "cozk_msm_batch", "cozk_msm_batch_device", "cozk_g1_sum", "cozk_set_option", "cozk_last_stats", "cozk_last_error",
     "cozk_dev_alloc", "cozk_dev_free", "cozk_dev_upload", "cozk_dev_download", "cozk_host_alloc_pinned",
     "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_testgen_bases", "cozk_testgen_scalars",
-    "cozk_srs_register_device", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench",
+    "cozk_srs_register_device", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench", "cozk_test_sort",
     "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_open",
     "cozk_pst13_combine_commitment_shares", "cozk_pst13_coordinate_prove", "cozk_combine_comm",
     "cozk_fixed_base_batch_mul",
@@ -53,15 +54,25 @@ class CozkError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    """Compile libcozk_msm.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", h) for h in ("cozk_msm.h", "cozk_rep3.h")]
-    if (not force and os.path.exists(LIB_PATH)
-            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
-        return LIB_PATH
+    """Compile libcozk_msm.so for sm_100a with nvcc (cross-compiles without a GPU).  One object per translation unit
+    under csrc/_obj/, stale ones rebuilt side by side, then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", h) for h in PUBLIC_HEADERS]
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-    subprocess.check_call(cmd, cwd=CSRC)
+    jobs, objs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(objdir, s + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_time, os.path.getmtime(src)):
+            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(lambda c: subprocess.check_call(c, cwd=CSRC), jobs))
+    if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(o) for o in objs):
+        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs, cwd=CSRC)
     return LIB_PATH
 
 
@@ -103,6 +114,7 @@ def lib():
     L.cozk_testgen_scalars.argtypes = [vp, ci, ci, u64, sz, sz, sz, ci, vp, sz]
     L.cozk_test_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
     L.cozk_test_g1_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.cozk_test_sort.argtypes = [vp, ci, vp, vp, sz, cu, vp, sz, cu, sz, ci, cu, cu, sz, sz, ci, vp, vp]
     L.cozk_microbench.argtypes = [vp, ci, ci, ci, ci, ci, cd, cd]
     L.cozk_pst13_commit.argtypes = [vp, u64, vp, sz, sz, ci, cu, vp]
     L.cozk_pst13_batch_commit.argtypes = [vp, u64, pp, sz, sz, sz, ci, ctypes.POINTER(cu), vp]
@@ -346,6 +358,37 @@ class Context:
             for x in (da, db, do):
                 if x:
                     x.free()
+
+    def sort_pairs(self, keys, vals, key_bits, device=0):
+        """The engine's pair sort on its own (include/cozk_test.h): stable sort of (key, val) uint32 pairs by key."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        m = keys.size
+        bufs = [self.alloc(max(m, 1) * 4, device) for _ in range(4)]
+        try:
+            bufs[0].upload(keys.view(np.uint8))
+            bufs[1].upload(vals.view(np.uint8))
+            _check(lib().cozk_test_sort(self.handle, device, ctypes.c_void_p(bufs[0].ptr), ctypes.c_void_p(bufs[1].ptr), m, key_bits,
+                                        None, 0, 0, 0, 0, 0, 0, 0, 0, 0, ctypes.c_void_p(bufs[2].ptr), ctypes.c_void_p(bufs[3].ptr)))
+            return bufs[2].download(m * 4).view(np.uint32), bufs[3].download(m * 4).view(np.uint32)
+        finally:
+            for b in bufs:
+                b.free()
+
+    def decompose_sort(self, dscalars, n, c, g=1, stride=32, form=MONT, windows=None, table_stride=0, val_offset=0, key_bits=0,
+                       fused=True, device=0):
+        """(keys, vals) of the plain decompose layout of g vectors of n device-resident scalars, sorted by key_bits key bits:
+        fused=True through the engine's fused first pass, fused=False decompose kernel + generic passes (key_bits=0: unsorted)."""
+        W = (254 + 1 + c - 1) // c if windows is None else windows
+        m = g * n * W
+        ko, vo = self.alloc(max(m, 1) * 4, device), self.alloc(max(m, 1) * 4, device)
+        try:
+            _check(lib().cozk_test_sort(self.handle, device, None, None, 0, key_bits, ctypes.c_void_p(dscalars.ptr), n, g, stride, form,
+                                        c, W, table_stride, val_offset, 1 if fused else 0, ctypes.c_void_p(ko.ptr), ctypes.c_void_p(vo.ptr)))
+            return ko.download(m * 4).view(np.uint32), vo.download(m * 4).view(np.uint32)
+        finally:
+            ko.free()
+            vo.free()
 
     def microbench(self, which, blocks, threads, iters, device=0):
         names = {"imad": 0, "fq_mul": 1, "fq_sqr": 2, "madd": 3, "imad_cc": 4, "imad_lo": 5, "imad_hi": 6, "fq_mul4": 7}

@@ -410,6 +410,47 @@ int cozk_test_g1_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, co
     return COZK_OK;
 }
 
+// The pair sort on its own.  d_scalars == NULL: sorts the m given (key, val) pairs by the low key_bits bits of their keys
+// (stable).  d_scalars != NULL: the pairs are those of the plain decompose layout of g vectors of n scalars (window c,
+// `windows` windows, table_stride / val_offset as in DecomposeArgs); fused != 0 produces them inside the first sort pass
+// (the engine's path), fused == 0 with the decompose kernel followed by generic passes; key_bits == 0 leaves them unsorted
+// (fused == 0 only).  Outputs: m = g * n * windows pairs.
+int cozk_test_sort(cozk_ctx* ctx, int device_index, const void* d_keys, const void* d_vals, size_t m, unsigned key_bits,
+                   const void* d_scalars, size_t n, unsigned g, size_t stride, int form, unsigned c, unsigned windows,
+                   size_t table_stride, size_t val_offset, int fused, void* d_keys_out, void* d_vals_out) {
+    Device* D;
+    int rc = get_device(ctx, device_index, &D);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(D->mu);
+    if (d_scalars) m = (size_t)g * n * windows;
+    if (m == 0) return COZK_OK;
+    if ((rc = D->keys_a.ensure(m * 4)) || (rc = D->vals_a.ensure(m * 4)) || (rc = D->keys_b.ensure(m * 4)) || (rc = D->vals_b.ensure(m * 4)))
+        return rc;
+    cudaStream_t st = D->stream;
+    uint32_t *ks = D->keys_a.as<uint32_t>(), *vs = D->vals_a.as<uint32_t>();
+    double launches = 0;
+    if (d_scalars) {
+        const size_t vstride = ((n - 1) * stride + 32 + 255) & ~(size_t)255;
+        DecomposeArgs DA{reinterpret_cast<const uint8_t*>(d_scalars), nullptr, vstride, stride, form, n, g, c, windows, nullptr,
+                         ks, vs, table_stride ? 1u : windows, table_stride, val_offset};
+        if (fused) {
+            rc = sort_pairs(*D, st, &DA, m, key_bits, &ks, &vs, &launches, nullptr);
+        } else {
+            rc = launch_decompose(DA, st);
+            if (!rc && key_bits) rc = sort_pairs(*D, st, nullptr, m, key_bits, &ks, &vs, &launches, nullptr);
+        }
+    } else {
+        COZK_CUDA(cudaMemcpyAsync(ks, d_keys, m * 4, cudaMemcpyDeviceToDevice, st));
+        COZK_CUDA(cudaMemcpyAsync(vs, d_vals, m * 4, cudaMemcpyDeviceToDevice, st));
+        rc = sort_pairs(*D, st, nullptr, m, key_bits, &ks, &vs, &launches, nullptr);
+    }
+    if (rc) return rc;
+    COZK_CUDA(cudaMemcpyAsync(d_keys_out, ks, m * 4, cudaMemcpyDeviceToDevice, st));
+    COZK_CUDA(cudaMemcpyAsync(d_vals_out, vs, m * 4, cudaMemcpyDeviceToDevice, st));
+    COZK_CUDA(cudaStreamSynchronize(st));
+    return COZK_OK;
+}
+
 int cozk_microbench(cozk_ctx* ctx, int device_index, int which, int blocks, int threads, int iters, double* out_ms,
                     double* out_ops) {
     Device* D;

@@ -135,6 +135,13 @@ int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const OpenKey* k
 // S[b] = P[2b] + P[2b+1] of a registered SRS into caller-provided device buffers on device 0 (half = n / 2 entries each).
 int srs_pair_sums_into(cozk_ctx* ctx, cozk_srs srs, affine* d_out, uint8_t* d_inf, size_t* half_out);
 int open_key_lookup(cozk_ctx* ctx, uint64_t h, OpenKey* out);
+// Pair sort (sort.cu / sort_kernels.cuh): see there.
+struct DecomposeArgs;
+int sort_setup_device();
+int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m, uint32_t key_bits, uint32_t** keys_out,
+               uint32_t** vals_out, double* launches, cudaEvent_t after_first);
+// the plain decompose kernel (msm.cu), for the test entry points of aux.cu
+int launch_decompose(const DecomposeArgs& A, cudaStream_t st);
 // The one entry every public MSM call funnels into (msm.cu).  only_device < 0: use all devices of the context.
 int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offset, size_t n, const void* const* host_scalars,
                  const void* const* dev_scalars, size_t k, size_t stride, int form, unsigned max_bits, void* out);

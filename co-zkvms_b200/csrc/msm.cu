@@ -4,8 +4,6 @@
 // Reference boundary this replaces: jolt_core::msm::{msm_field_elements, batch_msm} as called from
 // co-jolt/src/poly/commitment/pst13.rs:286, :319, :461 and ark_ec::VariableBaseMSM::msm_bigint as called from
 // co-noir-spartan/co-spartan/src/worker.rs:585, :804.  No CPU MSM path exists in this library.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -25,6 +23,7 @@ Device::~Device() {
     cudaSetDevice(id);
     DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
                       &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush, &buckets2,
+                      &dom_cand, &dom_counts, &dom_mode, &dom_off, &dom_len, &dom_cursor,
                       &open_in, &open_r[0], &open_r[1], &open_q, &open_qs};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -140,6 +139,44 @@ __global__ void __launch_bounds__(128) k_build_table(TableArgs A) {
 
 static inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 
+int launch_decompose(const DecomposeArgs& A, cudaStream_t st) {
+    k_decompose<<<grid_for((size_t)A.g * A.n, 256), 256, 0, st>>>(A);
+    COZK_CUDA(cudaGetLastError());
+    return COZK_OK;
+}
+
+// Accumulate stage: sorted (key, val) pairs -> bucket sums in `bucket_dst` (zeroed here), level by level on D.stream.
+static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, const uint32_t* vals, const affine* d_bases,
+                          xyzz* bucket_dst, double* launches) {
+    cudaStream_t st = D.stream;
+    int rc;
+    COZK_CUDA(cudaMemsetAsync(bucket_dst, 0, P.total_buckets * sizeof(xyzz), st));
+    for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
+        size_t m = P.acc_entries[lvl];
+        const int tile = P.acc_tile[lvl];
+        size_t T = (m + tile - 1) / tile;  // threads (serial body) or blocks (segmented scan)
+        DevBuf& pk_out = D.pk[lvl & 1];
+        DevBuf& pp_out = D.pp[lvl & 1];
+        if ((rc = pk_out.ensure(2 * T * 4))) return rc;
+        if ((rc = pp_out.ensure(2 * T * sizeof(xyzz)))) return rc;
+        AccumulateArgs A{m,
+                         lvl == 0 ? keys : D.pk[(lvl - 1) & 1].as<uint32_t>(),
+                         vals,
+                         d_bases,
+                         lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
+                         bucket_dst,
+                         pk_out.as<uint32_t>(),
+                         pp_out.as<xyzz>(),
+                         (uint32_t)tile};
+        if (lvl == 0) k_accumulate<true><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else if (tile == ACC_L) k_accumulate<false><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+    }
+    return COZK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ one group on one device
 // Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
 static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
@@ -160,9 +197,12 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     if ((rc = D.out.ensure((size_t)P.g * 72 + 256))) return rc;
 
     COZK_CUDA(cudaEventRecord(D.ev[1], st));
-    // 1 decompose
+    // 1 + 2: decompose and sort.  Plain layout: the pairs are produced inside the first pass of the sort (born
+    // partitioned by their low key digit, never stored unsorted).  Dominant-digit layout: compacted segments from the
+    // decompose kernel, then generic passes.  Stage times: "decompose" = up to and including the first sort pass.
     DecomposeArgs DA{d_scalars, d_vec_ptrs, vector_stride, stride, form, P.n, P.g, P.c, P.W, d_inf,
                      D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>(), P.Wb, table_stride, val_offset};
+    uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;
     if (dom) {
         DA.dom_mode = dom->dom_mode;
         DA.dom_cand = dom->dom_cand;
@@ -170,25 +210,14 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         DA.seg_cursor = dom->seg_cursor;
         DA.seg_len = dom->seg_len;
         DA.totals_index = dom->totals_index;
+        k_decompose<<<grid_for((size_t)P.g * P.n, 256), 256, 0, st>>>(DA);
+        *launches += 1;
+        COZK_CUDA(cudaGetLastError());
+        COZK_CUDA(cudaEventRecord(D.ev[2], st));
+        if ((rc = sort_pairs(D, st, nullptr, P.m, P.sort_bits, &sorted_keys, &sorted_vals, launches, nullptr))) return rc;
+    } else {
+        if ((rc = sort_pairs(D, st, &DA, P.m, P.sort_bits, &sorted_keys, &sorted_vals, launches, D.ev[2]))) return rc;
     }
-    k_decompose<<<grid_for((size_t)P.g * P.n, 256), 256, 0, st>>>(DA);
-    *launches += 1;
-    COZK_CUDA(cudaGetLastError());
-    COZK_CUDA(cudaEventRecord(D.ev[2], st));
-
-    // 2 sort (key, val) pairs by key
-    if (P.m > (size_t)0x7FFFFFFF) {
-        set_error("internal: group too large for the sort");
-        return COZK_ERR_INVALID_ARG;
-    }
-    size_t tmp_bytes = 0;
-    COZK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>(),
-                                              D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>(), (int)P.m, 0,
-                                              (int)P.sort_bits, st));
-    if ((rc = D.sort_tmp.ensure(tmp_bytes))) return rc;
-    COZK_CUDA(cub::DeviceRadixSort::SortPairs(D.sort_tmp.p, tmp_bytes, D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>(),
-                                              D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>(), (int)P.m, 0,
-                                              (int)P.sort_bits, st));
     COZK_CUDA(cudaEventRecord(D.ev[3], st));
 
     // 3 accumulate, level by level
@@ -197,30 +226,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         if ((rc = D.buckets2.ensure(P.total_buckets * sizeof(xyzz)))) return rc;
         bucket_dst = D.buckets2.as<xyzz>();
     }
-    COZK_CUDA(cudaMemsetAsync(bucket_dst, 0, P.total_buckets * sizeof(xyzz), st));
-    for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
-        size_t m = P.acc_entries[lvl];
-        const int tile = P.acc_tile[lvl];
-        size_t T = (m + tile - 1) / tile;  // threads (serial body) or blocks (segmented scan)
-        DevBuf& pk_out = D.pk[lvl & 1];
-        DevBuf& pp_out = D.pp[lvl & 1];
-        if ((rc = pk_out.ensure(2 * T * 4))) return rc;
-        if ((rc = pp_out.ensure(2 * T * sizeof(xyzz)))) return rc;
-        AccumulateArgs A{m,
-                         lvl == 0 ? D.keys_b.as<uint32_t>() : D.pk[(lvl - 1) & 1].as<uint32_t>(),
-                         D.vals_b.as<uint32_t>(),
-                         d_bases,
-                         lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
-                         bucket_dst,
-                         pk_out.as<uint32_t>(),
-                         pp_out.as<xyzz>(),
-                         (uint32_t)tile};
-        if (lvl == 0) k_accumulate<true><<<grid_for(T, 128), 128, 0, st>>>(A);
-        else if (tile == ACC_L) k_accumulate<false><<<grid_for(T, 128), 128, 0, st>>>(A);
-        else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
-        *launches += 1;
-        COZK_CUDA(cudaGetLastError());
-    }
+    if ((rc = run_accumulate(D, P, sorted_keys, sorted_vals, d_bases, bucket_dst, launches))) return rc;
     if (merge) {
         MergeArgs MA{D.buckets.as<xyzz>(), bucket_dst, P.total_buckets};
         launch_merge(MA, grid_for(P.total_buckets, 128), st);
@@ -443,6 +449,9 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         size_t per_vec = probe.m;
         size_t gmax = std::max<size_t>(1, (size_t)ctx->opt_group_pairs / std::max<size_t>(per_vec, 1));
         gmax = std::min<size_t>(gmax, 4096);
+        // ... and by the bucket budget: a fixed window (table or option) bounds g directly, a free one is searched
+        if (table_c || ctx->opt_window) gmax = std::min<size_t>(gmax, std::max<size_t>(1, max_buckets / ((size_t)probe.Wb * probe.B)));
+        else gmax = max_group_for(pn, (uint32_t)std::min<size_t>(gmax, k), bits, max_buckets);
         size_t vstride = ((pn - 1) * stride + 32 + 255) & ~(size_t)255;
 
         size_t ngroups = (k + gmax - 1) / gmax;
@@ -852,6 +861,10 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
             COZK_CUDA(cudaDeviceGetDefaultMemPool(&pool, id));
             uint64_t keep = UINT64_MAX;
             COZK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        {
+            int src = sort_setup_device();
+            if (src) return src;
         }
         COZK_CUDA(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
         COZK_CUDA(cudaStreamCreateWithFlags(&D->copy_stream, cudaStreamNonBlocking));

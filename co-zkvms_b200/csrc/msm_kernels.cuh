@@ -6,7 +6,8 @@
 // reference, co-jolt/src/poly/commitment/pst13.rs:319-323, asks for):
 //   1 decompose     scalar -> W signed c-bit digits -> (key, val) pairs.  key = (vector*W + window)*B + |digit|-1,
 //                   B = 2^(c-1); val = point index | sign << 31.  Zero digits keep a valid key and a skip mark in val.
-//   2 sort          pairs by key (cub radix sort in msm.cu) -> every bucket is one contiguous run.
+//   2 sort          pairs by key (sort_kernels.cuh: LSD radix sort, the first pass fused with the decompose step) ->
+//                   every bucket is one contiguous run.
 //   3 accumulate    load-balanced segmented sum: thread t owns pairs [t*L, (t+1)*L), whatever buckets they belong to.
 //                   Runs that lie inside one chunk are written straight to their bucket; the (at most two) runs that
 //                   cross a chunk edge are written as partial sums and summed by the same body one level up, until
@@ -158,6 +159,20 @@ COZK_HD uint32_t seg_take(uint32_t* cursor, uint32_t seg, uint32_t n) {
 #endif
 }
 
+// The (key, val) pair of window w of scalar (v, i): digit magnitude d with sign `neg`; `skip` = base at infinity.
+// A zero digit keeps a valid key (bucket 0 of its window) and is marked in val instead: the sort then needs no extra key
+// bit for a sentinel, which saves a whole radix pass when the bucket index is a multiple of 8 bits.
+COZK_HD void make_pair(const DecomposeArgs& A, uint32_t v, size_t i, uint32_t w, uint32_t d, uint32_t neg, bool skip,
+                       uint32_t& key, uint32_t& val) {
+    const uint32_t B = 1u << (A.c - 1);
+    const bool zero = (d == 0) || skip;
+    const uint32_t bw = A.table_stride ? 0u : w;
+    const uint32_t key0 = (v * A.bucket_windows + bw) * B;
+    const uint32_t point = (uint32_t)((size_t)w * A.table_stride + A.val_offset + i);
+    key = key0 + (zero ? 0u : d - 1);
+    val = zero ? VAL_SKIP : (point | neg);
+}
+
 // thread tid = v*n + i
 COZK_HD void decompose_body(size_t tid, const DecomposeArgs& A) {
     if (tid >= (size_t)A.g * A.n) return;
@@ -170,14 +185,12 @@ COZK_HD void decompose_body(size_t tid, const DecomposeArgs& A) {
     for (uint32_t w = 0; w < A.W; ++w) {
         uint32_t neg;
         const uint32_t d = signed_digit(s, w, A.c, carry, neg);
-        // A zero digit keeps a valid key (bucket 0 of its window) and is marked in val instead: the sort then needs no
-        // extra key bit for a sentinel, which saves a whole radix pass when the bucket index is a multiple of 8 bits.
         const bool zero = (d == 0) || skip;
+        uint32_t key, val;
+        make_pair(A, v, i, w, d, neg, skip, key, val);
         const uint32_t bw = A.table_stride ? 0u : w;
         const uint32_t key0 = (v * A.bucket_windows + bw) * B;
         const uint32_t point = (uint32_t)((size_t)w * A.table_stride + A.val_offset + i);
-        const uint32_t key = key0 + (zero ? 0u : d - 1);
-        const uint32_t val = zero ? VAL_SKIP : (point | neg);
         const uint32_t seg = v * A.W + w;
         const uint32_t mode = A.dom_mode ? A.dom_mode[seg] : 0u;
         if (mode == 0) {

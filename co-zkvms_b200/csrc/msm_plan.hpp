@@ -83,22 +83,24 @@ inline uint32_t windows_for(uint32_t bits, uint32_t c) { return (bits + 1 + c - 
 // cost, take the one whose top window is fullest.
 inline uint32_t top_window_bits(uint32_t bits, uint32_t c) { return bits + 1 - (windows_for(bits, c) - 1) * c; }
 
-// cost model in field multiplications: per window n mixed adds (+ the partial-merge overhead) and ~45 per bucket
+// cost model in field multiplications: per window n mixed adds (+ the partial-merge overhead) and ~45 per bucket.
+// Returns 0 when no window size keeps g * W * 2^(c-1) buckets inside max_buckets (and below 2^31: bucket keys share a
+// 32-bit word with the KEY_FILL mark): the caller has to split the group.
 inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_buckets) {
     double cost[C_MAX + 1];
+    for (double& x : cost) x = 1e300;
     double best_cost = 1e300;
     for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
-        cost[c] = 1e300;
         uint32_t W = windows_for(bits, c);
         double B = (double)(1u << (c - 1));
-        if ((double)g * W * B > (double)max_buckets) break;
-        if ((double)g * W * B >= 2147483647.0) break;
+        if ((double)g * W * B > (double)max_buckets || (double)g * W * B >= 2147483647.0) continue;
         cost[c] = (double)W * (11.0 * (double)n + 45.0 * B) + 400.0 * (double)((c + 2) / 4);
         if (cost[c] < best_cost) best_cost = cost[c];
     }
-    uint32_t best = C_MIN, best_top = 0;
+    if (best_cost >= 1e300) return 0;
+    uint32_t best = 0, best_top = 0;
     for (uint32_t c = C_MIN; c <= C_MAX; ++c) {
-        if (cost[c] > best_cost * 1.03) continue;
+        if (cost[c] >= 1e300 || cost[c] > best_cost * 1.03) continue;
         uint32_t tb = top_window_bits(bits, c);
         if (tb > best_top) {
             best_top = tb;
@@ -106,6 +108,14 @@ inline uint32_t choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_bu
         }
     }
     return best;
+}
+
+// the largest group size g <= want for which some window fits the bucket budget (>= 1: callers pass budgets that hold
+// one vector at c = C_MIN)
+inline uint32_t max_group_for(size_t n, uint32_t want, uint32_t bits, size_t max_buckets) {
+    uint32_t g = want ? want : 1;
+    while (g > 1 && choose_window(n, g, bits, max_buckets) == 0) g = (g + 1) / 2;
+    return g;
 }
 
 // window size for a registered SRS of n points whose windows all share one bucket set (precomputed table)
@@ -186,6 +196,7 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     p.g = g;
     p.bits = bits == 0 || bits > 254 ? 254 : bits;
     p.c = table_c ? table_c : (force_c ? force_c : choose_window(n, g, p.bits, max_buckets));
+    if (p.c == 0) p.c = C_MIN;  // no window fits the budget for this many vectors: callers bound g with max_group_for first
     p.W = windows_for(p.bits, p.c);
     p.Wb = table_c ? 1 : p.W;
     p.B = 1u << (p.c - 1);

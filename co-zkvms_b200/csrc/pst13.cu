@@ -1,6 +1,6 @@
-// Host-side mirror of the reference's PST13 / MultilinearPC interface for the MSM path (see pst13.hpp), plus the
+// Host-side mirror of the reference's PST13 / MultilinearPC interface for the MSM path (see include/cozk_pst13.h), plus the
 // two small kernels PST13's opening needs between its MSMs (fold r -> q, r').
-#include "pst13.hpp"
+#include "../../include/cozk_pst13.h"
 #include "../../include/cozk_rep3.h"
 
 #include <algorithm>

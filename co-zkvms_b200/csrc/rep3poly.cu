@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "engine.hpp"
-#include "pst13.hpp"
+#include "../../include/cozk_pst13.h"
 #include "rep3_kernels.cuh"
 
 namespace cozk {

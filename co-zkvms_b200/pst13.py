@@ -1,4 +1,4 @@
-"""Python face of csrc/pst13.hpp: the reference's PST13 commitment-scheme operations that reach the MSM.
+"""Python face of include/cozk_pst13.h: the reference's PST13 commitment-scheme operations that reach the MSM.
 
 Names follow co-jolt/src/poly/commitment/pst13.rs so that the parity tests read like the reference's own test
 (pst13.rs:476-547): PST13Setup, commit, batch_commit, batch_commit_rep3, open, combine_commitment_shares.

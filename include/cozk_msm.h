@@ -122,23 +122,8 @@ int cozk_host_alloc_pinned(size_t bytes, void** out);
 int cozk_host_free_pinned(void* ptr);
 int cozk_dev_flush_l2(cozk_ctx* ctx, int device_index); /* writes a 256 MiB scratch buffer */
 
-/* ---- synthetic inputs, generated on the device (bit-identical to oracle/bn254.c) */
-int cozk_testgen_bases(cozk_ctx* ctx, int device_index, uint64_t seed, size_t start, size_t n, void* d_out64);
-int cozk_testgen_scalars(cozk_ctx* ctx, int device_index, int dist, uint64_t seed, size_t start, size_t n, size_t total_n,
-                         int form, void* d_out, size_t stride_bytes);
 /* register bases that already live on device `device_index` (copied device-to-device; other devices get a peer copy) */
 int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_bases64, size_t n, cozk_srs* out);
-
-/* ---- element-wise kernels exposed for parity tests and roofline microbenchmarks (device pointers) */
-/* op: 0 fq_mul 1 fq_add 2 fq_sub 3 fq_sqr 4 fq_inv 5 fr_from_mont; arrays of n 32-byte elements */
-int cozk_test_field_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
-/* op: 0 xyzz_add 1 xyzz_madd 2 xyzz_dbl on arrays of n 72-byte wire points */
-int cozk_test_g1_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
-/* which: 0 = independent IMAD.WIDE chains (pipe peak), 1 = dependent fq_mul chains, 2 = fq_sqr chains, 3 = xyzz_madd chain,
- * 4 = IMAD.WIDE carry chains (mad.lo.cc/madc.hi.cc rows), 5 = mad.lo.u32, 6 = mad.hi.u32, 7 = four fq_mul chains per thread.
- * Runs `iters` operations per thread on blocks x threads; returns elapsed ms and the operation count. */
-int cozk_microbench(cozk_ctx* ctx, int device_index, int which, int blocks, int threads, int iters, double* out_ms,
-                    double* out_ops);
 
 #ifdef __cplusplus
 }

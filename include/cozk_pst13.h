@@ -1,4 +1,4 @@
-/* pst13.hpp - host-side mirror of the reference's commitment-scheme interface for the MSM path, above the
+/* cozk_pst13.h - host-side mirror of the reference's commitment-scheme interface for the MSM path, above the
  * MSM C ABI (include/cozk_msm.h).  Same operations, argument meaning and error behaviour as
  *
  *   PST13::commit                      co-jolt/src/poly/commitment/pst13.rs:282-296
@@ -16,9 +16,9 @@
  * A commitment is the reference's PST13Commitment{nv, g_product} (pst13.rs:398-401) laid out as
  *   u64 nv || 72-byte wire point                                                        (80 B)
  */
-#ifndef COZK_PST13_HPP
-#define COZK_PST13_HPP
-#include "../../include/cozk_msm.h"
+#ifndef COZK_PST13_H
+#define COZK_PST13_H
+#include "cozk_msm.h"
 
 #ifdef __cplusplus
 extern "C" {

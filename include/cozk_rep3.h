@@ -115,7 +115,7 @@ int cozk_pst13_open_key_release(cozk_ctx* ctx, cozk_open_key key);
 /* PST13 opening of a device-resident shared polynomial (share a) or public polynomial of 2^nv coefficients on device 0.
  * key != 0: the keyed schedule above (level_srs / nv are taken from the key); key == 0: the reference's schedule, one MSM
  * per level over the duplicated quotient scalars.  All folds run on the device; nothing but the nv proof points and the
- * evaluation comes back.  point / out_proofs / out_eval as cozk_pst13_open (csrc/pst13.hpp). */
+ * evaluation comes back.  point / out_proofs / out_eval as cozk_pst13_open (cozk_pst13.h). */
 int cozk_pst13_open_poly(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, cozk_open_key key, cozk_poly poly,
                          const void* point, void* out_proofs, void* out_eval);
 

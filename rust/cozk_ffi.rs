@@ -2,7 +2,7 @@
 //!
 //! Drop this file into `co-jolt/src/poly/commitment/cozk.rs` (and `co-noir-spartan/co-spartan/src/cozk.rs`), add
 //! `mod cozk;`, link `libcozk_msm.so` from a `build.rs`, and swap the call sites listed in INTEGRATION.md section 2.
-//! Every `extern "C"` item below is declared in `include/cozk_msm.h` / `co-zkvms_b200/csrc/pst13.hpp` and exported by the
+//! Every `extern "C"` item below is declared in `include/cozk_msm.h` / `include/cozk_pst13.h` and exported by the
 //! library (checked by `tests/test_abi.py`).
 
 #![allow(dead_code)]
@@ -38,7 +38,7 @@ extern "C" {
                                      form: c_int, out_points72: *mut c_void, out_srs: *mut CozkSrs) -> c_int;
     pub fn cozk_set_option(ctx: *mut CozkCtx, name: *const c_char, value: c_long) -> c_int;
     pub fn cozk_last_error() -> *const c_char;
-    // csrc/pst13.hpp
+    // include/cozk_pst13.h
     pub fn cozk_pst13_commit(ctx: *mut CozkCtx, srs: CozkSrs, evals: *const c_void, n: usize, stride_bytes: usize, form: c_int,
                              max_num_bits: c_uint, out_commitment: *mut c_void) -> c_int;
     pub fn cozk_pst13_batch_commit(ctx: *mut CozkCtx, srs: CozkSrs, polys: *const *const c_void, k: usize, n: usize, stride_bytes: usize,

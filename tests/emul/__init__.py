@@ -23,6 +23,8 @@ def lib():
         L = ctypes.CDLL(LIB)
         vp, sz, u32, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
         L.emul_msm.argtypes = [vp, sz, vp, sz, sz, ci, u32, u32, u32, vp, vp, vp, u32, sz, sz, u32]
+        L.emul_choose_window.argtypes = [sz, u32, u32, sz, ctypes.c_double, vp]
+        L.emul_choose_window.restype = None
         L.emul_set_dominant.argtypes = [ci]
         L.emul_set_dominant.restype = None
         L.emul_set_acc_chunk.argtypes = [sz, ci]
@@ -43,6 +45,13 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def choose_window(n, g, bits, max_buckets, poison=0.0):
+    """(window size or 0 when none fits, largest group size <= g that fits) as the engine's plan chooses them."""
+    out = np.zeros(2, np.uint32)
+    lib().emul_choose_window(n, g, bits, max_buckets, poison, _p(out))
+    return int(out[0]), int(out[1])
 
 
 def set_dominant(on):

@@ -26,6 +26,19 @@ extern "C" {
 
 void emul_set_dominant(int on) { g_dominant = on; }
 
+// The plan's window choice with the caller's stack poisoned first (choose_window once read cost[] entries it had
+// never written).  out[0] = c (0 = no window fits), out[1] = max_group_for(n, g, ...).
+__attribute__((noinline)) static void poison_stack(double fill) {
+    volatile double junk[64];
+    for (int i = 0; i < 64; ++i) junk[i] = fill;
+}
+void emul_choose_window(size_t n, uint32_t g, uint32_t bits, size_t max_buckets, double poison, uint32_t* out) {
+    poison_stack(poison);
+    out[0] = choose_window(n, g, bits, max_buckets);
+    poison_stack(poison);
+    out[1] = max_group_for(n, g, bits, max_buckets);
+}
+
 // level-1 chunk length of the accumulate stage: resident != 0 lets the plan choose it as the engine does (wave filling),
 // force_l != 0 fixes it
 void emul_set_acc_chunk(size_t resident, int force_l) {

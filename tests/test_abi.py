@@ -21,7 +21,7 @@ def _declared(path):
 def test_library_exports_every_declared_symbol(cozk):
     L = cozk.lib()
     declared = (_declared(os.path.join(ROOT, "include", "cozk_msm.h")) + _declared(os.path.join(ROOT, "include", "cozk_rep3.h"))
-                + _declared(os.path.join(ROOT, "co-zkvms_b200", "csrc", "pst13.hpp")))
+                + _declared(os.path.join(ROOT, "include", "cozk_pst13.h")) + _declared(os.path.join(ROOT, "include", "cozk_test.h")))
     assert len(declared) >= 25
     for name in declared:
         assert hasattr(L, name), name

@@ -37,6 +37,27 @@ def test_group_law_bodies(orc):
     assert (emul.g1_op("add", pts, np.roll(pts, 1, axis=0)) == orc.g1_op("add", pts, np.roll(pts, 1, axis=0))).all()
 
 
+def test_window_choice_respects_bucket_budget():
+    """Large batches: every window that is considered keeps g * W * 2^(c-1) buckets inside the budget whatever the stack
+    held before the call (cost[] entries behind the first misfit were read unwritten)."""
+    budget = 1 << 25
+    for g in (1, 3, 54, 138, 256, 1000, 4096):
+        for n in (1 << 10, 1 << 16, 1 << 20):
+            seen = set()
+            for poison in (0.0, -1.0, 1e300, 5.0):
+                c, gfit = emul.choose_window(n, g, 254, budget, poison)
+                seen.add((c, gfit))
+                if c:
+                    W = (254 + 1 + c - 1) // c
+                    assert g * W * (1 << (c - 1)) <= budget, (g, n, c)
+                assert 1 <= gfit <= g
+                cf, _ = emul.choose_window(n, gfit, 254, budget, poison)
+                Wf = (254 + 1 + cf - 1) // cf
+                assert cf and gfit * Wf * (1 << (cf - 1)) <= budget
+            assert len(seen) == 1, (g, n, seen)
+    assert emul.choose_window(1 << 16, 1 << 26, 254, budget)[0] == 0
+
+
 def test_msm_golden():
     for case in H.golden()["msm"]:
         if case["n"] > 300:

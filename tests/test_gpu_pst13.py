@@ -1,4 +1,4 @@
-"""GPU tier: the reference-facing commitment-scheme operations (csrc/pst13.hpp).  test_combine_commitments follows
+"""GPU tier: the reference-facing commitment-scheme operations (include/cozk_pst13.h).  test_combine_commitments follows
 the reference's own test, co-jolt/src/poly/commitment/pst13.rs:476-547 (linearity of commit under
 combine_commitments); the opening is checked against a direct restatement of open() (pst13.rs:428-474) on the oracle."""
 import numpy as np
