@@ -16,6 +16,11 @@ roofline: the dominant kernel (bucket accumulation) against the SELF-MEASURED in
           (MEASURED_PEAKS.json has no integer figure); HBM traffic is reported to show it is not the bound.
 cpu_baseline: the CPU oracle (C restatement of arkworks' Pippenger; the Rust reference cannot be built here) on the
           box's host cores.  --impl reference prints only that, as its own line.
+strong  : BASELINE.json configs[3] through the library's own single-process multi-device path (the Rust caller's shape):
+          ONE context over all N GPUs on rank 0, the SRS registered in slices (each GPU holds only its point range and its
+          table), ONE 2^24-point MSM from pinned host scalars through cozk_msm_batch, partial sums combined inside the call;
+          the result is compared with the CPU oracle.  The other ranks idle meanwhile.  --strong-log2n 0 skips it.
+parity_vs_oracle: the (combined) point of the timed MSM against the CPU oracle, at every N.
 """
 import argparse
 import importlib
@@ -109,6 +114,60 @@ def cpu_reference_run(log2n, dist, steps, warmup, threads):
     return n * len(times) / total / 1e6, 1e3 * total / len(times), "2^%d points, %s scalars, %d threads" % (log2n, dist, threads)
 
 
+def strong_record(cozk, args, n_devices, check):
+    """BASELINE.json configs[3]: one MSM of 2^strong_log2n points sharded by point range over all GPUs of the box, driven
+    by ONE process through cozk_msm_batch with host scalars (what the Rust caller does); sliced SRS."""
+    n = 1 << args.strong_log2n
+    rec = {"log2_points_total": args.strong_log2n, "n_devices": n_devices, "scalar_dist": args.dist,
+           "path": "one cozk_ctx over all devices, cozk_srs_register_sliced, cozk_msm_batch(host scalars, k=1); partial sums "
+                   "added on the host inside the timed call"}
+    with cozk.Context(devices=list(range(n_devices))) as mctx:
+        gb = mctx.testgen_bases(1, n)
+        hb = gb.download().reshape(n, 64)
+        gb.free()
+        gs = mctx.testgen_scalars(args.dist, 2, n)
+        pinned = cozk.PinnedBuffer(n * 32)
+        pinned.array[:] = gs.download()
+        gs.free()
+        t0 = time.perf_counter()
+        srs = mctx.srs_register(hb, sliced=True)
+        rec["srs_register_ms"] = 1e3 * (time.perf_counter() - t0)
+        out = np.zeros((1, 72), dtype=np.uint8)
+        for _ in range(2):
+            mctx.msm_batch_ptrs(srs, [pinned.ptr], n, out=out)
+        wall, dev_total, dev_compute = 0.0, 0.0, 0.0
+        pairs = mults = 0.0
+        for _ in range(args.strong_steps):
+            for d in range(n_devices):
+                mctx.flush_l2(d)
+            t0 = time.perf_counter()
+            mctx.msm_batch_ptrs(srs, [pinned.ptr], n, out=out)
+            wall += time.perf_counter() - t0
+            sts = [mctx.last_stats(d) for d in range(n_devices)]
+            dev_total += max(st["total_ms"] for st in sts)
+            dev_compute += max(st["total_ms"] - st["h2d_ms"] for st in sts)
+            pairs = sum(st["pairs"] for st in sts)
+            mults = sum(st["field_mults"] for st in sts)
+        k_ = args.strong_steps
+        rec.update({"steps": k_, "e2e_ms": 1e3 * wall / k_, "e2e_mpoints_per_s": n / (wall / k_) / 1e6,
+                    "device_ms_max": dev_total / k_, "device_mpoints_per_s": n / (dev_total / k_ * 1e-3) / 1e6,
+                    "compute_ms_max": dev_compute / k_,
+                    "timing_note": "e2e = wall clock around cozk_msm_batch (H2D of every device's slice, kernels, D2H, host combine); "
+                                   "device_ms_max = the slowest device's CUDA-event time of its part (its H2D included); compute_ms_max "
+                                   "leaves the H2D wait out",
+                    "window_bits": int(sts[0]["window"]), "windows": int(sts[0]["windows"]),
+                    "canonical_limb_products": n * CANON_MULTS_PER_POINT * LIMB_PRODUCTS_PER_MULT,
+                    "actual_limb_products": pairs * LIMB_PRODUCTS_PER_MADD + (mults - 10.0 * pairs) * LIMB_PRODUCTS_PER_MULT,
+                    "result_x_le": bytes(out[0][:8]).hex()})
+        if check:
+            from oracle import orc as _o
+            want = _o.msm(hb, pinned.array.reshape(n, 32))
+            rec["parity_vs_oracle"] = bool((want == out[0]).all())
+        mctx.srs_release(srs)
+        pinned.free()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -119,14 +178,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-log2n", type=int, default=24, help="total points of the strong-scaling record (0 = skip)")
+    ap.add_argument("--strong-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    from oracle import orc
-    cores = orc.ncores()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     config = {"workload": "standalone BN254 G1 MSM, 2^%d %s share scalars per GPU (BASELINE.json configs[1]), "
                           "k=1, point-range sharded across GPUs" % (args.log2n, args.dist),
               "log2_points_per_gpu": args.log2n, "scalar_dist": args.dist, "scalar_form": "Fr Montgomery, stride 32",
@@ -172,7 +235,9 @@ def main():
         ctx.set_option("window", args.window)
     # rank r owns points [r*n, (r+1)*n) of the global MSM: generate only that slice, on the device
     dbases = ctx.testgen_bases(1, n, start=rank * n)
+    t_reg = time.perf_counter()
     srs = ctx.srs_register_device(dbases, n)
+    srs_register_ms = 1e3 * (time.perf_counter() - t_reg)
     dbases.free()
     dscal = ctx.testgen_scalars(args.dist, 2, n, start=rank * n, total_n=world * n)
     pinned = cozk.PinnedBuffer(n * 32)
@@ -228,15 +293,31 @@ def main():
     partial = out.copy()
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s * 1e3, wall_ms], dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_s * 1e3, wall_ms, srs_register_ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms_total, wall_ms = [float(x) for x in t]
+        dev_ms, e2e_ms_total, wall_ms, srs_register_ms = [float(x) for x in t]
         e2e_s = e2e_ms_total / 1e3
         allp = sharding.gather_partials(partial)
         total_point = sharding.combine(allp, cozk.g1_sum)[0]
     else:
         total_point = partial[0]
 
+    parity = None
+    strong = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # the checker (never the thing measured): the combined point of the timed MSM against the CPU oracle
+        from oracle import orc as _o
+        _o.build()
+        total_n = world * n
+        if total_n <= (1 << 24):
+            gb = ctx.testgen_bases(1, total_n)
+            hb = gb.download().reshape(total_n, 64)
+            gb.free()
+            want = _o.msm(hb, _o.gen_scalars(args.dist, 2, total_n))
+            parity = bool((want == total_point).all())
+            del hb
+    if rank == 0 and args.strong_log2n:
+        strong = strong_record(cozk, args, world, not args.no_cpu_baseline)
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = world * n / (ms_per_step * 1e-3) / 1e6
@@ -259,8 +340,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "Mpoints/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 72,
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": launches,
-                "gpu_launches_note": "engine kernels only (decompose, accumulate levels, reduce levels, finish); the cub "
-                                     "radix sort adds its own launches per step",
+                "gpu_launches_note": "every kernel of the call is the engine's own: fused decompose + sort passes (count / scan / "
+                                     "scatter), accumulate levels, reduce levels, finish",
                 "roofline": {"bound": "imad", "kernel": "k_accumulate (bucket accumulation, all levels)",
                              "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "G limb-products/s (IMAD.WIDE.U32 lane-ops)",
                              "frac": achieved / imad_peak, "traffic": traffic,
@@ -286,21 +367,24 @@ def main():
                              "madd_per_s_measured": madd_rate, "madd_frac_of_imad_peak": madd_rate * 10 * LIMB_PRODUCTS_PER_MULT / imad_peak,
                              "hbm_algorithmic_gbs": (n * (64 + 32) + st["pairs"] * (64 + 8 * 4 * 2)) / (ms_per_step * 1e-3) / 1e9},
                 "stages_ms": {k_: v / args.steps for k_, v in stage.items()},
+                "stages_note": "decompose_ms = digit decomposition fused with the first sort pass; sort_ms = the remaining passes",
+                "srs_register_ms": srs_register_ms,
                 "wall_ms_per_step_incl_flush": wall_ms / args.steps,
                 "clocks": sampler.summary(),
                 "result_x_le": bytes(total_point[:8]).hex(), "result_infinity": int(total_point[64])}
+        if parity is not None:
+            line["parity_vs_oracle"] = parity
+        if strong is not None:
+            line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
             log2c = min(args.log2n, 20 if cores >= 8 else 18)
             v, ms_c, sample = cpu_reference_run(log2c, args.dist, 2, 1, cores)
+            anchor = 0.125 * cores
             line["cpu_baseline"] = {"value": v, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample,
-                                    "ms_per_msm": ms_c, "per_core": v / cores,
+                                    "ms_per_msm": ms_c, "per_core": v / cores, "vs_anchor": v / anchor,
                                     "anchor": "the reference's own traces give 0.12-0.13 Mpoints/s per vCPU for arkworks / jolt-core "
-                                              "(SURVEY.md section 6): the port is not a straw man"}
-            if log2c == args.log2n:
-                # the CPU baseline doubles as a parity check of the timed MSM
-                from oracle import orc as _o
-                want = _o.msm(_o.gen_bases(1, n), _o.gen_scalars(args.dist, 2, n))
-                line["parity_vs_oracle"] = bool((want == total_point).all())
+                                              "(SURVEY.md section 6); vs_anchor = this port / (0.125 Mpoints/s x cores): below 1 the "
+                                              "port is slower than the real reference and every GPU/CPU ratio is inflated by 1 / vs_anchor"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -31,7 +31,7 @@ DIST = {"uniform": 0, "const": 1, "wminus": 2, "dup": 3, "small16": 4, "zero_hal
 
 # every symbol include/cozk_msm.h, cozk_pst13.h and cozk_test.h declare (checked by tests/test_abi.py without a GPU)
 ABI_SYMBOLS = [
-    "cozk_init", "cozk_destroy", "cozk_device_count", "cozk_srs_register", "cozk_srs_release", "cozk_srs_len",
+    "cozk_init", "cozk_destroy", "cozk_device_count", "cozk_srs_register", "cozk_srs_register_sliced", "cozk_srs_release", "cozk_last_stats_device", "cozk_srs_len",
     "cozk_msm_batch", "cozk_msm_batch_device", "cozk_g1_sum", "cozk_set_option", "cozk_last_stats", "cozk_last_error",
     "cozk_dev_alloc", "cozk_dev_free", "cozk_dev_upload", "cozk_dev_download", "cozk_host_alloc_pinned",
     "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_testgen_bases", "cozk_testgen_scalars",
@@ -94,6 +94,8 @@ def lib():
     L.cozk_destroy.restype = None
     L.cozk_device_count.argtypes = [vp]
     L.cozk_srs_register.argtypes = [vp, vp, sz, sz, vp, ctypes.POINTER(u64)]
+    L.cozk_srs_register_sliced.argtypes = [vp, vp, sz, sz, vp, ctypes.POINTER(u64)]
+    L.cozk_last_stats_device.argtypes = [vp, ci, cd]
     L.cozk_srs_register_device.argtypes = [vp, ci, vp, sz, ctypes.POINTER(u64)]
     L.cozk_srs_release.argtypes = [vp, u64]
     L.cozk_srs_len.argtypes = [vp, u64, ctypes.POINTER(sz)]
@@ -234,14 +236,18 @@ class Context:
         return lib().cozk_device_count(self.handle)
 
     # ---- SRS
-    def srs_register(self, bases, infinity=None, stride=None):
-        """bases: uint8 array (n, stride>=64), each row x||y Fq Montgomery (arkworks in-memory limbs)."""
+    def srs_register(self, bases, infinity=None, stride=None, sliced=False):
+        """bases: uint8 array (n, stride>=64), each row x||y Fq Montgomery (arkworks in-memory limbs).  sliced=True: every
+        device of the context keeps only its point range (cozk_srs_register_sliced)."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         n = bases.shape[0]
         stride = bases.shape[1] if stride is None else stride
         inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
+        if inf is not None and inf.size < n:
+            raise ValueError("infinity flags: %d for %d bases" % (inf.size, n))
         h = ctypes.c_uint64()
-        _check(lib().cozk_srs_register(self.handle, _ptr(bases), n, stride, _ptr(inf), ctypes.byref(h)))
+        fn = lib().cozk_srs_register_sliced if sliced else lib().cozk_srs_register
+        _check(fn(self.handle, _ptr(bases), n, stride, _ptr(inf), ctypes.byref(h)))
         return h.value
 
     def srs_register_device(self, dbuf, n, device=0):
@@ -271,6 +277,9 @@ class Context:
         k = len(vecs)
         if n is None:
             n = vecs[0].size // stride if k else 0
+        for j, v in enumerate(vecs):  # the C ABI has no length arguments: a short buffer would be read past its end
+            if n and v.size < (n - 1) * stride + 32:
+                raise ValueError("scalar vector %d holds %d bytes, %d points at stride %d need %d" % (j, v.size, n, stride, (n - 1) * stride + 32))
         ptrs = (ctypes.c_void_p * max(k, 1))(*[v.ctypes.data for v in vecs])
         out = np.zeros((k, 72), dtype=np.uint8)
         _check(lib().cozk_msm_batch(self.handle, srs, base_offset, n, ptrs, k, stride, form, max_num_bits, _ptr(out)))
@@ -302,9 +311,9 @@ class Context:
     def set_option(self, name, value):
         _check(lib().cozk_set_option(self.handle, name.encode(), int(value)))
 
-    def last_stats(self):
+    def last_stats(self, device=0):
         s = (ctypes.c_double * 12)()
-        _check(lib().cozk_last_stats(self.handle, s))
+        _check(lib().cozk_last_stats_device(self.handle, device, s))
         keys = ["h2d_ms", "decompose_ms", "sort_ms", "accumulate_ms", "reduce_ms", "finish_ms", "total_ms", "launches",
                 "window", "windows", "field_mults", "pairs"]
         return dict(zip(keys, list(s)))

@@ -72,12 +72,33 @@ struct Device {
     ~Device();
 };
 
+// Device memory of one registered SRS.  Shared by the handle table and by every call in flight that looked the SRS up:
+// cozk_srs_release only drops the table's reference, the memory goes when the last user lets go.
+struct SrsMem {
+    std::vector<int> cuda_id;        // CUDA device id per context device
+    std::vector<affine*> bases;      // per context device: table_W rows of n points (row 0 = the bases) + row totals; null = not on this device
+    std::vector<uint8_t*> inf;       // per context device, may be null
+    bool owns = true;                // false: a view into another SRS's memory (row views of the totals computation)
+    ~SrsMem();
+};
+
+struct SrsEntry;
+// One slice of a sliced SRS (cozk_srs_register_sliced): points [lo, lo + len) live on context device `dev` only, as a
+// complete single-device SRS with its own table and row totals.
+struct SrsSlice {
+    int dev = 0;
+    size_t lo = 0, len = 0;
+    std::shared_ptr<SrsEntry> entry;
+};
+
 struct SrsEntry {
     size_t n = 0;
-    std::vector<affine*> d_bases;    // per device: table_W rows of n points, row w = 2^(table_c*w) * bases (row 0 = bases)
-    std::vector<uint8_t*> d_inf;     // per device, may be null
+    std::shared_ptr<SrsMem> mem;     // null for a sliced SRS (its slices own the memory)
+    std::vector<SrsSlice> slices;    // non-empty: sliced SRS, every call is sharded by point range along these slices
+    affine* bases(int dev) const { return mem && dev < (int)mem->bases.size() ? mem->bases[dev] : nullptr; }
+    uint8_t* inf(int dev) const { return mem && dev < (int)mem->inf.size() ? mem->inf[dev] : nullptr; }
     uint32_t table_c = 0;            // window size the table rows were built for; 0 = no table
-    uint32_t table_W = 1;            // rows
+    uint32_t table_W = 1;            // rows: row w = 2^(table_c*w) * bases
     // Dominant-digit mode: behind the table, entry table_W * n + j * table_W + w holds the sum of the first n >> j points of
     // row w, for j = 0 .. total_levels - 1 (n >> j >= 1024): whole-SRS calls and power-of-two prefixes (a 2^16 polynomial
     // against a 2^22 SRS).  Bit j of total_ok: level j is usable (every row sum is a finite point).
@@ -98,6 +119,10 @@ struct PolyEntry {
     int user_kind = 0;      // the COZK_POLY_* constant it was created as
     unsigned bits = 0;      // max_num_bits hint for the MSM (8/16/32/64 for small unsigned kinds, 0 otherwise)
     uint8_t* d_data = nullptr;
+    // Set when the entry is published in the handle table: owns d_data (stream-ordered free on the owning device's stream
+    // when the last copy of the entry goes).  A call that looked the polynomial up holds a copy, so cozk_poly_release on
+    // another thread cannot free the memory under it.
+    std::shared_ptr<void> hold;
     size_t total = 0, lo = 0, len = 0;
     size_t elem_bytes() const { return kind == 0 ? 64 : 32; }
     const uint8_t* chunk() const { return d_data + lo * elem_bytes(); }
@@ -120,7 +145,11 @@ struct OpenKey {
 struct cozk_ctx;
 namespace cozk {
 // Register n points that already live on device `device_index` (d_inf: optional per-point infinity flags, device memory).
-int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out);
+// only_device < 0: the SRS is replicated on every device of the context; >= 0: it lives on that device alone (the
+// internal SRSs of an opening key, which only device 0 ever reads).
+int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out,
+                             int only_device = -1);
+int srs_lookup(cozk_ctx* ctx, cozk_srs srs, SrsEntry* out);
 // Where the 2^nv evaluations of an opening come from: host memory (staged through a scratch buffer) or device 0.
 struct OpenSource {
     const void* host = nullptr;      // element i at host + i * stride

@@ -357,6 +357,10 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                          const void* const* host_scalars, const void* const* dev_scalars, size_t k, size_t stride, int form,
                          unsigned max_bits, uint8_t* out) {
     Device& D = *ctx->devs[dev_index];
+    if (!S.bases(dev_index)) {
+        set_error("this SRS does not live on the device the call was sent to");
+        return COZK_ERR_INVALID_ARG;
+    }
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
     for (double& s : D.stats) s = 0;
@@ -374,7 +378,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     for (size_t pass = 0; pass < passes; ++pass) {
         size_t lo = pass * MAX_POINTS_PER_PASS;
         size_t pn = std::min(MAX_POINTS_PER_PASS, n - lo);
-        const uint8_t* d_inf = S.d_inf[dev_index] ? S.d_inf[dev_index] + offset + lo : nullptr;
+        const uint8_t* d_inf = S.inf(dev_index) ? S.inf(dev_index) + offset + lo : nullptr;
         uint8_t* pass_out = passes > 1 ? partial.data() + pass * k * 72 : out;
 
         // With a precomputed table (2^(c*w) * P rows built at registration) all windows share one bucket set; use it
@@ -385,7 +389,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             MsmPlan without = make_plan(pn, 1, bits, max_buckets, 0, 0);
             if (with_table.W <= S.table_W && with_table.model_cost() <= without.model_cost()) table_c = S.table_c;
         }
-        const affine* d_bases = table_c ? S.d_bases[dev_index] : S.d_bases[dev_index] + offset + lo;
+        const affine* d_bases = table_c ? S.bases(dev_index) : S.bases(dev_index) + offset + lo;
         const size_t table_stride = table_c ? S.n : 0, val_offset = table_c ? offset + lo : 0;
 
         // One long vector from host memory: feed it in point chunks through ONE bucket set, so that the H2D copy of
@@ -573,13 +577,8 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
     }
     SrsEntry S;
     {
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        auto it = ctx->srs.find(srs);
-        if (it == ctx->srs.end()) {
-            set_error("unknown SRS handle");
-            return COZK_ERR_BAD_HANDLE;
-        }
-        S = it->second;
+        int lrc = srs_lookup(ctx, srs, &S);
+        if (lrc) return lrc;
     }
     if (base_offset > S.n || n > S.n - base_offset) {
         set_error("Key length error: base_offset + n exceeds the registered SRS");
@@ -593,6 +592,52 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
         }
         return COZK_OK;
     }
+    if (!S.slices.empty()) {
+        // Sliced SRS: every device holds only its point range (with its own table); the call is cut along the slices, the
+        // devices run side by side (one host thread each) and the partial sums are added on the host - the reference's
+        // split_ck + combine_comm scheme (co-noir-spartan/co-spartan/src/utils.rs:38-83, snarks-core/src/poly/commitment.rs:56-63).
+        if (!host_scalars || only_device >= 0) {
+            set_error("a sliced SRS takes host scalars through cozk_msm_batch");
+            return COZK_ERR_INVALID_ARG;
+        }
+        struct Part {
+            const SrsSlice* sl;
+            size_t off, cnt, skip;  // offset inside the slice, points, points of the call before this part
+        };
+        std::vector<Part> parts;
+        for (const SrsSlice& sl : S.slices) {
+            const size_t a = std::max(base_offset, sl.lo), b = std::min(base_offset + n, sl.lo + sl.len);
+            if (a < b) parts.push_back({&sl, a - sl.lo, b - a, a - base_offset});
+        }
+        const size_t np = parts.size();
+        std::vector<int> rcs(np, COZK_OK);
+        std::vector<std::string> errs(np);
+        std::vector<uint8_t> partial(np * k * 72);
+        std::vector<std::vector<const void*>> ptrs(np, std::vector<const void*>(k));
+        auto work = [&](size_t pi) {
+            const Part& pt = parts[pi];
+            for (size_t j = 0; j < k; ++j) ptrs[pi][j] = reinterpret_cast<const uint8_t*>(host_scalars[j]) + pt.skip * stride;
+            rcs[pi] = run_on_device(ctx, pt.sl->dev, *pt.sl->entry, pt.off, pt.cnt, ptrs[pi].data(), nullptr, k, stride, form, max_bits,
+                                    &partial[pi * k * 72]);
+            if (rcs[pi]) errs[pi] = g_error;
+        };
+        std::vector<std::thread> th;
+        for (size_t pi = 1; pi < np; ++pi) th.emplace_back(work, pi);
+        work(0);
+        for (auto& t : th) t.join();
+        for (size_t pi = 0; pi < np; ++pi) {
+            if (rcs[pi]) {
+                set_error(errs[pi]);
+                return rcs[pi];
+            }
+        }
+        std::vector<uint8_t> col(np * 72);
+        for (size_t j = 0; j < k; ++j) {
+            for (size_t pi = 0; pi < np; ++pi) memcpy(&col[72 * pi], &partial[(pi * k + j) * 72], 72);
+            host_sum(col.data(), np, o + 72 * j);
+        }
+        return COZK_OK;
+    }
     int nd = (int)ctx->devs.size();
     if (only_device >= 0 || nd == 1) {
         int d = only_device >= 0 ? only_device : 0;
@@ -603,6 +648,10 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
         return run_on_device(ctx, d, S, base_offset, n, host_scalars, dev_scalars, k, stride, form, max_bits, o);
     }
     // several devices: shard by vector when there are enough of them, else by point range; combine on the host
+    if (!host_scalars) {
+        set_error("device-resident scalars need a device index (cozk_msm_batch_device)");
+        return COZK_ERR_INVALID_ARG;
+    }
     std::vector<int> rcs(nd, COZK_OK);
     std::vector<std::string> errs(nd);
     std::vector<std::thread> th;
@@ -653,8 +702,33 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
     return COZK_OK;
 }
 
-// rows of the precomputed table for an SRS of n points under the context's memory policy (1 = bases only)
-static void srs_table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t* W) {
+SrsMem::~SrsMem() {
+    if (!owns) return;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (size_t j = 0; j < bases.size(); ++j) {
+        if (!bases[j] && !inf[j]) continue;
+        cudaSetDevice(cuda_id[j]);
+        if (bases[j]) cudaFree(bases[j]);  // cudaFree waits for the device: nothing in flight still reads the memory
+        if (inf[j]) cudaFree(inf[j]);
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+}
+
+int srs_lookup(cozk_ctx* ctx, cozk_srs srs, SrsEntry* out) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->srs.find(srs);
+    if (it == ctx->srs.end()) {
+        set_error("unknown SRS handle");
+        return COZK_ERR_BAD_HANDLE;
+    }
+    *out = it->second;  // shares the device memory: a concurrent cozk_srs_release cannot free it under this call
+    return COZK_OK;
+}
+
+// rows of the precomputed table for an SRS of n points on the given devices under the context's memory policy
+// (1 = bases only)
+static void srs_table_shape(const cozk_ctx* ctx, const std::vector<int>& devices, size_t n, uint32_t* c, uint32_t* W) {
     *c = 0;
     *W = 1;
     if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
@@ -662,157 +736,216 @@ static void srs_table_shape(const cozk_ctx* ctx, size_t n, uint32_t* c, uint32_t
     uint32_t tw = windows_for(254, tc);
     const double table_bytes = (double)tw * (double)n * sizeof(affine);
     if (table_bytes > (double)ctx->opt_table_max_bytes) return;
-    // never more than half of what is free on the device now (sort buffers, buckets and resident polynomials need the rest)
-    size_t free_b = 0, total_b = 0;
-    if (!ctx->devs.empty() && cudaSetDevice(ctx->devs[0]->id) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
-        table_bytes > 0.5 * (double)free_b)
-        return;
+    // never more than half of what is free on a device now (sort buffers, buckets and resident polynomials need the rest)
+    for (int di : devices) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaSetDevice(ctx->devs[di]->id) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+            table_bytes > 0.5 * (double)free_b)
+            return;
+    }
     if ((double)tw * (double)n >= 2147483647.0) return;  // table indices share 31 bits with the point index; all-ones is the skip mark
     *c = tc;
     *W = tw;
 }
-// Launches the table build on the device's stream and returns: with several devices the tables are built side by side
-// (the current device must be D's); srs_wait_tables waits for all of them.
-static int srs_build_table(Device& D, affine* d_table, size_t n, uint32_t c, uint32_t W) {
-    if (W <= 1 || n == 0) return COZK_OK;
-    TableArgs A{d_table, n, c, W};
-    k_build_table<<<grid_for(n, 128), 128, 0, D.stream>>>(A);
-    COZK_CUDA(cudaGetLastError());
-    return COZK_OK;
-}
-static int srs_wait_tables(cozk_ctx* ctx, size_t n_devices) {
-    for (size_t j = 0; j < n_devices; ++j) {
-        COZK_CUDA(cudaSetDevice(ctx->devs[j]->id));
-        COZK_CUDA(cudaStreamSynchronize(ctx->devs[j]->stream));
-    }
-    return COZK_OK;
-}
 
 // The sums of every table row over the whole SRS and over its power-of-two prefixes (down to 1024 points), stored behind
-// the table: what the dominant-digit mode of the decompose pass needs (msm_kernels.cuh).  Each sum is an MSM whose scalars
-// are all 1 - one window, one bucket - run through the engine's own pipeline on a view of the row.  Setup-time work
-// (2^20 points, 15 rows: ~30 ms for all prefix lengths together).
-static int srs_compute_totals(cozk_ctx* ctx, SrsEntry& S) {
+// the table: what the dominant-digit mode of the decompose pass needs (msm_kernels.cuh).  ONE segmented sum per group of
+// rows: the points of a row fall into `levels` blocks - [0, n >> (L-1)), then [n >> (L-j), n >> (L-j-1)) - whose keys are
+// born sorted, the accumulate stage adds every block up, and the host forms the prefix sums over the blocks and
+// normalises them (levels x rows points).  Setup-time work.
+__global__ void __launch_bounds__(256) k_totals_pairs(size_t n, uint32_t levels, uint32_t row0, uint32_t rows, uint32_t* keys, uint32_t* vals) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)rows * n) return;
+    const uint32_t r = (uint32_t)(t / n);
+    const size_t i = t - (size_t)r * n;
+    uint32_t b = 0;
+    while (b + 1 < levels && i >= (n >> (levels - 1 - b))) ++b;
+    keys[t] = r * levels + b;
+    vals[t] = (uint32_t)((size_t)(row0 + r) * n + i);
+}
+
+static int srs_compute_totals(cozk_ctx* ctx, int di, SrsEntry& S) {
     S.total_levels = 0;
     S.total_ok = 0;
     const uint32_t levels = SrsEntry::totals_levels_for(S.n);
-    if (levels == 0) return COZK_OK;
-    for (uint8_t* f : S.d_inf)
-        if (f) return COZK_OK;  // bases at infinity: the totals would have to leave them out; not worth a second code path
-    const uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t ok = ~(uint64_t)0;
-    for (size_t di = 0; di < S.d_bases.size(); ++di) {
-        Device& D = *ctx->devs[di];
-        uint32_t* d_one = nullptr;
-        COZK_CUDA(cudaSetDevice(D.id));
-        COZK_CUDA(cudaMalloc(&d_one, 32));
-        // on the engine's stream and synchronised there (a pageable cudaMemcpy is only STAGED when it returns, and the
-        // engine's non-blocking streams do not wait for the legacy default stream)
-        cudaError_t e = cudaMemcpyAsync(d_one, one, 32, cudaMemcpyHostToDevice, D.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-        int rc = e == cudaSuccess ? COZK_OK : COZK_ERR_CUDA;
-        for (uint32_t j = 0; j < levels && !rc; ++j) {
-            const size_t len = S.n >> j;
-            if (len << j != S.n) {  // only exact halvings of the SRS length
-                ok &= ~((uint64_t)1 << j);
-                continue;
-            }
-            for (uint32_t r = 0; r < S.table_W && !rc; ++r) {
-                SrsEntry V;
-                V.n = len;
-                V.d_bases.assign(S.d_bases.size(), nullptr);
-                V.d_inf.assign(S.d_bases.size(), nullptr);
-                V.d_bases[di] = S.d_bases[di] + (size_t)r * S.n;
-                const void* ptr = d_one;
-                uint8_t out[72];
-                rc = run_on_device(ctx, (int)di, V, 0, len, nullptr, &ptr, 1, 0, COZK_CANON, 1, out);
-                if (rc) break;
-                if (out[64]) {
-                    ok &= ~((uint64_t)1 << j);  // a sum that is the identity has no affine form: plain path for this length
-                    continue;
-                }
-                COZK_CUDA(cudaSetDevice(D.id));
-                e = cudaMemcpyAsync(S.d_bases[di] + (size_t)S.table_W * S.n + (size_t)j * S.table_W + r, out, 64,
-                                    cudaMemcpyHostToDevice, D.stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-                if (e != cudaSuccess) rc = COZK_ERR_CUDA;
-            }
-        }
-        cudaSetDevice(D.id);
-        cudaFree(d_one);
-        if (rc) {
-            if (rc == COZK_ERR_CUDA) set_error("SRS registration: row totals failed");
+    if (levels == 0 || S.inf(di)) return COZK_OK;  // bases at infinity: the totals would have to leave them out; not worth a second code path
+    Device& D = *ctx->devs[di];
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    const size_t n = S.n;
+    const uint32_t rows_per_pass = (uint32_t)std::max<size_t>(1, std::min<size_t>(S.table_W, ((size_t)1 << 28) / n));
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, 0};
+    std::vector<xyzz> sums((size_t)S.table_W * levels);
+    double launches = 0;
+    int rc;
+    for (uint32_t row0 = 0; row0 < S.table_W; row0 += rows_per_pass) {
+        const uint32_t rows = std::min(rows_per_pass, S.table_W - row0);
+        MsmPlan P;
+        P.n = n;
+        P.g = 1;
+        P.acc = acc_tuning;
+        P.total_buckets = (size_t)rows * levels;
+        plan_set_pairs(P, (size_t)rows * n);
+        if ((rc = D.keys_b.ensure(P.m * 4)) || (rc = D.vals_b.ensure(P.m * 4)) || (rc = D.buckets.ensure(P.total_buckets * sizeof(xyzz))))
             return rc;
+        k_totals_pairs<<<grid_for(P.m, 256), 256, 0, D.stream>>>(n, levels, row0, rows, D.keys_b.as<uint32_t>(), D.vals_b.as<uint32_t>());
+        COZK_CUDA(cudaGetLastError());
+        if ((rc = run_accumulate(D, P, D.keys_b.as<uint32_t>(), D.vals_b.as<uint32_t>(), S.bases(di), D.buckets.as<xyzz>(), &launches)))
+            return rc;
+        COZK_CUDA(cudaMemcpyAsync(&sums[(size_t)row0 * levels], D.buckets.p, P.total_buckets * sizeof(xyzz), cudaMemcpyDeviceToHost, D.stream));
+        COZK_CUDA(cudaStreamSynchronize(D.stream));
+    }
+    // total of level j (the first n >> j points) = blocks 0 .. levels-1-j; only exact halvings of the SRS length are used
+    uint64_t ok = 0;
+    std::vector<affine> host_totals((size_t)levels * S.table_W);
+    memset(host_totals.data(), 0, host_totals.size() * sizeof(affine));
+    for (uint32_t j = 0; j < levels; ++j)
+        if (((n >> j) << j) == n) ok |= (uint64_t)1 << j;
+    for (uint32_t r = 0; r < S.table_W; ++r) {
+        xyzz acc = xyzz_identity();
+        for (uint32_t b = 0; b < levels; ++b) {
+            acc = xyzz_add(acc, sums[(size_t)r * levels + b]);
+            const uint32_t j = levels - 1 - b;
+            uint8_t wire[72];
+            xyzz_to_wire(acc, wire);
+            if (wire[64]) ok &= ~((uint64_t)1 << j);  // a sum that is the identity has no affine form: plain path for this length
+            else memcpy(&host_totals[(size_t)j * S.table_W + r], wire, 64);
         }
     }
+    COZK_CUDA(cudaMemcpyAsync(S.bases(di) + (size_t)S.table_W * n, host_totals.data(), host_totals.size() * sizeof(affine),
+                              cudaMemcpyHostToDevice, D.stream));
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
     S.total_levels = levels;
     S.total_ok = ok;
     return COZK_OK;
 }
 
-// Bases (and optional infinity flags) that already live on one device of the context: copied device-to-device, every
-// other device gets a peer copy; the precomputed table is built on each.
-int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out) {
-    if (!ctx || !out || (!d_bases64 && n) || device_index < 0 || device_index >= (int)ctx->devs.size()) {
-        set_error("bad argument");
-        return COZK_ERR_INVALID_ARG;
-    }
+// Where the bases of a registration come from: host memory, or the memory of one device of the context.
+struct SrsSource {
+    const void* host = nullptr;
+    size_t stride = 64;
+    const uint8_t* host_inf = nullptr;
+    const void* dev = nullptr;
+    int dev_index = -1;
+    const uint8_t* dev_inf = nullptr;
+};
+
+// n points -> every device in `devices` gets the bases (+ flags), its precomputed table and the row totals.  The
+// devices work side by side (one host thread each).
+static int srs_register_core(cozk_ctx* ctx, const SrsSource& src, size_t n, const std::vector<int>& devices, SrsEntry* out) {
     SrsEntry S;
     S.n = n;
-    srs_table_shape(ctx, n, &S.table_c, &S.table_W);
-    auto undo = [&]() {
-        for (size_t j = 0; j < S.d_bases.size(); ++j) {
-            cudaSetDevice(ctx->devs[j]->id);
-            if (S.d_bases[j]) cudaFree(S.d_bases[j]);
-            if (S.d_inf[j]) cudaFree(S.d_inf[j]);
-        }
-    };
+    S.mem = std::make_shared<SrsMem>();
+    const size_t nd = ctx->devs.size();
+    S.mem->cuda_id.resize(nd);
+    for (size_t d = 0; d < nd; ++d) S.mem->cuda_id[d] = ctx->devs[d]->id;
+    S.mem->bases.assign(nd, nullptr);
+    S.mem->inf.assign(nd, nullptr);
+    srs_table_shape(ctx, devices, n, &S.table_c, &S.table_W);
     bool any_inf = false;
-    if (d_inf && n) {
+    if (src.host_inf) {
+        for (size_t i = 0; i < n && !any_inf; ++i) any_inf = src.host_inf[i] != 0;
+    } else if (src.dev_inf && n) {
         std::vector<uint8_t> flags(n);
-        COZK_CUDA(cudaSetDevice(ctx->devs[device_index]->id));
-        Device& S0 = *ctx->devs[device_index];
-        COZK_CUDA(cudaMemcpyAsync(flags.data(), d_inf, n, cudaMemcpyDeviceToHost, S0.stream));
+        Device& S0 = *ctx->devs[src.dev_index];
+        COZK_CUDA(cudaSetDevice(S0.id));
+        COZK_CUDA(cudaMemcpyAsync(flags.data(), src.dev_inf, n, cudaMemcpyDeviceToHost, S0.stream));
         COZK_CUDA(cudaStreamSynchronize(S0.stream));
         for (size_t i = 0; i < n && !any_inf; ++i) any_inf = flags[i] != 0;
     }
-    for (size_t di = 0; di < ctx->devs.size(); ++di) {
+    const size_t entries = std::max<size_t>(n, 1) * S.table_W + (size_t)S.table_W * (SrsEntry::totals_levels_for(n) + 1);
+    std::vector<int> rcs(devices.size(), COZK_OK);
+    std::vector<std::string> errs(devices.size());
+    std::vector<SrsEntry> per_dev(devices.size(), S);  // each thread fills its own totals fields
+    auto work = [&](size_t k) -> int {
+        const int di = devices[k];
         Device& D = *ctx->devs[di];
         affine* d = nullptr;
         uint8_t* dinf = nullptr;
-        cudaError_t e = cudaSetDevice(D.id);
-        if (e == cudaSuccess) e = cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + (size_t)S.table_W * (SrsEntry::totals_levels_for(n) + 1)) * sizeof(affine));
-        // on the destination device's own stream and synchronised there: nothing in this library relies on the legacy
-        // default stream, which its non-blocking streams do not wait for (the source is complete: callers synchronise)
-        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(d, D.id, d_bases64, ctx->devs[device_index]->id, n * sizeof(affine), D.stream);
-        if (e == cudaSuccess && any_inf) e = cudaMalloc(&dinf, n);
-        if (e == cudaSuccess && any_inf) e = cudaMemcpyPeerAsync(dinf, D.id, d_inf, ctx->devs[device_index]->id, n, D.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-        int rc = COZK_OK;
-        if (e != cudaSuccess) {
-            set_error(std::string("SRS registration failed: ") + cudaGetErrorString(e));
-            rc = COZK_ERR_CUDA;
-        } else {
-            rc = srs_build_table(D, d, n, S.table_c, S.table_W);
+        {
+            std::lock_guard<std::mutex> lock(D.mu);
+            COZK_CUDA(cudaSetDevice(D.id));
+            COZK_CUDA(cudaMalloc(&d, entries * sizeof(affine)));
+            S.mem->bases[di] = d;  // from here on the memory is released with S.mem
+            if (any_inf) {
+                COZK_CUDA(cudaMalloc(&dinf, n));
+                S.mem->inf[di] = dinf;
+            }
+            // Copies go through the engine's own stream and are synchronised there.  A plain cudaMemcpy from pageable memory
+            // returns once the data is STAGED - its DMA runs on the legacy default stream, which the engine's non-blocking
+            // streams do not wait for, so the table build could read row 0 before the tail of the copy had landed.
+            if (src.host) {
+                if (src.stride == 64) COZK_CUDA(cudaMemcpyAsync(d, src.host, n * 64, cudaMemcpyHostToDevice, D.stream));
+                else COZK_CUDA(cudaMemcpy2DAsync(d, 64, src.host, src.stride, 64, n, cudaMemcpyHostToDevice, D.stream));
+                if (any_inf) COZK_CUDA(cudaMemcpyAsync(dinf, src.host_inf, n, cudaMemcpyHostToDevice, D.stream));
+            } else {
+                const int sid = ctx->devs[src.dev_index]->id;
+                COZK_CUDA(cudaMemcpyPeerAsync(d, D.id, src.dev, sid, n * sizeof(affine), D.stream));
+                if (any_inf) COZK_CUDA(cudaMemcpyPeerAsync(dinf, D.id, src.dev_inf, sid, n, D.stream));
+            }
+            if (S.table_W > 1 && n) {
+                TableArgs A{d, n, S.table_c, S.table_W};
+                k_build_table<<<grid_for(n, 128), 128, 0, D.stream>>>(A);
+                COZK_CUDA(cudaGetLastError());
+            }
+            COZK_CUDA(cudaStreamSynchronize(D.stream));
         }
-        if (rc) {
-            if (d) cudaFree(d);
-            if (dinf) cudaFree(dinf);
-            undo();
-            return rc;
+        return srs_compute_totals(ctx, di, per_dev[k]);
+    };
+    auto guarded = [&](size_t k) {
+        rcs[k] = work(k);
+        if (rcs[k]) errs[k] = g_error;
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < devices.size(); ++k) th.emplace_back(guarded, k);
+    if (!devices.empty()) guarded(0);
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < devices.size(); ++k) {
+        if (rcs[k]) {
+            set_error(errs[k].empty() ? "SRS registration failed" : errs[k]);
+            return rcs[k];  // S.mem goes out of scope: everything allocated so far is given back
         }
-        S.d_bases.push_back(d);
-        S.d_inf.push_back(dinf);
     }
-    int wrc = srs_wait_tables(ctx, S.d_bases.size());
-    if (!wrc) wrc = srs_compute_totals(ctx, S);
-    if (wrc) {
-        undo();
-        return wrc;
+    if (!devices.empty()) {
+        // the same points and the same plan on every device: the totals agree; keep the intersection of the usable levels
+        S.total_levels = per_dev[0].total_levels;
+        S.total_ok = per_dev[0].total_ok;
+        for (size_t k = 1; k < devices.size(); ++k) {
+            S.total_levels = std::min(S.total_levels, per_dev[k].total_levels);
+            S.total_ok &= per_dev[k].total_ok;
+        }
     }
+    *out = S;
+    return COZK_OK;
+}
+
+static std::vector<int> all_devices(const cozk_ctx* ctx) {
+    std::vector<int> v(ctx->devs.size());
+    for (size_t d = 0; d < v.size(); ++d) v[d] = (int)d;
+    return v;
+}
+static cozk_srs srs_publish(cozk_ctx* ctx, const SrsEntry& S) {
     std::lock_guard<std::mutex> lock(ctx->mu);
-    *out = ctx->next_handle++;
-    ctx->srs[*out] = S;
+    const cozk_srs h = ctx->next_handle++;
+    ctx->srs[h] = S;
+    return h;
+}
+
+int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out,
+                             int only_device) {
+    if (!ctx || !out || (!d_bases64 && n) || device_index < 0 || device_index >= (int)ctx->devs.size() ||
+        only_device >= (int)ctx->devs.size()) {
+        set_error("bad argument");
+        return COZK_ERR_INVALID_ARG;
+    }
+    SrsSource src;
+    src.dev = d_bases64;
+    src.dev_index = device_index;
+    src.dev_inf = d_inf;
+    SrsEntry S;
+    int rc = srs_register_core(ctx, src, n, only_device >= 0 ? std::vector<int>{only_device} : all_devices(ctx), &S);
+    if (rc) return rc;
+    *out = srs_publish(ctx, S);
     return COZK_OK;
 }
 
@@ -878,10 +1011,7 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
 
 void cozk_destroy(cozk_ctx* ctx) {
     if (!ctx) return;
-    for (auto& kv : ctx->polys) {
-        cudaSetDevice(ctx->devs[kv.second.dev]->id);
-        if (kv.second.d_data) cudaFree(kv.second.d_data);  // also valid for stream-ordered allocations; synchronises
-    }
+    ctx->polys.clear();  // published entries own their memory (PolyEntry::hold): stream-ordered frees, drained below
     for (auto& D : ctx->devs) {
         cudaMemPool_t pool;
         if (cudaSetDevice(D->id) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, D->id) == cudaSuccess) {
@@ -889,13 +1019,7 @@ void cozk_destroy(cozk_ctx* ctx) {
             cudaMemPoolTrimTo(pool, 0);
         }
     }
-    for (auto& kv : ctx->srs) {
-        for (size_t d = 0; d < kv.second.d_bases.size(); ++d) {
-            cudaSetDevice(ctx->devs[d]->id);
-            if (kv.second.d_bases[d]) cudaFree(kv.second.d_bases[d]);
-            if (kv.second.d_inf[d]) cudaFree(kv.second.d_inf[d]);
-        }
-    }
+    ctx->srs.clear();  // the entries own their device memory (SrsMem)
     delete ctx;
 }
 
@@ -906,56 +1030,68 @@ int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_
         set_error("null pointer or stride < 64");
         return COZK_ERR_INVALID_ARG;
     }
+    SrsSource src;
+    src.host = bases;
+    src.stride = stride_bytes;
+    src.host_inf = infinity;
     SrsEntry S;
-    S.n = n;
-    srs_table_shape(ctx, n, &S.table_c, &S.table_W);
-    bool any_inf = false;
-    if (infinity)
-        for (size_t i = 0; i < n && !any_inf; ++i) any_inf = infinity[i] != 0;
-    for (auto& D : ctx->devs) {
-        COZK_CUDA(cudaSetDevice(D->id));
-        affine* d = nullptr;
-        uint8_t* di = nullptr;
-        COZK_CUDA(cudaMalloc(&d, (std::max<size_t>(n, 1) * S.table_W + (size_t)S.table_W * (SrsEntry::totals_levels_for(n) + 1)) * sizeof(affine)));
-        // Copies go through the engine's own stream and are synchronised there.  A plain cudaMemcpy from pageable memory
-        // returns once the data is STAGED - its DMA runs on the legacy default stream, which the engine's non-blocking
-        // streams do not wait for, so the table build could read row 0 before the tail of the copy had landed.
-        if (stride_bytes == 64) {
-            COZK_CUDA(cudaMemcpyAsync(d, bases, n * 64, cudaMemcpyHostToDevice, D->stream));
-        } else {
-            COZK_CUDA(cudaMemcpy2DAsync(d, 64, bases, stride_bytes, 64, n, cudaMemcpyHostToDevice, D->stream));
-        }
-        if (any_inf) {
-            COZK_CUDA(cudaMalloc(&di, n));
-            COZK_CUDA(cudaMemcpyAsync(di, infinity, n, cudaMemcpyHostToDevice, D->stream));
-        }
-        COZK_CUDA(cudaStreamSynchronize(D->stream));
-        S.d_bases.push_back(d);
-        S.d_inf.push_back(di);
-        int rc = srs_build_table(*D, d, n, S.table_c, S.table_W);
-        if (rc) {
-            // nothing registered yet: give back what was allocated so far
-            for (size_t j = 0; j < S.d_bases.size(); ++j) {
-                cudaSetDevice(ctx->devs[j]->id);
-                cudaFree(S.d_bases[j]);
-                if (S.d_inf[j]) cudaFree(S.d_inf[j]);
-            }
-            return rc;
+    int rc = srs_register_core(ctx, src, n, all_devices(ctx), &S);
+    if (rc) return rc;
+    *out = srs_publish(ctx, S);
+    return COZK_OK;
+}
+
+// Device d of the context gets points [n*d/D, n*(d+1)/D) only - with their own table and row totals - instead of a copy
+// of everything: SURVEY.md 8(e) "each GPU holds only its slice", the reference's split_ck
+// (co-noir-spartan/co-spartan/src/utils.rs:38-83).  Every MSM over such an SRS is sharded by point range along the slices.
+int cozk_srs_register_sliced(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out) {
+    if (!ctx || !out || (!bases && n) || stride_bytes < 64) {
+        set_error("null pointer or stride < 64");
+        return COZK_ERR_INVALID_ARG;
+    }
+    const size_t nd = ctx->devs.size();
+    SrsEntry P;
+    P.n = n;
+    std::vector<SrsSlice> slices;
+    for (size_t d = 0; d < nd; ++d) {
+        SrsSlice sl;
+        sl.dev = (int)d;
+        sl.lo = n * d / nd;
+        sl.len = n * (d + 1) / nd - sl.lo;
+        if (sl.len) slices.push_back(sl);
+    }
+    std::vector<int> rcs(slices.size(), COZK_OK);
+    std::vector<std::string> errs(slices.size());
+    auto work = [&](size_t k) {
+        SrsSlice& sl = slices[k];
+        SrsSource src;
+        src.host = reinterpret_cast<const uint8_t*>(bases) + sl.lo * stride_bytes;
+        src.stride = stride_bytes;
+        src.host_inf = infinity ? infinity + sl.lo : nullptr;
+        sl.entry = std::make_shared<SrsEntry>();
+        rcs[k] = srs_register_core(ctx, src, sl.len, std::vector<int>{sl.dev}, sl.entry.get());
+        if (rcs[k]) errs[k] = g_error;
+    };
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < slices.size(); ++k) th.emplace_back(work, k);
+    if (!slices.empty()) work(0);
+    for (auto& t : th) t.join();
+    for (size_t k = 0; k < slices.size(); ++k) {
+        if (rcs[k]) {
+            set_error(errs[k]);
+            return rcs[k];
         }
     }
-    int wrc = srs_wait_tables(ctx, S.d_bases.size());
-    if (!wrc) wrc = srs_compute_totals(ctx, S);
-    if (wrc) {
-        for (size_t j = 0; j < S.d_bases.size(); ++j) {
-            cudaSetDevice(ctx->devs[j]->id);
-            cudaFree(S.d_bases[j]);
-            if (S.d_inf[j]) cudaFree(S.d_inf[j]);
-        }
-        return wrc;
+    if (slices.empty()) {  // n == 0: an ordinary empty SRS
+        SrsSource src;
+        src.host = bases;
+        src.stride = stride_bytes;
+        int rc = srs_register_core(ctx, src, 0, all_devices(ctx), &P);
+        if (rc) return rc;
+    } else {
+        P.slices = slices;
     }
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    *out = ctx->next_handle++;
-    ctx->srs[*out] = S;
+    *out = srs_publish(ctx, P);
     return COZK_OK;
 }
 
@@ -963,6 +1099,7 @@ int cozk_srs_register_device(cozk_ctx* ctx, int device_index, const void* d_base
     return srs_register_from_device(ctx, device_index, d_bases64, nullptr, n, out);
 }
 
+// Drops the handle.  Calls that looked the SRS up before this point keep its device memory alive until they return.
 int cozk_srs_release(cozk_ctx* ctx, cozk_srs srs) {
     if (!ctx) return COZK_ERR_INVALID_ARG;
     SrsEntry S;
@@ -976,13 +1113,7 @@ int cozk_srs_release(cozk_ctx* ctx, cozk_srs srs) {
         S = it->second;
         ctx->srs.erase(it);
     }
-    for (size_t d = 0; d < S.d_bases.size(); ++d) {
-        std::lock_guard<std::mutex> lock(ctx->devs[d]->mu);
-        cudaSetDevice(ctx->devs[d]->id);
-        if (S.d_bases[d]) cudaFree(S.d_bases[d]);
-        if (S.d_inf[d]) cudaFree(S.d_inf[d]);
-    }
-    return COZK_OK;
+    return COZK_OK;  // S leaves scope here, outside the context lock: the last reference frees the memory
 }
 
 int cozk_srs_len(cozk_ctx* ctx, cozk_srs srs, size_t* out_n) {
@@ -1078,9 +1209,11 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     return COZK_OK;
 }
 
-int cozk_last_stats(cozk_ctx* ctx, double* out12) {
-    if (!ctx || !out12) return COZK_ERR_INVALID_ARG;
-    Device& D = *ctx->devs[0];
+int cozk_last_stats(cozk_ctx* ctx, double* out12) { return cozk_last_stats_device(ctx, 0, out12); }
+
+int cozk_last_stats_device(cozk_ctx* ctx, int device_index, double* out12) {
+    if (!ctx || !out12 || device_index < 0 || device_index >= (int)ctx->devs.size()) return COZK_ERR_INVALID_ARG;
+    Device& D = *ctx->devs[device_index];
     std::lock_guard<std::mutex> lock(D.mu);
     for (int i = 0; i < 12; ++i) out12[i] = D.stats[i];
     return COZK_OK;

@@ -251,7 +251,7 @@ int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t 
         }
     }
     if (K.small_n) {
-        rc = srs_register_from_device(ctx, 0, d_small, d_small_inf, K.small_n, &K.small_srs);
+        rc = srs_register_from_device(ctx, 0, d_small, d_small_inf, K.small_n, &K.small_srs, 0);  // read by device 0 only
         if (rc) return fail(rc);
         std::lock_guard<std::mutex> lock(D.mu);
         cudaSetDevice(D.id);

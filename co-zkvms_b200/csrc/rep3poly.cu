@@ -67,7 +67,19 @@ static int lookup(cozk_ctx* ctx, cozk_poly h, PolyEntry* out) {
     return COZK_OK;
 }
 
-static cozk_poly publish(cozk_ctx* ctx, const PolyEntry& E) {
+static cozk_poly publish(cozk_ctx* ctx, const PolyEntry& E0) {
+    PolyEntry E = E0;
+    if (E.d_data && !E.hold) {
+        const cudaStream_t st = ctx->devs[E.dev]->stream;
+        const int id = ctx->devs[E.dev]->id;
+        E.hold = std::shared_ptr<void>(E.d_data, [st, id](void* p) {
+            int cur = -1;
+            cudaGetDevice(&cur);
+            cudaSetDevice(id);
+            cudaFreeAsync(p, st);  // ordered behind everything already queued on the owning device's stream
+            if (cur >= 0) cudaSetDevice(cur);
+        });
+    }
     std::lock_guard<std::mutex> lock(ctx->mu);
     cozk_poly h = ctx->next_handle++;
     ctx->polys[h] = E;
@@ -130,14 +142,11 @@ struct Reader {
 
 int srs_pair_sums_into(cozk_ctx* ctx, cozk_srs srs, affine* d_out, uint8_t* d_inf, size_t* half_out) {
     SrsEntry S;
-    {
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        auto it = ctx->srs.find(srs);
-        if (it == ctx->srs.end()) {
-            set_error("unknown SRS handle");
-            return COZK_ERR_BAD_HANDLE;
-        }
-        S = it->second;
+    int lrc = srs_lookup(ctx, srs, &S);
+    if (lrc) return lrc;
+    if (!S.bases(0)) {
+        set_error("pair sums need an SRS that lives on device 0 (not a sliced one)");
+        return COZK_ERR_INVALID_ARG;
     }
     if (S.n == 0 || (S.n & 1)) {
         set_error("pair sums need an even, non-zero number of bases");
@@ -147,7 +156,7 @@ int srs_pair_sums_into(cozk_ctx* ctx, cozk_srs srs, affine* d_out, uint8_t* d_in
     size_t half = S.n / 2;
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
-    PairSumArgs A{S.d_bases[0], S.d_inf[0], half, d_out, d_inf};  // row 0 of the table = the bases themselves
+    PairSumArgs A{S.bases(0), S.inf(0), half, d_out, d_inf};  // row 0 of the table = the bases themselves
     k_pair_sum<<<blocks_for(half, 128), 128, 0, D.stream>>>(A);
     COZK_CUDA(cudaGetLastError());
     COZK_CUDA(cudaStreamSynchronize(D.stream));
@@ -352,11 +361,7 @@ int cozk_poly_release(cozk_ctx* ctx, cozk_poly poly) {
         E = it->second;
         ctx->polys.erase(it);
     }
-    Device& D = *ctx->devs[E.dev];
-    std::lock_guard<std::mutex> lock(D.mu);
-    cudaSetDevice(D.id);
-    if (E.d_data) pool_free(D, E.d_data);
-    return COZK_OK;
+    return COZK_OK;  // E leaves scope outside the context lock; the last copy of the entry frees the device memory
 }
 
 int cozk_poly_info(cozk_ctx* ctx, cozk_poly poly, size_t* len, int* kind, int* device_index) {
@@ -925,7 +930,7 @@ int cozk_srs_pair_sums(cozk_ctx* ctx, cozk_srs srs, cozk_srs* out) {
         }
     }
     rc = srs_pair_sums_into(ctx, srs, d_out, d_inf, &half);
-    if (!rc) rc = srs_register_from_device(ctx, 0, d_out, d_inf, half, out);
+    if (!rc) rc = srs_register_from_device(ctx, 0, d_out, d_inf, half, out, 0);  // openings run on device 0 only
     std::lock_guard<std::mutex> lock(D.mu);
     cudaSetDevice(D.id);
     pool_free(D, d_out);

@@ -62,6 +62,12 @@ int cozk_device_count(const cozk_ctx* ctx);
 /* Upload n bases (replicated on every device of the context).  bases: point i at bases + i*stride_bytes,
  * stride_bytes >= 64.  infinity: n flags (non-zero = point at infinity, contributes nothing) or NULL. */
 int cozk_srs_register(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out);
+/* The same for a context with several devices when the SRS only serves point-range sharding (one long MSM, BASELINE.json
+ * configs[3]): device d keeps points [n*d/D, n*(d+1)/D) only, with their own table - 1/D of the memory and of the
+ * registration work on each GPU (the reference's split_ck, co-noir-spartan/co-spartan/src/utils.rs:38-83).
+ * Every cozk_msm_batch over such an SRS is cut along the slices, whatever k; cozk_msm_batch_device does not take it. */
+int cozk_srs_register_sliced(cozk_ctx* ctx, const void* bases, size_t n, size_t stride_bytes, const uint8_t* infinity, cozk_srs* out);
+/* Drops the handle; a call that is still using the SRS on another thread keeps the device memory alive until it returns. */
 int cozk_srs_release(cozk_ctx* ctx, cozk_srs srs);
 int cozk_srs_len(cozk_ctx* ctx, cozk_srs srs, size_t* out_n);
 
@@ -111,6 +117,7 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value);
  * [0] h2d  [1] decompose  [2] sort  [3] accumulate  [4] bucket-reduce  [5] finish+d2h  [6] total  [7] kernels launched
  * [8] window bits c  [9] windows W  [10] field mults (plan)  [11] pairs m */
 int cozk_last_stats(cozk_ctx* ctx, double* out12);
+int cozk_last_stats_device(cozk_ctx* ctx, int device_index, double* out12); /* the same for any device of the context */
 const char* cozk_last_error(void);
 
 /* ---- plain device-memory helpers so that callers (and the tests / bench) need no other CUDA binding */

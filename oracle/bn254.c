@@ -522,6 +522,13 @@ static void make_digits(const u64* a, unsigned w, int32_t* digits, unsigned coun
     digits[count - 1] += (int32_t)(carry << w);
 }
 
+/* digits of the last window are not re-centred: they reach 2^(bits left in the scalar) (top bits all set, plus carry) */
+static size_t last_window_buckets(unsigned c, unsigned count) {
+    unsigned bits_last = SCALAR_BITS - (count - 1) * c;
+    if (bits_last > c) bits_last = c;
+    return ((size_t)1 << bits_last) + 1;
+}
+
 typedef struct {
     const uint8_t* bases;
     const int32_t* digits; /* n x count */
@@ -535,8 +542,8 @@ typedef struct {
 
 static void window_chunk_sum(const msm_job* J, unsigned win, size_t lo, size_t hi, jac* out) {
     size_t nb = (size_t)1 << (J->c - 1);
-    /* the last window can hold an un-recentred digit up to 2^c (see make_digits) */
-    if (win == J->count - 1) nb = ((size_t)1 << J->c) + 1;
+    /* the last window holds an un-recentred digit (see make_digits): the scalar's remaining top bits plus the carry */
+    if (win == J->count - 1) nb = last_window_buckets(J->c, J->count);
     jac* buckets = (jac*)calloc(nb, sizeof(jac));
     for (size_t i = lo; i < hi; ++i) {
         int32_t d = J->digits[i * J->count + win];
@@ -560,6 +567,24 @@ static void window_chunk_sum(const msm_job* J, unsigned win, size_t lo, size_t h
     }
     free(buckets);
     *out = res;
+}
+
+typedef struct {
+    const uint8_t* scalars;
+    size_t stride;
+    int form;
+    size_t lo, hi;
+    unsigned c, count;
+    int32_t* digits;
+} digit_job;
+static void* digit_worker(void* arg) {
+    digit_job* d = (digit_job*)arg;
+    for (size_t i = d->lo; i < d->hi; ++i) {
+        u64 k[4];
+        load_scalar(d->scalars, d->stride, d->form, i, k);
+        make_digits(k, d->c, d->digits + i * d->count, d->count);
+    }
+    return NULL;
 }
 
 static void* msm_worker(void* arg) {
@@ -591,15 +616,34 @@ void orc_msm(const uint8_t* bases64, const uint8_t* scalars, size_t stride, int 
     unsigned c = (unsigned)orc_msm_window(n);
     unsigned count = (SCALAR_BITS + c - 1) / c;
     int32_t* digits = (int32_t*)malloc(n * count * sizeof(int32_t));
-    for (size_t i = 0; i < n; ++i) {
-        u64 k[4];
-        load_scalar(scalars, stride, form, i, k);
-        make_digits(k, c, digits + i * count, count);
+    /* digit recoding of all scalars, spread over the threads like everything else */
+    {
+        digit_job dj[512];
+        pthread_t th[512];
+        int nt = threads;
+        if ((size_t)nt > n) nt = (int)n;
+        for (int t = 0; t < nt; ++t) {
+            dj[t] = (digit_job){scalars, stride, form, n * (size_t)t / (size_t)nt, n * (size_t)(t + 1) / (size_t)nt, c, count, digits};
+            if (nt > 1) pthread_create(&th[t], NULL, digit_worker, &dj[t]);
+        }
+        if (nt == 1) digit_worker(&dj[0]);
+        else for (int t = 0; t < nt; ++t) pthread_join(th[t], NULL);
     }
     msm_job J;
     memset(&J, 0, sizeof J);
     J.bases = bases64; J.digits = digits; J.n = n; J.c = c; J.count = count;
-    J.nchunks = threads <= (int)count ? 1 : (unsigned)((threads + (int)count - 1) / (int)count);
+    /* arkworks spreads one MSM over its windows only (<= 17 threads busy, two rounds on 16 cores); jolt-core's batch_msm
+       fills the cores with whole polynomials.  Here: window x point-chunk tasks, the chunk count chosen to minimise
+       rounds x (points per chunk + the bucket reduction every chunk repeats). */
+    J.nchunks = 1;
+    if (threads > 1) {
+        double best = 0;
+        for (unsigned nc = 1; nc <= 32; ++nc) {
+            double tasks = (double)count * nc, rounds = (double)(size_t)((tasks + threads - 1) / threads);
+            double cost = rounds * ((double)n / nc + 3.0 * (double)((size_t)1 << (c - 1)));
+            if (nc == 1 || cost < best) { best = cost; J.nchunks = nc; }
+        }
+    }
     if ((size_t)J.nchunks > n) J.nchunks = (unsigned)n;
     J.results = (jac*)calloc((size_t)count * J.nchunks, sizeof(jac));
     pthread_mutex_init(&J.mu, NULL);

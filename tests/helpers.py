@@ -72,3 +72,14 @@ def golden_msm_inputs(case):
     else:
         sc = pyref.scalars(case["dist"], case["scalar_seed"], n)
     return pts, sc
+
+
+def multi_device_ids(want=4):
+    """Device ids for a multi-device context: the visible GPUs (at most `want`), or - on a single-GPU box - the SAME GPU
+    three times: the engine then drives three logical devices (own streams, scratch and SRS copies / slices) on one
+    physical GPU, which exercises every host-side sharding path (threads, slices, partial sums, peer-copy fallbacks)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev >= 2:
+        return list(range(min(ndev, want)))
+    return [0, 0, 0]

@@ -195,15 +195,13 @@ def test_properties_at_full_size(ctx, log2n):
 
 def test_multi_device_context(cozk, orc):
     """One process driving several GPUs (the Rust caller's shape): k >= devices shards by vector, otherwise by point
-    range with the partial sums added on the host (split_ck + combine_comm).  Skipped on a single-GPU box."""
-    import torch
-    ndev = torch.cuda.device_count()
-    if ndev < 2:
-        pytest.skip("needs at least 2 GPUs")
-    ndev = min(ndev, 8)
+    range with the partial sums added on the host (split_ck + combine_comm).  On a single-GPU box the context is opened
+    over the same GPU three times (helpers.multi_device_ids), so the sharding paths always run."""
+    ids = H.multi_device_ids(8)
+    ndev = len(ids)
     n = 1 << 15
     bases = orc.gen_bases(1, n)
-    with cozk.Context(devices=list(range(ndev))) as mctx:
+    with cozk.Context(devices=ids) as mctx:
         assert mctx.device_count == ndev
         srs = mctx.srs_register(bases)
         dists = ["uniform", "const", "wminus", "dup", "zero_half"] * 2
@@ -216,6 +214,101 @@ def test_multi_device_context(cozk, orc):
         odd = mctx.msm_batch(srs, vecs[:1], n=1001, base_offset=17, stride=64)
         assert (odd[0] == orc.msm(bases[17:1018], vecs[0][:1001])).all()
         mctx.srs_release(srs)
+
+
+def test_sliced_srs(cozk, orc):
+    """cozk_srs_register_sliced: every device keeps only its point range and its own table (the reference's
+    split_ck, co-noir-spartan/co-spartan/src/utils.rs:38-83); every call is cut along the slices, whatever k, prefix or
+    offset; points at infinity and the 72-byte stride travel with their slice.  Same bytes as the oracle."""
+    ids = H.multi_device_ids(8)
+    n = (1 << 15) + 321
+    bases = orc.gen_bases(5, n)
+    with cozk.Context(devices=ids) as mctx:
+        srs = mctx.srs_register(bases, sliced=True)
+        assert mctx.srs_len(srs) == n
+        vecs = [orc.gen_scalars(d, 60 + i, n, stride=64) for i, d in enumerate(("uniform", "const", "wminus", "zero_half", "dup"))]
+        want = [orc.msm(bases, v) for v in vecs]
+        got = mctx.msm_batch(srs, vecs, n=n, stride=64)            # k > devices: still by point range
+        for j in range(len(vecs)):
+            assert (got[j] == want[j]).all(), j
+        assert (mctx.msm_batch(srs, vecs[:1], n=n, stride=64)[0] == want[0]).all()
+        for off, m in ((0, 1000), (17, 20000), (n - 5, 5), (n // len(ids) - 3, 7), (1, n - 1)):
+            x = mctx.msm_batch(srs, [vecs[0]], n=m, base_offset=off, stride=64)
+            assert (x[0] == orc.msm(bases[off:off + m], vecs[0][:m])).all(), (off, m)
+        can = orc.gen_scalars("uniform", 8, n, form=1)
+        assert (mctx.msm_batch(srs, can, form=1)[0] == orc.msm(bases, can, form=1)).all()
+        with pytest.raises(cozk.CozkError) as e:
+            mctx.msm_batch(srs, np.zeros((n + 1, 32), np.uint8))
+        assert e.value.code == cozk.ERR_KEY_LENGTH
+        d = mctx.testgen_scalars("uniform", 3, 64)
+        with pytest.raises(cozk.CozkError):
+            mctx.msm_batch_ptrs(srs, [d.ptr], 64, device=0)        # device-resident scalars: not with a sliced SRS
+        d.free()
+        mctx.srs_release(srs)
+        b72 = np.zeros((n, 72), np.uint8)
+        b72[:, :64] = bases
+        inf = np.zeros(n, np.uint8)
+        inf[3::7] = 1
+        srs = mctx.srs_register(b72, infinity=inf, sliced=True)
+        masked = vecs[0].copy()
+        masked[3::7] = 0
+        assert (mctx.msm_batch(srs, [vecs[0]], n=n, stride=64)[0] == orc.msm(bases, masked)).all()
+        mctx.srs_release(srs)
+        tiny = mctx.srs_register(bases[:2], sliced=True)            # fewer points than devices: empty slices are dropped
+        assert (mctx.msm_batch(tiny, [vecs[0]], n=2, stride=64)[0] == orc.msm(bases[:2], vecs[0][:2])).all()
+        mctx.srs_release(tiny)
+
+
+def test_release_while_in_flight(cozk, ctx, orc):
+    """cozk_srs_release on one thread while another is inside an MSM over the same SRS: the handle goes at
+    once, the device memory only when the call in flight returns - its result is still exact."""
+    import threading
+    n = 1 << 16
+    bases = orc.gen_bases(9, n)
+    sc = orc.gen_scalars("uniform", 9, n)
+    want = orc.msm(bases, sc)
+    for _ in range(3):
+        srs = ctx.srs_register(bases)
+        res = {}
+
+        def call():
+            try:
+                res["out"] = ctx.msm_batch(srs, sc)[0]
+            except cozk.CozkError as e:  # released before the call looked the handle up
+                res["err"] = e.code
+
+        t = threading.Thread(target=call)
+        t.start()
+        ctx.srs_release(srs)
+        t.join(timeout=120)
+        assert ("out" in res and (res["out"] == want).all()) or res.get("err") == cozk.ERR_BAD_HANDLE, res
+        with pytest.raises(cozk.CozkError):
+            ctx.msm_batch(srs, sc)
+
+
+@pytest.mark.parametrize("log2n,dists", [(22, ("uniform", "const", "wminus")), (24, ("uniform",))])
+def test_oracle_parity_at_baseline_sizes(ctx, orc, log2n, dists):
+    """Direct comparison with the CPU oracle at the sizes BASELINE.json names: 2^22 canonical scalars (configs[2], the
+    form msm_bigint gets at co-noir-spartan/co-spartan/src/worker.rs:585/:804) in all three party distributions, and
+    2^24 (configs[3]) - through the host-scalar call (streamed in chunks from 2^23 points) and the device-resident one."""
+    n = 1 << log2n
+    dbases = ctx.testgen_bases(1, n)
+    bases = dbases.download().reshape(n, 64)
+    # the device generator is the oracle's generator: spot-check both ends
+    assert (bases[:2048] == orc.gen_bases(1, 2048)).all()
+    assert (bases[n - 1024:] == orc.gen_bases(1, 1024, start=n - 1024)).all()
+    srs = ctx.srs_register_device(dbases, n)
+    dbases.free()
+    for dist in dists:
+        sc = orc.gen_scalars(dist, 2, n, form=1)
+        want = orc.msm(bases, sc, form=1)
+        got = ctx.msm_batch(srs, sc, form=1)[0]
+        assert (got == want).all(), (log2n, dist, "host scalars")
+        d = ctx.alloc(n * 32).upload(sc)
+        got = ctx.msm_batch_ptrs(srs, [d.ptr], n, form=1, device=0)[0]
+        d.free()
+        assert (got == want).all(), (log2n, dist, "device scalars")
+    ctx.srs_release(srs)
 
 
 def test_precomputed_table_matches_plain_path(cozk, orc):

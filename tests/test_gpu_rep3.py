@@ -399,15 +399,14 @@ def test_multi_device_resident_flow(cozk, orc):
     """A party's polynomials dealt over several GPUs of one process: every device commits its own (side by side), the
     linear combination is formed per device and summed on device 0 by the kernel that reads the remote partials over
     peer mappings (and by the staged-copy fallback), and the joint polynomial opens there.  Same bytes as the
-    one-device flow and the restatement.  Skipped on a single-GPU box."""
-    import torch
-    ndev = min(torch.cuda.device_count(), 4)
-    if ndev < 2:
-        pytest.skip("needs at least 2 GPUs")
+    one-device flow and the restatement.  On a single-GPU box the context is opened over the same GPU three times
+    (helpers.multi_device_ids): every path but the direct peer read then still runs."""
+    ids = H.multi_device_ids(4)
+    ndev = len(ids)
     rep3, pst = cozk.rep3, cozk.pst13
     nv = 10
     n = 1 << nv
-    with cozk.Context(devices=list(range(ndev))) as mctx:
+    with cozk.Context(devices=ids) as mctx:
         levels = _levels(orc, nv, seed=13)
         setup = rep3.create_open_key(pst.PST13Setup(mctx, levels))
         shared = [list(zip(_rand_fr(100 + 2 * j, n), _rand_fr(101 + 2 * j, n))) for j in range(5)]
