@@ -18,8 +18,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # COZK_LIB: load another build of the same library (kernel experiments measured side by side with tools/sweep.py)
 LIB_PATH = os.environ.get("COZK_LIB") or os.path.join(HERE, "libcozk_msm.so")
+TEST_LIB_PATH = os.path.join(HERE, "libcozk_test.so")  # include/cozk_test.h: generators, test kernels, microbenchmarks
 SOURCES = ["msm.cu", "sort.cu", "depth_kernels.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
-HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "sort_kernels.cuh", "rep3_kernels.cuh", "msm_plan.hpp", "engine.hpp",
+TEST_SOURCES = ["testlib.cu"]
+HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "sort_kernels.cuh", "rep3_kernels.cuh", "bulk_copy.cuh", "msm_plan.hpp", "engine.hpp",
            "depth_kernels.hpp"]
 PUBLIC_HEADERS = ["cozk_msm.h", "cozk_rep3.h", "cozk_pst13.h", "cozk_test.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,9 +36,8 @@ ABI_SYMBOLS = [
     "cozk_init", "cozk_destroy", "cozk_device_count", "cozk_srs_register", "cozk_srs_register_sliced", "cozk_srs_release", "cozk_last_stats_device", "cozk_srs_len",
     "cozk_msm_batch", "cozk_msm_batch_device", "cozk_g1_sum", "cozk_set_option", "cozk_last_stats", "cozk_last_error",
     "cozk_dev_alloc", "cozk_dev_free", "cozk_dev_upload", "cozk_dev_download", "cozk_host_alloc_pinned",
-    "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_testgen_bases", "cozk_testgen_scalars",
-    "cozk_srs_register_device", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench", "cozk_test_sort",
-    "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_open",
+    "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_srs_register_device",
+    "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_batch_commit_packed", "cozk_pst13_open",
     "cozk_pst13_combine_commitment_shares", "cozk_pst13_coordinate_prove", "cozk_combine_comm",
     "cozk_fixed_base_batch_mul",
     # include/cozk_rep3.h
@@ -45,6 +46,11 @@ ABI_SYMBOLS = [
     "cozk_pst13_open_key_create", "cozk_pst13_open_key_release", "cozk_pst13_open_poly", "cozk_pst13_open_keyed",
     "cozk_rep3_last_stats", "cozk_rep3_evaluate_at_chi_poly", "cozk_eq_evals", "cozk_spartan_batch_open_worker",
 ]
+
+
+# include/cozk_test.h, exported by libcozk_test.so
+TEST_ABI_SYMBOLS = ["cozk_testgen_bases", "cozk_testgen_scalars", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench",
+                    "cozk_test_sort"]
 
 
 class CozkError(RuntimeError):
@@ -62,17 +68,23 @@ def build(force=False, verbose=False):
     objdir = os.path.join(CSRC, "_obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    jobs, objs = [], []
-    for s in SOURCES:
+    jobs, objs, test_objs = [], [], []
+    for s, into in [(x, objs) for x in SOURCES] + [(x, test_objs) for x in TEST_SOURCES]:
         src, obj = os.path.join(CSRC, s), os.path.join(objdir, s + ".o")
-        objs.append(obj)
+        into.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_time, os.path.getmtime(src)):
             jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
             list(ex.map(lambda c: subprocess.check_call(c, cwd=CSRC), jobs))
-    if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(o) for o in objs):
-        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs, cwd=CSRC)
+    arch = ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(o) for o in objs):
+        subprocess.check_call([nvcc, "-shared"] + arch + ["-o", LIB_PATH] + objs, cwd=CSRC)
+    # the test library calls into the product library (engine internals); the product library knows nothing of it
+    if (not os.path.exists(TEST_LIB_PATH) or os.path.getmtime(TEST_LIB_PATH) < os.path.getmtime(LIB_PATH)
+            or any(os.path.getmtime(TEST_LIB_PATH) < os.path.getmtime(o) for o in test_objs)):
+        subprocess.check_call([nvcc, "-shared"] + arch + ["-o", TEST_LIB_PATH] + test_objs +
+                              ["-L" + HERE, "-lcozk_msm", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"], cwd=CSRC)
     return LIB_PATH
 
 
@@ -112,16 +124,11 @@ def lib():
     L.cozk_host_alloc_pinned.argtypes = [sz, pp]
     L.cozk_host_free_pinned.argtypes = [vp]
     L.cozk_dev_flush_l2.argtypes = [vp, ci]
-    L.cozk_testgen_bases.argtypes = [vp, ci, u64, sz, sz, vp]
-    L.cozk_testgen_scalars.argtypes = [vp, ci, ci, u64, sz, sz, sz, ci, vp, sz]
-    L.cozk_test_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
-    L.cozk_test_g1_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
-    L.cozk_test_sort.argtypes = [vp, ci, vp, vp, sz, cu, vp, sz, cu, sz, ci, cu, cu, sz, sz, ci, vp, vp]
-    L.cozk_microbench.argtypes = [vp, ci, ci, ci, ci, ci, cd, cd]
     L.cozk_pst13_commit.argtypes = [vp, u64, vp, sz, sz, ci, cu, vp]
     L.cozk_pst13_batch_commit.argtypes = [vp, u64, pp, sz, sz, sz, ci, ctypes.POINTER(cu), vp]
     L.cozk_pst13_batch_commit_rep3.argtypes = [vp, u64, pp, ctypes.POINTER(ctypes.c_uint8), sz, sz, ci, ctypes.POINTER(cu), ci, vp,
                                                ctypes.POINTER(ctypes.c_uint8)]
+    L.cozk_pst13_batch_commit_packed.argtypes = [vp, u64, pp, ctypes.POINTER(ci), sz, sz, ci, vp, ctypes.POINTER(ctypes.c_uint8)]
     L.cozk_pst13_open.argtypes = [vp, ctypes.POINTER(u64), sz, vp, sz, vp, ci, vp, vp]
     L.cozk_pst13_combine_commitment_shares.argtypes = [vp, sz, vp]
     L.cozk_pst13_coordinate_prove.argtypes = [vp, sz, sz, vp]
@@ -147,6 +154,31 @@ def lib():
     L.cozk_eq_evals.argtypes = [vp, ci, vp, sz, ci, pu64]
     L.cozk_spartan_batch_open_worker.argtypes = [vp, u64, pu64, sz, pu64, sz, sz, vp, vp, vp, vp, vp]
     _lib = L
+    return L
+
+
+_testlib = None
+
+
+def testlib():
+    """libcozk_test.so (include/cozk_test.h): synthetic inputs, test kernels, microbenchmarks - used by tests/, bench.py and
+    tools/ only.  Loading it pulls in the product library first (it links against it)."""
+    global _testlib
+    if _testlib is not None:
+        return _testlib
+    lib()
+    if not os.path.exists(TEST_LIB_PATH):
+        raise ImportError("libcozk_test.so is not built (run __graft_entry__.build())")
+    L = ctypes.CDLL(TEST_LIB_PATH)
+    vp, sz, u64, ci, cu, cd = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint,
+                               ctypes.POINTER(ctypes.c_double))
+    L.cozk_testgen_bases.argtypes = [vp, ci, u64, sz, sz, vp]
+    L.cozk_testgen_scalars.argtypes = [vp, ci, ci, u64, sz, sz, sz, ci, vp, sz]
+    L.cozk_test_field_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.cozk_test_g1_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    L.cozk_test_sort.argtypes = [vp, ci, vp, vp, sz, cu, vp, sz, cu, sz, ci, cu, cu, sz, sz, ci, vp, vp]
+    L.cozk_microbench.argtypes = [vp, ci, ci, ci, ci, ci, cd, cd]
+    _testlib = L
     return L
 
 
@@ -327,12 +359,12 @@ class Context:
 
     def testgen_bases(self, seed, n, start=0, device=0):
         buf = self.alloc(max(n, 1) * 64, device)
-        _check(lib().cozk_testgen_bases(self.handle, device, seed, start, n, ctypes.c_void_p(buf.ptr)))
+        _check(testlib().cozk_testgen_bases(self.handle, device, seed, start, n, ctypes.c_void_p(buf.ptr)))
         return buf
 
     def testgen_scalars(self, dist, seed, n, form=MONT, stride=32, start=0, total_n=None, device=0):
         buf = self.alloc(max(n, 1) * stride, device)
-        _check(lib().cozk_testgen_scalars(self.handle, device, DIST[dist], seed, start, n,
+        _check(testlib().cozk_testgen_scalars(self.handle, device, DIST[dist], seed, start, n,
                                           n if total_n is None else total_n, form, ctypes.c_void_p(buf.ptr), stride))
         return buf
 
@@ -344,7 +376,7 @@ class Context:
         db = self.alloc(a.nbytes, device).upload(np.ascontiguousarray(b, dtype=np.uint8)) if b is not None else None
         do = self.alloc(a.nbytes, device)
         try:
-            _check(lib().cozk_test_field_op(self.handle, device, ops[op], ctypes.c_void_p(da.ptr),
+            _check(testlib().cozk_test_field_op(self.handle, device, ops[op], ctypes.c_void_p(da.ptr),
                                             ctypes.c_void_p(db.ptr) if db else None, ctypes.c_void_p(do.ptr), n))
             return do.download().reshape(n, 32)
         finally:
@@ -360,7 +392,7 @@ class Context:
         db = self.alloc(a.nbytes, device).upload(np.ascontiguousarray(b, dtype=np.uint8)) if b is not None else None
         do = self.alloc(a.nbytes, device)
         try:
-            _check(lib().cozk_test_g1_op(self.handle, device, ops[op], ctypes.c_void_p(da.ptr),
+            _check(testlib().cozk_test_g1_op(self.handle, device, ops[op], ctypes.c_void_p(da.ptr),
                                          ctypes.c_void_p(db.ptr) if db else None, ctypes.c_void_p(do.ptr), n))
             return do.download().reshape(n, 72)
         finally:
@@ -369,15 +401,17 @@ class Context:
                     x.free()
 
     def sort_pairs(self, keys, vals, key_bits, device=0):
-        """The engine's pair sort on its own (include/cozk_test.h): stable sort of (key, val) uint32 pairs by key."""
+        """The engine's pair sort on its own (include/cozk_test.h): (key, val) uint32 pairs grouped by key, keys ascending."""
         keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        if keys.size and int(keys.max()) >> key_bits:
+            raise ValueError("keys must be below 2^key_bits")
         vals = np.ascontiguousarray(vals, dtype=np.uint32)
         m = keys.size
         bufs = [self.alloc(max(m, 1) * 4, device) for _ in range(4)]
         try:
             bufs[0].upload(keys.view(np.uint8))
             bufs[1].upload(vals.view(np.uint8))
-            _check(lib().cozk_test_sort(self.handle, device, ctypes.c_void_p(bufs[0].ptr), ctypes.c_void_p(bufs[1].ptr), m, key_bits,
+            _check(testlib().cozk_test_sort(self.handle, device, ctypes.c_void_p(bufs[0].ptr), ctypes.c_void_p(bufs[1].ptr), m, key_bits,
                                         None, 0, 0, 0, 0, 0, 0, 0, 0, 0, ctypes.c_void_p(bufs[2].ptr), ctypes.c_void_p(bufs[3].ptr)))
             return bufs[2].download(m * 4).view(np.uint32), bufs[3].download(m * 4).view(np.uint32)
         finally:
@@ -392,7 +426,7 @@ class Context:
         m = g * n * W
         ko, vo = self.alloc(max(m, 1) * 4, device), self.alloc(max(m, 1) * 4, device)
         try:
-            _check(lib().cozk_test_sort(self.handle, device, None, None, 0, key_bits, ctypes.c_void_p(dscalars.ptr), n, g, stride, form,
+            _check(testlib().cozk_test_sort(self.handle, device, None, None, 0, key_bits, ctypes.c_void_p(dscalars.ptr), n, g, stride, form,
                                         c, W, table_stride, val_offset, 1 if fused else 0, ctypes.c_void_p(ko.ptr), ctypes.c_void_p(vo.ptr)))
             return ko.download(m * 4).view(np.uint32), vo.download(m * 4).view(np.uint32)
         finally:
@@ -402,7 +436,7 @@ class Context:
     def microbench(self, which, blocks, threads, iters, device=0):
         names = {"imad": 0, "fq_mul": 1, "fq_sqr": 2, "madd": 3, "imad_cc": 4, "imad_lo": 5, "imad_hi": 6, "fq_mul4": 7}
         ms, ops = ctypes.c_double(), ctypes.c_double()
-        _check(lib().cozk_microbench(self.handle, device, names[which], blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops)))
+        _check(testlib().cozk_microbench(self.handle, device, names[which], blocks, threads, iters, ctypes.byref(ms), ctypes.byref(ops)))
         return ms.value, ops.value
 
 

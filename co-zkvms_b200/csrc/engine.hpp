@@ -189,6 +189,8 @@ struct cozk_ctx {
     long opt_dominant_min_points = 1L << 21;  // ... when the call has at least this many (vector, point) pairs: the look costs ~35 us
     long opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first
     long opt_acc_chunk = 0;          // pairs per level-1 accumulate thread; 0 = chosen per call (msm_plan.hpp, choose_acc_l)
+    long opt_acc_chunk_up = 0;       // partial slots per thread at the serial accumulate levels >= 2; 0 = ACC_L
+    long opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
     long opt_stream_min_points = 1L << 23;  // host-resident single vectors this long are streamed in chunks (0 = never)

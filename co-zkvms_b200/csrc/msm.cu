@@ -169,7 +169,7 @@ static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, con
                          pp_out.as<xyzz>(),
                          (uint32_t)tile};
         if (lvl == 0) k_accumulate<true><<<grid_for(T, 128), 128, 0, st>>>(A);
-        else if (tile == ACC_L) k_accumulate<false><<<grid_for(T, 128), 128, 0, st>>>(A);
+        else if (tile != ACC_TILE) k_accumulate<false><<<grid_for(T, 128), 128, 0, st>>>(A);
         else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
@@ -373,7 +373,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     double plan_mults = 0, plan_pairs = 0, host_finish_ms = 0;
     uint32_t last_c = 0, last_W = 0;
     // k_accumulate<true>: 4 blocks of 128 threads per SM are resident
-    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk};
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l};
 
     for (size_t pass = 0; pass < passes; ++pass) {
         size_t lo = pass * MAX_POINTS_PER_PASS;
@@ -774,7 +774,7 @@ static int srs_compute_totals(cozk_ctx* ctx, int di, SrsEntry& S) {
     COZK_CUDA(cudaSetDevice(D.id));
     const size_t n = S.n;
     const uint32_t rows_per_pass = (uint32_t)std::max<size_t>(1, std::min<size_t>(S.table_W, ((size_t)1 << 28) / n));
-    const AccTuning acc_tuning{(size_t)D.sm_count * 512, 0};
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, 0, (int)ctx->opt_acc_chunk_up, 0};
     std::vector<xyzz> sums((size_t)S.table_W * levels);
     double launches = 0;
     int rc;
@@ -1169,6 +1169,14 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // pairs per thread at level 1 of the accumulate stage: 0 = choose per call (fill the last wave of threads)
         if (value != 0 && (value < 4 || value > 256)) return COZK_ERR_INVALID_ARG;
         ctx->opt_acc_chunk = value;
+    } else if (!strcmp(name, "acc_chunk_up")) {
+        // partial slots per thread at the serial accumulate levels >= 2 (0 = 32); never ACC_TILE, which selects the scan kernel
+        if (value != 0 && (value < 2 || value > 128 || value == ACC_TILE)) return COZK_ERR_INVALID_ARG;
+        ctx->opt_acc_chunk_up = value;
+    } else if (!strcmp(name, "group_l")) {
+        // buckets per thread in the group step of the bucket reduce: a power of two, 0 = chosen from the bucket count
+        if (value != 0 && (value < 1 || value > 64 || (value & (value - 1)))) return COZK_ERR_INVALID_ARG;
+        ctx->opt_group_l = value;
     } else if (!strcmp(name, "dominant")) {
         // 1: whole-SRS calls look for windows dominated by one digit and use the row totals; 0: always the plain layout
         if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;

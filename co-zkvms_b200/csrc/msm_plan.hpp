@@ -23,6 +23,8 @@ constexpr uint32_t C_MIN = 2, C_MAX = 22;
 struct AccTuning {
     size_t resident = 0;
     int force_l = 0;
+    int up_l = 0;  // option "acc_chunk_up": partial slots per thread at the serial levels >= 2 (0 = ACC_L)
+    int group_l = 0;  // option "group_l": buckets per thread in the group step of the bucket reduce (0 = chosen from the bucket count)
 };
 
 // Level-1 chunk length.  32 pairs per thread is the measured optimum once the kernel fills the device (2^20 points:
@@ -153,7 +155,7 @@ inline void plan_set_pairs(MsmPlan& p, size_t m) {
     p.acc_tile.push_back(l1);
     for (size_t t = (e + l1 - 1) / l1; t > 1;) {
         e = 2 * t;
-        int tile = e > ACC_SCAN_MAX ? ACC_L : ACC_TILE;
+        int tile = e > ACC_SCAN_MAX ? (p.acc.up_l ? p.acc.up_l : ACC_L) : ACC_TILE;
         p.acc_entries.push_back(e);
         p.acc_tile.push_back(tile);
         t = (e + tile - 1) / tile;
@@ -209,6 +211,7 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     // few buckets: shallow groups (depth is what costs); millions of buckets: the stage is throughput bound and the
     // NS masked sums per group dominate, so make groups larger
     uint32_t gl = p.total_buckets <= ((size_t)1 << 20) ? GROUP_L : (p.total_buckets <= ((size_t)1 << 22) ? 2 * GROUP_L : 4 * GROUP_L);
+    if (acc.group_l) gl = (uint32_t)acc.group_l;
     p.group_l = p.B < gl ? p.B : gl;
     p.log_l = 0;
     while ((1u << p.log_l) < p.group_l) ++p.log_l;

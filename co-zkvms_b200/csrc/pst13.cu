@@ -166,6 +166,49 @@ static int open_check_args(cozk_ctx* ctx, const void* evals, const void* point, 
     return COZK_OK;
 }
 
+int cozk_pst13_batch_commit_packed(cozk_ctx* ctx, cozk_srs srs, const void* const* polys, const int* kinds, size_t k, size_t n,
+                                   int commit_to_public, void* out_commitments, uint8_t* present) {
+    if (!ctx || !polys || !kinds || !out_commitments || !present || k == 0) {
+        set_error("null pointer or k == 0");
+        return COZK_ERR_INVALID_ARG;
+    }
+    // The packed image goes to the device as it is (cozk_poly_upload widens the small kinds there), the commitments run
+    // over the resident polynomials, nothing stays behind.  Public polynomials nobody keeps are not even uploaded.
+    const int nd = cozk_device_count(ctx);
+    std::vector<cozk_poly> handles;
+    std::vector<size_t> index;
+    uint8_t* o = reinterpret_cast<uint8_t*>(out_commitments);
+    int rc = COZK_OK;
+    for (size_t j = 0; j < k && !rc; ++j) {
+        present[j] = 0;
+        memset(o + COZK_COMMITMENT_BYTES * j, 0, COZK_COMMITMENT_BYTES);
+        if (!polys[j]) {
+            set_error("null polynomial");
+            rc = COZK_ERR_INVALID_ARG;
+            break;
+        }
+        if (kinds[j] != COZK_POLY_SHARED && !commit_to_public) continue;  // MaybeShared::Public(None)
+        cozk_poly h = 0;
+        rc = cozk_poly_upload(ctx, (int)(handles.size() % (size_t)nd), polys[j], n, kinds[j], &h);
+        if (!rc) {
+            handles.push_back(h);
+            index.push_back(j);
+        }
+    }
+    if (!rc && !handles.empty()) {
+        std::vector<uint8_t> comm(handles.size() * COZK_COMMITMENT_BYTES), pres(handles.size());
+        rc = cozk_pst13_batch_commit_polys(ctx, srs, handles.data(), handles.size(), 1, comm.data(), pres.data());
+        for (size_t q = 0; q < handles.size() && !rc; ++q) {
+            present[index[q]] = pres[q];
+            memcpy(o + COZK_COMMITMENT_BYTES * index[q], &comm[q * COZK_COMMITMENT_BYTES], COZK_COMMITMENT_BYTES);
+        }
+    }
+    const std::string keep = rc ? cozk_last_error() : "";
+    for (cozk_poly h : handles) cozk_poly_release(ctx, h);
+    if (rc) set_error(keep);
+    return rc;
+}
+
 int cozk_pst13_open(cozk_ctx* ctx, const cozk_srs* level_srs, size_t nv, const void* evals, size_t stride_bytes,
                     const void* point, int form, void* out_proofs, void* out_eval) {
     int rc = open_check_args(ctx, evals, point, out_proofs, out_eval, nv, stride_bytes, form);

@@ -10,11 +10,70 @@
 
 #include "engine.hpp"
 #include "../../include/cozk_pst13.h"
+#include "bulk_copy.cuh"
 #include "rep3_kernels.cuh"
 
 namespace cozk {
 
 __global__ void __launch_bounds__(256) k_ingest(IngestArgs A) { ingest_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+
+// k_ingest with the data streamed through shared memory by the copy engine.  Output contract = ingest_body for every
+// element (that body is what the host tier runs).  Both HBM directions of this in-place conversion are bulk copies of
+// whole 8 KiB slabs: a block owns tiles b, b + grid, ..; one elected thread keeps two loads in flight ahead of the slab
+// being converted and sends every converted slab back with a bulk store; the 256 threads only touch shared memory.
+constexpr int ING_THREADS = 256, ING_STAGES = 3;
+__global__ void __launch_bounds__(ING_THREADS) k_ingest_bulk(IngestArgs A) {
+    __shared__ __align__(128) uint8_t buf[ING_STAGES][ING_THREADS * 32];
+    __shared__ __align__(8) uint64_t bar[ING_STAGES];
+    const uint32_t t = threadIdx.x;
+    const size_t tiles = (A.n_fr + ING_THREADS - 1) / ING_THREADS;
+    auto tile_bytes = [&](size_t tile) -> uint32_t {
+        const size_t left = A.n_fr - tile * ING_THREADS;
+        return (uint32_t)(left < ING_THREADS ? left : ING_THREADS) * 32u;
+    };
+    if (t == 0) {
+        for (int s = 0; s < ING_STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const size_t first = blockIdx.x, step = gridDim.x;
+    if (t == 0) {
+        for (int s = 0; s < ING_STAGES - 1; ++s) {
+            const size_t tile = first + (size_t)s * step;
+            if (tile < tiles) {
+                mbar_arrive_expect(&bar[s], tile_bytes(tile));
+                bulk_load(buf[s], A.data + tile * ING_THREADS * 32, tile_bytes(tile), &bar[s]);
+            }
+        }
+    }
+    uint32_t it = 0;
+    for (size_t tile = first; tile < tiles; tile += step, ++it) {
+        const int s = it % ING_STAGES;
+        if (t == 0) {
+            const size_t ahead = tile + (size_t)(ING_STAGES - 1) * step;
+            if (ahead < tiles) {
+                const int sa = (it + ING_STAGES - 1) % ING_STAGES;  // the stage the slab before this one was stored from
+                bulk_wait_read<0>();
+                mbar_arrive_expect(&bar[sa], tile_bytes(ahead));
+                bulk_load(buf[sa], A.data + ahead * ING_THREADS * 32, tile_bytes(ahead), &bar[sa]);
+            }
+        }
+        mbar_wait(&bar[s], (it / ING_STAGES) & 1u);
+        if (tile * ING_THREADS + t < A.n_fr) {
+            fr x = load_fq(buf[s] + 32 * t);
+            if (!fr_is_canonical(x)) *A.bad = 1;  // every writer stores the same value; the slab goes back unconverted
+            else store_fq(buf[s] + 32 * t, fr_mont_from_canon(x));
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            bulk_store(A.data + tile * ING_THREADS * 32, buf[s], tile_bytes(tile));
+            bulk_commit();
+        }
+    }
+    if (t == 0) bulk_wait_all();
+}
+
 __global__ void __launch_bounds__(256) k_widen(WidenArgs A) { widen_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 // descriptors and coefficients are the same for every thread: each block stages them in shared memory once
 // (k * (24 + 64) bytes) so that the inner loop reads them with broadcast loads instead of going through L1/L2
@@ -32,6 +91,63 @@ __global__ void __launch_bounds__(128, 4) k_lincomb(LincombArgs A, int staged) {
     lincomb_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
 __global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+
+// k_chi_partial with the polynomial and chi slabs streamed through shared memory by the copy engine.  Same partial sums
+// as chi_partial_body (thread t of polynomial j adds elements t, t + T, ..): a block of 128 threads owns 128 consecutive
+// t, so round r needs ONE contiguous slab of the polynomial (128 x 64 or 32 bytes) and one of the chi table (128 x 32):
+// an elected thread keeps CHI_STAGES - 1 rounds in flight as bulk copies, the others read their element from shared
+// memory - no lane fetches 16 bytes at a 64-byte stride from L1 any more.
+constexpr int CHI_THREADS = 128, CHI_STAGES = 4;
+struct ChiStage {
+    uint8_t poly[CHI_THREADS * 64];
+    uint8_t chi[CHI_THREADS * 32];
+};
+__global__ void __launch_bounds__(CHI_THREADS) k_chi_partial_bulk(ChiArgs A) {
+    extern __shared__ __align__(128) uint8_t chi_smem_raw[];
+    ChiStage* st = reinterpret_cast<ChiStage*>(chi_smem_raw);
+    __shared__ __align__(8) uint64_t bar[CHI_STAGES];
+    const uint32_t t = threadIdx.x;
+    const uint32_t blocks_per_poly = A.T / CHI_THREADS;  // T is a multiple of the block size (power of two >= 128)
+    const uint32_t j = blockIdx.x / blocks_per_poly;
+    const size_t tbase = (size_t)(blockIdx.x - j * blocks_per_poly) * CHI_THREADS;
+    const PolyDesc d = A.polys[j];
+    const size_t lim = d.len < A.n ? d.len : A.n;
+    const uint32_t eb = d.kind == POLY_SHARED ? 64u : 32u;
+    const size_t rounds = lim > tbase ? (lim - tbase + A.T - 1) / A.T : 0;
+    auto issue = [&](size_t r) {  // elected thread: slab of round r into its stage
+        const int s = (int)(r % CHI_STAGES);
+        const size_t e0 = r * A.T + tbase;
+        const uint32_t cnt = (uint32_t)(lim - e0 < CHI_THREADS ? lim - e0 : CHI_THREADS);
+        mbar_arrive_expect(&bar[s], cnt * (eb + 32u));
+        bulk_load(st[s].poly, d.data + e0 * eb, cnt * eb, &bar[s]);
+        bulk_load(st[s].chi, reinterpret_cast<const uint8_t*>(A.chis) + e0 * 32, cnt * 32u, &bar[s]);
+    };
+    if (t == 0) {
+        for (int s = 0; s < CHI_STAGES; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (t == 0)
+        for (size_t r = 0; r < (size_t)(CHI_STAGES - 1) && r < rounds; ++r) issue(r);
+    fr_wide acc = fr_wide_zero();
+    for (size_t r = 0; r < rounds; ++r) {
+        const int s = (int)(r % CHI_STAGES);
+        // the stage of round r - 1 has been read by everybody (barrier at the end of that round): refill it
+        if (t == 0 && r + CHI_STAGES - 1 < rounds) issue(r + CHI_STAGES - 1);
+        mbar_wait(&bar[s], (uint32_t)(r / CHI_STAGES) & 1u);
+        if (r * A.T + tbase + t < lim) {
+            fr v;
+            if (d.kind == POLY_SHARED) v = fr_add(load_fq(st[s].poly + 64 * t), load_fq(st[s].poly + 64 * t + 32));
+            else {
+                v = load_fq(st[s].poly + 32 * t);
+                if (d.kind == POLY_CANON) v = fr_mont_from_canon(v);
+            }
+            fr_wide_mac(acc, v, load_fq(st[s].chi + 32 * t));
+        }
+        __syncthreads();
+    }
+    store_fq(&A.partial[(size_t)j * A.T + tbase + t], fr_wide_reduce(acc));
+}
 __global__ void k_chi_reduce(ChiReduceArgs A) { chi_reduce_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(256) k_sum_partials(SumPartialsArgs A) { sum_partials_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
 __global__ void __launch_bounds__(128) k_eq_small(EqArgs A) { eq_small_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
@@ -324,7 +440,9 @@ int cozk_poly_from_wire(cozk_ctx* ctx, int device_index, const void* bytes, size
     if (e == cudaSuccess && E.total) {
         IngestArgs A{d, 2 * E.total, d_bad};
         T.start();
-        k_ingest<<<blocks_for(A.n_fr, 256), 256, 0, D.stream>>>(A);
+        // persistent blocks, a few per SM, each walking its tiles (k_ingest - the plain form - is what the host tier checks)
+        const unsigned tiles = blocks_for(A.n_fr, ING_THREADS);
+        k_ingest_bulk<<<std::min<unsigned>(tiles, (unsigned)D.sm_count * 8), ING_THREADS, 0, D.stream>>>(A);
         e = cudaGetLastError();
         conv = T.stop();
     }
@@ -775,7 +893,12 @@ static int evaluate_at_chi_core(cozk_ctx* ctx, const cozk_poly* polys, size_t k,
         ChiArgs A{d_desc, (uint32_t)k, d_chis_in ? d_chis_in : d_chis, n, T, d_part};
         StageTimer St(D);
         St.start();
-        k_chi_partial<<<blocks_for(k * (size_t)T, 128), 128, 0, D.stream>>>(A);
+        if (T >= CHI_THREADS) {
+            static_assert(sizeof(ChiStage) * CHI_STAGES <= 48 * 1024, "chi stages fit the default dynamic shared-memory limit");
+            k_chi_partial_bulk<<<(unsigned)(k * (size_t)(T / CHI_THREADS)), CHI_THREADS, sizeof(ChiStage) * CHI_STAGES, D.stream>>>(A);
+        } else {
+            k_chi_partial<<<blocks_for(k * (size_t)T, 128), 128, 0, D.stream>>>(A);  // tiny tables
+        }
         ChiReduceArgs R1{d_desc, (uint32_t)k, d_part, T, d_mid, Tmid, 0}, R2{d_desc, (uint32_t)k, d_mid, Tmid, d_res, 1, 1};
         k_chi_reduce<<<blocks_for(k * (size_t)Tmid, 64), 64, 0, D.stream>>>(R1);
         k_chi_reduce<<<blocks_for(k, 64), 64, 0, D.stream>>>(R2);

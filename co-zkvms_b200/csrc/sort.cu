@@ -5,18 +5,19 @@
 namespace cozk {
 
 static const size_t SORT_SMEM_FULL = sizeof(SortSmem);
-static const size_t SORT_SMEM_COUNT = offsetof(SortSmem, staged);
+static const size_t SORT_SMEM_COUNT = offsetof(SortSmem, delta);
+static const size_t SORTGEN_SMEM_FULL = sizeof(SortGenSmem);  // the fused kernels keep the scalars' limbs behind the sort's own arrays
 
 // Both limits are per device: called from cozk_init for every device of the context (the current device is set).
 int sort_setup_device() {
     COZK_CUDA(cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_FULL));
-    COZK_CUDA(cudaFuncSetAttribute(k_sortgen_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_FULL));
+    COZK_CUDA(cudaFuncSetAttribute(k_sortgen_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORTGEN_SMEM_FULL));
     COZK_CUDA(cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_COUNT));
-    COZK_CUDA(cudaFuncSetAttribute(k_sortgen_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM_COUNT));
+    COZK_CUDA(cudaFuncSetAttribute(k_sortgen_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORTGEN_SMEM_FULL));
     return COZK_OK;
 }
 
-// Sorts m pairs by the low key_bits bits of their keys on stream st.
+// Groups m pairs by key on stream st (keys must be below 2^key_bits; the order inside a group is unspecified).
 //   fused == nullptr: the pairs lie in (D.keys_a, D.vals_a);
 //   fused != nullptr: the pairs are those of the plain decompose layout of *fused (m = g * n * W): they are generated in
 //                     the first pass and never stored unsorted.  fused->keys / vals are ignored.
@@ -27,11 +28,10 @@ int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m,
     uint32_t* bufk[2] = {D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>()};
     uint32_t* bufv[2] = {D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>()};
     const SortPlan plan = SortPlan::for_bits(key_bits);
-    if (m == 0 || m > (size_t)0x7FFFFFFF || plan.passes > SORT_MAX_PASSES) {
+    if (m == 0 || m > (size_t)0x7FFFFFFF || plan.passes > SORT_MAX_PASSES || key_bits > 31) {
         set_error("internal: group too large for the sort");
         return COZK_ERR_INVALID_ARG;
     }
-    // row storage for the largest grid of this call
     uint32_t gen_blocks = 0, gen_per = 0, fus_blocks = 0, fus_per = 0;
     sort_grid((m + SORT_TILE - 1) / SORT_TILE, &gen_blocks, &gen_per);
     size_t scalars = 0;
@@ -39,31 +39,45 @@ int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m,
         scalars = (size_t)fused->g * fused->n;
         sort_grid((scalars + SORT_THREADS - 1) / SORT_THREADS, &fus_blocks, &fus_per);
     }
-    const size_t max_blocks = gen_blocks > fus_blocks ? gen_blocks : fus_blocks;
-    int rc = D.sort_tmp.ensure((SORT_DIGITS * max_blocks + SORT_DIGITS) * sizeof(uint32_t));
+    // histogram / cursor array (reused by the passes; the last one has an entry per key value) and two `starts` arrays
+    // (first positions of this pass and of the one before: the rows of this pass's scan start there)
+    const size_t max_entries = (size_t)1 << plan.key_bits;
+    const size_t prev_entries = plan.passes > 1 ? (size_t)1 << (plan.key_bits - plan.shift[plan.passes - 2]) : 1;
+    int rc = D.sort_tmp.ensure((2 * max_entries + prev_entries + 64) * sizeof(uint32_t));
     if (rc) return rc;
-    uint32_t* counts = D.sort_tmp.as<uint32_t>();
-    uint32_t* totals = counts + SORT_DIGITS * max_blocks;
+    uint32_t* cursor = D.sort_tmp.as<uint32_t>();
+    uint32_t* starts[2] = {cursor + max_entries, cursor + 2 * max_entries};
+    // the last pass writes its starts into starts[0] (max_entries), every earlier pass fits prev_entries: alternate so that
+    // pass p reads the starts of pass p - 1 while writing its own
+    auto starts_of = [&](uint32_t p) { return (plan.passes - 1 - p) % 2 == 0 ? starts[0] : starts[1]; };
 
     for (uint32_t p = 0; p < plan.passes; ++p) {
         SortPass P{};
         P.shift = plan.shift[p];
-        P.r = plan.r[p];
-        P.counts = counts;
-        P.totals = totals;
+        P.prev_shift = plan.prev_shift[p];
+        P.cursor = cursor;
         P.keys_in = bufk[p & 1];
         P.vals_in = bufv[p & 1];
         P.keys_out = bufk[(p + 1) & 1];
         P.vals_out = bufv[(p + 1) & 1];
+        const size_t entries = (size_t)1 << (plan.key_bits - P.shift);
+        COZK_CUDA(cudaMemsetAsync(cursor, 0, entries * sizeof(uint32_t), st));
+        auto rowscan = [&](uint32_t pass) -> int {
+            const uint32_t log_row = (pass == 0 ? plan.key_bits : plan.shift[pass - 1]) - plan.shift[pass];  // digit bits of this pass
+            const uint32_t rows = (uint32_t)(entries >> log_row);
+            k_sort_rowscan<<<(rows + 7) / 8, 256, 0, st>>>(cursor, starts_of(pass), pass == 0 ? nullptr : starts_of(pass - 1), rows, log_row);
+            COZK_CUDA(cudaGetLastError());
+            *launches += 1;
+            return COZK_OK;
+        };
         if (p == 0 && fused) {
             P.m = scalars;
             P.nblocks = fus_blocks;
             P.tiles_per_block = fus_per;
-            k_sortgen_count<<<P.nblocks, SORT_THREADS, SORT_SMEM_COUNT, st>>>(*fused, P);
+            k_sortgen_count<<<P.nblocks, SORT_THREADS, SORTGEN_SMEM_FULL, st>>>(*fused, P);
             COZK_CUDA(cudaGetLastError());
-            k_sort_scan<<<1u << P.r, 256, 0, st>>>(P);
-            COZK_CUDA(cudaGetLastError());
-            k_sortgen_scatter<<<P.nblocks, SORT_THREADS, SORT_SMEM_FULL, st>>>(*fused, P);
+            if ((rc = rowscan(p))) return rc;
+            k_sortgen_scatter<<<P.nblocks, SORT_THREADS, SORTGEN_SMEM_FULL, st>>>(*fused, P);
             COZK_CUDA(cudaGetLastError());
         } else {
             P.m = m;
@@ -71,12 +85,11 @@ int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m,
             P.tiles_per_block = gen_per;
             k_sort_count<<<P.nblocks, SORT_THREADS, SORT_SMEM_COUNT, st>>>(P);
             COZK_CUDA(cudaGetLastError());
-            k_sort_scan<<<1u << P.r, 256, 0, st>>>(P);
-            COZK_CUDA(cudaGetLastError());
+            if ((rc = rowscan(p))) return rc;
             k_sort_scatter<<<P.nblocks, SORT_THREADS, SORT_SMEM_FULL, st>>>(P);
             COZK_CUDA(cudaGetLastError());
         }
-        *launches += 3;
+        *launches += 2;
         if (p == 0 && after_first) COZK_CUDA(cudaEventRecord(after_first, st));
     }
     *keys_out = bufk[plan.passes & 1];

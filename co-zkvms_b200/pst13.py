@@ -98,6 +98,9 @@ def batch_commit_rep3(setup, polys, is_shared, commit_to_public, form=0, max_num
     polys = [np.ascontiguousarray(p, dtype=np.uint8) for p in polys]
     k = len(polys)
     n = polys[0].size // (64 if is_shared[0] else 32)
+    for p, sh in zip(polys, is_shared):  # pst13.rs:307-309 asserts equal lengths; a short buffer would be read past its end
+        if p.size != n * (64 if sh else 32):
+            raise ValueError("polynomial holds %d bytes, %d coefficients need %d" % (p.size, n, n * (64 if sh else 32)))
     flags = (ctypes.c_uint8 * k)(*[1 if s else 0 for s in is_shared])
     present = (ctypes.c_uint8 * k)()
     out = np.zeros((k, COMMITMENT_BYTES), dtype=np.uint8)
@@ -107,11 +110,37 @@ def batch_commit_rep3(setup, polys, is_shared, commit_to_public, form=0, max_num
     return [PST13Commitment.from_bytes(out[j]) if present[j] else None for j in range(k)]
 
 
+ELEM_BYTES = {0: 64, 1: 32, 2: 1, 3: 2, 4: 4, 5: 8, 6: 8}  # COZK_POLY_SHARED, PUBLIC, U8, U16, U32, U64, I64
+
+
+def batch_commit_packed(setup, polys, kinds, commit_to_public=True):
+    """PST13::batch_commit / batch_commit_rep3 over the reference's packed in-memory polynomial forms
+    (MultilinearPolynomial::{LargeScalars, U8Scalars .. I64Scalars}, multilinear_polynomial.rs:226-268, and
+    Rep3DensePolynomial share arrays): small-scalar polynomials cross PCIe at 1 - 8 bytes per coefficient and are
+    widened on the device.  polys[j]: numpy array in its natural dtype (uint8 .. int64) or (n, 32) / (n, 64) uint8 images;
+    kinds[j]: a COZK_POLY_* constant (co-zkvms_b200.rep3: SHARED, PUBLIC, U8, U16, U32, U64, I64)."""
+    arrs = [np.ascontiguousarray(p) for p in polys]
+    k = len(arrs)
+    n = arrs[0].nbytes // ELEM_BYTES[kinds[0]]
+    for a, kd in zip(arrs, kinds):  # the reference asserts equal lengths (pst13.rs:307-309); the C ABI has no length arguments
+        if a.nbytes != n * ELEM_BYTES[kd]:
+            raise ValueError("polynomial of kind %d holds %d bytes, %d coefficients need %d" % (kd, a.nbytes, n, n * ELEM_BYTES[kd]))
+    ptrs = (ctypes.c_void_p * k)(*[a.ctypes.data for a in arrs])
+    kd = (ctypes.c_int * k)(*kinds)
+    present = (ctypes.c_uint8 * k)()
+    out = np.zeros((k, COMMITMENT_BYTES), dtype=np.uint8)
+    _check(_lib().cozk_pst13_batch_commit_packed(setup.ctx.handle, setup.srs, ptrs, kd, k, n, 1 if commit_to_public else 0,
+                                                 out.ctypes.data_as(ctypes.c_void_p), present))
+    return [PST13Commitment.from_bytes(out[j]) if present[j] else None for j in range(k)]
+
+
 def open(setup, evals, point, stride=32):  # noqa: A001 - the reference's name
     """open() behind PST13::prove_rep3 (pst13.rs:428-474).  Returns (proofs (nv, 72), evaluation (32,))."""
     evals = np.ascontiguousarray(evals, dtype=np.uint8)
     point = np.ascontiguousarray(point, dtype=np.uint8).reshape(-1, 32)
     nv = point.shape[0]
+    if evals.size < ((1 << nv) - 1) * stride + 32:  # pst13.rs:438 asserts the polynomial size
+        raise ValueError("2^%d evaluations at stride %d need %d bytes, got %d" % (nv, stride, ((1 << nv) - 1) * stride + 32, evals.size))
     srs = (ctypes.c_uint64 * nv)(*setup.level_srs[:nv])
     proofs = np.zeros((nv, 72), dtype=np.uint8)
     ev = np.zeros(32, dtype=np.uint8)

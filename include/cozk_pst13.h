@@ -44,6 +44,17 @@ int cozk_pst13_batch_commit_rep3(cozk_ctx* ctx, cozk_srs srs, const void* const*
                                  size_t n, int form, const unsigned* max_num_bits, int commit_to_public,
                                  void* out_commitments, uint8_t* present);
 
+/* The same for polynomials in the reference's PACKED in-memory forms: kinds[j] is one of COZK_POLY_* (cozk_rep3.h) -
+ * COZK_POLY_SHARED (n x Rep3PrimeFieldShare{a, b}, 64 B), COZK_POLY_PUBLIC (MultilinearPolynomial::LargeScalars, n x Fr
+ * Montgomery) or COZK_POLY_U8 / U16 / U32 / U64 / I64 (MultilinearPolynomial::U8Scalars .. I64Scalars,
+ * co-jolt/src/poly/multilinear_polynomial.rs:226-268: n x 1 / 2 / 4 / 8 bytes).  The small-scalar polynomials - about 60 of
+ * the ~198 trace polynomials - cross PCIe as they lie in memory (1 - 8 bytes per coefficient instead of 32) and are widened
+ * on the device; `batch_msm` dispatches on the same enum (pst13.rs:319-323).  Public kinds are committed only when
+ * commit_to_public != 0; present[] as above.  With several devices the polynomials are dealt round-robin and the devices
+ * commit side by side (the SRS must be a replicated one). */
+int cozk_pst13_batch_commit_packed(cozk_ctx* ctx, cozk_srs srs, const void* const* polys, const int* kinds, size_t k, size_t n,
+                                   int commit_to_public, void* out_commitments, uint8_t* present);
+
 /* PST13 opening: level_srs[i] holds ck.powers_of_g[i] (2^(nv-i) points), i < nv.  evals: 2^nv Fr values (Montgomery)
  * at stride_bytes; point: nv Fr values (Montgomery) in the order open() receives them (prove_rep3 reverses the
  * opening point first, pst13.rs:134).  out_proofs: nv wire points; out_eval: r[0][0] (Fr Montgomery, 32 B). */

@@ -24,8 +24,8 @@ int cozk_test_g1_op(cozk_ctx* ctx, int device_index, int op, const void* d_a, co
 int cozk_microbench(cozk_ctx* ctx, int device_index, int which, int blocks, int threads, int iters, double* out_ms,
                     double* out_ops);
 
-/* The pair sort on its own (csrc/sort_kernels.cuh).  d_scalars == NULL: sorts the m given (key, val) pairs by the low
- * key_bits bits of their keys (stable).  d_scalars != NULL: the pairs are those of the plain decompose layout of g vectors
+/* The pair sort on its own (csrc/sort_kernels.cuh).  d_scalars == NULL: groups the m given (key, val) pairs by key, keys
+ * ascending (every key below 2^key_bits; the order inside a group is unspecified).  d_scalars != NULL: the pairs are those of the plain decompose layout of g vectors
  * of n scalars (vector v at d_scalars + v * round_up((n-1)*stride + 32, 256)); fused != 0 produces them inside the first
  * sort pass (the engine's path), fused == 0 with the decompose kernel followed by generic passes (key_bits == 0: left
  * unsorted).  Outputs hold m = g * n * windows pairs. */

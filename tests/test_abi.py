@@ -21,11 +21,22 @@ def _declared(path):
 def test_library_exports_every_declared_symbol(cozk):
     L = cozk.lib()
     declared = (_declared(os.path.join(ROOT, "include", "cozk_msm.h")) + _declared(os.path.join(ROOT, "include", "cozk_rep3.h"))
-                + _declared(os.path.join(ROOT, "include", "cozk_pst13.h")) + _declared(os.path.join(ROOT, "include", "cozk_test.h")))
+                + _declared(os.path.join(ROOT, "include", "cozk_pst13.h")))
     assert len(declared) >= 25
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(set(declared)) == sorted(cozk.ABI_SYMBOLS)
+
+
+def test_test_entry_points_live_in_their_own_library(cozk):
+    """include/cozk_test.h (generators, test kernels, microbenchmarks) is served by libcozk_test.so; the product library
+    exports none of it."""
+    T, L = cozk.testlib(), cozk.lib()
+    declared = [n for n in _declared(os.path.join(ROOT, "include", "cozk_test.h"))]
+    assert sorted(declared) == sorted(cozk.TEST_ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(T, name), name
+        assert not hasattr(L, name), name
 
 
 def test_product_does_not_import_oracle():

@@ -74,6 +74,45 @@ def test_batch_commit_rep3_matches_reference_semantics(cozk, ctx, orc):
     setup.release()
 
 
+def test_batch_commit_packed_small_scalar_polynomials(cozk, ctx, orc):
+    """MultilinearPolynomial::{U8..I64Scalars} (multilinear_polynomial.rs:226-268) through the host boundary in their packed
+    form (1 - 8 bytes per coefficient over PCIe, widened on the device): same commitments as the widened 32-byte images and
+    the oracle; I64 negatives are full-width field elements; public polynomials are dropped on parties 1 / 2."""
+    pst, rep3 = cozk.pst13, cozk.rep3
+    nv = 11
+    n = 1 << nv
+    bases = orc.gen_bases(1, n)
+    setup = pst.PST13Setup(ctx, [bases])
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 2, n).astype(np.uint8)                   # 0/1 flags
+    u16 = rng.integers(0, 1 << 16, n).astype(np.uint16)
+    u32 = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    u64 = rng.integers(0, 1 << 63, n, dtype=np.uint64) * 2 + 1
+    i64 = rng.integers(-(1 << 62), 1 << 62, n).astype(np.int64)
+    i64[0], i64[1] = -1, np.iinfo(np.int64).min
+    large = [pyref.scalar_uniform(21, i) for i in range(n)]
+    share = np.zeros((n, 64), np.uint8)
+    share[:, :32] = H.scalars_wire([pyref.scalar_uniform(22, i) for i in range(n)])
+    share[:, 32:] = H.scalars_wire([pyref.scalar_uniform(23, i) for i in range(n)])
+    polys = [u8, u16, share, u32, u64, i64, H.scalars_wire(large)]
+    kinds = [rep3.U8, rep3.U16, rep3.SHARED, rep3.U32, rep3.U64, rep3.I64, rep3.PUBLIC]
+    ints = [[int(x) for x in u8], [int(x) for x in u16], None, [int(x) for x in u32], [int(x) for x in u64],
+            [int(x) % H.R for x in i64], large]
+    got = pst.batch_commit_packed(setup, polys, kinds, commit_to_public=True)
+    for j, vals in enumerate(ints):
+        want = orc.msm(bases, share[:, :32].copy() if vals is None else H.scalars_wire(vals))
+        assert got[j].nv == nv and (got[j].g_product == want).all(), j
+    other = pst.batch_commit_packed(setup, polys, kinds, commit_to_public=False)      # parties 1 / 2
+    assert [c is not None for c in other] == [False, False, True, False, False, False, False]
+    assert (other[2].g_product == got[2].g_product).all()
+    with pytest.raises(ValueError):
+        pst.batch_commit_packed(setup, [u8, u16[:-1]], [rep3.U8, rep3.U16])
+    with pytest.raises(cozk.CozkError) as e:                                          # longer than the SRS: Key length error
+        pst.batch_commit_packed(setup, [np.zeros(2 * n, np.uint8)], [rep3.U8])
+    assert e.value.code == cozk.ERR_KEY_LENGTH
+    setup.release()
+
+
 def _open_reference(orc, levels, evals, point):
     """open() restated on Python ints + the oracle MSM (pst13.rs:428-474)."""
     nv = len(point)
@@ -102,6 +141,42 @@ def test_open(cozk, ctx, orc, nv, stride):
     want_proofs, want_ev = _open_reference(orc, levels, evals, point)
     assert (proofs == want_proofs).all()
     assert pyref.from_mont(H.to_int(ev), H.R) == want_ev
+    setup.release()
+
+
+@pytest.mark.parametrize("nv", [1, 3, 4])
+def test_opening_satisfies_the_verifier_equation(cozk, ctx, orc, nv):
+    """The reference accepts an opening through the pairing check (pst13.rs:536-545: PST13::verify -> MultilinearPC::check).
+    With a real eq-basis SRS (oracle/pairing.py: powers_of_g from a seeded trapdoor, h and h_mask in G2) the engine's
+    commitment, proofs and evaluation - host path, keyed path and resident-polynomial path - satisfy
+    e(C - v g, h) = prod e(proof_i, h_mask_i - point_i h); the same proofs fail it for a wrong value or a reversed point.
+    Unlike _open_reference this witness shares no code with open(): a wrong level / point / base order would not pass."""
+    from oracle import pairing as pr
+    pst, rep3 = cozk.pst13, cozk.rep3
+    levels_pts, vk, _ = pr.setup(nv, seed=70 + nv)
+    levels = [H.bases_wire(lv) for lv in levels_pts]
+    setup = rep3.create_open_key(pst.PST13Setup(ctx, levels))
+    n = 1 << nv
+    evals = [pyref.scalar_uniform(80 + nv, i) for i in range(n)]
+    point = [pyref.scalar_uniform(90 + nv, i) for i in range(nv)]
+    comm = orc.wire_to_point(pst.commit(setup, H.scalars_wire(evals)).g_product)
+    poly = rep3.Rep3DensePolynomial.upload(ctx, H.scalars_wire(evals), rep3.PUBLIC)
+    runs = {"host": pst.open(setup, H.scalars_wire(evals), H.scalars_wire(point)),
+            "keyed": rep3.open_keyed(setup, H.scalars_wire(evals), H.scalars_wire(point)),
+            "resident": rep3.open_poly(setup, poly, H.scalars_wire(point)),
+            "resident, reference schedule": rep3.open_poly(setup, poly, H.scalars_wire(point), keyed=False)}
+    for name, (proofs, ev) in runs.items():
+        value = pyref.from_mont(H.to_int(ev), H.R)
+        pts = [orc.wire_to_point(p) for p in proofs]
+        assert pr.verify_opening(vk, comm, point, value, pts), name
+    proofs, ev = runs["host"]
+    pts = [orc.wire_to_point(p) for p in proofs]
+    value = pyref.from_mont(H.to_int(ev), H.R)
+    assert not pr.verify_opening(vk, comm, point, (value + 1) % H.R, pts)
+    if nv > 1:
+        assert not pr.verify_opening(vk, comm, point[::-1], value, pts)
+    poly.release()
+    rep3.release_open_key(setup)
     setup.release()
 
 

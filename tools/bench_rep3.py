@@ -45,6 +45,7 @@ def main():
     rep3, pst = cozk.rep3, cozk.pst13
     ctx = cozk.Context()
     L = cozk.lib()
+    T = cozk.testlib()
     n = 1 << args.log2n
     peak, peak_src = hbm_peak()
     ms, ops = ctx.microbench("fq_mul", 148 * 8, 256, 512)
@@ -81,7 +82,7 @@ def main():
     tmp = ctx.alloc(n * 64)
     for j in range(args.k):
         for half in (0, 1):
-            cozk._check(L.cozk_testgen_scalars(ctx.handle, 0, cozk.DIST["uniform"], 100 + 2 * j + half, 0, n, n, cozk.MONT,
+            cozk._check(T.cozk_testgen_scalars(ctx.handle, 0, cozk.DIST["uniform"], 100 + 2 * j + half, 0, n, n, cozk.MONT,
                                                ctypes.c_void_p(tmp.ptr + 32 * half), 64))
         polys.append(rep3.Rep3DensePolynomial.from_device(ctx, tmp, n))
     tmp.free()

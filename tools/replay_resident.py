@@ -37,9 +37,10 @@ N_SHARED, N_FINAL = 138, 54
 def wire_image(ctx, dist, seed, n):
     """Pinned ark-serialize image of a Rep3DensePolynomial of n coefficients: share a ~ dist, share b uniform."""
     L = cozk.lib()
+    T = cozk.testlib()
     d = ctx.alloc(n * 64)
     for half, (dd, sd) in enumerate(((dist, seed), ("uniform", seed + 1000))):
-        cozk._check(L.cozk_testgen_scalars(ctx.handle, 0, cozk.DIST[dd], sd, 0, n, n, cozk.CANON,
+        cozk._check(T.cozk_testgen_scalars(ctx.handle, 0, cozk.DIST[dd], sd, 0, n, n, cozk.CANON,
                                            ctypes.c_void_p(d.ptr + 32 * half), 64))
     nv = n.bit_length() - 1
     header = nv.to_bytes(8, "little") + n.to_bytes(8, "little")

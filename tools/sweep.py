@@ -24,6 +24,9 @@ ap.add_argument("--stream-min", type=int, default=-1, help="stream_min_points op
 ap.add_argument("--stream-chunks", type=int, default=0)
 ap.add_argument("--table-window", type=int, default=-1, help="-1 auto, 0 no table, else forced table window")
 ap.add_argument("--acc-chunk", type=int, default=0, help="pairs per level-1 accumulate thread (0 = chosen per call)")
+ap.add_argument("--acc-chunk-up", type=int, default=0, help="partial slots per thread at the serial accumulate levels >= 2")
+ap.add_argument("--group-l", type=int, default=0, help="buckets per thread in the group step of the bucket reduce")
+ap.add_argument("--exact", action="store_true", help="register an SRS of exactly each size (the bench's shape) instead of prefixes of the largest")
 ap.add_argument("--dominant", type=int, default=-1, help="-1 default, 0 off, 1 on (dominant-digit mode of whole-SRS calls)")
 ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
@@ -35,6 +38,10 @@ if args.dominant >= 0:
     ctx.set_option("dominant", args.dominant)
 if args.acc_chunk:
     ctx.set_option("acc_chunk", args.acc_chunk)
+if args.acc_chunk_up:
+    ctx.set_option("acc_chunk_up", args.acc_chunk_up)
+if args.group_l:
+    ctx.set_option("group_l", args.group_l)
 if args.stream_min >= 0:
     ctx.set_option("stream_min_points", args.stream_min)
 if args.stream_chunks:
@@ -45,9 +52,11 @@ elif args.table_window > 0:
     ctx.set_option("table_window", args.table_window)
 sizes = [int(x) for x in args.sizes.split(",")]
 nmax = 1 << max(sizes)
-dbases = ctx.testgen_bases(1, nmax)
-srs = ctx.srs_register_device(dbases, nmax)
-dbases.free()
+srs = None
+if not args.exact:
+    dbases = ctx.testgen_bases(1, nmax)
+    srs = ctx.srs_register_device(dbases, nmax)
+    dbases.free()
 rows = []
 for dist in args.dists.split(","):
     ds = [ctx.testgen_scalars(dist, 2 + j, nmax, stride=args.stride) for j in range(args.batch)]
@@ -59,6 +68,12 @@ for dist in args.dists.split(","):
             pins.append(pb)
     for lg in sizes:
         n = 1 << lg
+        if args.exact:
+            if srs is not None:
+                ctx.srs_release(srs)
+            db = ctx.testgen_bases(1, n)
+            srs = ctx.srs_register_device(db, n)
+            db.free()
         out = np.zeros((args.batch, 72), np.uint8)
         ptrs = [pb.ptr for pb in pins] if args.host else [d.ptr for d in ds]
         dev = None if args.host else 0
