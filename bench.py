@@ -168,6 +168,28 @@ def strong_record(cozk, args, n_devices, check):
     return rec
 
 
+def replay_record(cozk, args, n_devices):
+    """BASELINE.json configs[4] ("co-jolt 3-party proof of a 2^22-cycle guest trace, all party commitments on GPU") as a
+    replay of one party's commitment-path calls (tools/replay_cojolt.py: 138 shared + 60 packed public trace polynomials,
+    the single commits, 54 final_cts polynomials, the opening) through the reference-facing PST13 calls with HOST buffers,
+    on one context over all GPUs of the box; next to the reference's own trace numbers.  The Rust prover cannot run here, so
+    the party prove time is a projection: the trace's non-MSM time + the measured GPU time."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("replay_cojolt", os.path.join(ROOT, "tools", "replay_cojolt.py"))
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    lt = args.replay_log2t
+    out = {"log2_T": lt, "n_devices": n_devices, "parties": []}
+    with cozk.Context(devices=list(range(n_devices))) as rctx:
+        setup, srs_s = rc.make_setup(rctx, lt)
+        out["srs_generate_register_s"] = round(srs_s, 3)
+        for party in (0, 2):  # party 1 has the shape of party 0 (a constant share vector)
+            out["parties"].append(rc.replay_party(rctx, setup, lt, party, gpus=n_devices, srs_s=srs_s))
+        for h in setup.level_srs:
+            rctx.srs_release(h)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +202,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong-log2n", type=int, default=24, help="total points of the strong-scaling record (0 = skip)")
     ap.add_argument("--strong-steps", type=int, default=5)
+    ap.add_argument("--replay-log2t", type=int, default=22,
+                    help="co-jolt party commitment-path replay for a 2^T-cycle trace (BASELINE.json configs[4]); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -318,6 +342,9 @@ def main():
             del hb
     if rank == 0 and args.strong_log2n:
         strong = strong_record(cozk, args, world, not args.no_cpu_baseline)
+    replay = None
+    if rank == 0 and args.replay_log2t:
+        replay = replay_record(cozk, args, world)
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = world * n / (ms_per_step * 1e-3) / 1e6
@@ -376,6 +403,8 @@ def main():
             line["parity_vs_oracle"] = parity
         if strong is not None:
             line["strong"] = strong
+        if replay is not None:
+            line["cojolt_replay"] = replay
         if not args.no_cpu_baseline and world == 1:
             log2c = min(args.log2n, 20 if cores >= 8 else 18)
             v, ms_c, sample = cpu_reference_run(log2c, args.dist, 2, 1, cores)

@@ -190,10 +190,14 @@ struct cozk_ctx {
     long opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first
     long opt_acc_chunk = 0;          // pairs per level-1 accumulate thread; 0 = chosen per call (msm_plan.hpp, choose_acc_l)
     long opt_acc_chunk_up = 0;       // partial slots per thread at the serial accumulate levels >= 2; 0 = ACC_L
+    long opt_bulk_copy = 0;          // 1: ingest / chi kernels stream their slabs through shared memory with bulk copies (TMA); 0: plain per-lane
+                                     // loads.  Measured equal or slower (2^22: ingest 0.161 against 0.152 ms, chi 2.21 against 2.20 ms; 2^20: chi
+                                     // 0.67 against 0.59 ms): the access pattern is not what holds these kernels back.  Kept as an option.
+    long opt_chi_waves = 1;          // threads per polynomial of the chi kernels: enough for this many full waves of the device
     long opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
     long opt_window = 0;             // 0 = choose per call
     long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
-    long opt_stream_min_points = 1L << 23;  // host-resident single vectors this long are streamed in chunks (0 = never)
+    long opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never): 2^22 in 2 chunks 12.7 against 13.3 ms; 2^20 loses (3.86 against 3.80 ms: every chunk repeats the latency-bound upper accumulate levels)
     long opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
     long opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     long opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables

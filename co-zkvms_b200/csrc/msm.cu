@@ -1173,6 +1173,12 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // partial slots per thread at the serial accumulate levels >= 2 (0 = 32); never ACC_TILE, which selects the scan kernel
         if (value != 0 && (value < 2 || value > 128 || value == ACC_TILE)) return COZK_ERR_INVALID_ARG;
         ctx->opt_acc_chunk_up = value;
+    } else if (!strcmp(name, "bulk_copy")) {
+        if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;
+        ctx->opt_bulk_copy = value;
+    } else if (!strcmp(name, "chi_waves")) {
+        if (value < 1 || value > 16) return COZK_ERR_INVALID_ARG;
+        ctx->opt_chi_waves = value;
     } else if (!strcmp(name, "group_l")) {
         // buckets per thread in the group step of the bucket reduce: a power of two, 0 = chosen from the bucket count
         if (value != 0 && (value < 1 || value > 64 || (value & (value - 1)))) return COZK_ERR_INVALID_ARG;

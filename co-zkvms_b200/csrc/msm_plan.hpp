@@ -9,6 +9,8 @@ namespace cozk {
 
 constexpr int ACC_L = 32;          // entries per thread of the serial accumulate body (level 1: the default, see choose_acc_l)
 constexpr int ACC_L_MIN = 16;
+constexpr int ACC_L_UP = 8;        // partial slots per thread at the serial levels >= 2: 4x the threads of chunks of 32, a quarter of
+                                   // the serial chain (2^16 points: 0.68 -> 0.62 ms; 2^20: 3.17 -> 3.15; 2^22: 10.91 -> 10.82)
 constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at small levels >= 2 (block-cooperative segmented scan)
 constexpr size_t ACC_SCAN_MAX = 65536;  // levels with more slots than this stay on the serial, work-efficient body
 constexpr uint32_t SUM_CHUNK = 1024;  // groups per thread block in the first level of the bucket-reduce sums
@@ -23,7 +25,7 @@ constexpr uint32_t C_MIN = 2, C_MAX = 22;
 struct AccTuning {
     size_t resident = 0;
     int force_l = 0;
-    int up_l = 0;  // option "acc_chunk_up": partial slots per thread at the serial levels >= 2 (0 = ACC_L)
+    int up_l = 0;  // option "acc_chunk_up": partial slots per thread at the serial levels >= 2 (0 = ACC_L_UP)
     int group_l = 0;  // option "group_l": buckets per thread in the group step of the bucket reduce (0 = chosen from the bucket count)
 };
 
@@ -155,7 +157,7 @@ inline void plan_set_pairs(MsmPlan& p, size_t m) {
     p.acc_tile.push_back(l1);
     for (size_t t = (e + l1 - 1) / l1; t > 1;) {
         e = 2 * t;
-        int tile = e > ACC_SCAN_MAX ? (p.acc.up_l ? p.acc.up_l : ACC_L) : ACC_TILE;
+        int tile = e > ACC_SCAN_MAX ? (p.acc.up_l ? p.acc.up_l : ACC_L_UP) : ACC_TILE;
         p.acc_entries.push_back(e);
         p.acc_tile.push_back(tile);
         t = (e + tile - 1) / tile;
@@ -208,9 +210,13 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     while (((uint64_t)1 << sb) < (uint64_t)p.total_buckets) ++sb;  // keys are < total_buckets (no sentinel at level 1)
     p.sort_bits = sb;
     plan_set_pairs(p, p.m);
-    // few buckets: shallow groups (depth is what costs); millions of buckets: the stage is throughput bound and the
-    // NS masked sums per group dominate, so make groups larger
-    uint32_t gl = p.total_buckets <= ((size_t)1 << 20) ? GROUP_L : (p.total_buckets <= ((size_t)1 << 22) ? 2 * GROUP_L : 4 * GROUP_L);
+    // Buckets per thread in the group step.  Few buckets: shallow groups (depth is what costs); hundreds of thousands: the
+    // stage is throughput bound and the NS masked sums per group dominate, so groups grow.  Measured reduce times (B200):
+    // 16 Ki buckets 0.13 / 0.15 / 0.20 ms at l = 2 / 4 / 8; 64 Ki 0.24 / 0.21 / 0.31 ms at 4 / 8 / 16; 512 Ki 1.32 / 0.85 /
+    // 0.63 ms at 4 / 8 / 16.
+    uint32_t gl = p.total_buckets <= ((size_t)1 << 15) ? 2
+                : p.total_buckets <= ((size_t)1 << 17) ? GROUP_L
+                : p.total_buckets <= ((size_t)1 << 20) ? 2 * GROUP_L : 4 * GROUP_L;
     if (acc.group_l) gl = (uint32_t)acc.group_l;
     p.group_l = p.B < gl ? p.B : gl;
     p.log_l = 0;

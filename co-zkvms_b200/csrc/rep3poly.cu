@@ -15,7 +15,24 @@
 
 namespace cozk {
 
-__global__ void __launch_bounds__(256) k_ingest(IngestArgs A) { ingest_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A); }
+// Four elements per thread, a grid-stride apart, their loads issued before the first conversion.  One element per thread
+// (8.4 M threads = 32768 blocks that live for a microsecond each at 2^22 coefficients) is bound by the rate at which the
+// SMs can start blocks, not by HBM: 0.152 ms = 0.54 of the measured copy bandwidth.  Output contract = ingest_body.
+constexpr int ING_UNROLL = 4;
+__global__ void __launch_bounds__(256) k_ingest(IngestArgs A) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fr x[ING_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ING_UNROLL; ++u)
+        if (t + u * stride < A.n_fr) x[u] = load_fq(A.data + 32 * (t + u * stride));
+#pragma unroll
+    for (int u = 0; u < ING_UNROLL; ++u) {
+        if (t + u * stride >= A.n_fr) continue;
+        if (!fr_is_canonical(x[u])) *A.bad = 1;  // every writer stores the same value
+        else store_fq(A.data + 32 * (t + u * stride), fr_mont_from_canon(x[u]));
+    }
+}
 
 // k_ingest with the data streamed through shared memory by the copy engine.  Output contract = ingest_body for every
 // element (that body is what the host tier runs).  Both HBM directions of this in-place conversion are bulk copies of
@@ -97,7 +114,7 @@ __global__ void __launch_bounds__(128) k_chi_partial(ChiArgs A) { chi_partial_bo
 // t, so round r needs ONE contiguous slab of the polynomial (128 x 64 or 32 bytes) and one of the chi table (128 x 32):
 // an elected thread keeps CHI_STAGES - 1 rounds in flight as bulk copies, the others read their element from shared
 // memory - no lane fetches 16 bytes at a 64-byte stride from L1 any more.
-constexpr int CHI_THREADS = 128, CHI_STAGES = 4;
+constexpr int CHI_THREADS = 128, CHI_STAGES = 3;  // 3 x 12 KiB of slabs: inside the default 48 KiB of dynamic shared memory
 struct ChiStage {
     uint8_t poly[CHI_THREADS * 64];
     uint8_t chi[CHI_THREADS * 32];
@@ -442,7 +459,8 @@ int cozk_poly_from_wire(cozk_ctx* ctx, int device_index, const void* bytes, size
         T.start();
         // persistent blocks, a few per SM, each walking its tiles (k_ingest - the plain form - is what the host tier checks)
         const unsigned tiles = blocks_for(A.n_fr, ING_THREADS);
-        k_ingest_bulk<<<std::min<unsigned>(tiles, (unsigned)D.sm_count * 8), ING_THREADS, 0, D.stream>>>(A);
+        if (ctx->opt_bulk_copy) k_ingest_bulk<<<std::min<unsigned>(tiles, (unsigned)D.sm_count * 8), ING_THREADS, 0, D.stream>>>(A);
+        else k_ingest<<<blocks_for((A.n_fr + ING_UNROLL - 1) / ING_UNROLL, 256), 256, 0, D.stream>>>(A);
         e = cudaGetLastError();
         conv = T.stop();
     }
@@ -875,7 +893,7 @@ static int evaluate_at_chi_core(cozk_ctx* ctx, const cozk_poly* polys, size_t k,
     for (size_t j = 0; j < k; ++j) hd[j] = PolyDesc{E[j].chunk(), E[j].len, E[j].kind, 0};
     // threads per polynomial: enough to fill the chip a few times over, never more than one element per thread
     uint32_t T = 32;
-    while ((size_t)T * 2 <= n && (size_t)T * k < (size_t)D.sm_count * 2048 && T < 4096) T *= 2;
+    while ((size_t)T * 2 <= n && (size_t)T * k < (size_t)D.sm_count * 2048 * (size_t)ctx->opt_chi_waves && T < 16384) T *= 2;
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
     PolyDesc* d_desc = nullptr;
@@ -893,8 +911,8 @@ static int evaluate_at_chi_core(cozk_ctx* ctx, const cozk_poly* polys, size_t k,
         ChiArgs A{d_desc, (uint32_t)k, d_chis_in ? d_chis_in : d_chis, n, T, d_part};
         StageTimer St(D);
         St.start();
-        if (T >= CHI_THREADS) {
-            static_assert(sizeof(ChiStage) * CHI_STAGES <= 48 * 1024, "chi stages fit the default dynamic shared-memory limit");
+        if (T >= CHI_THREADS && ctx->opt_bulk_copy) {
+            static_assert(sizeof(ChiStage) * CHI_STAGES + 1024 <= 48 * 1024, "chi stages fit the default dynamic shared-memory limit");
             k_chi_partial_bulk<<<(unsigned)(k * (size_t)(T / CHI_THREADS)), CHI_THREADS, sizeof(ChiStage) * CHI_STAGES, D.stream>>>(A);
         } else {
             k_chi_partial<<<blocks_for(k * (size_t)T, 128), 128, 0, D.stream>>>(A);  // tiny tables

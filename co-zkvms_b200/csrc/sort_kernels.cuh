@@ -37,7 +37,10 @@ namespace cozk {
 #define COZK_SORT_MINBLOCKS 2
 #endif
 constexpr int SORT_THREADS = COZK_SORT_THREADS;
-constexpr int SORT_ITEMS = 16;                           // pairs per thread and tile
+#ifndef COZK_SORT_ITEMS
+#define COZK_SORT_ITEMS 16
+#endif
+constexpr int SORT_ITEMS = COZK_SORT_ITEMS;              // pairs per thread and tile
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;     // 8192 pairs
 constexpr uint32_t SORT_RMAX = 8;                        // digit bits per pass
 constexpr uint32_t SORT_RANGE = 2048;                    // prefix values a tile ranks through shared memory

@@ -20,6 +20,13 @@ pub const COZK_ERR_KEY_LENGTH: c_int = -2;
 pub const COZK_ERR_CUDA: c_int = -3;
 pub const COZK_ERR_NO_DEVICE: c_int = -4;
 pub const COZK_ERR_BAD_HANDLE: c_int = -5;
+pub const COZK_POLY_SHARED: c_int = 0; // include/cozk_rep3.h
+pub const COZK_POLY_PUBLIC: c_int = 1;
+pub const COZK_POLY_U8: c_int = 2;
+pub const COZK_POLY_U16: c_int = 3;
+pub const COZK_POLY_U32: c_int = 4;
+pub const COZK_POLY_U64: c_int = 5;
+pub const COZK_POLY_I64: c_int = 6;
 pub const COZK_MONT: c_int = 0;
 pub const COZK_CANON: c_int = 1;
 
@@ -29,6 +36,8 @@ extern "C" {
     pub fn cozk_destroy(ctx: *mut CozkCtx);
     pub fn cozk_device_count(ctx: *const CozkCtx) -> c_int;
     pub fn cozk_srs_register(ctx: *mut CozkCtx, bases: *const c_void, n: usize, stride_bytes: usize, infinity: *const u8, out: *mut CozkSrs) -> c_int;
+    /// every device keeps only its point range (+ its table): for an SRS that only serves one long MSM sharded by point range
+    pub fn cozk_srs_register_sliced(ctx: *mut CozkCtx, bases: *const c_void, n: usize, stride_bytes: usize, infinity: *const u8, out: *mut CozkSrs) -> c_int;
     pub fn cozk_srs_release(ctx: *mut CozkCtx, srs: CozkSrs) -> c_int;
     pub fn cozk_srs_len(ctx: *mut CozkCtx, srs: CozkSrs, out_n: *mut usize) -> c_int;
     pub fn cozk_msm_batch(ctx: *mut CozkCtx, srs: CozkSrs, base_offset: usize, n: usize, scalars: *const *const c_void, k: usize,
@@ -46,6 +55,10 @@ extern "C" {
     pub fn cozk_pst13_batch_commit_rep3(ctx: *mut CozkCtx, srs: CozkSrs, polys: *const *const c_void, is_shared: *const u8, k: usize,
                                         n: usize, form: c_int, max_num_bits: *const c_uint, commit_to_public: c_int,
                                         out_commitments: *mut c_void, present: *mut u8) -> c_int;
+    /// polys[j] in its in-memory form: kinds[j] = COZK_POLY_SHARED (Rep3PrimeFieldShare array), COZK_POLY_PUBLIC (LargeScalars) or
+    /// COZK_POLY_U8 .. COZK_POLY_I64 (MultilinearPolynomial::U8Scalars .. I64Scalars as they lie in memory; widened on the device)
+    pub fn cozk_pst13_batch_commit_packed(ctx: *mut CozkCtx, srs: CozkSrs, polys: *const *const c_void, kinds: *const c_int, k: usize,
+                                          n: usize, commit_to_public: c_int, out_commitments: *mut c_void, present: *mut u8) -> c_int;
     pub fn cozk_pst13_open(ctx: *mut CozkCtx, level_srs: *const CozkSrs, nv: usize, evals: *const c_void, stride_bytes: usize,
                            point: *const c_void, form: c_int, out_proofs: *mut c_void, out_eval: *mut c_void) -> c_int;
     pub fn cozk_pst13_combine_commitment_shares(commitments: *const c_void, count: usize, out_commitment: *mut c_void) -> c_int;

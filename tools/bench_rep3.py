@@ -39,11 +39,15 @@ def main():
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--nv", type=int, default=18)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--chi-waves", type=int, default=1)
+    ap.add_argument("--bulk", type=int, default=0, help="1: bulk-copy (TMA) staged ingest / chi kernels, 0: plain per-lane loads")
     ap.add_argument("--small", default="12", help="comma list of open_small_log2 values to try for the keyed opening")
     args = ap.parse_args()
     cozk = importlib.import_module("co-zkvms_b200")
     rep3, pst = cozk.rep3, cozk.pst13
     ctx = cozk.Context()
+    ctx.set_option("bulk_copy", args.bulk)
+    ctx.set_option("chi_waves", args.chi_waves)
     L = cozk.lib()
     T = cozk.testlib()
     n = 1 << args.log2n

@@ -35,6 +35,98 @@ N_SHARED, N_PUBLIC, N_FINAL = 138, 60, 54
 PUBLIC_BITS = [1] * 40 + [16] * 10 + [32] * 5 + [64] * 5   # flags / u16 / u32 / u64 coefficient polynomials (inferred split)
 
 
+def make_setup(ctx, lt, with_open=True):
+    """SRS of a 2^lt-cycle proof: level i holds 2^(lt - i) points (pst13.rs:233-250); generated on the device, registered per
+    level.  Returns (setup, seconds)."""
+    levels, start = [], 0
+    t0 = time.perf_counter()
+    for i in range(lt if with_open else 1):
+        n = 1 << (lt - i)
+        d = ctx.testgen_bases(1, n, start=start)
+        levels.append(ctx.srs_register_device(d, n))
+        d.free()
+        start += n
+    setup = pst.PST13Setup.__new__(pst.PST13Setup)
+    setup.ctx, setup.level_srs, setup.num_vars = ctx, levels, lt
+    return setup, time.perf_counter() - t0
+
+
+def replay_party(ctx, setup, lt, party, do_open=True, gpus=1, srs_s=0.0):
+    """One party's commitment-path calls for a 2^lt-cycle trace; returns the JSON-able record."""
+    rep3 = cozk.rep3
+    T = 1 << lt
+    dist = {0: "const", 1: "const", 2: "wminus"}[party]
+    seed = 100 + party
+    # one pinned AoS share buffer of length T (a = the share, b = filler) and the public polynomials in their PACKED forms
+    # (MultilinearPolynomial::U8Scalars .. U64Scalars, multilinear_polynomial.rs:226-268): 1 - 8 bytes per coefficient over PCIe
+    aos = cozk.PinnedBuffer(T * 64)
+    d = ctx.testgen_scalars(dist, seed, T, stride=64)
+    aos.array[:] = d.download()
+    d.free()
+    shared = aos.array.reshape(T, 64)
+    kind_of = {1: (rep3.U8, np.uint8), 16: (rep3.U16, np.uint16), 32: (rep3.U32, np.uint32), 64: (rep3.U64, np.uint64)}
+    pubs = {}
+    for bits in sorted(set(PUBLIC_BITS)):
+        kd, dt = kind_of[bits]
+        pb = cozk.PinnedBuffer(T * np.dtype(dt).itemsize)
+        vals = np.random.default_rng(bits).integers(0, 2 if bits == 1 else (1 << min(bits, 63)), size=T, dtype=np.uint64).astype(dt)
+        pb.array[:] = vals.view(np.uint8)
+        pubs[bits] = (pb, kd, dt)
+    n_pub = N_PUBLIC if party == 0 else 0   # parties 1/2 drop the public results; the drop-in skips those MSMs
+    pub_polys = [pubs[b][0].array.view(pubs[b][2]) for b in PUBLIC_BITS[:n_pub]]
+    pub_kinds = [pubs[b][1] for b in PUBLIC_BITS[:n_pub]]
+    times = {}
+    # untimed warm-up with the real shapes: the engine's scratch buffers grow to their final size here
+    pst.batch_commit_rep3(setup, [shared] * N_SHARED, [True] * N_SHARED, commit_to_public=False)
+    if n_pub:
+        pst.batch_commit_packed(setup, pub_polys, pub_kinds, commit_to_public=True)
+    t0 = time.perf_counter()
+    out = pst.batch_commit_rep3(setup, [shared] * N_SHARED, [True] * N_SHARED, commit_to_public=False)
+    times["trace_polys_shared_s"] = time.perf_counter() - t0
+    if n_pub:
+        t0 = time.perf_counter()
+        pst.batch_commit_packed(setup, pub_polys, pub_kinds, commit_to_public=True)
+        times["trace_polys_public_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(2):
+        pst.batch_commit_rep3(setup, [shared], [True], commit_to_public=False)     # v_final, t_final
+    if party == 0:
+        pst.batch_commit_packed(setup, [pubs[32][0].array.view(np.uint32)], [rep3.U32])  # bytecode t_final (public)
+    times["single_commits_s"] = time.perf_counter() - t0
+    n16 = min(T, 1 << 16)
+    t0 = time.perf_counter()
+    pst.batch_commit_rep3(setup, [shared[:n16]] * N_FINAL, [True] * N_FINAL, commit_to_public=False)
+    times["final_cts_s"] = time.perf_counter() - t0
+    if do_open:
+        point = np.zeros((lt, 32), np.uint8)
+        dpt = ctx.testgen_scalars("uniform", 7, lt)
+        point[:] = dpt.download().reshape(lt, 32)
+        dpt.free()
+        t0 = time.perf_counter()
+        pst.open(setup, shared, point, stride=64)
+        times["open_s"] = time.perf_counter() - t0
+    msm_gpu = sum(v for k, v in times.items() if k != "open_s")
+    vcpu, prove, msm_ref, open_ref = REF.get(lt, (None, None, None, None))
+    line = {"config": "co-jolt party MSM replay", "log2_T": lt, "party": party, "share_dist": dist, "gpus": gpus,
+            "gpu_seconds": {k: round(v, 4) for k, v in times.items()},
+            "gpu_commit_msm_s": round(msm_gpu, 4), "gpu_open_s": round(times.get("open_s", 0.0), 4),
+            "large_scalar_point_mults": N_SHARED * T + N_FINAL * n16 + 2 * T,
+            "Mpoints_per_s_commit": round((N_SHARED * T + N_FINAL * n16 + 2 * T) / msm_gpu / 1e6, 1),
+            "srs_generate_register_s": round(srs_s, 3),
+            "public_polys": "%d in packed form (u8 / u16 / u32 / u64), widened on the device" % n_pub,
+            "x_first_commitment": bytes(out[0].g_product[:6]).hex()}
+    if prove is not None:
+        non_msm = prove - msm_ref - open_ref
+        line["reference_cpu"] = {"vcpu": vcpu, "party_prove_s": prove, "batch_msm_s": msm_ref, "prove_rep3_s": open_ref,
+                                 "source": "co-jolt/traces (BASELINE.md 1.1), party 0"}
+        line["projected_party_prove_s"] = round(non_msm + msm_gpu + times.get("open_s", 0.0), 2)
+        line["projection_note"] = "reference non-MSM time from the trace + measured GPU MSM/open time; the Rust prover cannot run here"
+    aos.free()
+    for pb, _, _ in pubs.values():
+        pb.free()
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2t", default="16")
@@ -43,99 +135,11 @@ def main():
     ap.add_argument("--no-open", action="store_true")
     args = ap.parse_args()
     ctx = cozk.Context(devices=list(range(args.gpus)))
-    dist_of_party = {0: "const", 1: "const", 2: "wminus"}
     for lt in [int(x) for x in args.log2t.split(",")]:
-        T = 1 << lt
-        # SRS: level i holds 2^(lt - i) points (pst13.rs:233-250); generated on the device, registered per level
-        levels = []
-        start = 0
-        t0 = time.perf_counter()
-        for i in range(lt if not args.no_open else 1):
-            n = 1 << (lt - i)
-            d = ctx.testgen_bases(1, n, start=start)
-            levels.append(ctx.srs_register_device(d, n))
-            d.free()
-            start += n
-        setup = pst.PST13Setup.__new__(pst.PST13Setup)
-        setup.ctx, setup.level_srs, setup.num_vars = ctx, levels, lt
-        srs_s = time.perf_counter() - t0
-        # a 2^16 prefix SRS for final_cts is just a prefix of level 0
+        setup, srs_s = make_setup(ctx, lt, with_open=not args.no_open)
         for party in [int(x) for x in args.parties.split(",")]:
-            dist = dist_of_party[party]
-            seed = 100 + party
-            # one pinned AoS share buffer of length T (a = the share, b = filler) and a few public buffers
-            aos = cozk.PinnedBuffer(T * 64)
-            d = ctx.testgen_scalars(dist, seed, T, stride=64)
-            aos.array[:] = d.download()
-            d.free()
-            shared = aos.array.reshape(T, 64)
-            pubs = {}
-            for bits in sorted(set(PUBLIC_BITS)):
-                pb = cozk.PinnedBuffer(T * 32)
-                raw = np.zeros((T, 32), np.uint8)
-                rnd = np.random.default_rng(bits).integers(0, 256, size=(T, 8), dtype=np.uint8)
-                nbytes = (bits + 7) // 8
-                raw[:, :nbytes] = rnd[:, :nbytes]
-                if bits == 1:
-                    raw[:, 0] &= 1
-                pb.array[:] = raw.reshape(-1)
-                pubs[bits] = pb
-            n_pub = N_PUBLIC if party == 0 else 0   # parties 1/2 drop the public results; the drop-in skips those MSMs
-            polys = [shared] * N_SHARED + [pubs[b].array.reshape(T, 32) for b in PUBLIC_BITS[:n_pub]]
-            flags = [True] * N_SHARED + [False] * n_pub
-            bits = [0] * N_SHARED + PUBLIC_BITS[:n_pub]
-            form_canon_pub = 1  # public coefficient polynomials are plain integers
-            times = {}
-            # untimed warm-up with the real shapes: the engine's scratch buffers grow to their final size here
-            pst.batch_commit_rep3(setup, polys[:N_SHARED], flags[:N_SHARED], commit_to_public=False)
-            if n_pub:
-                pst.batch_commit(setup, polys[N_SHARED:], stride=32, form=form_canon_pub, max_num_bits=bits[N_SHARED:])
-
-            t0 = time.perf_counter()
-            out = pst.batch_commit_rep3(setup, polys[:N_SHARED], flags[:N_SHARED], commit_to_public=False)
-            times["trace_polys_shared_s"] = time.perf_counter() - t0
-            if n_pub:
-                t0 = time.perf_counter()
-                pst.batch_commit(setup, polys[N_SHARED:], stride=32, form=form_canon_pub, max_num_bits=bits[N_SHARED:])
-                times["trace_polys_public_s"] = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            for _ in range(2):
-                pst.batch_commit_rep3(setup, [shared], [True], commit_to_public=False)     # v_final, t_final
-            if party == 0:
-                pst.commit(setup, pubs[32].array.reshape(T, 32), form=1, max_num_bits=32)  # bytecode t_final (public)
-            times["single_commits_s"] = time.perf_counter() - t0
-            n16 = min(T, 1 << 16)
-            t0 = time.perf_counter()
-            pst.batch_commit_rep3(setup, [shared[:n16]] * N_FINAL, [True] * N_FINAL, commit_to_public=False)
-            times["final_cts_s"] = time.perf_counter() - t0
-            if not args.no_open:
-                point = np.zeros((lt, 32), np.uint8)
-                dpt = ctx.testgen_scalars("uniform", 7, lt)
-                point[:] = dpt.download().reshape(lt, 32)
-                dpt.free()
-                t0 = time.perf_counter()
-                pst.open(setup, shared, point, stride=64)
-                times["open_s"] = time.perf_counter() - t0
-            msm_gpu = sum(v for k, v in times.items() if k != "open_s")
-            vcpu, prove, msm_ref, open_ref = REF.get(lt, (None, None, None, None))
-            line = {"config": "co-jolt party MSM replay", "log2_T": lt, "party": party, "share_dist": dist, "gpus": args.gpus,
-                    "gpu_seconds": {k: round(v, 4) for k, v in times.items()},
-                    "gpu_commit_msm_s": round(msm_gpu, 4), "gpu_open_s": round(times.get("open_s", 0.0), 4),
-                    "large_scalar_point_mults": N_SHARED * T + N_FINAL * n16 + 2 * T,
-                    "Mpoints_per_s_commit": round((N_SHARED * T + N_FINAL * n16 + 2 * T) / msm_gpu / 1e6, 1),
-                    "srs_generate_register_s": round(srs_s, 3),
-                    "x_first_commitment": bytes(out[0].g_product[:6]).hex()}
-            if prove is not None:
-                non_msm = prove - msm_ref - open_ref
-                line["reference_cpu"] = {"vcpu": vcpu, "party_prove_s": prove, "batch_msm_s": msm_ref, "prove_rep3_s": open_ref,
-                                         "source": "co-jolt/traces (BASELINE.md 1.1), party 0"}
-                line["projected_party_prove_s"] = round(non_msm + msm_gpu + times.get("open_s", 0.0), 2)
-                line["projection_note"] = "reference non-MSM time from the trace + measured GPU MSM/open time; the Rust prover cannot run here"
-            print(json.dumps(line), flush=True)
-            aos.free()
-            for pb in pubs.values():
-                pb.free()
-        for h in levels:
+            print(json.dumps(replay_party(ctx, setup, lt, party, do_open=not args.no_open, gpus=args.gpus, srs_s=srs_s)), flush=True)
+        for h in setup.level_srs:
             ctx.srs_release(h)
     ctx.close()
 
