@@ -34,7 +34,7 @@ DIST = {"uniform": 0, "const": 1, "wminus": 2, "dup": 3, "small16": 4, "zero_hal
 # every symbol include/cozk_msm.h, cozk_pst13.h and cozk_test.h declare (checked by tests/test_abi.py without a GPU)
 ABI_SYMBOLS = [
     "cozk_init", "cozk_destroy", "cozk_device_count", "cozk_srs_register", "cozk_srs_register_sliced", "cozk_srs_release", "cozk_last_stats_device", "cozk_srs_len",
-    "cozk_msm_batch", "cozk_msm_batch_device", "cozk_g1_sum", "cozk_set_option", "cozk_last_stats", "cozk_last_error",
+    "cozk_msm_batch", "cozk_msm_batch_device", "cozk_msm_ragged_device", "cozk_g1_sum", "cozk_set_option", "cozk_last_stats", "cozk_last_error",
     "cozk_dev_alloc", "cozk_dev_free", "cozk_dev_upload", "cozk_dev_download", "cozk_host_alloc_pinned",
     "cozk_host_free_pinned", "cozk_dev_flush_l2", "cozk_srs_register_device",
     "cozk_pst13_commit", "cozk_pst13_batch_commit", "cozk_pst13_batch_commit_rep3", "cozk_pst13_batch_commit_packed", "cozk_pst13_open",
@@ -113,6 +113,7 @@ def lib():
     L.cozk_srs_len.argtypes = [vp, u64, ctypes.POINTER(sz)]
     L.cozk_msm_batch.argtypes = [vp, u64, sz, sz, pp, sz, sz, ci, cu, vp]
     L.cozk_msm_batch_device.argtypes = [vp, ci, u64, sz, sz, pp, sz, sz, ci, cu, vp]
+    L.cozk_msm_ragged_device.argtypes = [vp, ci, u64, ctypes.POINTER(sz), ctypes.POINTER(sz), pp, sz, sz, ci, vp]
     L.cozk_g1_sum.argtypes = [vp, sz, vp]
     L.cozk_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
     L.cozk_last_stats.argtypes = [vp, cd]
@@ -327,6 +328,16 @@ class Context:
         else:
             _check(lib().cozk_msm_batch_device(self.handle, device, srs, base_offset, n, ptrs, k, stride, form,
                                                max_num_bits, _ptr(out)))
+        return out
+
+    def msm_ragged(self, srs, ptr_list, offsets, lens, stride=32, form=MONT, device=0):
+        """cozk_msm_ragged_device: vector j = lens[j] device-resident scalars at ptr_list[j] against bases offsets[j] .. of the SRS."""
+        k = len(ptr_list)
+        ptrs = (ctypes.c_void_p * k)(*ptr_list)
+        offs = (ctypes.c_size_t * k)(*offsets)
+        ln = (ctypes.c_size_t * k)(*lens)
+        out = np.zeros((k, 72), dtype=np.uint8)
+        _check(lib().cozk_msm_ragged_device(self.handle, device, srs, offs, ln, ptrs, k, stride, form, _ptr(out)))
         return out
 
     def fixed_base_batch_mul(self, base72, scalars, stride=32, form=MONT, register=False):

@@ -9,6 +9,9 @@
 // stack), the kernels shrink to a few KB and stay in the instruction cache.  Measured: bucket reduce 0.24 -> 0.21 ms at
 // 2^16 .. 2^20, 0.20 -> 0.15 ms at 2^12; whole MSM 2^12 0.615 -> 0.568 ms, 2^16 0.750 -> 0.718 ms; PST13 opening at
 // nv = 18 3.90 -> 3.73 ms.
+// (The macro only changes code under __CUDA_ARCH__: the host bodies of the inline field functions are the same in every
+// translation unit, and device code is compiled per translation unit - no relocatable device code, nothing is linked
+// across units - so the two device forms of fq_mul never meet.)
 #define COZK_FIELD_CALLS 1
 #include "depth_kernels.hpp"
 

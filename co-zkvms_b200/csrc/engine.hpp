@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <map>
 #include <memory>
@@ -56,6 +57,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     std::mutex mu;  // one MSM at a time per device
+    DevBuf rag;  // ragged groups: start / base arrays of the vectors
     DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2, pk[2], pp[2], rs[2], rw[2], out, flush;
     std::mutex open_mu;  // one PST13 opening at a time per device: it owns the four buffers below across its MSM calls
     DevBuf open_in, open_r[2], open_q, open_qs;
@@ -133,7 +135,8 @@ struct PolyEntry {
 struct OpenKey {
     size_t nv = 0;
     std::vector<cozk_srs> level_srs;   // as given by the caller (not owned)
-    std::vector<cozk_srs> pair_srs;    // owned: pair sums of level i, i < first_small
+    cozk_srs big_srs = 0;              // owned: pair sums of the levels i < first_small, level after level, ONE SRS with one table
+    std::vector<size_t> big_off;       // offset of level i inside big_srs
     size_t first_small = 0;            // levels [first_small, nv) go through one batched MSM
     cozk_srs small_srs = 0;            // owned: pair sums of the small levels, level after level
     size_t small_n = 0;
@@ -148,7 +151,7 @@ namespace cozk {
 // only_device < 0: the SRS is replicated on every device of the context; >= 0: it lives on that device alone (the
 // internal SRSs of an opening key, which only device 0 ever reads).
 int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out,
-                             int only_device = -1);
+                             int only_device = -1, uint32_t force_table_c = 0);
 int srs_lookup(cozk_ctx* ctx, cozk_srs srs, SrsEntry* out);
 // Where the 2^nv evaluations of an opening come from: host memory (staged through a scratch buffer) or device 0.
 struct OpenSource {
@@ -171,6 +174,12 @@ int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m,
                uint32_t** vals_out, double* launches, cudaEvent_t after_first);
 // the plain decompose kernel (msm.cu), for the test entry points of aux.cu
 int launch_decompose(const DecomposeArgs& A, cudaStream_t st);
+// Ragged batch on ONE device (msm.cu): vector j has lens[j] device-resident scalars (dense stride) and multiplies bases
+// [offsets[j], offsets[j] + lens[j]) of the SRS; one decompose / sort / accumulate / reduce for all of them.  Returns
+// COZK_ERR_INVALID_ARG (and touches nothing) when the group does not fit the bucket / pair budget: the caller falls back
+// to one call per vector.
+int msm_ragged_device(cozk_ctx* ctx, int device, cozk_srs srs, const size_t* offsets, const size_t* lens,
+                      const void* const* dev_scalars, size_t k, size_t stride, int form, void* out);
 // The one entry every public MSM call funnels into (msm.cu).  only_device < 0: use all devices of the context.
 int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offset, size_t n, const void* const* host_scalars,
                  const void* const* dev_scalars, size_t k, size_t stride, int form, unsigned max_bits, void* out);
@@ -178,27 +187,27 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
 
 struct cozk_ctx {
     std::vector<std::unique_ptr<cozk::Device>> devs;
-    std::mutex mu;  // guards the SRS table and options
+    std::mutex mu;  // guards the handle tables; the options below are atomics (set by cozk_set_option, read by calls in flight)
     std::map<uint64_t, cozk::SrsEntry> srs;
     std::map<uint64_t, cozk::PolyEntry> polys;
     std::map<uint64_t, cozk::OpenKey> open_keys;
-    long opt_open_small_log2 = 15;   // opening levels with at most 2^this quotient values share one batched MSM (measured at nv = 22 / 18: 13: 17.5 ms, 14: 17.2 / 4.13, 15: 17.0 / 3.91, 16: 17.5 / 4.42, 17: 18.0)
+    std::atomic<long> opt_open_small_log2 = 15;   // opening levels with at most 2^this quotient values share one batched MSM (measured at nv = 22 / 18: 13: 17.5 ms, 14: 17.2 / 4.13, 15: 17.0 / 3.91, 16: 17.5 / 4.42, 17: 18.0)
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;
-    long opt_dominant = 1;           // 1: whole-SRS calls look for windows dominated by one digit (constant co-jolt shares) and use the row totals
-    long opt_dominant_min_points = 1L << 21;  // ... when the call has at least this many (vector, point) pairs: the look costs ~35 us
-    long opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first
-    long opt_acc_chunk = 0;          // pairs per level-1 accumulate thread; 0 = chosen per call (msm_plan.hpp, choose_acc_l)
-    long opt_acc_chunk_up = 0;       // partial slots per thread at the serial accumulate levels >= 2; 0 = ACC_L
-    long opt_bulk_copy = 0;          // 1: ingest / chi kernels stream their slabs through shared memory with bulk copies (TMA); 0: plain per-lane
+    std::atomic<long> opt_dominant = 1;           // 1: whole-SRS calls look for windows dominated by one digit (constant co-jolt shares) and use the row totals
+    std::atomic<long> opt_dominant_min_points = 1L << 21;  // ... when the call has at least this many (vector, point) pairs: the look costs ~35 us
+    std::atomic<long> opt_peer_direct = 1;        // 1: kernels read other devices' partial results through peer mappings; 0: stage peer copies first
+    std::atomic<long> opt_acc_chunk = 0;          // pairs per level-1 accumulate thread; 0 = chosen per call (msm_plan.hpp, choose_acc_l)
+    std::atomic<long> opt_acc_chunk_up = 0;       // partial slots per thread at the serial accumulate levels >= 2; 0 = ACC_L
+    std::atomic<long> opt_bulk_copy = 0;          // 1: ingest / chi kernels stream their slabs through shared memory with bulk copies (TMA); 0: plain per-lane
                                      // loads.  Measured equal or slower (2^22: ingest 0.161 against 0.152 ms, chi 2.21 against 2.20 ms; 2^20: chi
                                      // 0.67 against 0.59 ms): the access pattern is not what holds these kernels back.  Kept as an option.
-    long opt_chi_waves = 1;          // threads per polynomial of the chi kernels: enough for this many full waves of the device
-    long opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
-    long opt_window = 0;             // 0 = choose per call
-    long opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
-    long opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never): 2^22 in 2 chunks 12.7 against 13.3 ms; 2^20 loses (3.86 against 3.80 ms: every chunk repeats the latency-bound upper accumulate levels)
-    long opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
-    long opt_table_window = 0;             // 0 = choose_table_window(n) at registration
-    long opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables
+    std::atomic<long> opt_chi_waves = 1;          // threads per polynomial of the chi kernels: enough for this many full waves of the device
+    std::atomic<long> opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
+    std::atomic<long> opt_window = 0;             // 0 = choose per call
+    std::atomic<long> opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
+    std::atomic<long> opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never): 2^22 in 2 chunks 12.7 against 13.3 ms; 2^20 loses (3.86 against 3.80 ms: every chunk repeats the latency-bound upper accumulate levels)
+    std::atomic<long> opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
+    std::atomic<long> opt_table_window = 0;             // 0 = choose_table_window(n) at registration
+    std::atomic<long> opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables
 };

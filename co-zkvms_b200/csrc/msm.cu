@@ -23,7 +23,7 @@ Device::~Device() {
     cudaSetDevice(id);
     DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
                       &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush, &buckets2,
-                      &dom_cand, &dom_counts, &dom_mode, &dom_off, &dom_len, &dom_cursor,
+                      &dom_cand, &dom_counts, &dom_mode, &dom_off, &dom_len, &dom_cursor, &rag,
                       &open_in, &open_r[0], &open_r[1], &open_q, &open_qs};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -181,7 +181,9 @@ static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, con
 // Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
 static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
                      const uint8_t* const* d_vec_ptrs, size_t vector_stride, size_t stride, int form, size_t table_stride,
-                     size_t val_offset, double* launches, int phases = 3, bool merge = false, const DecomposeArgs* dom = nullptr) {
+                     size_t val_offset, double* launches, int phases = 3, bool merge = false, const DecomposeArgs* dom = nullptr,
+                     const DecomposeArgs* rag = nullptr) {
+    // rag: ragged group (only its rag_start / rag_base / total fields are read), or null
     // dom: dominant-digit layout of this group (only its dom_* / seg_* / totals_index fields are read), or null
     // phases: bit 0 = decompose + sort + accumulate into the buckets, bit 1 = bucket reduce + finish.  A streamed MSM
     // (one vector fed in point chunks while the next chunk is still on the PCIe bus) runs bit 0 once per chunk, with
@@ -203,6 +205,11 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     DecomposeArgs DA{d_scalars, d_vec_ptrs, vector_stride, stride, form, P.n, P.g, P.c, P.W, d_inf,
                      D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>(), P.Wb, table_stride, val_offset};
     uint32_t *sorted_keys = nullptr, *sorted_vals = nullptr;
+    if (rag) {
+        DA.rag_start = rag->rag_start;
+        DA.rag_base = rag->rag_base;
+        DA.total = rag->total;
+    }
     if (dom) {
         DA.dom_mode = dom->dom_mode;
         DA.dom_cand = dom->dom_cand;
@@ -396,7 +403,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         // chunk i+1 overlaps decompose / sort / accumulate of chunk i; reduce and finish run once.
         // chunks: option "stream_chunks", or (0 = auto) 2 below 2^25 points and 4 from there on (measured end to end:
         // 2^24 45.8 / 45.6 / 48.5 ms, 2^25 87.7 / 84.9 / 86.9 ms, 2^26 171.0 / 163.5 / 163.3 ms with 2 / 4 / 8 chunks)
-        const long stream_chunks = ctx->opt_stream_chunks ? ctx->opt_stream_chunks : (pn >= ((size_t)1 << 25) ? 4 : 2);
+        const long opt_chunks = ctx->opt_stream_chunks;
+        const long stream_chunks = opt_chunks ? opt_chunks : (pn >= ((size_t)1 << 25) ? 4 : 2);
         if (host_scalars && k == 1 && stream_chunks > 1 && ctx->opt_stream_min_points > 0 &&
             pn >= (size_t)ctx->opt_stream_min_points) {
             const size_t C = (size_t)stream_chunks;
@@ -728,11 +736,12 @@ int srs_lookup(cozk_ctx* ctx, cozk_srs srs, SrsEntry* out) {
 
 // rows of the precomputed table for an SRS of n points on the given devices under the context's memory policy
 // (1 = bases only)
-static void srs_table_shape(const cozk_ctx* ctx, const std::vector<int>& devices, size_t n, uint32_t* c, uint32_t* W) {
+static void srs_table_shape(const cozk_ctx* ctx, const std::vector<int>& devices, size_t n, uint32_t* c, uint32_t* W,
+                            uint32_t force_c = 0) {
     *c = 0;
     *W = 1;
     if (n < 1024 || ctx->opt_table_max_bytes <= 0) return;
-    uint32_t tc = ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
+    uint32_t tc = force_c ? force_c : ctx->opt_table_window ? (uint32_t)ctx->opt_table_window : choose_table_window(n);
     uint32_t tw = windows_for(254, tc);
     const double table_bytes = (double)tw * (double)n * sizeof(affine);
     if (table_bytes > (double)ctx->opt_table_max_bytes) return;
@@ -832,7 +841,8 @@ struct SrsSource {
 
 // n points -> every device in `devices` gets the bases (+ flags), its precomputed table and the row totals.  The
 // devices work side by side (one host thread each).
-static int srs_register_core(cozk_ctx* ctx, const SrsSource& src, size_t n, const std::vector<int>& devices, SrsEntry* out) {
+static int srs_register_core(cozk_ctx* ctx, const SrsSource& src, size_t n, const std::vector<int>& devices, SrsEntry* out,
+                             uint32_t force_table_c = 0) {
     SrsEntry S;
     S.n = n;
     S.mem = std::make_shared<SrsMem>();
@@ -841,7 +851,7 @@ static int srs_register_core(cozk_ctx* ctx, const SrsSource& src, size_t n, cons
     for (size_t d = 0; d < nd; ++d) S.mem->cuda_id[d] = ctx->devs[d]->id;
     S.mem->bases.assign(nd, nullptr);
     S.mem->inf.assign(nd, nullptr);
-    srs_table_shape(ctx, devices, n, &S.table_c, &S.table_W);
+    srs_table_shape(ctx, devices, n, &S.table_c, &S.table_W, force_table_c);
     bool any_inf = false;
     if (src.host_inf) {
         for (size_t i = 0; i < n && !any_inf; ++i) any_inf = src.host_inf[i] != 0;
@@ -932,7 +942,7 @@ static cozk_srs srs_publish(cozk_ctx* ctx, const SrsEntry& S) {
 }
 
 int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_bases64, const uint8_t* d_inf, size_t n, cozk_srs* out,
-                             int only_device) {
+                             int only_device, uint32_t force_table_c) {
     if (!ctx || !out || (!d_bases64 && n) || device_index < 0 || device_index >= (int)ctx->devs.size() ||
         only_device >= (int)ctx->devs.size()) {
         set_error("bad argument");
@@ -943,9 +953,95 @@ int srs_register_from_device(cozk_ctx* ctx, int device_index, const void* d_base
     src.dev_index = device_index;
     src.dev_inf = d_inf;
     SrsEntry S;
-    int rc = srs_register_core(ctx, src, n, only_device >= 0 ? std::vector<int>{only_device} : all_devices(ctx), &S);
+    int rc = srs_register_core(ctx, src, n, only_device >= 0 ? std::vector<int>{only_device} : all_devices(ctx), &S, force_table_c);
     if (rc) return rc;
     *out = srs_publish(ctx, S);
+    return COZK_OK;
+}
+
+int msm_ragged_device(cozk_ctx* ctx, int device, cozk_srs srs, const size_t* offsets, const size_t* lens,
+                      const void* const* dev_scalars, size_t k, size_t stride, int form, void* out) {
+    if (!ctx || !offsets || !lens || !dev_scalars || !out || k == 0 || k > 4096 || device < 0 || device >= (int)ctx->devs.size() ||
+        stride < 32 || (stride & 15)) {
+        set_error("ragged batch: bad argument");
+        return COZK_ERR_INVALID_ARG;
+    }
+    SrsEntry S;
+    int rc = srs_lookup(ctx, srs, &S);
+    if (rc) return rc;
+    if (!S.bases(device)) {
+        set_error("ragged batch: the SRS does not live on this device");
+        return COZK_ERR_INVALID_ARG;
+    }
+    size_t total = 0;
+    std::vector<uint32_t> h_start(k + 1), h_base(k);
+    for (size_t j = 0; j < k; ++j) {
+        if (offsets[j] > S.n || lens[j] > S.n - offsets[j]) {
+            set_error("Key length error: a vector of the ragged batch exceeds the registered SRS");
+            return COZK_ERR_KEY_LENGTH;
+        }
+        if (!dev_scalars[j] || lens[j] == 0 || ((uintptr_t)dev_scalars[j] & 15)) {
+            set_error("ragged batch: empty, null or misaligned vector");
+            return COZK_ERR_INVALID_ARG;
+        }
+        h_start[j] = (uint32_t)total;
+        h_base[j] = (uint32_t)offsets[j];
+        total += lens[j];
+    }
+    h_start[k] = (uint32_t)total;
+    const size_t max_buckets = (size_t)1 << 25;
+    Device& D = *ctx->devs[device];
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l};
+    MsmPlan P = make_plan((total + k - 1) / k, (uint32_t)k, 254, max_buckets, (uint32_t)ctx->opt_window, ctx->opt_window ? 0 : S.table_c,
+                          acc_tuning);
+    const bool table = !ctx->opt_window && S.table_c != 0;
+    if (table && P.W > S.table_W) {
+        set_error("ragged batch: the SRS table has too few rows");
+        return COZK_ERR_INVALID_ARG;
+    }
+    if (P.total_buckets > max_buckets || (double)P.W * (double)total > (double)ctx->opt_group_pairs || total >= ((size_t)1 << 31)) {
+        set_error("ragged batch: over the bucket / pair budget");
+        return COZK_ERR_INVALID_ARG;
+    }
+    plan_set_pairs(P, (size_t)P.W * total);
+    std::lock_guard<std::mutex> lock(D.mu);
+    COZK_CUDA(cudaSetDevice(D.id));
+    for (double& st : D.stats) st = 0;
+    double launches = 0;
+    if ((rc = D.rag.ensure((2 * k + 1) * sizeof(uint32_t))) || (rc = D.vec_ptrs.ensure(2 * 4096 * sizeof(void*)))) return rc;
+    uint32_t* d_start = D.rag.as<uint32_t>();
+    uint32_t* d_base = d_start + (k + 1);
+    COZK_CUDA(cudaEventRecord(D.ev[0], D.stream));
+    COZK_CUDA(cudaMemcpyAsync(d_start, h_start.data(), (k + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, D.stream));
+    COZK_CUDA(cudaMemcpyAsync(d_base, h_base.data(), k * sizeof(uint32_t), cudaMemcpyHostToDevice, D.stream));
+    COZK_CUDA(cudaMemcpyAsync(D.vec_ptrs.p, dev_scalars, k * sizeof(void*), cudaMemcpyHostToDevice, D.stream));
+    COZK_CUDA(cudaStreamSynchronize(D.stream));  // the three host arrays are pageable
+    DecomposeArgs rag = {};
+    rag.rag_start = d_start;
+    rag.rag_base = d_base;
+    rag.total = total;
+    rc = run_group(D, P, S.bases(device), S.inf(device), nullptr, D.vec_ptrs.as<const uint8_t*>(), 0, stride, form, table ? S.n : 0, 0,
+                   &launches, 3, false, nullptr, &rag);
+    if (rc) return rc;
+    uint8_t* o = reinterpret_cast<uint8_t*>(out);
+    if (!D.finish_on_host) COZK_CUDA(cudaMemcpyAsync(o, D.out.p, k * 72, cudaMemcpyDeviceToHost, D.stream));
+    COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    add_stage_times(D);
+    if (D.finish_on_host) {
+        FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, o};
+        for (size_t v = 0; v < k; ++v) finish_body(v, F);
+    }
+    COZK_CUDA(cudaEventRecord(D.ev[7], D.stream));
+    COZK_CUDA(cudaStreamSynchronize(D.stream));
+    float total_ms = 0;
+    cudaEventElapsedTime(&total_ms, D.ev[0], D.ev[7]);
+    D.stats[6] = total_ms;
+    D.stats[7] = launches;
+    D.stats[8] = P.c;
+    D.stats[9] = P.W;
+    D.stats[10] = P.field_mults();
+    D.stats[11] = (double)P.m;
     return COZK_OK;
 }
 
@@ -1145,6 +1241,15 @@ int cozk_msm_batch_device(cozk_ctx* ctx, int device_index, cozk_srs srs, size_t 
         return COZK_ERR_INVALID_ARG;
     }
     return msm_dispatch(ctx, device_index, srs, base_offset, n, nullptr, d_scalars, k, stride_bytes, form, max_num_bits, out);
+}
+
+int cozk_msm_ragged_device(cozk_ctx* ctx, int device_index, cozk_srs srs, const size_t* base_offsets, const size_t* lens,
+                           const void* const* d_scalars, size_t k, size_t stride_bytes, int form, void* out) {
+    if (form != COZK_MONT && form != COZK_CANON) {
+        set_error("bad scalar form");
+        return COZK_ERR_INVALID_ARG;
+    }
+    return msm_ragged_device(ctx, device_index, srs, base_offsets, lens, d_scalars, k, stride_bytes, form, out);
 }
 
 int cozk_g1_sum(const void* points72, size_t count, void* out72) {

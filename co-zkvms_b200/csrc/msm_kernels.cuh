@@ -111,7 +111,16 @@ struct DecomposeArgs {
     uint32_t* seg_cursor;
     const uint64_t* seg_len;   // pairs of the segment (mode 1: its last pair is the total S)
     size_t totals_index;       // index (into the base table) of the total of table row 0; row w: + w (table mode)
+    // Ragged group (rag_start != null; fused sort path only): vector v has rag_start[v+1] - rag_start[v] scalars and pairs
+    // with bases rag_base[v] .. of the SRS (the levels of a PST13 opening against one concatenated SRS: one launch for
+    // vectors of 2^21, 2^20, .. points).  `n` is then unused; val_offset must be 0.
+    const uint32_t* rag_start; // [g + 1]
+    const uint32_t* rag_base;  // [g]
+    size_t total;              // scalars in the group; 0 = g * n
 };
+COZK_HD size_t decompose_total(const DecomposeArgs& A) { return A.total ? A.total : (size_t)A.g * A.n; }
+// index of the first base of vector v inside the SRS row (and inside the infinity flags)
+COZK_HD size_t decompose_base(const DecomposeArgs& A, uint32_t v) { return A.rag_base ? (size_t)A.rag_base[v] : A.val_offset; }
 
 // bits [off, off+c) of a 256-bit little-endian integer, c <= 24
 COZK_HD uint32_t extract_bits(const fr& s, uint32_t off, uint32_t c) {
@@ -136,8 +145,19 @@ COZK_HD uint32_t signed_digit(const fr& s, uint32_t w, uint32_t c, uint32_t& car
     return d;
 }
 COZK_HD fr decompose_load(size_t tid, const DecomposeArgs& A, uint32_t& v, size_t& i) {
-    v = (uint32_t)(tid / A.n);
-    i = tid - (size_t)v * A.n;
+    if (A.rag_start) {  // the vector whose range holds tid: largest v with rag_start[v] <= tid
+        uint32_t lo = 0, hi = A.g;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (A.rag_start[mid] <= tid) lo = mid;
+            else hi = mid;
+        }
+        v = lo;
+        i = tid - A.rag_start[v];
+    } else {
+        v = (uint32_t)(tid / A.n);
+        i = tid - (size_t)v * A.n;
+    }
     const uint8_t* vec = A.vec_ptrs ? A.vec_ptrs[v] : A.scalars + (size_t)v * A.vector_stride;
     fr s = load_fq(vec + i * A.stride);
     return A.form == SCALAR_MONT ? fr_from_mont(s) : fr_reduce_canon(s);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "msm_plan.hpp"
 #include "rep3_kernels.cuh"
 
 namespace cozk {
@@ -258,20 +259,29 @@ int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t 
     K.first_small = small_log2 == 0 ? nv : (nv > small_log2 + 1 ? nv - small_log2 - 1 : 0);
     K.small_n = K.first_small < nv ? ((size_t)1 << (nv - K.first_small)) - 1 : 0;
     Device& D = *ctx->devs[0];
-    affine* d_small = nullptr;
-    uint8_t* d_small_inf = nullptr;
+    // two concatenated SRSs of pair sums: the big levels (opened by ONE ragged batch: vectors of 2^(nv-1), 2^(nv-2), ..
+    // scalars through one decompose / sort / accumulate / reduce) and the small ones (one batched MSM, zero-padded vectors)
+    size_t big_n = 0;
+    for (size_t i = 0; i < K.first_small; ++i) {
+        K.big_off.push_back(big_n);
+        big_n += (size_t)1 << (nv - 1 - i);
+    }
+    affine *d_small = nullptr, *d_big = nullptr;
+    uint8_t *d_small_inf = nullptr, *d_big_inf = nullptr;
     auto fail = [&](int code) {
-        for (cozk_srs h : K.pair_srs) cozk_srs_release(ctx, h);
+        if (K.big_srs) cozk_srs_release(ctx, K.big_srs);
         cudaSetDevice(D.id);
-        if (d_small) cudaFree(d_small);
-        if (d_small_inf) cudaFree(d_small_inf);
+        for (void* p : {(void*)d_small, (void*)d_small_inf, (void*)d_big, (void*)d_big_inf})
+            if (p) cudaFree(p);
         return code;
     };
-    if (K.small_n) {
+    {
         std::lock_guard<std::mutex> lock(D.mu);
         cudaError_t e = cudaSetDevice(D.id);
-        if (e == cudaSuccess) e = cudaMalloc(&d_small, K.small_n * sizeof(affine));
-        if (e == cudaSuccess) e = cudaMalloc(&d_small_inf, K.small_n);
+        if (e == cudaSuccess && K.small_n) e = cudaMalloc(&d_small, K.small_n * sizeof(affine));
+        if (e == cudaSuccess && K.small_n) e = cudaMalloc(&d_small_inf, K.small_n);
+        if (e == cudaSuccess && big_n) e = cudaMalloc(&d_big, big_n * sizeof(affine));
+        if (e == cudaSuccess && big_n) e = cudaMalloc(&d_big_inf, big_n);
         if (e != cudaSuccess) {
             set_error(std::string("open key: allocation failed: ") + cudaGetErrorString(e));
             return fail(COZK_ERR_CUDA);
@@ -280,26 +290,43 @@ int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t 
     size_t off = 0;
     for (size_t i = 0; i < nv; ++i) {
         size_t half = (size_t)1 << (nv - 1 - i);
+        size_t got = 0;
         if (i < K.first_small) {
-            cozk_srs h = 0;
-            rc = cozk_srs_pair_sums(ctx, level_srs[i], &h);
+            rc = srs_pair_sums_into(ctx, level_srs[i], d_big + K.big_off[i], d_big_inf + K.big_off[i], &got);
             if (rc) return fail(rc);
-            K.pair_srs.push_back(h);
         } else {
-            size_t got = 0;
             rc = srs_pair_sums_into(ctx, level_srs[i], d_small + off, d_small_inf + off, &got);
             if (rc) return fail(rc);
             K.small_off.push_back(off);
             off += half;
         }
     }
+    if (big_n) {
+        // window of the big SRS's table: all levels share it, every level has its own bucket set:
+        // cost = 11 * W(c) * (points of all levels) + 45 * levels * 2^(c-1)
+        uint32_t best_c = 0;
+        double best = 0;
+        for (uint32_t c = 10; c <= C_MAX; ++c) {
+            const double W = (double)windows_for(254, c);
+            if (W * (double)big_n >= 2147483647.0) continue;
+            const double cost = 11.0 * W * (double)big_n + 45.0 * (double)K.first_small * (double)(1u << (c - 1));
+            if (!best_c || cost < best) {
+                best = cost;
+                best_c = c;
+            }
+        }
+        rc = srs_register_from_device(ctx, 0, d_big, d_big_inf, big_n, &K.big_srs, 0, best_c);  // read by device 0 only
+        if (rc) return fail(rc);
+    }
     if (K.small_n) {
         rc = srs_register_from_device(ctx, 0, d_small, d_small_inf, K.small_n, &K.small_srs, 0);  // read by device 0 only
         if (rc) return fail(rc);
+    }
+    {
         std::lock_guard<std::mutex> lock(D.mu);
         cudaSetDevice(D.id);
-        cudaFree(d_small);
-        cudaFree(d_small_inf);
+        for (void* p : {(void*)d_small, (void*)d_small_inf, (void*)d_big, (void*)d_big_inf})
+            if (p) cudaFree(p);
     }
     std::lock_guard<std::mutex> lock(ctx->mu);
     *out = ctx->next_handle++;
@@ -320,7 +347,7 @@ int cozk_pst13_open_key_release(cozk_ctx* ctx, cozk_open_key key) {
         K = it->second;
         ctx->open_keys.erase(it);
     }
-    for (cozk_srs h : K.pair_srs) cozk_srs_release(ctx, h);
+    if (K.big_srs) cozk_srs_release(ctx, K.big_srs);
     if (K.small_srs) cozk_srs_release(ctx, K.small_srs);
     return COZK_OK;
 }
@@ -413,11 +440,27 @@ int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const OpenKey* k
         return std::chrono::duration<double, std::milli>(now() - t0).count();
     };
     auto t_start = now();
-    for (size_t i = 0; i < first_small && !rc; ++i) {
+    bool big_done = false;
+    if (key && first_small) {
+        // all big levels in one ragged batch against the concatenated pair-sum SRS
+        auto t0 = now();
+        std::vector<size_t> offs(first_small), lens(first_small);
+        std::vector<const void*> vecs(first_small);
+        for (size_t i = 0; i < first_small; ++i) {
+            offs[i] = key->big_off[i];
+            lens[i] = (size_t)1 << (nv - 1 - i);
+            vecs[i] = d_q + q_off[i];
+        }
+        const int rrc = msm_ragged_device(ctx, 0, key->big_srs, offs.data(), lens.data(), vecs.data(), first_small, 32, COZK_MONT, proofs);
+        big_done = rrc == COZK_OK;
+        if (rrc != COZK_OK && rrc != COZK_ERR_INVALID_ARG) rc = rrc;  // over budget: fall back to one call per level below
+        if (trace) fprintf(stderr, "[open] %zu big levels in one ragged batch: %.3f ms (rc %d)\n", first_small, ms_since(t0), rrc);
+    }
+    for (size_t i = 0; i < first_small && !rc && !big_done; ++i) {
         auto t0 = now();
         const void* vec[1] = {d_q + q_off[i]};
         if (key)
-            rc = msm_dispatch(ctx, 0, key->pair_srs[i], 0, (size_t)1 << (nv - 1 - i), nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
+            rc = msm_dispatch(ctx, 0, key->big_srs, key->big_off[i], (size_t)1 << (nv - 1 - i), nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
         else
             rc = msm_dispatch(ctx, 0, level_srs[i], 0, (size_t)1 << (nv - i), nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
         if (trace) fprintf(stderr, "[open] level %zu: %.3f ms\n", i, ms_since(t0));

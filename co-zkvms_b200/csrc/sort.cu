@@ -36,7 +36,7 @@ int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m,
     sort_grid((m + SORT_TILE - 1) / SORT_TILE, &gen_blocks, &gen_per);
     size_t scalars = 0;
     if (fused) {
-        scalars = (size_t)fused->g * fused->n;
+        scalars = decompose_total(*fused);
         sort_grid((scalars + SORT_THREADS - 1) / SORT_THREADS, &fus_blocks, &fus_per);
     }
     // histogram / cursor array (reused by the passes; the last one has an entry per key value) and two `starts` arrays

@@ -346,13 +346,13 @@ __device__ __forceinline__ void sortgen_load(const DecomposeArgs& A, uint32_t* s
     skip = false;
     if (ok) {
         s = decompose_load(tid, A, v, i);
-        skip = A.infinity && A.infinity[i];
+        skip = A.infinity && A.infinity[A.rag_base ? A.rag_base[v] + i : i];
     }
 #pragma unroll
     for (int l = 0; l < 8; ++l) sv_t[l * SORT_THREADS] = s.v[l];
     sv_t[8 * SORT_THREADS] = 0;
     key0 = v * A.bucket_windows * (1u << (A.c - 1));
-    point0 = (uint32_t)(A.val_offset + i);
+    point0 = (uint32_t)(decompose_base(A, v) + i);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS, COZK_SORT_MINBLOCKS) k_sortgen_count(DecomposeArgs A, SortPass P) {

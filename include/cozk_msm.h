@@ -87,6 +87,14 @@ int cozk_msm_batch_device(cozk_ctx* ctx, int device_index, cozk_srs srs, size_t 
                           const void* const* d_scalars, size_t k, size_t stride_bytes, int form, unsigned max_num_bits,
                           void* out);
 
+/* Ragged batch on one device: out[j] = sum_{i < lens[j]} d_scalars[j][i] * bases[base_offsets[j] + i], j = 0 .. k-1, through
+ * ONE decompose / sort / accumulate / reduce - vectors of very different lengths against one SRS, e.g. the levels of a PST13
+ * opening (2^(nv-1), 2^(nv-2), .. quotient scalars; pst13.rs:461-467) against the concatenated level SRSs, which as separate
+ * calls pay the per-call latency nv times.  k <= 4096; returns COZK_ERR_INVALID_ARG when the group exceeds the engine's
+ * bucket / pair budget (split it then). */
+int cozk_msm_ragged_device(cozk_ctx* ctx, int device_index, cozk_srs srs, const size_t* base_offsets, const size_t* lens,
+                           const void* const* d_scalars, size_t k, size_t stride_bytes, int form, void* out);
+
 /* Host-side group helpers the shims need (sum of chunk commitments = combine_comm; sum of party shares =
  * PST13::combine_commitment_shares, pst13.rs:72-108).  Points are 72-byte results. */
 int cozk_g1_sum(const void* points72, size_t count, void* out72);

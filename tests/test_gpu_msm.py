@@ -259,6 +259,39 @@ def test_sliced_srs(cozk, orc):
         mctx.srs_release(tiny)
 
 
+def test_ragged_batch(cozk, orc):
+    """cozk_msm_ragged_device: vectors of very different lengths and offsets against one SRS in one launch (the shape of a
+    PST13 opening's levels), with and without the SRS table, with points at infinity, both scalar forms; bit-exact with one
+    oracle MSM per vector."""
+    n_srs = 40_000
+    bases = orc.gen_bases(17, n_srs)
+    shapes = [(0, 20_000), (20_000, 10_000), (30_000, 5_000), (35_000, 2_500), (37_500, 1), (123, 31), (39_999, 1), (0, n_srs)]
+    dists = ["uniform", "const", "wminus", "dup", "zero_half", "small16", "uniform", "uniform"]
+    with cozk.Context() as c2:
+        inf = np.zeros(n_srs, np.uint8)
+        inf[7::11] = 1
+        for table, flags in ((True, None), (False, None), (True, inf)):
+            c2.set_option("table_max_mib", 65536 if table else 0)
+            srs = c2.srs_register(bases, infinity=flags)
+            for form in (0, 1):
+                host = [orc.gen_scalars(d, 300 + j, ln, form=form) for j, (d, (_, ln)) in enumerate(zip(dists, shapes))]
+                dev = [c2.alloc(h.nbytes).upload(h) for h in host]
+                got = c2.msm_ragged(srs, [d.ptr for d in dev], [o for o, _ in shapes], [ln for _, ln in shapes], form=form)
+                for j, ((off, ln), h) in enumerate(zip(shapes, host)):
+                    sc = h.copy()
+                    if flags is not None:
+                        sc[flags[off:off + ln] != 0] = 0
+                    assert (got[j] == orc.msm(bases[off:off + ln], sc, form=form)).all(), (table, flags is not None, form, j)
+                for d in dev:
+                    d.free()
+            d = c2.alloc(64).upload(np.zeros(64, np.uint8))
+            with pytest.raises(cozk.CozkError) as e:
+                c2.msm_ragged(srs, [d.ptr], [n_srs - 1], [2])
+            assert e.value.code == cozk.ERR_KEY_LENGTH
+            d.free()
+            c2.srs_release(srs)
+
+
 def test_release_while_in_flight(cozk, ctx, orc):
     """cozk_srs_release on one thread while another is inside an MSM over the same SRS: the handle goes at
     once, the device memory only when the call in flight returns - its result is still exact."""
