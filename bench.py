@@ -122,6 +122,10 @@ def strong_record(cozk, args, n_devices, check):
            "path": "one cozk_ctx over all devices, cozk_srs_register_sliced, cozk_msm_batch(host scalars, k=1); partial sums "
                    "added on the host inside the timed call"}
     with cozk.Context(devices=list(range(n_devices))) as mctx:
+        for kv in [x for x in args.strong_opts.split(",") if x]:
+            name, val = kv.split("=")
+            mctx.set_option(name, int(val))
+            rec.setdefault("options", {})[name] = int(val)
         gb = mctx.testgen_bases(1, n)
         hb = gb.download().reshape(n, 64)
         gb.free()
@@ -202,6 +206,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong-log2n", type=int, default=24, help="total points of the strong-scaling record (0 = skip)")
     ap.add_argument("--strong-steps", type=int, default=5)
+    ap.add_argument("--strong-opts", default="", help="engine options for the strong record's context: name=value,name=value")
     ap.add_argument("--replay-log2t", type=int, default=22,
                     help="co-jolt party commitment-path replay for a 2^T-cycle trace (BASELINE.json configs[4]); 0 = skip")
     args = ap.parse_args()
@@ -373,7 +378,7 @@ def main():
                              "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "G limb-products/s (IMAD.WIDE.U32 lane-ops)",
                              "frac": achieved / imad_peak, "traffic": traffic,
                              "traffic_note": "DRAM bytes per launch of k_accumulate<true> (level 1) from the committed ncu --set full capture "
-                                             "(profiles/r3_accumulate_ncu.md); algorithmic bytes = pairs x 72",
+                                             "(profiles/round2_accumulate_ncu.md); algorithmic bytes = pairs x 72",
                              "peak_source": "self-measured in this run: max(carry-chained IMAD.WIDE.U32.X microbenchmark, "
                                             "fq_mul microbenchmark x 136); MEASURED_PEAKS.json has no integer figure; "
                                             "nominal 148 SM x 32 lanes/clk x 1.965 GHz = 9309 G/s",

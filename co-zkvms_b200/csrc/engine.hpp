@@ -207,6 +207,8 @@ struct cozk_ctx {
     std::atomic<long> opt_window = 0;             // 0 = choose per call
     std::atomic<long> opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
     std::atomic<long> opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never): 2^22 in 2 chunks 12.7 against 13.3 ms; 2^20 loses (3.86 against 3.80 ms: every chunk repeats the latency-bound upper accumulate levels)
+    std::atomic<long> opt_stream_min_points_sliced = 1L << 21;  // the same threshold for the parts of a call over a sliced SRS: several devices
+                                                                // copy from one host buffer at once, every copy is slower, overlap pays earlier
     std::atomic<long> opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
     std::atomic<long> opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     std::atomic<long> opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables

@@ -362,7 +362,9 @@ static int analyse_dominant(Device& D, MsmPlan& P, const uint8_t* d_scalars, con
 // All k vectors over bases [offset, offset+n) on ONE device.  host_scalars xor dev_scalars.
 static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t offset, size_t n,
                          const void* const* host_scalars, const void* const* dev_scalars, size_t k, size_t stride, int form,
-                         unsigned max_bits, uint8_t* out) {
+                         unsigned max_bits, uint8_t* out, long stream_min = -1) {
+    // stream_min: points from which a single host vector is streamed in chunks; -1 = option "stream_min_points"
+    if (stream_min < 0) stream_min = ctx->opt_stream_min_points;
     Device& D = *ctx->devs[dev_index];
     if (!S.bases(dev_index)) {
         set_error("this SRS does not live on the device the call was sent to");
@@ -405,8 +407,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         // 2^24 45.8 / 45.6 / 48.5 ms, 2^25 87.7 / 84.9 / 86.9 ms, 2^26 171.0 / 163.5 / 163.3 ms with 2 / 4 / 8 chunks)
         const long opt_chunks = ctx->opt_stream_chunks;
         const long stream_chunks = opt_chunks ? opt_chunks : (pn >= ((size_t)1 << 25) ? 4 : 2);
-        if (host_scalars && k == 1 && stream_chunks > 1 && ctx->opt_stream_min_points > 0 &&
-            pn >= (size_t)ctx->opt_stream_min_points) {
+        if (host_scalars && k == 1 && stream_chunks > 1 && stream_min > 0 && pn >= (size_t)stream_min) {
             const size_t C = (size_t)stream_chunks;
             const size_t cn_max = (((pn + C - 1) / C) + 31) & ~(size_t)31;
             const size_t chunks = (pn + cn_max - 1) / cn_max;
@@ -626,7 +627,7 @@ int msm_dispatch(cozk_ctx* ctx, int only_device, cozk_srs srs, size_t base_offse
             const Part& pt = parts[pi];
             for (size_t j = 0; j < k; ++j) ptrs[pi][j] = reinterpret_cast<const uint8_t*>(host_scalars[j]) + pt.skip * stride;
             rcs[pi] = run_on_device(ctx, pt.sl->dev, *pt.sl->entry, pt.off, pt.cnt, ptrs[pi].data(), nullptr, k, stride, form, max_bits,
-                                    &partial[pi * k * 72]);
+                                    &partial[pi * k * 72], np > 1 ? (long)ctx->opt_stream_min_points_sliced : -1);
             if (rcs[pi]) errs[pi] = g_error;
         };
         std::vector<std::thread> th;
@@ -1306,6 +1307,9 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // a single host-resident vector of at least this many points is streamed in chunks (0 = never)
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points = value;
+    } else if (!strcmp(name, "stream_min_points_sliced")) {
+        if (value < 0) return COZK_ERR_INVALID_ARG;
+        ctx->opt_stream_min_points_sliced = value;
     } else if (!strcmp(name, "stream_chunks")) {
         if (value < 0 || value > 64) return COZK_ERR_INVALID_ARG;  // 0 = chosen from the vector length
         ctx->opt_stream_chunks = value;

@@ -9,6 +9,8 @@ namespace cozk {
 
 constexpr int ACC_L = 32;          // entries per thread of the serial accumulate body (level 1: the default, see choose_acc_l)
 constexpr int ACC_L_MIN = 16;
+constexpr int ACC_L_BIG = 64;      // level-1 chunk once chunks of 64 still give every resident thread 8 of them: half the partial slots for
+                                   // the levels above (2^22: accumulate 8.71 -> 8.66 ms, 2^24: 31.66 -> 31.38 ms; 2^20 stays at 32: 2.60 against 2.62 ms)
 constexpr int ACC_L_UP = 8;        // partial slots per thread at the serial levels >= 2: 4x the threads of chunks of 32, a quarter of
                                    // the serial chain (2^16 points: 0.68 -> 0.62 ms; 2^20: 3.17 -> 3.15; 2^22: 10.91 -> 10.82)
 constexpr int ACC_TILE = 256;      // partial slots per thread BLOCK at small levels >= 2 (block-cooperative segmented scan)
@@ -38,6 +40,7 @@ inline int choose_acc_l(size_t m, const AccTuning& t) {
     if (t.force_l) return t.force_l;
     const size_t resident = t.resident;
     if (resident == 0 || m == 0) return ACC_L;
+    if (m / ACC_L_BIG >= 8 * resident) return ACC_L_BIG;
     if ((m + ACC_L - 1) / ACC_L >= resident) return ACC_L;
     size_t L = (m + resident - 1) / resident;   // the chunk length at which the threads just fill the device
     L = (L + 3) & ~(size_t)3;

@@ -89,13 +89,14 @@ def test_bench_reference_arm_line():
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    """The last bench line measured on the B200 (profiles/r3_bench_1gpu.json, copied from the gpurun call) carries every key
+    """The last bench line measured on the B200 (profiles/round2_bench_1gpu.json, copied from the gpurun call) carries every key
     the driver's contract names; a change of bench.py that drops one shows up here as soon as the line is refreshed."""
     import json
-    with open(os.path.join(ROOT, "profiles", "r3_bench_1gpu.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "round2_bench_1gpu.json")) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "parity_vs_oracle", "strong",
+              "cojolt_replay", "srs_register_ms"):
         assert k in line, k
     assert line["config"]["workload"] and "model" not in line["config"]
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
