@@ -57,6 +57,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     std::mutex mu;  // one MSM at a time per device
+    long sort_digit_bits = 8;  // digit bits per sort pass on this device (option "sort_digit_bits", copied from the context by every call)
     DevBuf rag;  // ragged groups: start / base arrays of the vectors
     DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2, pk[2], pp[2], rs[2], rw[2], out, flush;
     std::mutex open_mu;  // one PST13 opening at a time per device: it owns the four buffers below across its MSM calls
@@ -203,6 +204,7 @@ struct cozk_ctx {
                                      // loads.  Measured equal or slower (2^22: ingest 0.161 against 0.152 ms, chi 2.21 against 2.20 ms; 2^20: chi
                                      // 0.67 against 0.59 ms): the access pattern is not what holds these kernels back.  Kept as an option.
     std::atomic<long> opt_chi_waves = 1;          // threads per polynomial of the chi kernels: enough for this many full waves of the device
+    std::atomic<long> opt_sort_digit_bits = 8;   // digit bits per pass of the pair sort (7 .. 11)
     std::atomic<long> opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
     std::atomic<long> opt_window = 0;             // 0 = choose per call
     std::atomic<long> opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)

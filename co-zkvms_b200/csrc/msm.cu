@@ -372,6 +372,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     }
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
+    D.sort_digit_bits = ctx->opt_sort_digit_bits;
     for (double& s : D.stats) s = 0;
     double launches = 0;
     uint32_t bits = (max_bits == 0 || max_bits > 254) ? 254 : max_bits;
@@ -1007,6 +1008,7 @@ int msm_ragged_device(cozk_ctx* ctx, int device, cozk_srs srs, const size_t* off
     plan_set_pairs(P, (size_t)P.W * total);
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
+    D.sort_digit_bits = ctx->opt_sort_digit_bits;
     for (double& st : D.stats) st = 0;
     double launches = 0;
     if ((rc = D.rag.ensure((2 * k + 1) * sizeof(uint32_t))) || (rc = D.vec_ptrs.ensure(2 * 4096 * sizeof(void*)))) return rc;
@@ -1285,6 +1287,9 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "chi_waves")) {
         if (value < 1 || value > 16) return COZK_ERR_INVALID_ARG;
         ctx->opt_chi_waves = value;
+    } else if (!strcmp(name, "sort_digit_bits")) {
+        if (value < 7 || value > 11) return COZK_ERR_INVALID_ARG;  // 8 is the measured optimum (profiles/round2_summary.md)
+        ctx->opt_sort_digit_bits = value;
     } else if (!strcmp(name, "group_l")) {
         // buckets per thread in the group step of the bucket reduce: a power of two, 0 = chosen from the bucket count
         if (value != 0 && (value < 1 || value > 64 || (value & (value - 1)))) return COZK_ERR_INVALID_ARG;

@@ -27,7 +27,7 @@ int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m,
                uint32_t** vals_out, double* launches, cudaEvent_t after_first) {
     uint32_t* bufk[2] = {D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>()};
     uint32_t* bufv[2] = {D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>()};
-    const SortPlan plan = SortPlan::for_bits(key_bits);
+    const SortPlan plan = SortPlan::for_bits(key_bits, (uint32_t)D.sort_digit_bits);
     if (m == 0 || m > (size_t)0x7FFFFFFF || plan.passes > SORT_MAX_PASSES || key_bits > 31) {
         set_error("internal: group too large for the sort");
         return COZK_ERR_INVALID_ARG;

@@ -42,7 +42,8 @@ constexpr int SORT_THREADS = COZK_SORT_THREADS;
 #endif
 constexpr int SORT_ITEMS = COZK_SORT_ITEMS;              // pairs per thread and tile
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;     // 8192 pairs
-constexpr uint32_t SORT_RMAX = 8;                        // digit bits per pass
+constexpr uint32_t SORT_RMAX = 8;                        // digit bits per pass (default; option "sort_digit_bits")
+constexpr uint32_t SORT_RMAX_LIMIT = 11;                 // 2^11 = SORT_RANGE prefix values: what a tile's shared-memory counters cover
 constexpr uint32_t SORT_RANGE = 2048;                    // prefix values a tile ranks through shared memory
 constexpr int SORT_PER_THREAD = SORT_RANGE / SORT_THREADS;
 constexpr uint32_t SORT_MAX_PASSES = 4;                  // keys have at most 31 bits
@@ -276,31 +277,36 @@ __global__ void __launch_bounds__(256) k_sort_rowscan(uint32_t* cursor, uint32_t
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
-    const uint32_t len = 1u << log_row;                 // entries per row
-    const uint32_t per = len > 32 ? len >> 5 : 1;       // consecutive entries per lane
-    const uint32_t lanes = len > 32 ? 32 : len;         // lanes that hold entries
+    const uint32_t len = 1u << log_row;                      // entries per row (up to 2^SORT_RMAX_LIMIT)
+    const uint32_t piece = len < 256 ? len : 256;            // entries the warp scans at a time
+    const uint32_t per = piece > 32 ? piece >> 5 : 1;        // consecutive entries per lane
+    const uint32_t lanes = piece > 32 ? 32 : piece;          // lanes that hold entries
     uint32_t* c = cursor + ((size_t)row << log_row);
     uint32_t* st = starts + ((size_t)row << log_row);
-    uint32_t v[8], sum = 0;
+    uint32_t carry = row_start ? row_start[row] : 0u;
+    for (uint32_t base = 0; base < len; base += piece) {
+        uint32_t v[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        v[k] = ((uint32_t)k < per && lane < lanes) ? c[lane * per + k] : 0u;
-        sum += v[k];
-    }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= (uint32_t)d) inc += y;
-    }
-    uint32_t run = (row_start ? row_start[row] : 0u) + inc - sum;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if ((uint32_t)k < per && lane < lanes) {
-            c[lane * per + k] = run;
-            st[lane * per + k] = run;
+        for (int k = 0; k < 8; ++k) {
+            v[k] = ((uint32_t)k < per && lane < lanes) ? c[base + lane * per + k] : 0u;
+            sum += v[k];
         }
-        run += v[k];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        uint32_t run = carry + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if ((uint32_t)k < per && lane < lanes) {
+                c[base + lane * per + k] = run;
+                st[base + lane * per + k] = run;
+            }
+            run += v[k];
+        }
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
     }
 }
 
@@ -434,11 +440,13 @@ struct SortPlan {
     uint32_t shift[SORT_MAX_PASSES] = {}, prev_shift[SORT_MAX_PASSES] = {};
     uint32_t key_bits = 0;
     // digit widths as even as possible, top digit first: 16 bits -> 8 + 8, 21 -> 7 + 7 + 7
-    static SortPlan for_bits(uint32_t key_bits) {
+    static SortPlan for_bits(uint32_t key_bits, uint32_t rmax = SORT_RMAX) {
         SortPlan p;
         if (key_bits == 0) key_bits = 1;
+        if (rmax < 7) rmax = 7;  // 4 passes must cover the 25 key bits of the largest group
+        if (rmax > SORT_RMAX_LIMIT) rmax = SORT_RMAX_LIMIT;
         p.key_bits = key_bits;
-        p.passes = (key_bits + SORT_RMAX - 1) / SORT_RMAX;
+        p.passes = (key_bits + rmax - 1) / rmax;
         uint32_t left_bits = key_bits;
         for (uint32_t i = 0; i < p.passes && i < SORT_MAX_PASSES; ++i) {
             const uint32_t left = p.passes - i;

@@ -367,6 +367,7 @@ int cozk_test_sort(cozk_ctx* ctx, int device_index, const void* d_keys, const vo
     int rc = get_device(ctx, device_index, &D);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(D->mu);
+    D->sort_digit_bits = ctx->opt_sort_digit_bits;
     if (d_scalars) m = (size_t)g * n * windows;
     if (m == 0) return COZK_OK;
     if ((rc = D->keys_a.ensure(m * 4)) || (rc = D->vals_a.ensure(m * 4)) || (rc = D->keys_b.ensure(m * 4)) || (rc = D->vals_b.ensure(m * 4)))

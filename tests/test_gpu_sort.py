@@ -38,6 +38,29 @@ def test_generic_passes_group_by_key(ctx, m, key_bits):
     _check_sorted(keys, vals, key_bits, got_k, got_v)
 
 
+@pytest.mark.parametrize("digit_bits", [7, 9, 10, 11])
+def test_other_digit_widths(ctx, digit_bits):
+    """Option sort_digit_bits: passes of 7 .. 11 bits (11 = the whole shared-memory counter window of a tile; rows of up to
+    2048 entries in the row scan)."""
+    ctx.set_option("sort_digit_bits", digit_bits)
+    try:
+        for m, key_bits in ((70_000, 21), (200_000, 16), (5_000, 25), (40_000, 11)):
+            rng = np.random.default_rng(m + digit_bits)
+            keys = rng.integers(0, 1 << key_bits, size=m, dtype=np.uint64).astype(np.uint32)
+            vals = np.arange(m, dtype=np.uint32)
+            got_k, got_v = ctx.sort_pairs(keys, vals, key_bits)
+            _check_sorted(keys, vals, key_bits, got_k, got_v)
+        dsc = ctx.testgen_scalars("uniform", 5, 30_000)
+        plain_k, plain_v = ctx.decompose_sort(dsc, 30_000, 20, table_stride=30_000, key_bits=0, fused=False)
+        got_k, got_v = ctx.decompose_sort(dsc, 30_000, 20, table_stride=30_000, key_bits=19, fused=True)
+        wk, wv = _canon(plain_k, plain_v)
+        gk, gv = _canon(got_k, got_v)
+        assert (np.diff(got_k.astype(np.int64)) >= 0).all() and (gk == wk).all() and (gv == wv).all()
+        dsc.free()
+    finally:
+        ctx.set_option("sort_digit_bits", 8)
+
+
 @pytest.mark.parametrize("shape", ["all_equal", "two_values", "sorted", "reversed", "few_hot"])
 def test_degenerate_key_distributions(ctx, shape):
     """Constant share vectors put every pair of a window into ONE bucket: the sort must not care."""

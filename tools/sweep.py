@@ -25,6 +25,7 @@ ap.add_argument("--stream-chunks", type=int, default=0)
 ap.add_argument("--table-window", type=int, default=-1, help="-1 auto, 0 no table, else forced table window")
 ap.add_argument("--acc-chunk", type=int, default=0, help="pairs per level-1 accumulate thread (0 = chosen per call)")
 ap.add_argument("--acc-chunk-up", type=int, default=0, help="partial slots per thread at the serial accumulate levels >= 2")
+ap.add_argument("--sort-bits", type=int, default=0, help="digit bits per pass of the pair sort (7 .. 11; default 8)")
 ap.add_argument("--group-l", type=int, default=0, help="buckets per thread in the group step of the bucket reduce")
 ap.add_argument("--exact", action="store_true", help="register an SRS of exactly each size (the bench's shape) instead of prefixes of the largest")
 ap.add_argument("--dominant", type=int, default=-1, help="-1 default, 0 off, 1 on (dominant-digit mode of whole-SRS calls)")
@@ -40,6 +41,8 @@ if args.acc_chunk:
     ctx.set_option("acc_chunk", args.acc_chunk)
 if args.acc_chunk_up:
     ctx.set_option("acc_chunk_up", args.acc_chunk_up)
+if args.sort_bits:
+    ctx.set_option("sort_digit_bits", args.sort_bits)
 if args.group_l:
     ctx.set_option("group_l", args.group_l)
 if args.stream_min >= 0:
