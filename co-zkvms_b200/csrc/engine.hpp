@@ -56,10 +56,12 @@ struct Device {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // streamed calls: the upper accumulate levels + bucket merge of chunk i run here, beside level 1 of chunk i + 1
+    std::vector<cudaEvent_t> chunk_ev;   // streamed calls: 4 events per chunk (start, sorted, level 1 done, chunk done), grown on demand
     std::mutex mu;  // one MSM at a time per device
     long sort_digit_bits = 8;  // digit bits per sort pass on this device (option "sort_digit_bits", copied from the context by every call)
     DevBuf rag;  // ragged groups: start / base arrays of the vectors
-    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2, pk[2], pp[2], rs[2], rw[2], out, flush;
+    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2[2], pk[4], pp[4], rs[2], rw[2], out, flush;
     std::mutex open_mu;  // one PST13 opening at a time per device: it owns the four buffers below across its MSM calls
     DevBuf open_in, open_r[2], open_q, open_qs;
     // dominant-digit analysis (msm_kernels.cuh, DomArgs): per-segment candidate digits, counters, modes, offsets, cursors
@@ -208,8 +210,9 @@ struct cozk_ctx {
     std::atomic<long> opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
     std::atomic<long> opt_window = 0;             // 0 = choose per call
     std::atomic<long> opt_group_pairs = 1L << 29; // (key, val) pairs per vector group (8 GiB of sort buffers; B200 has 180 GB)
-    std::atomic<long> opt_stream_min_points = 1L << 22;  // host-resident single vectors this long are streamed in chunks (0 = never): 2^22 in 2 chunks 12.7 against 13.3 ms; 2^20 loses (3.86 against 3.80 ms: every chunk repeats the latency-bound upper accumulate levels)
-    std::atomic<long> opt_stream_min_points_sliced = 1L << 21;  // the same threshold for the parts of a call over a sliced SRS: several devices
+    std::atomic<long> opt_stream_min_points = 1L << 20;  // host-resident single vectors this long are streamed in chunks (0 = never).  Pipelined on three
+                                                         // streams (msm.cu): 2^20 3.78 -> 3.70 ms in 2 chunks (3.84 / 3.98 in 3 / 4), 2^21 7.02 -> 6.80, 2^22 12.3 -> 12.15
+    std::atomic<long> opt_stream_min_points_sliced = 1L << 20;  // the same threshold for the parts of a call over a sliced SRS: several devices
                                                                 // copy from one host buffer at once, every copy is slower, overlap pays earlier
     std::atomic<long> opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
     std::atomic<long> opt_table_window = 0;             // 0 = choose_table_window(n) at registration

@@ -22,12 +22,15 @@ void set_error(const std::string& msg) { g_error = msg; }
 Device::~Device() {
     cudaSetDevice(id);
     DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
-                      &pk[0], &pk[1], &pp[0], &pp[1], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush, &buckets2,
+                      &pk[0], &pk[1], &pk[2], &pk[3], &pp[0], &pp[1], &pp[2], &pp[3], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush,
+                      &buckets2[0], &buckets2[1],
                       &dom_cand, &dom_counts, &dom_mode, &dom_off, &dom_len, &dom_cursor, &rag,
                       &open_in, &open_r[0], &open_r[1], &open_q, &open_qs};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : copy_done) if (e) cudaEventDestroy(e);
+    for (auto& e : chunk_ev) if (e) cudaEventDestroy(e);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }
@@ -145,25 +148,40 @@ int launch_decompose(const DecomposeArgs& A, cudaStream_t st) {
     return COZK_OK;
 }
 
-// Accumulate stage: sorted (key, val) pairs -> bucket sums in `bucket_dst` (zeroed here), level by level on D.stream.
-static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, const uint32_t* vals, const affine* d_bases,
-                          xyzz* bucket_dst, double* launches) {
-    cudaStream_t st = D.stream;
+// Partial-slot buffers of the accumulate levels: two sets (`parity`), so that the levels >= 2 of one chunk of a streamed
+// call can run beside level 1 of the next; inside a set, level l writes buffer l & 1 and reads the other.
+static int ensure_accumulate_buffers(Device& D, const MsmPlan& P, int parity) {
     int rc;
-    COZK_CUDA(cudaMemsetAsync(bucket_dst, 0, P.total_buckets * sizeof(xyzz), st));
     for (size_t lvl = 0; lvl < P.acc_entries.size(); ++lvl) {
+        const int tile = P.acc_tile[lvl];
+        const size_t T = (P.acc_entries[lvl] + tile - 1) / tile;
+        if ((rc = D.pk[2 * parity + (lvl & 1)].ensure(2 * T * 4))) return rc;
+        if ((rc = D.pp[2 * parity + (lvl & 1)].ensure(2 * T * sizeof(xyzz)))) return rc;
+    }
+    return COZK_OK;
+}
+
+// Accumulate stage: sorted (key, val) pairs -> bucket sums in `bucket_dst`, levels [lvl_begin, lvl_end) on stream st
+// (lvl_end = 0: all).  Level 0 zeroes the bucket set first.
+static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, const uint32_t* vals, const affine* d_bases,
+                          xyzz* bucket_dst, double* launches, cudaStream_t st = nullptr, int parity = 0, size_t lvl_begin = 0,
+                          size_t lvl_end = 0) {
+    if (!st) st = D.stream;
+    if (!lvl_end) lvl_end = P.acc_entries.size();
+    int rc;
+    if ((rc = ensure_accumulate_buffers(D, P, parity))) return rc;
+    if (lvl_begin == 0) COZK_CUDA(cudaMemsetAsync(bucket_dst, 0, P.total_buckets * sizeof(xyzz), st));
+    for (size_t lvl = lvl_begin; lvl < lvl_end; ++lvl) {
         size_t m = P.acc_entries[lvl];
         const int tile = P.acc_tile[lvl];
         size_t T = (m + tile - 1) / tile;  // threads (serial body) or blocks (segmented scan)
-        DevBuf& pk_out = D.pk[lvl & 1];
-        DevBuf& pp_out = D.pp[lvl & 1];
-        if ((rc = pk_out.ensure(2 * T * 4))) return rc;
-        if ((rc = pp_out.ensure(2 * T * sizeof(xyzz)))) return rc;
+        DevBuf& pk_out = D.pk[2 * parity + (lvl & 1)];
+        DevBuf& pp_out = D.pp[2 * parity + (lvl & 1)];
         AccumulateArgs A{m,
-                         lvl == 0 ? keys : D.pk[(lvl - 1) & 1].as<uint32_t>(),
+                         lvl == 0 ? keys : D.pk[2 * parity + ((lvl - 1) & 1)].as<uint32_t>(),
                          vals,
                          d_bases,
-                         lvl == 0 ? nullptr : D.pp[(lvl - 1) & 1].as<xyzz>(),
+                         lvl == 0 ? nullptr : D.pp[2 * parity + ((lvl - 1) & 1)].as<xyzz>(),
                          bucket_dst,
                          pk_out.as<uint32_t>(),
                          pp_out.as<xyzz>(),
@@ -230,8 +248,8 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     // 3 accumulate, level by level
     xyzz* bucket_dst = D.buckets.as<xyzz>();
     if (merge) {
-        if ((rc = D.buckets2.ensure(P.total_buckets * sizeof(xyzz)))) return rc;
-        bucket_dst = D.buckets2.as<xyzz>();
+        if ((rc = D.buckets2[0].ensure(P.total_buckets * sizeof(xyzz)))) return rc;
+        bucket_dst = D.buckets2[0].as<xyzz>();
     }
     if ((rc = run_accumulate(D, P, sorted_keys, sorted_vals, d_bases, bucket_dst, launches))) return rc;
     if (merge) {
@@ -404,51 +422,105 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
 
         // One long vector from host memory: feed it in point chunks through ONE bucket set, so that the H2D copy of
         // chunk i+1 overlaps decompose / sort / accumulate of chunk i; reduce and finish run once.
-        // chunks: option "stream_chunks", or (0 = auto) 2 below 2^25 points and 4 from there on (measured end to end:
-        // 2^24 45.8 / 45.6 / 48.5 ms, 2^25 87.7 / 84.9 / 86.9 ms, 2^26 171.0 / 163.5 / 163.3 ms with 2 / 4 / 8 chunks)
+        // chunks: option "stream_chunks", or (0 = auto) 2 below 2^24 points and 4 from there on (measured end to end with
+        // the pipeline below: 2^20 3.70 / 3.84 / 3.98 ms in 2 / 3 / 4 chunks; 2^22 12.15 / 12.05 / 12.23; 2^24 43.2 / 42.7 / 44.7
+        // and 2^26 - / 154.3 / 153.9 ms in 2 / 4 / 8 chunks)
         const long opt_chunks = ctx->opt_stream_chunks;
-        const long stream_chunks = opt_chunks ? opt_chunks : (pn >= ((size_t)1 << 25) ? 4 : 2);
+        const long stream_chunks = opt_chunks ? opt_chunks : (pn >= ((size_t)1 << 24) ? 4 : 2);
         if (host_scalars && k == 1 && stream_chunks > 1 && stream_min > 0 && pn >= (size_t)stream_min) {
+            // Pipeline without host synchronisation, three streams:
+            //   copy   H2D of chunk i + 1 (waits until the sort of chunk i - 1 has consumed the staging slot)
+            //   main   decompose + sort + LEVEL 1 of the accumulate stage of chunk i (the throughput-bound part)
+            //   aux    levels >= 2 and the bucket merge of chunk i (chains of a few dozen additions on a handful of warps:
+            //          bound by latency) - beside level 1 of chunk i + 1 instead of in front of it.
+            // Chunk 0 accumulates into the bucket set itself, chunk i > 0 into scratch set i & 1, merged on aux in order.
             const size_t C = (size_t)stream_chunks;
             const size_t cn_max = (((pn + C - 1) / C) + 31) & ~(size_t)31;
             const size_t chunks = (pn + cn_max - 1) / cn_max;
             const uint32_t cfix = table_c ? 0 : make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, 0).c;
+            const uint32_t cuse = cfix ? cfix : (uint32_t)ctx->opt_window;
             const uint8_t* src0 = reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride;
+            int rc;
+            // every buffer at its final size before the first launch: cudaFree / cudaMalloc would synchronise the device
+            const MsmPlan Pmax = make_plan(cn_max, 1, bits, max_buckets, cuse, table_c, acc_tuning);
+            for (int sl = 0; sl < 2; ++sl)
+                if ((rc = D.scalars[sl].ensure((cn_max - 1) * stride + 32 + 256))) return rc;
+            for (DevBuf* b : {&D.keys_a, &D.vals_a, &D.keys_b, &D.vals_b})
+                if ((rc = b->ensure(Pmax.m * 4))) return rc;
+            if ((rc = D.buckets.ensure(Pmax.total_buckets * sizeof(xyzz))) || (rc = D.out.ensure(72 + 256))) return rc;
+            for (int par = 0; par < 2; ++par) {
+                if (chunks > 1 && (rc = D.buckets2[par].ensure(Pmax.total_buckets * sizeof(xyzz)))) return rc;
+                if ((rc = ensure_accumulate_buffers(D, Pmax, par))) return rc;
+            }
+            if (!D.aux_stream) COZK_CUDA(cudaStreamCreateWithFlags(&D.aux_stream, cudaStreamNonBlocking));
+            while (D.chunk_ev.size() < 5 * chunks) {
+                cudaEvent_t e;
+                COZK_CUDA(cudaEventCreate(&e));
+                D.chunk_ev.push_back(e);
+            }
+            // events of chunk ci: 0 start, 1 first sort pass done, 2 sorted (staging slot free), 3 level 1 done, 4 chunk done
+            auto EV = [&](size_t ci, int which) { return D.chunk_ev[5 * ci + which]; };
             auto stage_chunk = [&](size_t ci) -> int {
-                int slot = (int)(ci & 1);
-                size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
-                int rc = D.scalars[slot].ensure((cn_max - 1) * stride + 32 + 256);
-                if (rc) return rc;
+                const int slot = (int)(ci & 1);
+                const size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
+                if (ci >= 2) COZK_CUDA(cudaStreamWaitEvent(D.copy_stream, EV(ci - 2, 2), 0));
                 COZK_CUDA(cudaMemcpyAsync(D.scalars[slot].p, src0 + clo * stride, (cn - 1) * stride + 32, cudaMemcpyHostToDevice,
                                           D.copy_stream));
                 COZK_CUDA(cudaEventRecord(D.copy_done[slot], D.copy_stream));
                 return COZK_OK;
             };
-            int rc = stage_chunk(0);
-            if (rc) return rc;
+            if ((rc = stage_chunk(0))) return rc;
             MsmPlan P;
             for (size_t ci = 0; ci < chunks; ++ci) {
-                int slot = (int)(ci & 1);
-                size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
-                P = make_plan(cn, 1, bits, max_buckets, cfix ? cfix : (uint32_t)ctx->opt_window, table_c, acc_tuning);
+                const int slot = (int)(ci & 1), par = (int)(ci & 1);
+                const size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
+                P = make_plan(cn, 1, bits, max_buckets, cuse, table_c, acc_tuning);
                 plan_mults += P.field_mults();
                 plan_pairs += (double)P.m;
                 last_c = P.c;
                 last_W = P.W;
+                COZK_CUDA(cudaEventRecord(EV(ci, 0), D.stream));
                 COZK_CUDA(cudaStreamWaitEvent(D.stream, D.copy_done[slot], 0));
-                if (ci + 1 < chunks && (rc = stage_chunk(ci + 1))) return rc;  // the other slot was released by the sync below
-                rc = run_group(D, P, table_c ? d_bases : d_bases + clo, d_inf ? d_inf + clo : nullptr, D.scalars[slot].as<uint8_t>(),
-                               nullptr, 0, stride, form, table_stride, val_offset + (table_c ? clo : 0), &launches, 1, ci > 0);
-                if (rc) return rc;
-                COZK_CUDA(cudaStreamSynchronize(D.stream));
-                add_stage_times(D, 1, 3);
+                if (ci + 1 < chunks && (rc = stage_chunk(ci + 1))) return rc;
+                const affine* cb = table_c ? d_bases : d_bases + clo;
+                DecomposeArgs DA{D.scalars[slot].as<uint8_t>(), nullptr, 0, stride, form, P.n, P.g, P.c, P.W, d_inf ? d_inf + clo : nullptr,
+                                 D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>(), P.Wb, table_stride, val_offset + (table_c ? clo : 0)};
+                uint32_t *sk = nullptr, *sv = nullptr;
+                if ((rc = sort_pairs(D, D.stream, &DA, P.m, P.sort_bits, &sk, &sv, &launches, EV(ci, 1)))) return rc;
+                COZK_CUDA(cudaEventRecord(EV(ci, 2), D.stream));
+                xyzz* dst = ci == 0 ? D.buckets.as<xyzz>() : D.buckets2[par].as<xyzz>();
+                // the partial-slot set and the scratch bucket set of this parity were last used by chunk ci - 2
+                if (ci >= 2) COZK_CUDA(cudaStreamWaitEvent(D.stream, EV(ci - 2, 4), 0));
+                if ((rc = run_accumulate(D, P, sk, sv, cb, dst, &launches, D.stream, par, 0, 1))) return rc;
+                COZK_CUDA(cudaEventRecord(EV(ci, 3), D.stream));
+                COZK_CUDA(cudaStreamWaitEvent(D.aux_stream, EV(ci, 3), 0));
+                if (P.acc_entries.size() > 1 && (rc = run_accumulate(D, P, nullptr, nullptr, cb, dst, &launches, D.aux_stream, par, 1, 0)))
+                    return rc;
+                if (ci > 0) {
+                    MergeArgs MA{D.buckets.as<xyzz>(), dst, P.total_buckets};
+                    launch_merge(MA, grid_for(P.total_buckets, 128), D.aux_stream);
+                    launches += 1;
+                    COZK_CUDA(cudaGetLastError());
+                }
+                COZK_CUDA(cudaEventRecord(EV(ci, 4), D.aux_stream));
             }
+            COZK_CUDA(cudaStreamWaitEvent(D.stream, EV(chunks - 1, 4), 0));  // aux runs in order: the last chunk closes them all
+            COZK_CUDA(cudaEventRecord(D.ev[4], D.stream));
             rc = run_group(D, P, d_bases, d_inf, nullptr, nullptr, 0, stride, form, table_stride, val_offset, &launches, 2, false);
             if (rc) return rc;
             if (!D.finish_on_host) COZK_CUDA(cudaMemcpyAsync(pass_out, D.out.p, 72, cudaMemcpyDeviceToHost, D.stream));
             COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
             COZK_CUDA(cudaStreamSynchronize(D.stream));
             add_stage_times(D, 4, 5);
+            // stage times of the chunks: decompose = up to the first sort pass, sort = the rest, accumulate = level 1 of every
+            // chunk + what the last chunk's upper levels and merge add behind it (the other chunks' run beside the next level 1)
+            for (size_t ci = 0; ci < chunks; ++ci) {
+                float ms;
+                if (cudaEventElapsedTime(&ms, EV(ci, 0), EV(ci, 1)) == cudaSuccess) D.stats[1] += ms;
+                if (cudaEventElapsedTime(&ms, EV(ci, 1), EV(ci, 2)) == cudaSuccess) D.stats[2] += ms;
+                if (cudaEventElapsedTime(&ms, EV(ci, 2), EV(ci, 3)) == cudaSuccess) D.stats[3] += ms;
+                if (ci + 1 == chunks && cudaEventElapsedTime(&ms, EV(ci, 3), EV(ci, 4)) == cudaSuccess) D.stats[3] += ms;
+            }
             if (D.finish_on_host) {
                 auto h0 = std::chrono::steady_clock::now();
                 FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out};
