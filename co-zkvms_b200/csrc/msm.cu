@@ -427,7 +427,32 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         // and 2^26 - / 154.3 / 153.9 ms in 2 / 4 / 8 chunks)
         const long opt_chunks = ctx->opt_stream_chunks;
         const long stream_chunks = opt_chunks ? opt_chunks : (pn >= ((size_t)1 << 24) ? 4 : 2);
-        if (host_scalars && k == 1 && stream_chunks > 1 && stream_min > 0 && pn >= (size_t)stream_min) {
+        bool stream_it = host_scalars && k == 1 && stream_chunks > 1 && stream_min > 0 && pn >= (size_t)stream_min;
+        if (stream_it) {
+            // The dominant-digit mode (constant and nearly constant share vectors: a 2^22 constant vector in 0.8 ms instead of
+            // 10) needs the whole vector on the device before it can lay the pairs out, so it does not stream.  Where its
+            // preconditions hold, look at the head of the vector first (1024 scalars: a 32 KB copy and two tiny kernels):
+            // if a window is dominated there, this call takes the one-shot path below.
+            uint32_t tl = 0;
+            while (tl < S.total_levels && (S.n >> tl) != pn) ++tl;
+            const bool totals_addressable = (double)S.table_W * (double)S.n + (double)(S.total_levels + 1) * S.table_W < 2147483647.0;
+            if (ctx->opt_dominant && tl < S.total_levels && ((S.total_ok >> tl) & 1) && (S.n >> tl << tl) == S.n && !d_inf &&
+                totals_addressable && passes == 1 && offset == 0 && (double)pn >= (double)ctx->opt_dominant_min_points) {
+                const size_t head = std::min<size_t>(pn, 1024);
+                int rc = D.scalars[0].ensure((head - 1) * stride + 32 + 256);
+                if (rc) return rc;
+                COZK_CUDA(cudaMemcpyAsync(D.scalars[0].p, reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride,
+                                          (head - 1) * stride + 32, cudaMemcpyHostToDevice, D.stream));
+                MsmPlan Ph = make_plan(head, 1, bits, max_buckets, (uint32_t)ctx->opt_window, table_c, acc_tuning);
+                if (!table_c) Ph = make_plan(head, 1, bits, max_buckets, make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, 0).c, 0, acc_tuning);
+                DecomposeArgs peek = {};
+                bool dominated = false;
+                rc = analyse_dominant(D, Ph, D.scalars[0].as<uint8_t>(), nullptr, 0, stride, form, 0, &peek, &dominated, &launches);
+                if (rc) return rc;
+                if (dominated) stream_it = false;
+            }
+        }
+        if (stream_it) {
             // Pipeline without host synchronisation, three streams:
             //   copy   H2D of chunk i + 1 (waits until the sort of chunk i - 1 has consumed the staging slot)
             //   main   decompose + sort + LEVEL 1 of the accumulate stage of chunk i (the throughput-bound part)

@@ -520,3 +520,18 @@ def test_streamed_host_vector(cozk, orc):
         assert (got[0] == orc.msm(bases[1234:1234 + 50001], sc[:50001])).all()
         c2.srs_release(srs_t)
         c2.srs_release(srs_p)
+        # a vector the dominant-digit mode applies to (whole SRS, constant share) is recognised from its head and takes the
+        # one-shot path with the row totals instead of being streamed; a uniform one is streamed
+        m2 = 1 << 15
+        c2.set_option("table_max_mib", 65536)
+        c2.set_option("dominant_min_points", 0)
+        c2.set_option("stream_chunks", 2)
+        srs2 = c2.srs_register(bases[:m2])
+        for dist, few in (("const", True), ("wminus", False), ("uniform", False)):
+            v = orc.gen_scalars(dist, 41, m2)
+            assert (c2.msm_batch(srs2, [v])[0] == orc.msm(bases[:m2], v)).all(), dist
+            st = c2.last_stats()
+            assert (st["pairs"] <= st["windows"] + 1) == few, (dist, st["pairs"])
+            if dist == "wminus":
+                assert st["pairs"] < 0.6 * st["windows"] * m2
+        c2.srs_release(srs2)
