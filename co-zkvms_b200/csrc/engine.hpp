@@ -206,6 +206,7 @@ struct cozk_ctx {
                                      // loads.  Measured equal or slower (2^22: ingest 0.161 against 0.152 ms, chi 2.21 against 2.20 ms; 2^20: chi
                                      // 0.67 against 0.59 ms): the access pattern is not what holds these kernels back.  Kept as an option.
     std::atomic<long> opt_chi_waves = 1;          // threads per polynomial of the chi kernels: enough for this many full waves of the device
+    std::atomic<long> opt_max_points_per_pass = 1L << 26;  // longer calls run as several passes whose results are added on the host
     std::atomic<long> opt_sort_digit_bits = 8;   // digit bits per pass of the pair sort (7 .. 11)
     std::atomic<long> opt_group_l = 0;            // buckets per thread in the group step of the bucket reduce; 0 = chosen from the bucket count
     std::atomic<long> opt_window = 0;             // 0 = choose per call

@@ -318,7 +318,7 @@ static void host_sum(const uint8_t* pts, size_t count, uint8_t* out) {
     xyzz_to_wire(acc, out);
 }
 
-constexpr size_t MAX_POINTS_PER_PASS = (size_t)1 << 26;
+constexpr size_t MAX_POINTS_PER_PASS = (size_t)1 << 26;  // default of option "max_points_per_pass"
 
 // Dominant-digit analysis of one group (scalars already on the device): candidate digits from every vector's first
 // scalar, a look at the first 1024 scalars of every vector, and - only if that sample shows a dominated window - the full
@@ -395,7 +395,9 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     double launches = 0;
     uint32_t bits = (max_bits == 0 || max_bits > 254) ? 254 : max_bits;
     const size_t max_buckets = (size_t)1 << 25;  // 4 GiB of XYZZ buckets per group
-    size_t passes = (n + MAX_POINTS_PER_PASS - 1) / MAX_POINTS_PER_PASS;
+    // a call longer than this runs as several passes over point ranges whose results are added on the host
+    const size_t per_pass = (size_t)std::max<long>(1, ctx->opt_max_points_per_pass);
+    size_t passes = (n + per_pass - 1) / per_pass;
     std::vector<uint8_t> partial(passes > 1 ? passes * k * 72 : 0);
     COZK_CUDA(cudaEventRecord(D.ev[0], D.stream));
     double plan_mults = 0, plan_pairs = 0, host_finish_ms = 0;
@@ -404,8 +406,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l};
 
     for (size_t pass = 0; pass < passes; ++pass) {
-        size_t lo = pass * MAX_POINTS_PER_PASS;
-        size_t pn = std::min(MAX_POINTS_PER_PASS, n - lo);
+        size_t lo = pass * per_pass;
+        size_t pn = std::min(per_pass, n - lo);
         const uint8_t* d_inf = S.inf(dev_index) ? S.inf(dev_index) + offset + lo : nullptr;
         uint8_t* pass_out = passes > 1 ? partial.data() + pass * k * 72 : out;
 
@@ -1384,6 +1386,9 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "chi_waves")) {
         if (value < 1 || value > 16) return COZK_ERR_INVALID_ARG;
         ctx->opt_chi_waves = value;
+    } else if (!strcmp(name, "max_points_per_pass")) {
+        if (value < 1 || value > (long)MAX_POINTS_PER_PASS) return COZK_ERR_INVALID_ARG;
+        ctx->opt_max_points_per_pass = value;
     } else if (!strcmp(name, "sort_digit_bits")) {
         if (value < 7 || value > 11) return COZK_ERR_INVALID_ARG;  // 8 is the measured optimum (profiles/round2_summary.md)
         ctx->opt_sort_digit_bits = value;

@@ -259,6 +259,29 @@ def test_sliced_srs(cozk, orc):
         mctx.srs_release(tiny)
 
 
+def test_multi_pass_calls(cozk, orc):
+    """A call longer than "max_points_per_pass" (2^26 by default) runs as several passes over point ranges whose partial
+    results are added on the host: exercised here with a small pass length - batches, prefix / offset, host and device
+    scalars, table and plain SRS."""
+    n = 20_000
+    bases = orc.gen_bases(19, n)
+    with cozk.Context() as c2:
+        c2.set_option("max_points_per_pass", 3000)
+        for table in (True, False):
+            c2.set_option("table_max_mib", 65536 if table else 0)
+            srs = c2.srs_register(bases)
+            vecs = [orc.gen_scalars(d, 500 + j, n) for j, d in enumerate(("uniform", "const", "wminus"))]
+            got = c2.msm_batch(srs, vecs)
+            for j, v in enumerate(vecs):
+                assert (got[j] == orc.msm(bases, v)).all(), (table, j)
+            x = c2.msm_batch(srs, [vecs[0]], n=7001, base_offset=999)
+            assert (x[0] == orc.msm(bases[999:8000], vecs[0][:7001])).all()
+            d = c2.alloc(n * 32).upload(vecs[0])
+            assert (c2.msm_batch_ptrs(srs, [d.ptr], n, device=0)[0] == orc.msm(bases, vecs[0])).all()
+            d.free()
+            c2.srs_release(srs)
+
+
 def test_ragged_batch(cozk, orc):
     """cozk_msm_ragged_device: vectors of very different lengths and offsets against one SRS in one launch (the shape of a
     PST13 opening's levels), with and without the SRS table, with points at infinity, both scalar forms; bit-exact with one
