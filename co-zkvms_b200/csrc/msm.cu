@@ -78,10 +78,23 @@ __global__ void __launch_bounds__(256) k_dom_count(DomArgs A) {
     if (t < W && sc[t]) atomicAdd(&A.count_cand[v * W + t], sc[t]);
     if (t >= 128 && t - 128 < W && sc[t]) atomicAdd(&A.count_zero[v * W + t - 128], sc[t]);
 }
+// Level 1 is bound by the integer-multiply pipe and by how many warps the register file holds (117 registers per thread:
+// 16 warps per SM as 4 blocks of 128).  COZK_ACC_BLOCK / COZK_ACC_MAXREG: build-time knobs for other shapes
+// (tools/gpu_variants.sh measures them side by side; __launch_bounds__ alone snaps from 128 straight to 96 registers).
+#ifndef COZK_ACC_BLOCK
+#define COZK_ACC_BLOCK 128
+#endif
 template <bool LEVEL1>
 __global__ void __launch_bounds__(128, 4) k_accumulate(AccumulateArgs A) {
     accumulate_body<LEVEL1>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
+#ifdef COZK_ACC_MAXREG
+__global__ void __maxnreg__(COZK_ACC_MAXREG) k_accumulate_l1(AccumulateArgs A) {
+    accumulate_body<true>((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
+}
+#else
+#define k_accumulate_l1 k_accumulate<true>
+#endif
 // Accumulate levels >= 2: block b owns partial slots [b*ACC_TILE, (b+1)*ACC_TILE).  Segmented inclusive scan by key
 // (keys are sorted, runs are contiguous), after which the last slot of every run holds the run's sum inside the tile.
 // Output contract = accumulate_body<false> with L = ACC_TILE run by ONE thread over the same tile (that body is the host
@@ -186,7 +199,7 @@ static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, con
                          pk_out.as<uint32_t>(),
                          pp_out.as<xyzz>(),
                          (uint32_t)tile};
-        if (lvl == 0) k_accumulate<true><<<grid_for(T, 128), 128, 0, st>>>(A);
+        if (lvl == 0) k_accumulate_l1<<<grid_for(T, COZK_ACC_BLOCK), COZK_ACC_BLOCK, 0, st>>>(A);
         else if (tile != ACC_TILE) k_accumulate<false><<<grid_for(T, 128), 128, 0, st>>>(A);
         else k_segscan<<<(unsigned)T, ACC_TILE, 0, st>>>(A);
         *launches += 1;
