@@ -19,9 +19,9 @@ CSRC = os.path.join(HERE, "csrc")
 # COZK_LIB: load another build of the same library (kernel experiments measured side by side with tools/sweep.py)
 LIB_PATH = os.environ.get("COZK_LIB") or os.path.join(HERE, "libcozk_msm.so")
 TEST_LIB_PATH = os.path.join(HERE, "libcozk_test.so")  # include/cozk_test.h: generators, test kernels, microbenchmarks
-SOURCES = ["msm.cu", "sort.cu", "depth_kernels.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
+SOURCES = ["msm.cu", "sort.cu", "affine.cu", "depth_kernels.cu", "aux.cu", "pst13.cu", "fixed_base.cu", "rep3poly.cu"]
 TEST_SOURCES = ["testlib.cu"]
-HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "sort_kernels.cuh", "rep3_kernels.cuh", "bulk_copy.cuh", "msm_plan.hpp", "engine.hpp",
+HEADERS = ["field.cuh", "field_ptx.inc", "curve.cuh", "msm_kernels.cuh", "sort_kernels.cuh", "affine_kernels.cuh", "rep3_kernels.cuh", "bulk_copy.cuh", "msm_plan.hpp", "engine.hpp",
            "depth_kernels.hpp"]
 PUBLIC_HEADERS = ["cozk_msm.h", "cozk_rep3.h", "cozk_pst13.h", "cozk_test.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
 
 # include/cozk_test.h, exported by libcozk_test.so
 TEST_ABI_SYMBOLS = ["cozk_testgen_bases", "cozk_testgen_scalars", "cozk_test_field_op", "cozk_test_g1_op", "cozk_microbench",
-                    "cozk_test_sort"]
+                    "cozk_test_sort", "cozk_test_affine_rounds"]
 
 
 class CozkError(RuntimeError):
@@ -179,6 +179,8 @@ def testlib():
     L.cozk_test_g1_op.argtypes = [vp, ci, ci, vp, vp, vp, sz]
     L.cozk_test_sort.argtypes = [vp, ci, vp, vp, sz, cu, vp, sz, cu, sz, ci, cu, cu, sz, sz, ci, vp, vp]
     L.cozk_microbench.argtypes = [vp, ci, ci, ci, ci, ci, cd, cd]
+    L.cozk_test_affine_rounds.argtypes = [vp, ci, vp, vp, sz, vp, sz, ci, ci, vp, vp, vp, ctypes.POINTER(sz), vp, vp, sz,
+                                          ctypes.POINTER(cu), cd]
     _testlib = L
     return L
 
@@ -443,6 +445,43 @@ class Context:
         finally:
             ko.free()
             vo.free()
+
+    def affine_rounds(self, keys, vals, dpts, total_buckets, rounds, reference=False, device=0, download=True):
+        """The batched-affine pre-reduction on its own (include/cozk_test.h): `rounds` halving rounds over pairs grouped by key
+        whose vals index into the device buffer dpts (64-byte affine points).  Returns (keys, vals, points[m, 64]) of the reduced
+        list, the overflow lists [(keys, points)] per round, and the time of the rounds in ms."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        m = keys.size
+        mo = m
+        for _ in range(rounds):
+            mo = (mo + 1) // 2
+        cap = min((m + 1) // 2, total_buckets + 1)
+        dk, dv = self.alloc(m * 4, device), self.alloc(m * 4, device)
+        ko, vo, po = self.alloc(mo * 4, device), self.alloc(mo * 4, device), self.alloc(mo * 64, device)
+        ok, op = (self.alloc(rounds * cap * 4, device), self.alloc(rounds * cap * 64, device)) if download else (None, None)
+        try:
+            dk.upload(keys.view(np.uint8))
+            dv.upload(vals.view(np.uint8))
+            out_m, ms = ctypes.c_size_t(), ctypes.c_double()
+            counts = (ctypes.c_uint * rounds)()
+            _check(testlib().cozk_test_affine_rounds(self.handle, device, ctypes.c_void_p(dk.ptr), ctypes.c_void_p(dv.ptr), m,
+                                                     ctypes.c_void_p(dpts.ptr), total_buckets, rounds, 1 if reference else 0,
+                                                     ctypes.c_void_p(ko.ptr), ctypes.c_void_p(vo.ptr), ctypes.c_void_p(po.ptr),
+                                                     ctypes.byref(out_m), ctypes.c_void_p(ok.ptr) if ok else None,
+                                                     ctypes.c_void_p(op.ptr) if op else None, cap, counts, ctypes.byref(ms)))
+            assert out_m.value == mo
+            if not download:
+                return None, None, ms.value
+            rk, rv = ko.download(mo * 4).view(np.uint32), vo.download(mo * 4).view(np.uint32)
+            rp = po.download(mo * 64).reshape(mo, 64)
+            allk, allp = ok.download(rounds * cap * 4).view(np.uint32), op.download(rounds * cap * 64).reshape(rounds * cap, 64)
+            ovf = [(allk[r * cap:r * cap + counts[r]].copy(), allp[r * cap:r * cap + counts[r]].copy()) for r in range(rounds)]
+            return (rk, rv, rp), ovf, ms.value
+        finally:
+            for b in (dk, dv, ko, vo, po, ok, op):
+                if b:
+                    b.free()
 
     def microbench(self, which, blocks, threads, iters, device=0):
         names = {"imad": 0, "fq_mul": 1, "fq_sqr": 2, "madd": 3, "imad_cc": 4, "imad_lo": 5, "imad_hi": 6, "fq_mul4": 7}

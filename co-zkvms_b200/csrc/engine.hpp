@@ -56,12 +56,19 @@ struct Device {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;   // streamed calls: the upper accumulate levels + bucket merge of chunk i run here, beside level 1 of chunk i + 1
-    std::vector<cudaEvent_t> chunk_ev;   // streamed calls: 4 events per chunk (start, sorted, level 1 done, chunk done), grown on demand
+    cudaStream_t aux_stream = nullptr;   // chunked calls: the upper accumulate levels + bucket merge of chunk i run here, beside level 1 of chunk i + 1
+    cudaStream_t prep_stream = nullptr;  // chunked calls: decompose + sort of chunk i + 1 (high priority), beside level 1 of chunk i
+    cudaStream_t l1b_stream = nullptr;   // chunked calls: level 1 of the odd chunks (the even ones run on `stream`): the tail of one chunk's kernel
+                                         // overlaps the head of the next one's
+    std::vector<cudaEvent_t> chunk_ev;   // chunked calls: 6 events per chunk, grown on demand
     std::mutex mu;  // one MSM at a time per device
+    long affine_rounds = 0, affine_min_pairs = 0;  // options "affine_rounds" / "affine_min_pairs", copied from the context by every call
     long sort_digit_bits = 8;  // digit bits per sort pass on this device (option "sort_digit_bits", copied from the context by every call)
+    DevBuf aff[2];  // batched-affine pre-reduction (affine.cu): round outputs, overflow lists, batch products (one set per chunk parity)
     DevBuf rag;  // ragged groups: start / base arrays of the vectors
-    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp, buckets, buckets2[2], pk[4], pp[4], rs[2], rw[2], out, flush;
+    DevBuf scalars[2], vec_ptrs, keys_a, vals_a, keys_b, vals_b, sort_tmp,
+           keys_a2, vals_a2, keys_b2, vals_b2,  // second set of sort buffers (chunked calls: chunk i + 1 is sorted while level 1 reads chunk i)
+           buckets, buckets2[2], pk[4], pp[4], rs[2], rw[2], out, flush;
     std::mutex open_mu;  // one PST13 opening at a time per device: it owns the four buffers below across its MSM calls
     DevBuf open_in, open_r[2], open_q, open_qs;
     // dominant-digit analysis (msm_kernels.cuh, DomArgs): per-segment candidate digits, counters, modes, offsets, cursors
@@ -174,7 +181,30 @@ int open_key_lookup(cozk_ctx* ctx, uint64_t h, OpenKey* out);
 struct DecomposeArgs;
 int sort_setup_device();
 int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m, uint32_t key_bits, uint32_t** keys_out,
-               uint32_t** vals_out, double* launches, cudaEvent_t after_first);
+               uint32_t** vals_out, double* launches, cudaEvent_t after_first, int set = 0);
+// Batched-affine pre-reduction of a sorted pair list (affine.cu / affine_kernels.cuh): see there.
+constexpr int AFF_MAX_ROUNDS = 6;
+struct AffineRoundArgs;
+struct OvfAddArgsPub {  // layout of OvfAddArgs (affine_kernels.cuh), so that this header needs no kernel definitions
+    const uint32_t* count;
+    const uint32_t* keys;
+    const affine* pts;
+    xyzz* buckets;
+    uint32_t cap;
+};
+struct AffineStage {
+    const uint32_t* keys = nullptr;  // the reduced list: keys, vals (index into pts, or the skip mark), points
+    const uint32_t* vals = nullptr;
+    const affine* pts = nullptr;
+    size_t m = 0;
+    int rounds = 0;
+    OvfAddArgsPub ovf[AFF_MAX_ROUNDS] = {};
+};
+int affine_setup_device();
+int affine_reduce(Device& D, cudaStream_t st, int parity, size_t m, size_t total_buckets, const uint32_t* keys, const uint32_t* vals,
+                  const affine* bases, int rounds, AffineStage* out, double* launches);
+int affine_overflow_adds(cudaStream_t st, const AffineStage& S, xyzz* buckets, double* launches);
+int affine_round_reference(cudaStream_t st, const AffineRoundArgs& A);
 // the plain decompose kernel (msm.cu), for the test entry points of aux.cu
 int launch_decompose(const DecomposeArgs& A, cudaStream_t st);
 // Ragged batch on ONE device (msm.cu): vector j has lens[j] device-resident scalars (dense stride) and multiplies bases
@@ -215,7 +245,12 @@ struct cozk_ctx {
                                                          // streams (msm.cu): 2^20 3.78 -> 3.70 ms in 2 chunks (3.84 / 3.98 in 3 / 4), 2^21 7.02 -> 6.80, 2^22 12.3 -> 12.15
     std::atomic<long> opt_stream_min_points_sliced = 1L << 20;  // the same threshold for the parts of a call over a sliced SRS: several devices
                                                                 // copy from one host buffer at once, every copy is slower, overlap pays earlier
-    std::atomic<long> opt_stream_chunks = 0;              // 0 = auto: 2 chunks below 2^25 points, 4 from there on (msm.cu has the measurements)
+    std::atomic<long> opt_affine_rounds = 0;              // batched-affine pre-reduction rounds in front of the accumulate levels (affine_kernels.cuh); 0 = off
+    std::atomic<long> opt_affine_min_pairs = 1L << 20;    // ... for pair lists of at least this many entries
+    std::atomic<long> opt_chunk_min_points = 0;           // device-resident single vectors this long run in chunks too (0 = never, the default).  Measured: there
+                                                          // is no copy to hide, and what runs beside the level-1 kernels (the next chunk's sort, the upper levels)
+                                                          // is throughput work itself: 2^20 3.16 ms in one piece, 3.29 / 3.42 / 3.53 in 2 / 3 / 4 chunks; 2^24 37.3, 38.0 / 38.8 / 39.5
+    std::atomic<long> opt_stream_chunks = 0;              // 0 = auto: 2 chunks (msm.cu has the measurements)
     std::atomic<long> opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     std::atomic<long> opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables
 };

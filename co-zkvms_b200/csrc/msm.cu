@@ -22,6 +22,7 @@ void set_error(const std::string& msg) { g_error = msg; }
 Device::~Device() {
     cudaSetDevice(id);
     DevBuf* bufs[] = {&scalars[0], &scalars[1], &vec_ptrs, &keys_a, &vals_a, &keys_b, &vals_b, &sort_tmp, &buckets,
+                      &keys_a2, &vals_a2, &keys_b2, &vals_b2, &aff[0], &aff[1],
                       &pk[0], &pk[1], &pk[2], &pk[3], &pp[0], &pp[1], &pp[2], &pp[3], &rs[0], &rs[1], &rw[0], &rw[1], &out, &flush,
                       &buckets2[0], &buckets2[1],
                       &dom_cand, &dom_counts, &dom_mode, &dom_off, &dom_len, &dom_cursor, &rag,
@@ -31,6 +32,8 @@ Device::~Device() {
     for (auto& e : copy_done) if (e) cudaEventDestroy(e);
     for (auto& e : chunk_ev) if (e) cudaEventDestroy(e);
     if (aux_stream) cudaStreamDestroy(aux_stream);
+    if (prep_stream) cudaStreamDestroy(prep_stream);
+    if (l1b_stream) cudaStreamDestroy(l1b_stream);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }
@@ -208,6 +211,35 @@ static int run_accumulate(Device& D, const MsmPlan& P, const uint32_t* keys, con
     return COZK_OK;
 }
 
+// Batched-affine pre-reduction in front of the accumulate levels (affine.cu): how many halving rounds pay for this pair
+// list.  A round needs runs to halve: after R rounds the average bucket still has to hold 4 entries.
+static int affine_rounds_for(const Device& D, size_t m, size_t total_buckets) {
+    int R = (int)D.affine_rounds;
+    if (R <= 0 || m < (size_t)D.affine_min_pairs) return 0;
+    if (R > AFF_MAX_ROUNDS) R = AFF_MAX_ROUNDS;
+    while (R > 0 && (m >> R) < 4 * total_buckets) --R;
+    return R;
+}
+
+// Level 1 of the accumulate stage on stream st, with the pre-reduction when it pays: sorted pairs -> partial slots of level 1
+// (+ closed runs in bucket_dst).  *Pacc is the plan the levels >= 2 continue with; *AS the stage whose overflow lists have to
+// join bucket_dst behind the last level (affine_overflow_adds; AS->rounds == 0: nothing to add).
+static int run_level1(Device& D, const MsmPlan& P, const uint32_t* keys, const uint32_t* vals, const affine* d_bases, xyzz* bucket_dst,
+                      double* launches, cudaStream_t st, int parity, MsmPlan* Pacc, AffineStage* AS) {
+    *Pacc = P;
+    AS->rounds = 0;
+    const int R = affine_rounds_for(D, P.m, P.total_buckets);
+    int rc;
+    if (R > 0) {
+        if ((rc = affine_reduce(D, st, parity, P.m, P.total_buckets, keys, vals, d_bases, R, AS, launches))) return rc;
+        plan_set_pairs(*Pacc, AS->m);
+        keys = AS->keys;
+        vals = AS->vals;
+        d_bases = AS->pts;
+    }
+    return run_accumulate(D, *Pacc, keys, vals, d_bases, bucket_dst, launches, st, parity, 0, 1);
+}
+
 // ------------------------------------------------------------------------------------------------ one group on one device
 // Scalars are already on the device (contiguous staging or caller-owned vectors).  Results: g wire points in D.out.
 static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const uint8_t* d_inf, const uint8_t* d_scalars,
@@ -264,7 +296,13 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         if ((rc = D.buckets2[0].ensure(P.total_buckets * sizeof(xyzz)))) return rc;
         bucket_dst = D.buckets2[0].as<xyzz>();
     }
-    if ((rc = run_accumulate(D, P, sorted_keys, sorted_vals, d_bases, bucket_dst, launches))) return rc;
+    {
+        MsmPlan Pacc;
+        AffineStage AS;
+        if ((rc = run_level1(D, P, sorted_keys, sorted_vals, d_bases, bucket_dst, launches, st, 0, &Pacc, &AS))) return rc;
+        if (Pacc.acc_entries.size() > 1 && (rc = run_accumulate(D, Pacc, nullptr, nullptr, nullptr, bucket_dst, launches, st, 0, 1, 0))) return rc;
+        if (AS.rounds && (rc = affine_overflow_adds(st, AS, bucket_dst, launches))) return rc;
+    }
     if (merge) {
         MergeArgs MA{D.buckets.as<xyzz>(), bucket_dst, P.total_buckets};
         launch_merge(MA, grid_for(P.total_buckets, 128), st);
@@ -404,6 +442,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
     D.sort_digit_bits = ctx->opt_sort_digit_bits;
+    D.affine_rounds = ctx->opt_affine_rounds;
+    D.affine_min_pairs = ctx->opt_affine_min_pairs;
     for (double& s : D.stats) s = 0;
     double launches = 0;
     uint32_t bits = (max_bits == 0 || max_bits > 254) ? 254 : max_bits;
@@ -435,17 +475,21 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
         const affine* d_bases = table_c ? S.bases(dev_index) : S.bases(dev_index) + offset + lo;
         const size_t table_stride = table_c ? S.n : 0, val_offset = table_c ? offset + lo : 0;
 
-        // One long vector from host memory: feed it in point chunks through ONE bucket set, so that the H2D copy of
-        // chunk i+1 overlaps decompose / sort / accumulate of chunk i; reduce and finish run once.
-        // chunks: option "stream_chunks", or (0 = auto) 2 below 2^24 points and 4 from there on (measured end to end with
-        // the pipeline below: 2^20 3.70 / 3.84 / 3.98 ms in 2 / 3 / 4 chunks; 2^22 12.15 / 12.05 / 12.23; 2^24 43.2 / 42.7 / 44.7
-        // and 2^26 - / 154.3 / 153.9 ms in 2 / 4 / 8 chunks)
+        // One long vector (host memory or device-resident): feed it in point chunks through ONE bucket set.  From host memory
+        // the H2D copy of chunk i + 1 overlaps the work on chunk i; in both cases the decompose + sort of chunk i + 1 and the
+        // latency-bound upper accumulate levels of chunk i run BESIDE the level-1 kernels, which follow each other without a
+        // gap (pipeline below); reduce and finish run once.
+        // chunks: option "stream_chunks", or (0 = auto) 2.  Measured end to end from pinned host memory, 2 / 3 / 4 / 6 chunks:
+        // 2^20 3.61 / 3.67 / 3.75 / 4.06 ms (round-2 three-stream form: 3.70 / 3.84 / 3.98), 2^22 11.62 / 11.65 / 11.89 / 12.33
+        // (12.15), 2^24 40.6 / 40.7 / 40.8 / 41.9 (43.2): every chunk more costs another set of upper levels and a merge.
         const long opt_chunks = ctx->opt_stream_chunks;
-        const long stream_chunks = opt_chunks ? opt_chunks : (pn >= ((size_t)1 << 24) ? 4 : 2);
-        bool stream_it = host_scalars && k == 1 && stream_chunks > 1 && stream_min > 0 && pn >= (size_t)stream_min;
+        const long stream_chunks = opt_chunks ? opt_chunks : 2;
+        const long chunk_min = host_scalars ? stream_min : (long)ctx->opt_chunk_min_points;
+        bool stream_it = k == 1 && stream_chunks > 1 && chunk_min > 0 && pn >= (size_t)chunk_min;
+        const uint8_t* resident0 = (!host_scalars && stream_it) ? reinterpret_cast<const uint8_t*>(dev_scalars[0]) + lo * stride : nullptr;
         if (stream_it) {
             // The dominant-digit mode (constant and nearly constant share vectors: a 2^22 constant vector in 0.8 ms instead of
-            // 10) needs the whole vector on the device before it can lay the pairs out, so it does not stream.  Where its
+            // 10) needs the whole vector on the device before it can lay the pairs out, so it does not run in chunks.  Where its
             // preconditions hold, look at the head of the vector first (1024 scalars: a 32 KB copy and two tiny kernels):
             // if a window is dominated there, this call takes the one-shot path below.
             uint32_t tl = 0;
@@ -454,38 +498,57 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             if (ctx->opt_dominant && tl < S.total_levels && ((S.total_ok >> tl) & 1) && (S.n >> tl << tl) == S.n && !d_inf &&
                 totals_addressable && passes == 1 && offset == 0 && (double)pn >= (double)ctx->opt_dominant_min_points) {
                 const size_t head = std::min<size_t>(pn, 1024);
-                int rc = D.scalars[0].ensure((head - 1) * stride + 32 + 256);
-                if (rc) return rc;
-                COZK_CUDA(cudaMemcpyAsync(D.scalars[0].p, reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride,
-                                          (head - 1) * stride + 32, cudaMemcpyHostToDevice, D.stream));
+                int rc;
+                const uint8_t* head_src = resident0;
+                if (host_scalars) {
+                    if ((rc = D.scalars[0].ensure((head - 1) * stride + 32 + 256))) return rc;
+                    COZK_CUDA(cudaMemcpyAsync(D.scalars[0].p, reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride,
+                                              (head - 1) * stride + 32, cudaMemcpyHostToDevice, D.stream));
+                    head_src = D.scalars[0].as<uint8_t>();
+                }
                 MsmPlan Ph = make_plan(head, 1, bits, max_buckets, (uint32_t)ctx->opt_window, table_c, acc_tuning);
                 if (!table_c) Ph = make_plan(head, 1, bits, max_buckets, make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, 0).c, 0, acc_tuning);
                 DecomposeArgs peek = {};
                 bool dominated = false;
-                rc = analyse_dominant(D, Ph, D.scalars[0].as<uint8_t>(), nullptr, 0, stride, form, 0, &peek, &dominated, &launches);
+                rc = analyse_dominant(D, Ph, head_src, nullptr, 0, stride, form, 0, &peek, &dominated, &launches);
                 if (rc) return rc;
                 if (dominated) stream_it = false;
             }
         }
         if (stream_it) {
-            // Pipeline without host synchronisation, three streams:
-            //   copy   H2D of chunk i + 1 (waits until the sort of chunk i - 1 has consumed the staging slot)
-            //   main   decompose + sort + LEVEL 1 of the accumulate stage of chunk i (the throughput-bound part)
+            // Pipeline without host synchronisation:
+            //   copy   H2D of chunk i + 1 into staging slot (i + 1) & 1 (waits until the sort of chunk i - 1 has consumed it)
+            //   prep   decompose + sort of chunk i into sort-buffer set i & 1 (high priority: its blocks get the next SM that
+            //          frees up, so the sorted pairs of chunk i + 1 are ready long before level 1 of chunk i ends)
+            //   l1[i & 1]  LEVEL 1 of the accumulate stage of chunk i - the throughput-bound part.  Alternating streams: the blocks
+            //          of chunk i + 1 fill the SMs that chunk i's last blocks leave, no tail, no gap
             //   aux    levels >= 2 and the bucket merge of chunk i (chains of a few dozen additions on a handful of warps:
             //          bound by latency) - beside level 1 of chunk i + 1 instead of in front of it.
             // Chunk 0 accumulates into the bucket set itself, chunk i > 0 into scratch set i & 1, merged on aux in order.
+            // Chunk lengths: the FIRST chunk is half of an equal share - nothing runs beside its copy and its sort - the others
+            // share the rest.
             const size_t C = (size_t)stream_chunks;
-            const size_t cn_max = (((pn + C - 1) / C) + 31) & ~(size_t)31;
-            const size_t chunks = (pn + cn_max - 1) / cn_max;
+            std::vector<size_t> cstart;  // chunk ci covers [cstart[ci], cstart[ci + 1])
+            {
+                const size_t first = std::min(pn, std::max<size_t>(32, ((pn / (2 * C)) + 31) & ~(size_t)31));
+                const size_t rest = C > 1 ? ((((pn - first) + (C - 1) - 1) / (C - 1)) + 31) & ~(size_t)31 : 0;
+                cstart.push_back(0);
+                for (size_t at = first; at < pn; at += std::max<size_t>(rest, 32)) cstart.push_back(at);
+                cstart.push_back(pn);
+            }
+            const size_t chunks = cstart.size() - 1;
+            size_t cn_max = 0;
+            for (size_t ci = 0; ci < chunks; ++ci) cn_max = std::max(cn_max, cstart[ci + 1] - cstart[ci]);
             const uint32_t cfix = table_c ? 0 : make_plan(pn, 1, bits, max_buckets, (uint32_t)ctx->opt_window, 0).c;
             const uint32_t cuse = cfix ? cfix : (uint32_t)ctx->opt_window;
-            const uint8_t* src0 = reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride;
+            const uint8_t* src0 = host_scalars ? reinterpret_cast<const uint8_t*>(host_scalars[0]) + lo * stride : nullptr;
             int rc;
             // every buffer at its final size before the first launch: cudaFree / cudaMalloc would synchronise the device
             const MsmPlan Pmax = make_plan(cn_max, 1, bits, max_buckets, cuse, table_c, acc_tuning);
-            for (int sl = 0; sl < 2; ++sl)
-                if ((rc = D.scalars[sl].ensure((cn_max - 1) * stride + 32 + 256))) return rc;
-            for (DevBuf* b : {&D.keys_a, &D.vals_a, &D.keys_b, &D.vals_b})
+            if (host_scalars)
+                for (int sl = 0; sl < 2; ++sl)
+                    if ((rc = D.scalars[sl].ensure((cn_max - 1) * stride + 32 + 256))) return rc;
+            for (DevBuf* b : {&D.keys_a, &D.vals_a, &D.keys_b, &D.vals_b, &D.keys_a2, &D.vals_a2, &D.keys_b2, &D.vals_b2})
                 if ((rc = b->ensure(Pmax.m * 4))) return rc;
             if ((rc = D.buckets.ensure(Pmax.total_buckets * sizeof(xyzz))) || (rc = D.out.ensure(72 + 256))) return rc;
             for (int par = 0; par < 2; ++par) {
@@ -493,49 +556,67 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                 if ((rc = ensure_accumulate_buffers(D, Pmax, par))) return rc;
             }
             if (!D.aux_stream) COZK_CUDA(cudaStreamCreateWithFlags(&D.aux_stream, cudaStreamNonBlocking));
-            while (D.chunk_ev.size() < 5 * chunks) {
+            if (!D.l1b_stream) COZK_CUDA(cudaStreamCreateWithFlags(&D.l1b_stream, cudaStreamNonBlocking));
+            if (!D.prep_stream) {
+                int prio_low = 0, prio_high = 0;
+                COZK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+                COZK_CUDA(cudaStreamCreateWithPriority(&D.prep_stream, cudaStreamNonBlocking, prio_high));
+            }
+            while (D.chunk_ev.size() < 6 * chunks) {
                 cudaEvent_t e;
                 COZK_CUDA(cudaEventCreate(&e));
                 D.chunk_ev.push_back(e);
             }
-            // events of chunk ci: 0 start, 1 first sort pass done, 2 sorted (staging slot free), 3 level 1 done, 4 chunk done
-            auto EV = [&](size_t ci, int which) { return D.chunk_ev[5 * ci + which]; };
+            // events of chunk ci: 0 sort starts, 1 first sort pass done, 2 sorted (staging slot free), 3 level 1 done (sort-buffer
+            // set free), 4 chunk done (partial-slot set and scratch bucket set free), 5 level 1 starts
+            auto EV = [&](size_t ci, int which) { return D.chunk_ev[6 * ci + which]; };
             auto stage_chunk = [&](size_t ci) -> int {
                 const int slot = (int)(ci & 1);
-                const size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
+                const size_t clo = cstart[ci], cn = cstart[ci + 1] - clo;
                 if (ci >= 2) COZK_CUDA(cudaStreamWaitEvent(D.copy_stream, EV(ci - 2, 2), 0));
                 COZK_CUDA(cudaMemcpyAsync(D.scalars[slot].p, src0 + clo * stride, (cn - 1) * stride + 32, cudaMemcpyHostToDevice,
                                           D.copy_stream));
                 COZK_CUDA(cudaEventRecord(D.copy_done[slot], D.copy_stream));
                 return COZK_OK;
             };
-            if ((rc = stage_chunk(0))) return rc;
+            // everything below is ordered behind what the caller's stream has done so far (the peek above, earlier calls)
+            COZK_CUDA(cudaEventRecord(D.ev[1], D.stream));
+            for (cudaStream_t s : {D.prep_stream, D.l1b_stream, D.aux_stream, D.copy_stream}) COZK_CUDA(cudaStreamWaitEvent(s, D.ev[1], 0));
+            if (host_scalars && (rc = stage_chunk(0))) return rc;
             MsmPlan P;
             for (size_t ci = 0; ci < chunks; ++ci) {
                 const int slot = (int)(ci & 1), par = (int)(ci & 1);
-                const size_t clo = ci * cn_max, cn = std::min(cn_max, pn - clo);
+                const size_t clo = cstart[ci], cn = cstart[ci + 1] - clo;
+                cudaStream_t l1 = par ? D.l1b_stream : D.stream;
                 P = make_plan(cn, 1, bits, max_buckets, cuse, table_c, acc_tuning);
                 plan_mults += P.field_mults();
                 plan_pairs += (double)P.m;
                 last_c = P.c;
                 last_W = P.W;
-                COZK_CUDA(cudaEventRecord(EV(ci, 0), D.stream));
-                COZK_CUDA(cudaStreamWaitEvent(D.stream, D.copy_done[slot], 0));
-                if (ci + 1 < chunks && (rc = stage_chunk(ci + 1))) return rc;
+                if (host_scalars) COZK_CUDA(cudaStreamWaitEvent(D.prep_stream, D.copy_done[slot], 0));
+                if (ci >= 2) COZK_CUDA(cudaStreamWaitEvent(D.prep_stream, EV(ci - 2, 3), 0));  // level 1 of chunk ci - 2 read this set
+                COZK_CUDA(cudaEventRecord(EV(ci, 0), D.prep_stream));
+                if (host_scalars && ci + 1 < chunks && (rc = stage_chunk(ci + 1))) return rc;
                 const affine* cb = table_c ? d_bases : d_bases + clo;
-                DecomposeArgs DA{D.scalars[slot].as<uint8_t>(), nullptr, 0, stride, form, P.n, P.g, P.c, P.W, d_inf ? d_inf + clo : nullptr,
-                                 D.keys_a.as<uint32_t>(), D.vals_a.as<uint32_t>(), P.Wb, table_stride, val_offset + (table_c ? clo : 0)};
+                const uint8_t* csrc = host_scalars ? D.scalars[slot].as<uint8_t>() : resident0 + clo * stride;
+                DecomposeArgs DA{csrc, nullptr, 0, stride, form, P.n, P.g, P.c, P.W, d_inf ? d_inf + clo : nullptr,
+                                 nullptr, nullptr, P.Wb, table_stride, val_offset + (table_c ? clo : 0)};
                 uint32_t *sk = nullptr, *sv = nullptr;
-                if ((rc = sort_pairs(D, D.stream, &DA, P.m, P.sort_bits, &sk, &sv, &launches, EV(ci, 1)))) return rc;
-                COZK_CUDA(cudaEventRecord(EV(ci, 2), D.stream));
+                if ((rc = sort_pairs(D, D.prep_stream, &DA, P.m, P.sort_bits, &sk, &sv, &launches, EV(ci, 1), par))) return rc;
+                COZK_CUDA(cudaEventRecord(EV(ci, 2), D.prep_stream));
                 xyzz* dst = ci == 0 ? D.buckets.as<xyzz>() : D.buckets2[par].as<xyzz>();
+                COZK_CUDA(cudaStreamWaitEvent(l1, EV(ci, 2), 0));
                 // the partial-slot set and the scratch bucket set of this parity were last used by chunk ci - 2
-                if (ci >= 2) COZK_CUDA(cudaStreamWaitEvent(D.stream, EV(ci - 2, 4), 0));
-                if ((rc = run_accumulate(D, P, sk, sv, cb, dst, &launches, D.stream, par, 0, 1))) return rc;
-                COZK_CUDA(cudaEventRecord(EV(ci, 3), D.stream));
+                if (ci >= 2) COZK_CUDA(cudaStreamWaitEvent(l1, EV(ci - 2, 4), 0));
+                COZK_CUDA(cudaEventRecord(EV(ci, 5), l1));
+                MsmPlan Pacc;
+                AffineStage AS;
+                if ((rc = run_level1(D, P, sk, sv, cb, dst, &launches, l1, par, &Pacc, &AS))) return rc;
+                COZK_CUDA(cudaEventRecord(EV(ci, 3), l1));
                 COZK_CUDA(cudaStreamWaitEvent(D.aux_stream, EV(ci, 3), 0));
-                if (P.acc_entries.size() > 1 && (rc = run_accumulate(D, P, nullptr, nullptr, cb, dst, &launches, D.aux_stream, par, 1, 0)))
+                if (Pacc.acc_entries.size() > 1 && (rc = run_accumulate(D, Pacc, nullptr, nullptr, cb, dst, &launches, D.aux_stream, par, 1, 0)))
                     return rc;
+                if (AS.rounds && (rc = affine_overflow_adds(D.aux_stream, AS, dst, &launches))) return rc;
                 if (ci > 0) {
                     MergeArgs MA{D.buckets.as<xyzz>(), dst, P.total_buckets};
                     launch_merge(MA, grid_for(P.total_buckets, 128), D.aux_stream);
@@ -552,14 +633,14 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
             COZK_CUDA(cudaStreamSynchronize(D.stream));
             add_stage_times(D, 4, 5);
-            // stage times of the chunks: decompose = up to the first sort pass, sort = the rest, accumulate = level 1 of every
-            // chunk + what the last chunk's upper levels and merge add behind it (the other chunks' run beside the next level 1)
-            for (size_t ci = 0; ci < chunks; ++ci) {
+            // Stage times.  The stages of different chunks overlap, so they are reported as what each adds to the critical
+            // path: "decompose" = the first chunk up to its first sort pass, "sort" = the rest of the first chunk's sort,
+            // "accumulate" = from the first level-1 launch to the end of the last chunk's upper levels and merge.
+            {
                 float ms;
-                if (cudaEventElapsedTime(&ms, EV(ci, 0), EV(ci, 1)) == cudaSuccess) D.stats[1] += ms;
-                if (cudaEventElapsedTime(&ms, EV(ci, 1), EV(ci, 2)) == cudaSuccess) D.stats[2] += ms;
-                if (cudaEventElapsedTime(&ms, EV(ci, 2), EV(ci, 3)) == cudaSuccess) D.stats[3] += ms;
-                if (ci + 1 == chunks && cudaEventElapsedTime(&ms, EV(ci, 3), EV(ci, 4)) == cudaSuccess) D.stats[3] += ms;
+                if (cudaEventElapsedTime(&ms, D.ev[1], EV(0, 1)) == cudaSuccess) D.stats[1] += ms;
+                if (cudaEventElapsedTime(&ms, EV(0, 1), EV(0, 2)) == cudaSuccess) D.stats[2] += ms;
+                if (cudaEventElapsedTime(&ms, EV(0, 2), EV(chunks - 1, 4)) == cudaSuccess) D.stats[3] += ms;
             }
             if (D.finish_on_host) {
                 auto h0 = std::chrono::steady_clock::now();
@@ -1121,6 +1202,8 @@ int msm_ragged_device(cozk_ctx* ctx, int device, cozk_srs srs, const size_t* off
     std::lock_guard<std::mutex> lock(D.mu);
     COZK_CUDA(cudaSetDevice(D.id));
     D.sort_digit_bits = ctx->opt_sort_digit_bits;
+    D.affine_rounds = ctx->opt_affine_rounds;
+    D.affine_min_pairs = ctx->opt_affine_min_pairs;
     for (double& st : D.stats) st = 0;
     double launches = 0;
     if ((rc = D.rag.ensure((2 * k + 1) * sizeof(uint32_t))) || (rc = D.vec_ptrs.ensure(2 * 4096 * sizeof(void*)))) return rc;
@@ -1209,6 +1292,7 @@ int cozk_init(cozk_ctx** out, const int* device_ids, int n_devices) {
         {
             int src = sort_setup_device();
             if (src) return src;
+            if ((src = affine_setup_device())) return src;
         }
         COZK_CUDA(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
         COZK_CUDA(cudaStreamCreateWithFlags(&D->copy_stream, cudaStreamNonBlocking));
@@ -1427,6 +1511,16 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // a single host-resident vector of at least this many points is streamed in chunks (0 = never)
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points = value;
+    } else if (!strcmp(name, "affine_rounds")) {
+        // halving rounds of the batched-affine pre-reduction in front of the accumulate levels (0 = off)
+        if (value < 0 || value > AFF_MAX_ROUNDS) return COZK_ERR_INVALID_ARG;
+        ctx->opt_affine_rounds = value;
+    } else if (!strcmp(name, "affine_min_pairs")) {
+        if (value < 0) return COZK_ERR_INVALID_ARG;
+        ctx->opt_affine_min_pairs = value;
+    } else if (!strcmp(name, "chunk_min_points")) {
+        if (value < 0) return COZK_ERR_INVALID_ARG;
+        ctx->opt_chunk_min_points = value;
     } else if (!strcmp(name, "stream_min_points_sliced")) {
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points_sliced = value;

@@ -22,11 +22,12 @@ int sort_setup_device() {
 //   fused != nullptr: the pairs are those of the plain decompose layout of *fused (m = g * n * W): they are generated in
 //                     the first pass and never stored unsorted.  fused->keys / vals are ignored.
 // The sorted pairs end up in one of the two buffer pairs of the device; *keys_out / *vals_out say which.  The caller
-// has sized keys_a / vals_a / keys_b / vals_b for m entries.  after_first (optional) is recorded behind the first pass.
+// has sized keys_a / vals_a / keys_b / vals_b (set 1: keys_a2 .. vals_b2) for m entries.  after_first (optional) is recorded
+// behind the first pass.  Sorts of one device are serialised by their callers (they share sort_tmp).
 int sort_pairs(Device& D, cudaStream_t st, const DecomposeArgs* fused, size_t m, uint32_t key_bits, uint32_t** keys_out,
-               uint32_t** vals_out, double* launches, cudaEvent_t after_first) {
-    uint32_t* bufk[2] = {D.keys_a.as<uint32_t>(), D.keys_b.as<uint32_t>()};
-    uint32_t* bufv[2] = {D.vals_a.as<uint32_t>(), D.vals_b.as<uint32_t>()};
+               uint32_t** vals_out, double* launches, cudaEvent_t after_first, int set) {
+    uint32_t* bufk[2] = {(set ? D.keys_a2 : D.keys_a).as<uint32_t>(), (set ? D.keys_b2 : D.keys_b).as<uint32_t>()};
+    uint32_t* bufv[2] = {(set ? D.vals_a2 : D.vals_a).as<uint32_t>(), (set ? D.vals_b2 : D.vals_b).as<uint32_t>()};
     const SortPlan plan = SortPlan::for_bits(key_bits, (uint32_t)D.sort_digit_bits);
     if (m == 0 || m > (size_t)0x7FFFFFFF || plan.passes > SORT_MAX_PASSES || key_bits > 31) {
         set_error("internal: group too large for the sort");

@@ -4,6 +4,7 @@
 // libcozk_msm.so for the engine's internals; nothing in the product library depends on this file.
 #include "../../include/cozk_test.h"
 #include "engine.hpp"
+#include "affine_kernels.cuh"
 #include "msm_kernels.cuh"
 
 namespace cozk {
@@ -394,6 +395,100 @@ int cozk_test_sort(cozk_ctx* ctx, int device_index, const void* d_keys, const vo
     COZK_CUDA(cudaMemcpyAsync(d_keys_out, ks, m * 4, cudaMemcpyDeviceToDevice, st));
     COZK_CUDA(cudaMemcpyAsync(d_vals_out, vs, m * 4, cudaMemcpyDeviceToDevice, st));
     COZK_CUDA(cudaStreamSynchronize(st));
+    return COZK_OK;
+}
+
+// The batched-affine pre-reduction on its own (csrc/affine_kernels.cuh): `rounds` halving rounds over m pairs grouped by key
+// (vals index into d_pts).  reference == 0: the engine's batched kernels; != 0: the serial contract kernel (its own inversion per
+// addition).  Outputs (device pointers, may be NULL): the reduced list - out_m[0] entries of keys, vals (index into d_pts_out, or the
+// skip mark) and points - and per round r the overflow list at d_ovf_keys + r * ovf_stride / d_ovf_pts + r * ovf_stride (64-byte
+// points), ovf_counts[r] entries (host array).  out_ms: time of the rounds (CUDA events).
+int cozk_test_affine_rounds(cozk_ctx* ctx, int device_index, const void* d_keys, const void* d_vals, size_t m, const void* d_pts,
+                            size_t total_buckets, int rounds, int reference, void* d_keys_out, void* d_vals_out, void* d_pts_out,
+                            size_t* out_m, void* d_ovf_keys, void* d_ovf_pts, size_t ovf_stride, unsigned* ovf_counts, double* out_ms) {
+    Device* D;
+    int rc = get_device(ctx, device_index, &D);
+    if (rc) return rc;
+    if (rounds < 1 || rounds > AFF_MAX_ROUNDS || m < 2 || !out_m) return COZK_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(D->mu);
+    cudaStream_t st = D->stream;
+    cudaEvent_t e0, e1;
+    COZK_CUDA(cudaEventCreate(&e0));
+    COZK_CUDA(cudaEventCreate(&e1));
+    AffineStage AS;
+    double launches = 0;
+    std::vector<void*> tmp;
+    auto dalloc = [&](size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes + 256) != cudaSuccess) return nullptr;
+        tmp.push_back(p);
+        return p;
+    };
+    COZK_CUDA(cudaEventRecord(e0, st));
+    if (!reference) {
+        rc = affine_reduce(*D, st, 0, m, total_buckets, (const uint32_t*)d_keys, (const uint32_t*)d_vals, (const affine*)d_pts, rounds,
+                           &AS, &launches);
+    } else {
+        uint32_t* counters = (uint32_t*)dalloc(256);
+        if (!counters) return COZK_ERR_CUDA;
+        COZK_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+        const uint32_t *kin = (const uint32_t*)d_keys, *vin = (const uint32_t*)d_vals;
+        const affine* pin = (const affine*)d_pts;
+        size_t mr = m;
+        AS.rounds = rounds;
+        for (int r = 0; r < rounds && !rc; ++r) {
+            const size_t mo = affine_round_out(mr), cap = std::min(mo, total_buckets + 1);
+            AffineRoundArgs A{};
+            A.m = mr;
+            A.keys_in = kin;
+            A.vals_in = vin;
+            A.pts_in = pin;
+            A.keys_out = (uint32_t*)dalloc(mo * 4);
+            A.vals_out = (uint32_t*)dalloc(mo * 4);
+            A.pts_out = (affine*)dalloc(mo * sizeof(affine));
+            A.ovf_count = counters + r;
+            A.ovf_keys = (uint32_t*)dalloc(cap * 4);
+            A.ovf_pts = (affine*)dalloc(cap * sizeof(affine));
+            A.ovf_cap = (uint32_t)cap;
+            if (!A.keys_out || !A.vals_out || !A.pts_out || !A.ovf_keys || !A.ovf_pts) return COZK_ERR_CUDA;
+            rc = affine_round_reference(st, A);
+            AS.ovf[r] = OvfAddArgsPub{A.ovf_count, A.ovf_keys, A.ovf_pts, nullptr, A.ovf_cap};
+            kin = A.keys_out;
+            vin = A.vals_out;
+            pin = A.pts_out;
+            mr = mo;
+        }
+        AS.keys = kin;
+        AS.vals = vin;
+        AS.pts = pin;
+        AS.m = mr;
+    }
+    if (rc) return rc;
+    COZK_CUDA(cudaEventRecord(e1, st));
+    *out_m = AS.m;
+    if (d_keys_out) COZK_CUDA(cudaMemcpyAsync(d_keys_out, AS.keys, AS.m * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_vals_out) COZK_CUDA(cudaMemcpyAsync(d_vals_out, AS.vals, AS.m * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_pts_out) COZK_CUDA(cudaMemcpyAsync(d_pts_out, AS.pts, AS.m * sizeof(affine), cudaMemcpyDeviceToDevice, st));
+    for (int r = 0; r < rounds; ++r) {
+        uint32_t cnt = 0;
+        COZK_CUDA(cudaMemcpyAsync(&cnt, AS.ovf[r].count, 4, cudaMemcpyDeviceToHost, st));
+        COZK_CUDA(cudaStreamSynchronize(st));
+        if (cnt > AS.ovf[r].cap || cnt > ovf_stride) {
+            set_error("overflow list of a round outgrew its bound");
+            return COZK_ERR_INVALID_ARG;
+        }
+        if (ovf_counts) ovf_counts[r] = cnt;
+        if (d_ovf_keys && cnt) COZK_CUDA(cudaMemcpyAsync((uint32_t*)d_ovf_keys + r * ovf_stride, AS.ovf[r].keys, cnt * 4, cudaMemcpyDeviceToDevice, st));
+        if (d_ovf_pts && cnt)
+            COZK_CUDA(cudaMemcpyAsync((affine*)d_ovf_pts + r * ovf_stride, AS.ovf[r].pts, cnt * sizeof(affine), cudaMemcpyDeviceToDevice, st));
+    }
+    COZK_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    COZK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (out_ms) *out_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    for (void* p : tmp) cudaFree(p);
     return COZK_OK;
 }
 

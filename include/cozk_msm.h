@@ -119,8 +119,9 @@ int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, const void* sca
  * that many (vector, point) pairs looks for windows in which (nearly) every scalar has the same digit - the constant and
  * nearly constant share vectors of co-jolt (co-jolt/src/poly/dense_mlpoly.rs:567-585) - and replaces those pairs by the
  * precomputed sum of the table row.  Same result, far fewer additions; uniform vectors pay one look at a sample.
- * "stream_min_points" (default 2^20; 0 = never) / "stream_chunks" (0 = auto): a single HOST vector of at least that many
- * points is cut into chunks whose H2D copies, sorts and accumulate levels run as a pipeline on three streams.
+ * "stream_min_points" (host vectors) / "chunk_min_points" (device-resident vectors; both default 2^20, 0 = never) /
+ * "stream_chunks" (0 = auto): a single vector of at least that many points is cut into chunks whose H2D copies, sorts and
+ * accumulate levels run as a pipeline on several streams (same result: the chunks share one bucket set).
  * "acc_chunk", "acc_chunk_up", "group_l", "sort_digit_bits", "table_window", "open_small_log2", "peer_direct", "bulk_copy",
  * "chi_waves", "stream_min_points_sliced": tuning knobs, see msm.cu / engine.hpp (defaults are the measured optima). */
 int cozk_set_option(cozk_ctx* ctx, const char* name, long value);

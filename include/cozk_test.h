@@ -33,6 +33,15 @@ int cozk_test_sort(cozk_ctx* ctx, int device_index, const void* d_keys, const vo
                    const void* d_scalars, size_t n, unsigned g, size_t stride, int form, unsigned c, unsigned windows,
                    size_t table_stride, size_t val_offset, int fused, void* d_keys_out, void* d_vals_out);
 
+/* The batched-affine pre-reduction on its own (csrc/affine_kernels.cuh): `rounds` halving rounds over m pairs grouped by key
+ * (vals index into d_pts: 64-byte affine points; bit 31 = negate; all ones = skip).  reference == 0: the engine's batched kernels,
+ * != 0: the serial contract kernel.  Outputs (device pointers, may be NULL): the reduced list of out_m[0] entries, and per round r the
+ * overflow list at d_ovf_keys + r * ovf_stride entries / d_ovf_pts + r * ovf_stride points, ovf_counts[r] entries (host array).
+ * out_ms: time of the rounds. */
+int cozk_test_affine_rounds(cozk_ctx* ctx, int device_index, const void* d_keys, const void* d_vals, size_t m, const void* d_pts,
+                            size_t total_buckets, int rounds, int reference, void* d_keys_out, void* d_vals_out, void* d_pts_out,
+                            size_t* out_m, void* d_ovf_keys, void* d_ovf_pts, size_t ovf_stride, unsigned* ovf_counts, double* out_ms);
+
 #ifdef __cplusplus
 }
 #endif

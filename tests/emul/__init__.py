@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         deps = [os.path.join(HERE, "emul.cpp")] + [os.path.join(CSRC, f) for f in
-                                                   ("field.cuh", "curve.cuh", "msm_kernels.cuh", "msm_plan.hpp", "rep3_kernels.cuh")]
+                                                   ("field.cuh", "curve.cuh", "msm_kernels.cuh", "affine_kernels.cuh", "msm_plan.hpp", "rep3_kernels.cuh")]
         if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
             os.makedirs(os.path.dirname(LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB,
@@ -27,6 +27,12 @@ def lib():
         L.emul_choose_window.restype = None
         L.emul_set_dominant.argtypes = [ci]
         L.emul_set_dominant.restype = None
+        L.emul_set_affine_rounds.argtypes = [ci]
+        L.emul_set_affine_rounds.restype = None
+        L.emul_affine_stats.argtypes = [vp]
+        L.emul_affine_stats.restype = None
+        L.emul_affine_round.argtypes = [vp, vp, sz, vp, vp, vp, vp, vp, vp, vp, u32]
+        L.emul_affine_round.restype = None
         L.emul_set_acc_chunk.argtypes = [sz, ci]
         L.emul_set_acc_chunk.restype = None
         L.emul_field_op.argtypes = [ci, vp, vp, vp, sz]
@@ -58,6 +64,34 @@ def set_dominant(on):
     """1: calls that cover the whole SRS go through the engine's dominant-digit path (analysis pass, compacted segments,
     row totals); 0: the plain pair layout."""
     lib().emul_set_dominant(1 if on else 0)
+
+
+def set_affine_rounds(rounds):
+    """> 0: the batched-affine pre-reduction runs in front of the accumulate levels, with the engine's rule for how many rounds
+    pay (msm.cu, affine_rounds_for); < 0: exactly -rounds rounds whatever the run lengths; 0: off."""
+    lib().emul_set_affine_rounds(rounds)
+
+
+def affine_stats():
+    """(entries of the reduced list, overflow entries of all rounds) of the last chunk of the last msm() call."""
+    out = np.zeros(2, np.uint32)
+    lib().emul_affine_stats(_p(out))
+    return int(out[0]), int(out[1])
+
+
+def affine_round(keys, vals, pts, cap=None):
+    """One halving round of the contract body: ((keys, vals, points), (overflow keys, overflow points))."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    vals = np.ascontiguousarray(vals, dtype=np.uint32)
+    pts = np.ascontiguousarray(pts, dtype=np.uint8)
+    m = keys.size
+    mo = (m + 1) // 2
+    cap = mo if cap is None else cap
+    ko, vo, po = np.zeros(mo, np.uint32), np.zeros(mo, np.uint32), np.zeros((mo, 64), np.uint8)
+    cnt, ok, op = np.zeros(1, np.uint32), np.zeros(max(cap, 1), np.uint32), np.zeros((max(cap, 1), 64), np.uint8)
+    lib().emul_affine_round(_p(keys), _p(vals), m, _p(pts), _p(ko), _p(vo), _p(po), _p(cnt), _p(ok), _p(op), cap)
+    c = int(cnt[0])
+    return (ko, vo, po), (ok[:c], op[:c])
 
 
 def set_acc_chunk(resident=0, force_l=0):

@@ -11,6 +11,7 @@
 #include <numeric>
 #include <vector>
 
+#include "../../co-zkvms_b200/csrc/affine_kernels.cuh"
 #include "../../co-zkvms_b200/csrc/msm_kernels.cuh"
 #include "../../co-zkvms_b200/csrc/msm_plan.hpp"
 #include "../../co-zkvms_b200/csrc/rep3_kernels.cuh"
@@ -21,10 +22,25 @@ using namespace cozk;
 static AccTuning g_acc;  // emul_set_acc_chunk
 static uint32_t g_last_pairs = 0, g_last_dominant = 0;  // of the last chunk of the last emul_msm call (stats[4], stats[5])
 static int g_dominant = 0;  // 1: run the dominant-digit path of the engine (whole-SRS calls)
+static int g_affine_rounds = 0;  // > 0: the batched-affine pre-reduction in front of the accumulate levels (contract body)
+static uint32_t g_last_overflow = 0, g_last_reduced = 0;  // of the last chunk: overflow entries of all rounds, entries of the reduced list
 
 extern "C" {
 
 void emul_set_dominant(int on) { g_dominant = on; }
+void emul_set_affine_rounds(int rounds) { g_affine_rounds = rounds; }
+void emul_affine_stats(uint32_t* out) {
+    out[0] = g_last_reduced;
+    out[1] = g_last_overflow;
+}
+// `rounds` halving rounds through the contract body; outputs sized by the caller ((m + 1) / 2 entries for one round)
+void emul_affine_round(const uint32_t* keys, const uint32_t* vals, size_t m, const uint8_t* pts, uint32_t* keys_out, uint32_t* vals_out,
+                       uint8_t* pts_out, uint32_t* ovf_count, uint32_t* ovf_keys, uint8_t* ovf_pts, uint32_t ovf_cap) {
+    AffineRoundArgs A{m, keys, vals, reinterpret_cast<const affine*>(pts), keys_out, vals_out, reinterpret_cast<affine*>(pts_out),
+                      ovf_count, ovf_keys, reinterpret_cast<affine*>(ovf_pts), ovf_cap, nullptr, nullptr};
+    *ovf_count = 0;
+    for (size_t o = 0; o < affine_round_out(m); ++o) affine_round_body(o, A);
+}
 
 // The plan's window choice with the caller's stack poisoned first (choose_window once read cost[] entries it had
 // never written).  out[0] = c (0 = no window fits), out[1] = max_group_for(n, g, ...).
@@ -161,6 +177,38 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             scratch.resize(P.total_buckets);
             memset(scratch.data(), 0, scratch.size() * sizeof(xyzz));
         }
+        // batched-affine pre-reduction (the engine's affine_rounds_for rule), then the accumulate levels over the reduced list
+        std::vector<std::vector<uint32_t>> rk, rv, ok;
+        std::vector<std::vector<affine>> rp, op;
+        std::vector<uint32_t> ocount;
+        {
+            int R = g_affine_rounds < 0 ? -g_affine_rounds : g_affine_rounds;  // negative: exactly that many rounds, whatever the run lengths
+            while (g_affine_rounds > 0 && R > 0 && (Pc.m >> R) < 4 * Pc.total_buckets) --R;
+            while (R > 0 && (Pc.m >> (R - 1)) < 2) --R;
+            const uint32_t *kin = sk.data(), *vin = sv.data();
+            const affine* pin = chunk_bases;
+            size_t mr = Pc.m;
+            rk.resize(R), rv.resize(R), rp.resize(R), ok.resize(R), op.resize(R), ocount.assign(R, 0);
+            g_last_overflow = 0;
+            for (int r = 0; r < R; ++r) {
+                const size_t mo = affine_round_out(mr), cap = std::min(mo, Pc.total_buckets + 1);
+                rk[r].assign(mo, 0xDEADBEEFu), rv[r].assign(mo, 0xDEADBEEFu), rp[r].resize(mo), ok[r].resize(cap), op[r].resize(cap);
+                AffineRoundArgs A{mr, kin, vin, pin, rk[r].data(), rv[r].data(), rp[r].data(), &ocount[r], ok[r].data(), op[r].data(),
+                                  (uint32_t)cap, nullptr, nullptr};
+                for (size_t o = 0; o < mo; ++o) affine_round_body(o, A);
+                if (ocount[r] > cap) return 3;
+                g_last_overflow += ocount[r];
+                kin = rk[r].data(), vin = rv[r].data(), pin = rp[r].data();
+                mr = mo;
+            }
+            if (R > 0) {
+                plan_set_pairs(Pc, mr);
+                sk.assign(kin, kin + mr);
+                sv.assign(vin, vin + mr);
+                chunk_bases = pin;
+            }
+            g_last_reduced = (uint32_t)mr;
+        }
         for (size_t lvl = 0; lvl < Pc.acc_entries.size(); ++lvl) {
             size_t m = Pc.acc_entries[lvl];
             const int tile = Pc.acc_tile[lvl];
@@ -178,6 +226,10 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
             }
             pk_in.swap(pk_out);
             pp_in.swap(pp_out);
+        }
+        for (size_t r = 0; r < ocount.size(); ++r) {
+            OvfAddArgs OA{&ocount[r], ok[r].data(), op[r].data(), ci > 0 ? scratch.data() : buckets.data(), (uint32_t)ok[r].size()};
+            for (size_t i = 0; i < ocount[r]; ++i) ovf_add_body(i, OA);
         }
         if (ci > 0) {
             MergeArgs MA{buckets.data(), scratch.data(), P.total_buckets};
