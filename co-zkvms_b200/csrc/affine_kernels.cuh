@@ -175,6 +175,9 @@ COZK_HD void ovf_add_body(size_t i, const OvfAddArgs& A) {
 #ifndef COZK_AFF_K
 #define COZK_AFF_K 16
 #endif
+#ifndef COZK_AFF_PREFETCH
+#define COZK_AFF_PREFETCH 0
+#endif
 #ifndef COZK_AFF_MINBLOCKS
 #define COZK_AFF_MINBLOCKS 3
 #endif
@@ -292,13 +295,33 @@ __global__ void __launch_bounds__(AFF_T, COZK_AFF_MINBLOCKS) k_affine_apply(Affi
     }
     __syncthreads();
     fq inv_run = aff_ld(S->red, t);  // 1 / (d_0 .. d_{K-1}) of this thread
+#if COZK_AFF_PREFETCH
+    // the points of step k - 1 are requested before the arithmetic of step k starts
+    affine q0, q1;
+    q0.x = q0.y = q1.x = q1.y = fq_zero();
+    if (((codes >> (2 * (AFF_K - 1))) & 3u) >= AFF_ADD) {
+        const size_t o = aff_out_index(batch, AFF_K - 1, t);
+        q0 = affine_load_signed(A.pts_in, A.vals_in[2 * o]);
+        q1 = affine_load_signed(A.pts_in, A.vals_in[2 * o + 1]);
+    }
+#endif
 #pragma unroll 1
     for (int k = AFF_K - 1; k >= 0; --k) {
         const uint32_t code = (codes >> (2 * k)) & 3u;
         const size_t o = aff_out_index(batch, k, t);
+#if COZK_AFF_PREFETCH
+        const affine p0 = q0, p1 = q1;
+        if (k > 0 && ((codes >> (2 * (k - 1))) & 3u) >= AFF_ADD) {
+            const size_t on = aff_out_index(batch, k - 1, t);
+            q0 = affine_load_signed(A.pts_in, A.vals_in[2 * on]);
+            q1 = affine_load_signed(A.pts_in, A.vals_in[2 * on + 1]);
+        }
+#endif
         if (code >= AFF_ADD) {
+#if !COZK_AFF_PREFETCH
             const uint32_t v0 = A.vals_in[2 * o], v1 = A.vals_in[2 * o + 1];
             const affine p0 = affine_load_signed(A.pts_in, v0), p1 = affine_load_signed(A.pts_in, v1);
+#endif
             const fq d = code == AFF_ADD ? fq_sub(p1.x, p0.x) : fq_dbl(p0.y);
             fq inv_d = inv_run;
             if (k > 0) {

@@ -530,7 +530,9 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             const size_t C = (size_t)stream_chunks;
             std::vector<size_t> cstart;  // chunk ci covers [cstart[ci], cstart[ci + 1])
             {
-                const size_t first = std::min(pn, std::max<size_t>(32, ((pn / (2 * C)) + 31) & ~(size_t)31));
+                // option "stream_first_pct": the first chunk's share of an equal share, in percent (default 50)
+                const size_t pct = (size_t)std::max<long>(1, std::min<long>(100 * (long)C, ctx->opt_stream_first_pct));
+                const size_t first = std::min(pn, std::max<size_t>(32, ((pn * pct / (100 * C)) + 31) & ~(size_t)31));
                 const size_t rest = C > 1 ? ((((pn - first) + (C - 1) - 1) / (C - 1)) + 31) & ~(size_t)31 : 0;
                 cstart.push_back(0);
                 for (size_t at = first; at < pn; at += std::max<size_t>(rest, 32)) cstart.push_back(at);
@@ -1524,6 +1526,9 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "stream_min_points_sliced")) {
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points_sliced = value;
+    } else if (!strcmp(name, "stream_first_pct")) {
+        if (value < 1 || value > 6400) return COZK_ERR_INVALID_ARG;
+        ctx->opt_stream_first_pct = value;
     } else if (!strcmp(name, "stream_chunks")) {
         if (value < 0 || value > 64) return COZK_ERR_INVALID_ARG;  // 0 = chosen from the vector length
         ctx->opt_stream_chunks = value;
