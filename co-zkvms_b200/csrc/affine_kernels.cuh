@@ -211,12 +211,67 @@ __device__ __forceinline__ fq aff_shfl_xor(const fq& a, int s) {
 // output handled by thread t at step k of batch `batch`: consecutive threads take consecutive outputs
 __device__ __forceinline__ size_t aff_out_index(size_t batch, int k, int t) { return batch * AFF_BATCH + (size_t)k * AFF_T + t; }
 
+// What the forward pass needs of output o, loaded without looking at it: the loads of several steps are in flight together.
+struct AffLoaded {
+    uint32_t state;  // AFF_NOP, AFF_PASS, or AFF_ADD = a pair of live entries of one bucket whose x coordinates are loaded
+    uint32_t v0, v1;
+    fq x0, x1;
+};
+__device__ __forceinline__ void aff_issue(size_t o, const AffineRoundArgs& A, AffLoaded& L) {
+    L.state = AFF_NOP;
+    if (o >= affine_round_out(A.m)) return;
+    L.state = AFF_PASS;
+    const size_t i0 = 2 * o;
+    if (i0 + 1 >= A.m) return;
+    const uint2 kk = *reinterpret_cast<const uint2*>(A.keys_in + i0), vv = *reinterpret_cast<const uint2*>(A.vals_in + i0);
+    L.v0 = vv.x;
+    L.v1 = vv.y;
+    if (kk.x != kk.y || vv.x == VAL_SKIP || vv.y == VAL_SKIP || affine_key_null(kk.x)) return;
+    L.state = AFF_ADD;
+    L.x0 = load_fq(&A.pts_in[vv.x & ~VAL_NEG].x);
+    L.x1 = load_fq(&A.pts_in[vv.y & ~VAL_NEG].x);
+}
+// same decision and denominator as affine_classify
+__device__ __forceinline__ uint32_t aff_decide(const AffLoaded& L, const AffineRoundArgs& A, fq& d) {
+    if (L.state != AFF_ADD) return L.state;
+    if (!fq_eq(L.x0, L.x1)) {
+        d = fq_sub(L.x1, L.x0);
+        return AFF_ADD;
+    }
+    const fq y0 = fq_cneg(load_fq(&A.pts_in[L.v0 & ~VAL_NEG].y), (L.v0 & VAL_NEG) != 0);
+    const fq y1 = fq_cneg(load_fq(&A.pts_in[L.v1 & ~VAL_NEG].y), (L.v1 & VAL_NEG) != 0);
+    if (fq_eq(y0, y1) && !fq_is_zero(y0)) {
+        d = fq_dbl(y0);
+        return AFF_DBL;
+    }
+    return AFF_PASS;
+}
+
 // Forward pass of one thread: the product of its AFF_K denominators (1 for an output without an addition); KEEP: the prefix
 // products go to shared memory.  codes: 2 bits per step.
 template <bool KEEP>
 __device__ __forceinline__ fq aff_forward(const AffineRoundArgs& A, size_t batch, int t, AffineSmem* S, uint32_t& codes) {
     fq run = fq_one();
     codes = 0;
+#if COZK_AFF_PREFETCH
+    constexpr int G = 4;  // steps whose loads are in flight together
+    static_assert(AFF_K % G == 0, "AFF_K must be a multiple of 4");
+#pragma unroll 1
+    for (int k0 = 0; k0 < AFF_K; k0 += G) {
+        AffLoaded L[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) aff_issue(aff_out_index(batch, k0 + j, t), A, L[j]);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int k = k0 + j;
+            fq d;
+            const uint32_t code = aff_decide(L[j], A, d);
+            codes |= code << (2 * k);
+            if (KEEP && k > 0) aff_st(S->pre + (size_t)(k - 1) * 2 * AFF_T, t, run);
+            if (code >= AFF_ADD) run = k == 0 ? d : fq_mul(run, d);
+        }
+    }
+#else
 #pragma unroll 1
     for (int k = 0; k < AFF_K; ++k) {
         fq d;
@@ -225,6 +280,7 @@ __device__ __forceinline__ fq aff_forward(const AffineRoundArgs& A, size_t batch
         if (KEEP && k > 0) aff_st(S->pre + (size_t)(k - 1) * 2 * AFF_T, t, run);
         if (code >= AFF_ADD) run = k == 0 ? d : fq_mul(run, d);
     }
+#endif
     return run;
 }
 
@@ -296,13 +352,16 @@ __global__ void __launch_bounds__(AFF_T, COZK_AFF_MINBLOCKS) k_affine_apply(Affi
     __syncthreads();
     fq inv_run = aff_ld(S->red, t);  // 1 / (d_0 .. d_{K-1}) of this thread
 #if COZK_AFF_PREFETCH
-    // the points of step k - 1 are requested before the arithmetic of step k starts
+    // the points of step k - 1 are requested before the arithmetic of step k starts (raw: the sign is applied where they are used)
     affine q0, q1;
+    uint32_t qv0 = 0, qv1 = 0;
     q0.x = q0.y = q1.x = q1.y = fq_zero();
     if (((codes >> (2 * (AFF_K - 1))) & 3u) >= AFF_ADD) {
         const size_t o = aff_out_index(batch, AFF_K - 1, t);
-        q0 = affine_load_signed(A.pts_in, A.vals_in[2 * o]);
-        q1 = affine_load_signed(A.pts_in, A.vals_in[2 * o + 1]);
+        const uint2 vv = *reinterpret_cast<const uint2*>(A.vals_in + 2 * o);
+        qv0 = vv.x, qv1 = vv.y;
+        q0 = load_affine(&A.pts_in[qv0 & ~VAL_NEG]);
+        q1 = load_affine(&A.pts_in[qv1 & ~VAL_NEG]);
     }
 #endif
 #pragma unroll 1
@@ -310,11 +369,18 @@ __global__ void __launch_bounds__(AFF_T, COZK_AFF_MINBLOCKS) k_affine_apply(Affi
         const uint32_t code = (codes >> (2 * k)) & 3u;
         const size_t o = aff_out_index(batch, k, t);
 #if COZK_AFF_PREFETCH
-        const affine p0 = q0, p1 = q1;
+        affine p0 = q0, p1 = q1;
+        const uint32_t pv0 = qv0, pv1 = qv1;
         if (k > 0 && ((codes >> (2 * (k - 1))) & 3u) >= AFF_ADD) {
             const size_t on = aff_out_index(batch, k - 1, t);
-            q0 = affine_load_signed(A.pts_in, A.vals_in[2 * on]);
-            q1 = affine_load_signed(A.pts_in, A.vals_in[2 * on + 1]);
+            const uint2 vv = *reinterpret_cast<const uint2*>(A.vals_in + 2 * on);
+            qv0 = vv.x, qv1 = vv.y;
+            q0 = load_affine(&A.pts_in[qv0 & ~VAL_NEG]);
+            q1 = load_affine(&A.pts_in[qv1 & ~VAL_NEG]);
+        }
+        if (code >= AFF_ADD) {
+            p0.y = fq_cneg(p0.y, (pv0 & VAL_NEG) != 0);
+            p1.y = fq_cneg(p1.y, (pv1 & VAL_NEG) != 0);
         }
 #endif
         if (code >= AFF_ADD) {

@@ -30,6 +30,7 @@ ap.add_argument("--group-l", type=int, default=0, help="buckets per thread in th
 ap.add_argument("--exact", action="store_true", help="register an SRS of exactly each size (the bench's shape) instead of prefixes of the largest")
 ap.add_argument("--dominant", type=int, default=-1, help="-1 default, 0 off, 1 on (dominant-digit mode of whole-SRS calls)")
 ap.add_argument("--stream-first-pct", type=int, default=0)
+ap.add_argument("--chunk-min", type=int, default=-1, help="chunk_min_points option: device-resident vectors this long run in chunks (0 never)")
 ap.add_argument("--affine-rounds", type=int, default=-1, help="batched-affine pre-reduction rounds (-1 default, 0 off)")
 ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
@@ -47,6 +48,8 @@ if args.sort_bits:
     ctx.set_option("sort_digit_bits", args.sort_bits)
 if args.group_l:
     ctx.set_option("group_l", args.group_l)
+if args.chunk_min >= 0:
+    ctx.set_option("chunk_min_points", args.chunk_min)
 if args.stream_first_pct:
     ctx.set_option("stream_first_pct", args.stream_first_pct)
 if args.affine_rounds >= 0:
