@@ -122,7 +122,10 @@ int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, const void* sca
  * "stream_min_points" (host vectors) / "chunk_min_points" (device-resident vectors; both default 2^20, 0 = never) /
  * "stream_chunks" (0 = auto): a single vector of at least that many points is cut into chunks whose H2D copies, sorts and
  * accumulate levels run as a pipeline on several streams (same result: the chunks share one bucket set).
- * "acc_chunk", "acc_chunk_up", "group_l", "sort_digit_bits", "table_window", "open_small_log2", "peer_direct", "bulk_copy",
+ * "affine_rounds" (default 0 = off) / "affine_min_pairs": halving rounds of batched-affine additions (shared inversions) over
+ * the sorted pair list in front of the XYZZ accumulate levels - same result; measured slower than the XYZZ kernel alone on
+ * B200 (profiles/round2_affine.md), kept as an option.
+ * "acc_chunk", "acc_chunk_up", "stream_first_pct", "group_l", "sort_digit_bits", "table_window", "open_small_log2", "peer_direct", "bulk_copy",
  * "chi_waves", "stream_min_points_sliced": tuning knobs, see msm.cu / engine.hpp (defaults are the measured optima). */
 int cozk_set_option(cozk_ctx* ctx, const char* name, long value);
 /* Timings (ms, CUDA events) of the stages of the last cozk_msm_batch* call on device 0 of the context:
