@@ -54,6 +54,55 @@ __global__ void __launch_bounds__(ACC_TILE) k_treesum(TreeSumArgs A) {
     }
     if (t == 0) store_xyzz(&A.out[(win * A.NS + id) * (size_t)A.chunks + q], acc);
 }
+// block-wide sum of one value per thread (tree in shared memory); valid in thread 0
+__device__ __forceinline__ xyzz block_tree_sum(ShPoints& sp, xyzz acc) {
+    const int t = threadIdx.x;
+    sh_store(sp, t, acc);
+    __syncthreads();
+    for (int d = ACC_TILE / 2; d > 0; d >>= 1) {
+        if (t < d) {
+            acc = xyzz_add(acc, sh_load(sp, t + d));
+            sh_store(sp, t, acc);
+        }
+        __syncthreads();
+    }
+    return acc;
+}
+// Row / column form of the bucket reduce (MsmPlan::reduce_2d; output contracts: rowcol_body, masksum_body).
+__global__ void __launch_bounds__(ACC_TILE) k_rowcol(RowColArgs A) {
+    __shared__ ShPoints sp;
+    const size_t rows = (size_t)1 << A.hi_bits, cols = (size_t)1 << A.lo_bits;
+    const size_t blk = blockIdx.x, win = blk / (rows + cols), i = blk % (rows + cols);
+    const xyzz* b = A.buckets + win * rows * cols;
+    xyzz acc = xyzz_identity();
+    if (i < rows) {
+        for (size_t e = threadIdx.x; e < cols; e += ACC_TILE) acc = xyzz_add(acc, load_xyzz(&b[i * cols + e]));
+    } else {
+        for (size_t e = threadIdx.x; e < rows; e += ACC_TILE) acc = xyzz_add(acc, load_xyzz(&b[e * cols + (i - rows)]));
+    }
+    acc = block_tree_sum(sp, acc);
+    if (threadIdx.x == 0) store_xyzz(&A.rc[blk], acc);
+}
+__global__ void __launch_bounds__(ACC_TILE) k_masksum(MaskSumArgs A) {
+    __shared__ ShPoints sp;
+    const size_t rows = (size_t)1 << A.hi_bits, cols = (size_t)1 << A.lo_bits;
+    const size_t blk = blockIdx.x, win = blk / A.NS;
+    const uint32_t id = (uint32_t)(blk % A.NS);
+    const xyzz* r = A.rc + win * (rows + cols);
+    const xyzz* c = r + rows;
+    xyzz acc = xyzz_identity();
+    if (id == 1) {
+        for (size_t e = threadIdx.x; e < cols; e += ACC_TILE) acc = xyzz_add(acc, load_xyzz(&c[e]));
+    } else if (id >= 2 && id - 2 < A.lo_bits) {
+        for (size_t e = threadIdx.x; e < cols; e += ACC_TILE)
+            if ((e >> (id - 2)) & 1u) acc = xyzz_add(acc, load_xyzz(&c[e]));
+    } else if (id >= 2) {
+        for (size_t e = threadIdx.x; e < rows; e += ACC_TILE)
+            if ((e >> (id - 2 - A.lo_bits)) & 1u) acc = xyzz_add(acc, load_xyzz(&r[e]));
+    }
+    acc = block_tree_sum(sp, acc);
+    if (threadIdx.x == 0) store_xyzz(&A.out[blk], acc);
+}
 __global__ void __launch_bounds__(32) k_finish(FinishArgs A) {
     finish_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, A);
 }
@@ -63,5 +112,7 @@ void launch_merge(const MergeArgs& A, unsigned blocks, cudaStream_t st) { k_merg
 void launch_group(const GroupArgs& A, unsigned blocks, cudaStream_t st) { k_group<<<blocks, 64, 0, st>>>(A); }
 void launch_treesum(const TreeSumArgs& A, unsigned blocks, cudaStream_t st) { k_treesum<<<blocks, ACC_TILE, 0, st>>>(A); }
 void launch_finish(const FinishArgs& A, unsigned blocks, cudaStream_t st) { k_finish<<<blocks, 32, 0, st>>>(A); }
+void launch_rowcol(const RowColArgs& A, cudaStream_t st) { k_rowcol<<<(unsigned)A.blocks, ACC_TILE, 0, st>>>(A); }
+void launch_masksum(const MaskSumArgs& A, cudaStream_t st) { k_masksum<<<(unsigned)A.blocks, ACC_TILE, 0, st>>>(A); }
 
 }  // namespace cozk

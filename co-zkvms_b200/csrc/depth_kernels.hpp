@@ -51,5 +51,7 @@ void launch_merge(const MergeArgs& A, unsigned blocks, cudaStream_t st);        
 void launch_group(const GroupArgs& A, unsigned blocks, cudaStream_t st);                  // 64 threads per block
 void launch_treesum(const TreeSumArgs& A, unsigned blocks, cudaStream_t st);              // ACC_TILE threads per block
 void launch_finish(const FinishArgs& A, unsigned blocks, cudaStream_t st);                // 32 threads per block
+void launch_rowcol(const RowColArgs& A, cudaStream_t st);                                 // A.blocks blocks of ACC_TILE threads
+void launch_masksum(const MaskSumArgs& A, cudaStream_t st);                               // A.blocks blocks of ACC_TILE threads
 
 }  // namespace cozk

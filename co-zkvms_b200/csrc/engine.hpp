@@ -245,6 +245,7 @@ struct cozk_ctx {
                                                          // streams (msm.cu): 2^20 3.78 -> 3.70 ms in 2 chunks (3.84 / 3.98 in 3 / 4), 2^21 7.02 -> 6.80, 2^22 12.3 -> 12.15
     std::atomic<long> opt_stream_min_points_sliced = 1L << 20;  // the same threshold for the parts of a call over a sliced SRS: several devices
                                                                 // copy from one host buffer at once, every copy is slower, overlap pays earlier
+    std::atomic<long> opt_reduce_2d = 0;                  // bucket reduce in row / column form (msm_plan.hpp, MsmPlan::reduce_2d)
     std::atomic<long> opt_affine_rounds = 0;              // batched-affine pre-reduction rounds in front of the accumulate levels (affine_kernels.cuh); 0 = off
     std::atomic<long> opt_affine_min_pairs = 1L << 20;    // ... for pair lists of at least this many entries
     std::atomic<long> opt_chunk_min_points = 0;           // device-resident single vectors this long run in chunks too (0 = never, the default).  Measured: there

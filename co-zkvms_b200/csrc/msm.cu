@@ -313,8 +313,28 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     }  // phase bit 0
     if (!(phases & 2)) return COZK_OK;
 
-    // 4 bucket reduce: group running sums, then NS plain sums per window
+    // 4 bucket reduce.  Row / column form: two block-cooperative tree sums.  Group form: group running sums, then NS plain
+    // sums per window.
     size_t windows = (size_t)P.g * P.Wb;
+    size_t nsums = windows * P.NS;
+    xyzz* cur = nullptr;
+    if (P.reduce_2d) {
+        const size_t rc_n = windows * (((size_t)1 << P.hi_bits) + ((size_t)1 << P.lo_bits));
+        if (rc_n > 0x7FFFFFFFull || nsums > 0x7FFFFFFFull) {
+            set_error("internal: too many bucket sets for the row / column reduce");
+            return COZK_ERR_INVALID_ARG;
+        }
+        if ((rc = D.rs[0].ensure(rc_n * sizeof(xyzz)))) return rc;
+        if ((rc = D.rs[1].ensure(nsums * sizeof(xyzz)))) return rc;
+        RowColArgs RA{D.buckets.as<xyzz>(), D.rs[0].as<xyzz>(), P.lo_bits, P.hi_bits, rc_n};
+        launch_rowcol(RA, st);
+        COZK_CUDA(cudaGetLastError());
+        MaskSumArgs MA{D.rs[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.lo_bits, P.hi_bits, P.NS, nsums};
+        launch_masksum(MA, st);
+        COZK_CUDA(cudaGetLastError());
+        *launches += 2;
+        cur = D.rs[1].as<xyzz>();
+    } else {
     size_t groups = windows * P.G;
     if ((rc = D.rs[0].ensure(groups * sizeof(xyzz)))) return rc;
     if ((rc = D.rw[0].ensure(groups * sizeof(xyzz)))) return rc;
@@ -322,20 +342,20 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     launch_group(GA, grid_for(groups, 64), st);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
-    size_t nsums = windows * P.NS;
     if ((rc = D.rs[1].ensure(nsums * P.sum_chunks * sizeof(xyzz)))) return rc;
     if ((rc = D.rw[1].ensure(nsums * sizeof(xyzz)))) return rc;
     TreeSumArgs TA{D.rs[0].as<xyzz>(), D.rw[0].as<xyzz>(), D.rs[1].as<xyzz>(), P.G, P.NS, P.sum_chunk, P.sum_chunks, 1};
     launch_treesum(TA, (unsigned)(windows * P.NS * P.sum_chunks), st);
     *launches += 1;
     COZK_CUDA(cudaGetLastError());
-    xyzz* cur = D.rs[1].as<xyzz>();
+    cur = D.rs[1].as<xyzz>();
     if (P.sum_chunks > 1) {
         TreeSumArgs TB{cur, nullptr, D.rw[1].as<xyzz>(), P.sum_chunks, P.NS, P.sum_chunks, 1, 0};
         launch_treesum(TB, (unsigned)(windows * P.NS), st);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
         cur = D.rw[1].as<xyzz>();
+    }
     }
     COZK_CUDA(cudaEventRecord(D.ev[5], st));
 
@@ -456,7 +476,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
     double plan_mults = 0, plan_pairs = 0, host_finish_ms = 0;
     uint32_t last_c = 0, last_W = 0;
     // k_accumulate<true>: 4 blocks of 128 threads per SM are resident
-    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l};
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l,
+                               (int)ctx->opt_reduce_2d};
 
     for (size_t pass = 0; pass < passes; ++pass) {
         size_t lo = pass * per_pass;
@@ -516,6 +537,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             }
         }
         if (stream_it) {
+            // (as a lambda: a failure in the middle must not leave work of this call pending on the side streams)
+            const int crc = [&]() -> int {
             // Pipeline without host synchronisation:
             //   copy   H2D of chunk i + 1 into staging slot (i + 1) & 1 (waits until the sort of chunk i - 1 has consumed it)
             //   prep   decompose + sort of chunk i into sort-buffer set i & 1 (high priority: its blocks get the next SM that
@@ -649,6 +672,12 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                 FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out};
                 finish_body(0, F);
                 host_finish_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+            }
+            return COZK_OK;
+            }();
+            if (crc) {
+                cudaDeviceSynchronize();
+                return crc;
             }
             continue;
         }
@@ -1188,7 +1217,8 @@ int msm_ragged_device(cozk_ctx* ctx, int device, cozk_srs srs, const size_t* off
     h_start[k] = (uint32_t)total;
     const size_t max_buckets = (size_t)1 << 25;
     Device& D = *ctx->devs[device];
-    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l};
+    const AccTuning acc_tuning{(size_t)D.sm_count * 512, (int)ctx->opt_acc_chunk, (int)ctx->opt_acc_chunk_up, (int)ctx->opt_group_l,
+                               (int)ctx->opt_reduce_2d};
     MsmPlan P = make_plan((total + k - 1) / k, (uint32_t)k, 254, max_buckets, (uint32_t)ctx->opt_window, ctx->opt_window ? 0 : S.table_c,
                           acc_tuning);
     const bool table = !ctx->opt_window && S.table_c != 0;
@@ -1513,6 +1543,10 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // a single host-resident vector of at least this many points is streamed in chunks (0 = never)
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points = value;
+    } else if (!strcmp(name, "reduce_2d")) {
+        // bucket reduce: 1 = row / column form (two tree sums), 0 = group running sums + masked sums
+        if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;
+        ctx->opt_reduce_2d = value;
     } else if (!strcmp(name, "affine_rounds")) {
         // halving rounds of the batched-affine pre-reduction in front of the accumulate levels (0 = off)
         if (value < 0 || value > AFF_MAX_ROUNDS) return COZK_ERR_INVALID_ARG;

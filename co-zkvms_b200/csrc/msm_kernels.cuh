@@ -472,6 +472,57 @@ COZK_HD void plainsum_body(size_t tid, const PlainSumArgs& A) {
     store_xyzz(&A.out[tid], acc);
 }
 
+// Row / column form (MsmPlan::reduce_2d).  Serial output contracts of the two block-cooperative kernels k_rowcol and
+// k_masksum (depth_kernels.cu); the GPU adds in tree order, so the XYZZ representation of a sum may differ, the group
+// element does not.
+struct RowColArgs {
+    const xyzz* buckets;  // [windows << (lo_bits + hi_bits)]
+    xyzz* rc;             // [windows * (rows + cols)]: per window the row sums R_hi, then the column sums C_lo
+    uint32_t lo_bits, hi_bits;
+    size_t blocks;        // windows * (rows + cols)
+};
+// "block" blk = win * (rows + cols) + i:  i < rows: sum of row i;  else: sum of column i - rows
+COZK_HD void rowcol_body(size_t blk, const RowColArgs& A) {
+    if (blk >= A.blocks) return;
+    const size_t rows = (size_t)1 << A.hi_bits, cols = (size_t)1 << A.lo_bits;
+    const size_t win = blk / (rows + cols), i = blk % (rows + cols);
+    const xyzz* b = A.buckets + win * rows * cols;
+    xyzz acc = xyzz_identity();
+    if (i < rows) {
+        for (size_t e = 0; e < cols; ++e) acc = xyzz_add(acc, load_xyzz(&b[i * cols + e]));
+    } else {
+        for (size_t e = 0; e < rows; ++e) acc = xyzz_add(acc, load_xyzz(&b[e * cols + (i - rows)]));
+    }
+    store_xyzz(&A.rc[blk], acc);
+}
+struct MaskSumArgs {
+    const xyzz* rc;   // as written by the row / column pass
+    xyzz* out;        // [windows * NS]
+    uint32_t lo_bits, hi_bits, NS;  // NS = lo_bits + hi_bits + 2
+    size_t blocks;    // windows * NS
+};
+// "block" blk = win * NS + id:  id 0: identity;  id 1: sum of all buckets (= of the column sums);  id 2 + j: the column
+// sums whose index has bit j set (j < lo_bits), the row sums whose index has bit j - lo_bits set (otherwise)
+COZK_HD void masksum_body(size_t blk, const MaskSumArgs& A) {
+    if (blk >= A.blocks) return;
+    const size_t rows = (size_t)1 << A.hi_bits, cols = (size_t)1 << A.lo_bits;
+    const size_t win = blk / A.NS;
+    const uint32_t id = (uint32_t)(blk % A.NS);
+    const xyzz* r = A.rc + win * (rows + cols);
+    const xyzz* c = r + rows;
+    xyzz acc = xyzz_identity();
+    if (id == 1) {
+        for (size_t e = 0; e < cols; ++e) acc = xyzz_add(acc, load_xyzz(&c[e]));
+    } else if (id >= 2 && id - 2 < A.lo_bits) {
+        for (size_t e = 0; e < cols; ++e)
+            if ((e >> (id - 2)) & 1u) acc = xyzz_add(acc, load_xyzz(&c[e]));
+    } else if (id >= 2) {
+        for (size_t e = 0; e < rows; ++e)
+            if ((e >> (id - 2 - A.lo_bits)) & 1u) acc = xyzz_add(acc, load_xyzz(&r[e]));
+    }
+    store_xyzz(&A.out[blk], acc);
+}
+
 // ------------------------------------------------------------------------------------------------ 5 finish
 // result = sum_w 2^(c*w) * V_w = sum over bit positions: position c*w carries sums[w][0] + sums[w][1], position
 // c*w + a + j (a = log2 l, j < J, a + J = c - 1) carries sums[w][2+j].  One Horner pass from the top bit down,

@@ -29,6 +29,7 @@ struct AccTuning {
     int force_l = 0;
     int up_l = 0;  // option "acc_chunk_up": partial slots per thread at the serial levels >= 2 (0 = ACC_L_UP)
     int group_l = 0;  // option "group_l": buckets per thread in the group step of the bucket reduce (0 = chosen from the bucket count)
+    int reduce_2d = 0;  // option "reduce_2d": 1 = row / column form of the bucket reduce (MsmPlan::reduce_2d)
 };
 
 // Level-1 chunk length.  32 pairs per thread is the measured optimum once the kernel fills the device (2^20 points:
@@ -65,6 +66,14 @@ struct MsmPlan {
     uint32_t G = 1, NS = 2;          // groups per window, plain sums per window (log2 G + 2)
     uint32_t sum_chunk = 1;          // groups summed per block in the masked level (min(G, SUM_CHUNK))
     uint32_t sum_chunks = 1;         // G / sum_chunk partial sums per (window, id); > 1 needs the second, plain level
+    // Row / column form of the bucket reduce: the bucket index b = hi * 2^lo_bits + lo.  With R_hi = sum of row hi and
+    // C_lo = sum of column lo,  sum_b b * bucket[b] = sum_lo lo * C_lo + 2^lo_bits * sum_hi hi * R_hi, and each of the two
+    // small weighted sums is one masked plain sum per index bit: T_j = sum of the C_lo (R_hi) whose index has bit j set.
+    // So NS = (c - 1) + 2 sums per window (id 0 = identity, id 1 = sum of all buckets, id 2 + j = T_j) for 2 additions per
+    // bucket, and the depth is two block-cooperative tree sums (over a row / column, then over the row / column sums)
+    // instead of a serial group pass plus two.  The finish stage reads it as the group form with l = 1.
+    bool reduce_2d = false;
+    uint32_t lo_bits = 0, hi_bits = 0;
 
     // field multiplications this plan performs (for the roofline's "actual" figure): 10 per mixed add, 14 per full add
     double field_mults() const {
@@ -72,8 +81,9 @@ struct MsmPlan {
         double mul = 10.0 * pairs;
         for (size_t k = 1; k < acc_entries.size(); ++k) mul += 14.0 * 0.5 * (double)acc_entries[k];
         double nb = (double)total_buckets;
-        mul += 14.0 * 2.0 * nb;                                   // group step
-        mul += 14.0 * (double)g * Wb * G * (1.0 + NS / 2.0);      // masked sums + the tree above them
+        mul += 14.0 * 2.0 * nb;                                   // group step (row / column form: row sums + column sums)
+        if (reduce_2d) mul += 14.0 * (double)g * Wb * NS * 0.5 * (double)((1u << lo_bits) + (1u << hi_bits));
+        else mul += 14.0 * (double)g * Wb * G * (1.0 + NS / 2.0);      // masked sums + the tree above them
         mul += (double)g * Wb * (9.0 * c + 14.0 * NS);            // bit-position Horner
         return mul;
     }
@@ -230,6 +240,17 @@ inline MsmPlan make_plan(size_t n, uint32_t g, uint32_t bits, size_t max_buckets
     p.NS = J + 2;
     p.sum_chunk = p.G < SUM_CHUNK ? p.G : SUM_CHUNK;
     p.sum_chunks = p.G / p.sum_chunk;
+    if (acc.reduce_2d) {
+        p.reduce_2d = true;
+        p.lo_bits = (p.c - 1) / 2;
+        p.hi_bits = (p.c - 1) - p.lo_bits;
+        p.group_l = 1;
+        p.log_l = 0;
+        p.G = p.B;
+        p.NS = (p.c - 1) + 2;
+        p.sum_chunk = 1;
+        p.sum_chunks = 1;
+    }
     return p;
 }
 

@@ -27,6 +27,8 @@ def lib():
         L.emul_choose_window.restype = None
         L.emul_set_dominant.argtypes = [ci]
         L.emul_set_dominant.restype = None
+        L.emul_set_reduce_2d.argtypes = [ci]
+        L.emul_set_reduce_2d.restype = None
         L.emul_set_affine_rounds.argtypes = [ci]
         L.emul_set_affine_rounds.restype = None
         L.emul_affine_stats.argtypes = [vp]
@@ -64,6 +66,11 @@ def set_dominant(on):
     """1: calls that cover the whole SRS go through the engine's dominant-digit path (analysis pass, compacted segments,
     row totals); 0: the plain pair layout."""
     lib().emul_set_dominant(1 if on else 0)
+
+
+def set_reduce_2d(on):
+    """1: the bucket reduce runs in its row / column form (two tree sums, MsmPlan::reduce_2d); 0: group sums + masked sums."""
+    lib().emul_set_reduce_2d(1 if on else 0)
 
 
 def set_affine_rounds(rounds):

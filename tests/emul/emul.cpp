@@ -61,6 +61,8 @@ void emul_set_acc_chunk(size_t resident, int force_l) {
     g_acc.resident = resident;
     g_acc.force_l = force_l;
 }
+// 1: the row / column form of the bucket reduce (MsmPlan::reduce_2d)
+void emul_set_reduce_2d(int on) { g_acc.reduce_2d = on; }
 
 // bases: n x 64 B; scalars: g vectors, vector v at scalars + v*vector_stride, element i at + i*stride; out: g x 72 B
 int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vector_stride, size_t stride, int form,
@@ -241,12 +243,22 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         for (uint32_t k : pk_in) if (k != KEY_SENTINEL) return 2;
 
     size_t windows = (size_t)g * P.Wb;
+    std::vector<xyzz> cur, nxt;
+    if (P.reduce_2d) {
+        const size_t rc_n = windows * (((size_t)1 << P.hi_bits) + ((size_t)1 << P.lo_bits));
+        std::vector<xyzz> rc(rc_n);
+        RowColArgs RA{buckets.data(), rc.data(), P.lo_bits, P.hi_bits, rc_n};
+        for (size_t b = 0; b < rc_n; ++b) rowcol_body(b, RA);
+        cur.resize(windows * P.NS);
+        MaskSumArgs MA{rc.data(), cur.data(), P.lo_bits, P.hi_bits, P.NS, windows * P.NS};
+        for (size_t b = 0; b < MA.blocks; ++b) masksum_body(b, MA);
+    } else {
     std::vector<xyzz> gs(windows * P.G), gw(windows * P.G);
     GroupArgs GA{buckets.data(), gs.data(), gw.data(), P.group_l, windows * P.G};
     for (size_t t = 0; t < GA.threads; ++t) group_body(t, GA);
     // on the GPU these two levels are k_treesum (masked, then plain); same output contract as the bodies below
     uint32_t schunks = P.sum_chunks;
-    std::vector<xyzz> cur(windows * P.NS * schunks), nxt;
+    cur.resize(windows * P.NS * schunks);
     BitsumArgs BA{gs.data(), gw.data(), cur.data(), P.G, P.NS, P.sum_chunk, schunks, windows * P.NS * schunks};
     for (size_t t = 0; t < BA.threads; ++t) bitsum_body(t, BA);
     if (schunks > 1) {
@@ -255,6 +267,7 @@ int emul_msm(const uint8_t* bases, size_t n, const uint8_t* scalars, size_t vect
         PlainSumArgs SA{cur.data(), nxt.data(), schunks, threads};
         for (size_t t = 0; t < threads; ++t) plainsum_body(t, SA);
         cur.swap(nxt);
+    }
     }
     FinishArgs F{cur.data(), g, P.Wb, P.c, P.NS, P.log_l, out};
     for (size_t v = 0; v < g; ++v) finish_body(v, F);

@@ -244,3 +244,27 @@ def test_streamed_chunks_merge_into_one_bucket_set(orc):
     masked[::5] = 0
     got, _ = emul.msm(bases, u, infinity=inf, stream_chunks=3)
     assert (got[0] == orc.msm(bases, masked)).all()
+
+
+@pytest.mark.parametrize("dist", ["uniform", "const", "dup", "zero_half"])
+def test_row_column_bucket_reduce(orc, dist):
+    """The row / column form of the bucket reduce (two tree sums instead of group running sums + masked sums) for every
+    window size - odd and even bucket-index widths, one bucket - with and without a table, single vector and batch."""
+    n = 260
+    bases = orc.gen_bases(3, n)
+    sc = orc.gen_scalars(dist, 8, n)
+    want = orc.msm(bases, sc)
+    try:
+        emul.set_reduce_2d(1)
+        for c in (2, 3, 4, 5, 8, 11, 14):
+            got, st = emul.msm(bases, sc, c=c)
+            assert (got[0] == want).all(), (dist, c)
+        for tc in (3, 6, 9):
+            got, _ = emul.msm(bases, sc, table_c=tc)
+            assert (got[0] == want).all(), (dist, tc)
+        vecs = [orc.gen_scalars(d, 50 + i, n, stride=64) for i, d in enumerate(("uniform", "wminus", "small16"))]
+        got, _ = emul.msm(bases, np.concatenate(vecs), g=3, stride=64, table_c=7)
+        for j in range(3):
+            assert (got[j] == orc.msm(bases, vecs[j])).all(), j
+    finally:
+        emul.set_reduce_2d(0)

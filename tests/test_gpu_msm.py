@@ -558,3 +558,40 @@ def test_streamed_host_vector(cozk, orc):
             if dist == "wminus":
                 assert st["pairs"] < 0.6 * st["windows"] * m2
         c2.srs_release(srs2)
+
+
+def test_row_column_bucket_reduce(cozk, orc):
+    """Option reduce_2d: the bucket reduce as row sums + column sums + one masked sum per index bit (two tree sums deep)
+    instead of group running sums.  Every window size, table and per-window buckets, batches (on-device finish), a chunked
+    host call, a resident device vector: the same bytes as the oracle's."""
+    n = 3000
+    bases = orc.gen_bases(2, n)
+    with cozk.Context() as c2:
+        c2.set_option("reduce_2d", 1)
+        srs = c2.srs_register(bases)
+        u, c0 = orc.gen_scalars("uniform", 4, n), orc.gen_scalars("const", 4, n)
+        wu, wc = orc.msm(bases, u), orc.msm(bases, c0)
+        assert (c2.msm_batch(srs, u)[0] == wu).all()  # table mode
+        for c in range(2, 23):
+            c2.set_option("window", c)
+            assert (c2.msm_batch(srs, u)[0] == wu).all(), c
+            assert (c2.msm_batch(srs, c0)[0] == wc).all(), c
+        c2.set_option("window", 0)
+        vecs = [orc.gen_scalars(d, 70 + j, n) for j, d in enumerate(("uniform", "const", "wminus", "dup", "zero_half", "small16", "uniform"))]
+        got = c2.msm_batch(srs, vecs, n=n)  # 7 vectors: finish on the device
+        for j, v in enumerate(vecs):
+            assert (got[j] == orc.msm(bases, v)).all(), j
+        c2.srs_release(srs)
+        m = 1 << 17
+        bases2 = orc.gen_bases(5, m)
+        srs2 = c2.srs_register(bases2)
+        c2.set_option("stream_min_points", 1 << 14)
+        for dist in ("uniform", "wminus"):
+            v = orc.gen_scalars(dist, 9, m)
+            want = orc.msm(bases2, v)
+            assert (c2.msm_batch(srs2, [v])[0] == want).all(), dist  # chunked host call
+            dv = c2.alloc(v.nbytes)
+            dv.upload(v)
+            assert (c2.msm_batch_ptrs(srs2, [dv.ptr], m, device=0)[0] == want).all(), dist
+            dv.free()
+        c2.srs_release(srs2)

@@ -31,6 +31,7 @@ ap.add_argument("--exact", action="store_true", help="register an SRS of exactly
 ap.add_argument("--dominant", type=int, default=-1, help="-1 default, 0 off, 1 on (dominant-digit mode of whole-SRS calls)")
 ap.add_argument("--stream-first-pct", type=int, default=0)
 ap.add_argument("--chunk-min", type=int, default=-1, help="chunk_min_points option: device-resident vectors this long run in chunks (0 never)")
+ap.add_argument("--reduce-2d", type=int, default=-1, help="bucket reduce: 1 row / column form, 0 group form (-1 default)")
 ap.add_argument("--affine-rounds", type=int, default=-1, help="batched-affine pre-reduction rounds (-1 default, 0 off)")
 ap.add_argument("--host", action="store_true", help="scalars in pinned host memory (end to end)")
 args = ap.parse_args()
@@ -52,6 +53,8 @@ if args.chunk_min >= 0:
     ctx.set_option("chunk_min_points", args.chunk_min)
 if args.stream_first_pct:
     ctx.set_option("stream_first_pct", args.stream_first_pct)
+if args.reduce_2d >= 0:
+    ctx.set_option("reduce_2d", args.reduce_2d)
 if args.affine_rounds >= 0:
     ctx.set_option("affine_rounds", args.affine_rounds)
 if args.stream_min >= 0:
