@@ -225,6 +225,7 @@ struct cozk_ctx {
     std::map<uint64_t, cozk::PolyEntry> polys;
     std::map<uint64_t, cozk::OpenKey> open_keys;
     std::atomic<long> opt_open_small_log2 = 15;   // opening levels with at most 2^this quotient values share one batched MSM (measured at nv = 22 / 18: 13: 17.5 ms, 14: 17.2 / 4.13, 15: 17.0 / 3.91, 16: 17.5 / 4.42, 17: 18.0)
+    std::atomic<long> opt_open_small_ragged = 1;  // 1: the small levels of a keyed opening run as a ragged batch (their real scalars only); 0: zero-padded batch
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;
     std::atomic<long> opt_dominant = 1;           // 1: whole-SRS calls look for windows dominated by one digit (constant co-jolt shares) and use the row totals

@@ -259,7 +259,7 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
     if ((rc = D.keys_b.ensure(P.m * 4))) return rc;
     if ((rc = D.vals_b.ensure(P.m * 4))) return rc;
     if ((rc = D.buckets.ensure(P.total_buckets * sizeof(xyzz)))) return rc;
-    if ((rc = D.out.ensure((size_t)P.g * 72 + 256))) return rc;
+    if ((rc = D.out.ensure((size_t)P.g * sizeof(xyzz) + 256))) return rc;
 
     COZK_CUDA(cudaEventRecord(D.ev[1], st));
     // 1 + 2: decompose and sort.  Plain layout: the pairs are produced inside the first pass of the sort (born
@@ -366,7 +366,9 @@ static int run_group(Device& D, const MsmPlan& P, const affine* d_bases, const u
         COZK_CUDA(cudaMemcpyAsync(D.host_sums.data(), cur, nsums * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
         D.finish_on_host = true;
     } else {
-        FinishArgs F{cur, P.g, P.Wb, P.c, P.NS, P.log_l, D.out.as<uint8_t>()};
+        // the Horner pass on the device, one thread per vector; the sums stay un-normalised (D.out: g XYZZ points) and the
+        // caller normalises them on the host (fetch_device_finish / host_normalize_batch: one inversion for the whole batch)
+        FinishArgs F{cur, P.g, P.Wb, P.c, P.NS, P.log_l, nullptr, D.out.as<xyzz>()};
         launch_finish(F, grid_for(P.g, 32), st);
         *launches += 1;
         COZK_CUDA(cudaGetLastError());
@@ -394,6 +396,41 @@ constexpr size_t MAX_POINTS_PER_PASS = (size_t)1 << 26;  // default of option "m
 // Dominant-digit analysis of one group (scalars already on the device): candidate digits from every vector's first
 // scalar, a look at the first 1024 scalars of every vector, and - only if that sample shows a dominated window - the full
 // count.  Fills `dom` and shrinks the plan's pair count when at least one segment is special; returns false otherwise.
+// g un-normalised sums -> 72-byte wire points with ONE inversion (Montgomery's trick over the ZZ * ZZZ of the finite ones);
+// the same canonical bytes as xyzz_to_wire point by point
+static void host_normalize_batch(const xyzz* pts, size_t g, uint8_t* out72) {
+    std::vector<fq> den(g), pre(g);
+    fq run = fq_one();
+    for (size_t v = 0; v < g; ++v) {
+        pre[v] = run;
+        if (xyzz_is_identity(pts[v])) continue;
+        den[v] = fq_mul(pts[v].ZZ, pts[v].ZZZ);
+        run = fq_mul(run, den[v]);
+    }
+    fq inv = fq_inv(run);
+    for (size_t v = g; v-- > 0;) {
+        uint8_t* o = out72 + 72 * v;
+        if (xyzz_is_identity(pts[v])) {
+            memset(o, 0, 72);
+            o[64] = 1;
+            continue;
+        }
+        const fq I = fq_mul(inv, pre[v]);  // 1 / (ZZ * ZZZ) of point v
+        inv = fq_mul(inv, den[v]);
+        const fq x = fq_mul(pts[v].X, fq_mul(I, pts[v].ZZZ)), y = fq_mul(pts[v].Y, fq_mul(I, pts[v].ZZ));
+        memcpy(o, x.v, 32);
+        memcpy(o + 32, y.v, 32);
+        memset(o + 64, 0, 8);
+    }
+}
+// After run_group chose the on-device finish: bring the g un-normalised sums back (enqueued; valid after the stream's next
+// synchronisation) ...
+static int fetch_device_finish(Device& D, size_t g, cudaStream_t st) {
+    D.host_sums.resize(g);
+    COZK_CUDA(cudaMemcpyAsync(D.host_sums.data(), D.out.p, g * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+    return COZK_OK;
+}
+
 static int analyse_dominant(Device& D, MsmPlan& P, const uint8_t* d_scalars, const uint8_t* const* d_vec_ptrs, size_t vector_stride,
                             size_t stride, int form, size_t totals_index, DecomposeArgs* dom, bool* use, double* launches) {
     *use = false;
@@ -654,7 +691,7 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             COZK_CUDA(cudaEventRecord(D.ev[4], D.stream));
             rc = run_group(D, P, d_bases, d_inf, nullptr, nullptr, 0, stride, form, table_stride, val_offset, &launches, 2, false);
             if (rc) return rc;
-            if (!D.finish_on_host) COZK_CUDA(cudaMemcpyAsync(pass_out, D.out.p, 72, cudaMemcpyDeviceToHost, D.stream));
+            if (!D.finish_on_host && (rc = fetch_device_finish(D, 1, D.stream))) return rc;
             COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
             COZK_CUDA(cudaStreamSynchronize(D.stream));
             add_stage_times(D, 4, 5);
@@ -672,6 +709,8 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                 FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out};
                 finish_body(0, F);
                 host_finish_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+            } else {
+                host_normalize_batch(D.host_sums.data(), 1, pass_out);
             }
             return COZK_OK;
             }();
@@ -751,15 +790,18 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
             rc = run_group(D, P, d_bases, d_inf, g_scalars, g_ptrs, vstride, stride, form, table_stride, val_offset, &launches, 3,
                            false, use_dom ? &dom : nullptr);
             if (rc) return rc;
-            if (!D.finish_on_host)
-                COZK_CUDA(cudaMemcpyAsync(pass_out + v0 * 72, D.out.p, g * 72, cudaMemcpyDeviceToHost, D.stream));
+            if (!D.finish_on_host && (rc = fetch_device_finish(D, g, D.stream))) return rc;
             COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
             COZK_CUDA(cudaStreamSynchronize(D.stream));
             add_stage_times(D);
-            if (D.finish_on_host) {
+            {
                 auto h0 = std::chrono::steady_clock::now();
-                FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out + v0 * 72};
-                for (size_t v = 0; v < g; ++v) finish_body(v, F);
+                if (D.finish_on_host) {
+                    FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, pass_out + v0 * 72};
+                    for (size_t v = 0; v < g; ++v) finish_body(v, F);
+                } else {
+                    host_normalize_batch(D.host_sums.data(), g, pass_out + v0 * 72);
+                }
                 host_finish_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
             }
         }
@@ -1254,13 +1296,15 @@ int msm_ragged_device(cozk_ctx* ctx, int device, cozk_srs srs, const size_t* off
                    &launches, 3, false, nullptr, &rag);
     if (rc) return rc;
     uint8_t* o = reinterpret_cast<uint8_t*>(out);
-    if (!D.finish_on_host) COZK_CUDA(cudaMemcpyAsync(o, D.out.p, k * 72, cudaMemcpyDeviceToHost, D.stream));
+    if (!D.finish_on_host && (rc = fetch_device_finish(D, k, D.stream))) return rc;
     COZK_CUDA(cudaEventRecord(D.ev[6], D.stream));
     COZK_CUDA(cudaStreamSynchronize(D.stream));
     add_stage_times(D);
     if (D.finish_on_host) {
         FinishArgs F{D.host_sums.data(), P.g, P.Wb, P.c, P.NS, P.log_l, o};
         for (size_t v = 0; v < k; ++v) finish_body(v, F);
+    } else {
+        host_normalize_batch(D.host_sums.data(), k, o);
     }
     COZK_CUDA(cudaEventRecord(D.ev[7], D.stream));
     COZK_CUDA(cudaStreamSynchronize(D.stream));
@@ -1543,6 +1587,9 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // a single host-resident vector of at least this many points is streamed in chunks (0 = never)
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points = value;
+    } else if (!strcmp(name, "open_small_ragged")) {
+        if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;
+        ctx->opt_open_small_ragged = value;
     } else if (!strcmp(name, "reduce_2d")) {
         // bucket reduce: 1 = row / column form (two tree sums), 0 = group running sums + masked sums
         if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;

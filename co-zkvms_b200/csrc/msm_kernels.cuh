@@ -532,6 +532,8 @@ struct FinishArgs {
     const xyzz* sums;  // [g * W * NS]
     uint32_t g, W, c, NS, log_l;
     uint8_t* out;      // [g] 72-byte wire points
+    xyzz* out_xyzz;    // if non-null: the un-normalised sums go here instead (the inversion is 150 us deep on a GPU thread; the
+                       // host normalises a whole batch with ONE inversion in a few microseconds)
 };
 
 COZK_HD void finish_body(size_t v, const FinishArgs& A) {
@@ -546,7 +548,8 @@ COZK_HD void finish_body(size_t v, const FinishArgs& A) {
             if (pos == 0) acc = xyzz_add(acc, xyzz_add(load_xyzz(&sw[0]), load_xyzz(&sw[1])));
         }
     }
-    xyzz_to_wire(acc, A.out + 72 * v);
+    if (A.out_xyzz) store_xyzz(&A.out_xyzz[v], acc);
+    else xyzz_to_wire(acc, A.out + 72 * v);
 }
 
 }  // namespace cozk

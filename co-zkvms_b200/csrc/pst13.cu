@@ -465,7 +465,25 @@ int pst13_open_device(cozk_ctx* ctx, const cozk_srs* level_srs, const OpenKey* k
             rc = msm_dispatch(ctx, 0, level_srs[i], 0, (size_t)1 << (nv - i), nullptr, vec, 1, 32, COZK_MONT, 0, proofs + 72 * i);
         if (trace) fprintf(stderr, "[open] level %zu: %.3f ms\n", i, ms_since(t0));
     }
-    if (!rc && g_small) {
+    bool small_done = false;
+    if (!rc && g_small && ctx->opt_open_small_ragged) {
+        // the small levels as ONE ragged batch too: only their 2^(nv - first_small) - 1 real scalars are decomposed and sorted
+        // (the zero-padded batch below makes g_small times as many pairs, nearly all of them skipped)
+        auto t0 = now();
+        std::vector<size_t> offs(g_small), lens(g_small);
+        std::vector<const void*> vecs(g_small);
+        for (size_t j = 0; j < g_small; ++j) {
+            offs[j] = key->small_off[j];
+            lens[j] = (size_t)1 << (nv - 1 - (first_small + j));
+            vecs[j] = d_qs + j * key->small_n + key->small_off[j];
+        }
+        const int rrc = msm_ragged_device(ctx, 0, key->small_srs, offs.data(), lens.data(), vecs.data(), g_small, 32, COZK_MONT,
+                                          proofs + 72 * first_small);
+        small_done = rrc == COZK_OK;
+        if (rrc != COZK_OK && rrc != COZK_ERR_INVALID_ARG) rc = rrc;
+        if (trace) fprintf(stderr, "[open] %zu small levels in one ragged batch: %.3f ms (rc %d)\n", g_small, ms_since(t0), rrc);
+    }
+    if (!rc && g_small && !small_done) {
         auto t0 = now();
         std::vector<const void*> vecs(g_small);
         for (size_t j = 0; j < g_small; ++j) vecs[j] = d_qs + j * key->small_n;

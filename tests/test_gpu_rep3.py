@@ -229,6 +229,13 @@ def test_open_resident_polynomial_with_key(cozk, ctx, orc, nv, small):
         proofs, ev = rep3.open_poly(setup, poly, H.scalars_wire(point), keyed=keyed)
         assert (proofs == want_proofs).all(), keyed
         assert pyref.from_mont(H.to_int(ev), R) == want_ev
+    # the small levels as a zero-padded batch instead of a ragged one: the same proofs
+    ctx.set_option("open_small_ragged", 0)
+    try:
+        proofs, _ = rep3.open_poly(setup, poly, H.scalars_wire(point), keyed=True)
+        assert (proofs == want_proofs).all()
+    finally:
+        ctx.set_option("open_small_ragged", 1)
     proofs, ev = rep3.open_keyed(setup, H.scalars_wire(a), H.scalars_wire(point))
     assert (proofs == want_proofs).all() and pyref.from_mont(H.to_int(ev), R) == want_ev
     # prove_rep3 reverses the opening point first (pst13.rs:134)
