@@ -703,6 +703,18 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                 if (cudaEventElapsedTime(&ms, D.ev[1], EV(0, 1)) == cudaSuccess) D.stats[1] += ms;
                 if (cudaEventElapsedTime(&ms, EV(0, 1), EV(0, 2)) == cudaSuccess) D.stats[2] += ms;
                 if (cudaEventElapsedTime(&ms, EV(0, 2), EV(chunks - 1, 4)) == cudaSuccess) D.stats[3] += ms;
+                if (getenv("COZK_CHUNK_TRACE")) {  // timeline of the chunks on stderr, ms since the call entered the pipeline
+                    auto at = [&](cudaEvent_t e) {
+                        float t = -1;
+                        cudaEventElapsedTime(&t, D.ev[1], e);
+                        return t;
+                    };
+                    for (size_t ci = 0; ci < chunks; ++ci)
+                        fprintf(stderr, "[chunk %zu: %zu points] sort %.3f .. first pass %.3f .. %.3f | level 1 %.3f .. %.3f | upper levels + merge .. %.3f\n",
+                                ci, cstart[ci + 1] - cstart[ci], at(EV(ci, 0)), at(EV(ci, 1)), at(EV(ci, 2)), at(EV(ci, 5)), at(EV(ci, 3)),
+                                at(EV(ci, 4)));
+                    fprintf(stderr, "[reduce] %.3f .. %.3f | finish copy .. %.3f\n", at(D.ev[4]), at(D.ev[5]), at(D.ev[6]));
+                }
             }
             if (D.finish_on_host) {
                 auto h0 = std::chrono::steady_clock::now();
