@@ -225,6 +225,8 @@ struct cozk_ctx {
     std::map<uint64_t, cozk::PolyEntry> polys;
     std::map<uint64_t, cozk::OpenKey> open_keys;
     std::atomic<long> opt_open_small_log2 = 15;   // opening levels with at most 2^this quotient values share one batched MSM (measured at nv = 22 / 18: 13: 17.5 ms, 14: 17.2 / 4.13, 15: 17.0 / 3.91, 16: 17.5 / 4.42, 17: 18.0)
+    std::atomic<long> opt_open_one_batch_max_nv = 20;  // opening keys up to this nv put ALL levels into the one ragged batch of "small" levels
+    std::atomic<long> opt_open_small_window = 0;  // table window of the small levels' SRS of opening keys created from now on; 0 = cost model
     std::atomic<long> opt_open_small_ragged = 1;  // 1: the small levels of a keyed opening run as a ragged batch (their real scalars only); 0: zero-padded batch
     double rep3_stats[8] = {};
     uint64_t next_handle = 1;

@@ -1599,6 +1599,12 @@ int cozk_set_option(cozk_ctx* ctx, const char* name, long value) {
         // a single host-resident vector of at least this many points is streamed in chunks (0 = never)
         if (value < 0) return COZK_ERR_INVALID_ARG;
         ctx->opt_stream_min_points = value;
+    } else if (!strcmp(name, "open_one_batch_max_nv")) {
+        if (value < 0 || value > 30) return COZK_ERR_INVALID_ARG;
+        ctx->opt_open_one_batch_max_nv = value;
+    } else if (!strcmp(name, "open_small_window")) {
+        if (value != 0 && (value < (long)C_MIN || value > (long)C_MAX)) return COZK_ERR_INVALID_ARG;
+        ctx->opt_open_small_window = value;
     } else if (!strcmp(name, "open_small_ragged")) {
         if (value != 0 && value != 1) return COZK_ERR_INVALID_ARG;
         ctx->opt_open_small_ragged = value;

@@ -255,6 +255,10 @@ int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t 
         std::lock_guard<std::mutex> lock(ctx->mu);
         small_log2 = (size_t)ctx->opt_open_small_log2;
     }
+    // up to nv = 20 every level goes into the one batch of "small" levels (measured, keyed opening at nv = 18 / 20: 2.04 / 4.42 ms
+    // with two batches, 1.76 / 4.30 ms with one; at nv = 22 two batches win, 12.9 against 13.2 ms)
+    // (option "open_one_batch_max_nv", default 20; 0 = always split by "open_small_log2")
+    if (small_log2 != 0 && nv <= (size_t)ctx->opt_open_one_batch_max_nv && small_log2 + 1 < nv) small_log2 = nv - 1;
     // level i has 2^(nv-1-i) quotient scalars; the levels with at most 2^small_log2 of them are batched (none if 0)
     K.first_small = small_log2 == 0 ? nv : (nv > small_log2 + 1 ? nv - small_log2 - 1 : 0);
     K.small_n = K.first_small < nv ? ((size_t)1 << (nv - K.first_small)) - 1 : 0;
@@ -319,7 +323,20 @@ int cozk_pst13_open_key_create(cozk_ctx* ctx, const cozk_srs* level_srs, size_t 
         if (rc) return fail(rc);
     }
     if (K.small_n) {
-        rc = srs_register_from_device(ctx, 0, d_small, d_small_inf, K.small_n, &K.small_srs, 0);  // read by device 0 only
+        // the same rule for the small levels (one ragged batch, a bucket set per level); option "open_small_window" overrides
+        const size_t g_small = nv - K.first_small;
+        uint32_t small_c = (uint32_t)ctx->opt_open_small_window;
+        if (!small_c) {
+            double best = 0;
+            for (uint32_t c = 8; c <= C_MAX; ++c) {
+                const double cost = 11.0 * (double)windows_for(254, c) * (double)K.small_n + 45.0 * (double)g_small * (double)(1u << (c - 1));
+                if (!small_c || cost < best) {
+                    best = cost;
+                    small_c = c;
+                }
+            }
+        }
+        rc = srs_register_from_device(ctx, 0, d_small, d_small_inf, K.small_n, &K.small_srs, 0, small_c);  // read by device 0 only
         if (rc) return fail(rc);
     }
     {

@@ -205,7 +205,7 @@ def test_pair_sum_srs(cozk, ctx, orc):
     ctx.srs_release(srs)
 
 
-@pytest.mark.parametrize("nv,small", [(1, 12), (5, 12), (10, 12), (10, 3), (10, 0), (15, 12)])
+@pytest.mark.parametrize("nv,small", [(1, 12), (5, 12), (10, 12), (10, 3), (10, 0), (15, 12), (15, 11), (15, 6)])
 def test_open_resident_polynomial_with_key(cozk, ctx, orc, nv, small):
     """open() on a resident polynomial, with the opening key (pair sums, batched small levels) and with the reference's
     schedule, against the restated open()."""
@@ -216,10 +216,12 @@ def test_open_resident_polynomial_with_key(cozk, ctx, orc, nv, small):
         levels[1][1, 32:] = H.fq_mont((-pyref.from_mont(H.to_int(levels[1][0, 32:]), H.P)) % H.P)
         levels[1][1, :32] = levels[1][0, :32]  # P + (-P): the pair sum is the point at infinity
     ctx.set_option("open_small_log2", small)
+    ctx.set_option("open_one_batch_max_nv", 0 if small != 12 else 20)  # 0: split the levels by open_small_log2 as asked
     try:
         setup = rep3.create_open_key(pst.PST13Setup(ctx, levels))
     finally:
         ctx.set_option("open_small_log2", 15)
+        ctx.set_option("open_one_batch_max_nv", 20)
     n = 1 << nv
     a, b = _rand_fr(60, n), _rand_fr(62, n)
     point = _rand_fr(61, nv)

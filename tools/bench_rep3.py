@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--chi-waves", type=int, default=1)
     ap.add_argument("--bulk", type=int, default=0, help="1: bulk-copy (TMA) staged ingest / chi kernels, 0: plain per-lane loads")
+    ap.add_argument("--one-batch-max-nv", type=int, default=-1, help="open_one_batch_max_nv option (-1 default)")
+    ap.add_argument("--small-window", type=int, default=0, help="open_small_window option (0 = cost model)")
     ap.add_argument("--small-ragged", type=int, default=-1, help="open_small_ragged option (-1 default)")
     ap.add_argument("--small", default="12", help="comma list of open_small_log2 values to try for the keyed opening")
     args = ap.parse_args()
@@ -49,6 +51,10 @@ def main():
     ctx = cozk.Context()
     ctx.set_option("bulk_copy", args.bulk)
     ctx.set_option("chi_waves", args.chi_waves)
+    if args.one_batch_max_nv >= 0:
+        ctx.set_option("open_one_batch_max_nv", args.one_batch_max_nv)
+    if args.small_window:
+        ctx.set_option("open_small_window", args.small_window)
     if args.small_ragged >= 0:
         ctx.set_option("open_small_ragged", args.small_ragged)
     L = cozk.lib()
