@@ -256,6 +256,7 @@ struct cozk_ctx {
                                                           // is throughput work itself: 2^20 3.16 ms in one piece, 3.29 / 3.42 / 3.53 in 2 / 3 / 4 chunks; 2^24 37.3, 38.0 / 38.8 / 39.5
     std::atomic<long> opt_stream_first_pct = 50;          // chunked calls: length of the first chunk in percent of an equal share
     std::atomic<long> opt_stream_chunks = 0;              // 0 = auto: 2 chunks (msm.cu has the measurements)
+    std::atomic<long> opt_table_rowwise = 0;            // 1: build SRS tables with the row-by-row kernel (the contract form); 0: chain + one inversion per point
     std::atomic<long> opt_table_window = 0;             // 0 = choose_table_window(n) at registration
     std::atomic<long> opt_table_max_bytes = 64L << 30;  // per-SRS budget for the precomputed 2^(c*w) * P table (12 x 4 GiB at 2^26; the GPU has 180 GB), and never more than half of the free device memory; 0 disables tables
 };

@@ -309,6 +309,46 @@ COZK_HD void table_body(size_t i, const TableArgs& A) {
     }
 }
 
+// The same table in two steps, for the GPU (table_body stays the output contract: identical bytes): an inversion is ~390
+// multiplications, and table_body spends W - 1 of them per point - more than its (W - 1) * c doublings cost.  Step 1 walks the
+// chain in XYZZ and parks the un-normalised multiples in a scratch array; step 2 normalises the W - 1 multiples of a point
+// with ONE inversion (Montgomery's trick over ZZ * ZZZ; a finite point of the prime-order group never doubles to the
+// identity, and the entries of a point flagged at infinity are never read).  Slab of `slab` points starting at `first`.
+constexpr uint32_t TABLE_MAX_ROWS = 128;
+struct TableSlabArgs {
+    affine* table;   // [W*n], row 0 holds the bases
+    xyzz* tmp;       // [(W-1) * slab]: multiple w of slab point j at tmp[(w-1) * slab + j]
+    size_t n, first, slab;
+    uint32_t c, W;
+};
+COZK_HD void table_chain_body(size_t j, const TableSlabArgs& A) {
+    if (j >= A.slab || A.first + j >= A.n) return;
+    xyzz p = xyzz_from_affine(load_affine(&A.table[A.first + j]));
+    for (uint32_t w = 1; w < A.W; ++w) {
+        for (uint32_t k = 0; k < A.c; ++k) p = xyzz_dbl(p);
+        store_xyzz(&A.tmp[(size_t)(w - 1) * A.slab + j], p);
+    }
+}
+COZK_HD void table_norm_body(size_t j, const TableSlabArgs& A) {
+    if (j >= A.slab || A.first + j >= A.n) return;
+    fq pre[TABLE_MAX_ROWS];  // pre[w] = product of the denominators of rows 1 .. w-1
+    fq run = fq_one();
+    for (uint32_t w = 1; w < A.W; ++w) {
+        const xyzz* q = &A.tmp[(size_t)(w - 1) * A.slab + j];
+        pre[w] = run;
+        run = fq_mul(run, fq_mul(load_fq(&q->ZZ), load_fq(&q->ZZZ)));
+    }
+    fq inv = fq_inv(run);
+    for (uint32_t w = A.W - 1; w >= 1; --w) {
+        const xyzz p = load_xyzz(&A.tmp[(size_t)(w - 1) * A.slab + j]);
+        const fq I = fq_mul(inv, pre[w]);  // 1 / (ZZ * ZZZ) of row w
+        inv = fq_mul(inv, fq_mul(p.ZZ, p.ZZZ));
+        affine* o = &A.table[(size_t)w * A.n + A.first + j];
+        store_fq(&o->x, fq_mul(p.X, fq_mul(I, p.ZZZ)));
+        store_fq(&o->y, fq_mul(p.Y, fq_mul(I, p.ZZ)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 3 accumulate
 // One body for all levels.  LEVEL1: entries are (key, val) pairs pointing into the base table (mixed additions);
 // otherwise entries are (key, xyzz partial sum) produced by the level below (full additions).

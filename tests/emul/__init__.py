@@ -27,6 +27,8 @@ def lib():
         L.emul_choose_window.restype = None
         L.emul_set_dominant.argtypes = [ci]
         L.emul_set_dominant.restype = None
+        L.emul_build_table.argtypes = [vp, sz, u32, u32, ci, sz, vp]
+        L.emul_build_table.restype = None
         L.emul_set_reduce_2d.argtypes = [ci]
         L.emul_set_reduce_2d.restype = None
         L.emul_set_affine_rounds.argtypes = [ci]
@@ -66,6 +68,16 @@ def set_dominant(on):
     """1: calls that cover the whole SRS go through the engine's dominant-digit path (analysis pass, compacted segments,
     row totals); 0: the plain pair layout."""
     lib().emul_set_dominant(1 if on else 0)
+
+
+def build_table(bases, c, rows, mode=0, slab=None):
+    """The SRS table (rows x n affine points, row w = 2^(c w) P): mode 0 = the row-by-row contract body, 1 = the engine's two
+    steps (chain in XYZZ, one inversion per point) in slabs of `slab` points."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    n = bases.shape[0]
+    out = np.zeros((rows * n, 64), np.uint8)
+    lib().emul_build_table(_p(bases), n, c, rows, mode, slab or n, _p(out))
+    return out
 
 
 def set_reduce_2d(on):

@@ -28,6 +28,23 @@ static uint32_t g_last_overflow = 0, g_last_reduced = 0;  // of the last chunk: 
 extern "C" {
 
 void emul_set_dominant(int on) { g_dominant = on; }
+// SRS table of n points (64 B each), rows x n entries out: mode 0 = table_body (the contract), 1 = chain + batch normalisation
+// in slabs of `slab` points
+void emul_build_table(const uint8_t* bases, size_t n, uint32_t c, uint32_t rows, int mode, size_t slab, uint8_t* out) {
+    affine* t = reinterpret_cast<affine*>(out);
+    memcpy(t, bases, n * sizeof(affine));
+    if (mode == 0) {
+        TableArgs A{t, n, c, rows};
+        for (size_t i = 0; i < n; ++i) table_body(i, A);
+        return;
+    }
+    std::vector<xyzz> tmp((size_t)(rows - 1) * slab);
+    for (size_t first = 0; first < n; first += slab) {
+        TableSlabArgs A{t, tmp.data(), n, first, slab, c, rows};
+        for (size_t j = 0; j < slab; ++j) table_chain_body(j, A);
+        for (size_t j = 0; j < slab; ++j) table_norm_body(j, A);
+    }
+}
 void emul_set_affine_rounds(int rounds) { g_affine_rounds = rounds; }
 void emul_affine_stats(uint32_t* out) {
     out[0] = g_last_reduced;

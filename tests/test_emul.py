@@ -268,3 +268,21 @@ def test_row_column_bucket_reduce(orc, dist):
             assert (got[j] == orc.msm(bases, vecs[j])).all(), j
     finally:
         emul.set_reduce_2d(0)
+
+
+def test_table_build_in_two_steps(orc):
+    """SRS table: the engine's chain + batch-normalisation kernels (one inversion per point) give the bytes of the row-by-row
+    contract body (one inversion per row and point), for slabs that do and do not divide the SRS."""
+    n = 37
+    bases = orc.gen_bases(5, n)
+    for c, rows in ((3, 5), (7, 4), (13, 20)):
+        want = emul.build_table(bases, c, rows)
+        for slab in (n, 16, 5):
+            assert (emul.build_table(bases, c, rows, mode=1, slab=slab) == want).all(), (c, rows, slab)
+    # row w really is 2^(c w) P
+    pts = [(pyref.from_mont(H.to_int(r[:32]), H.P), pyref.from_mont(H.to_int(r[32:]), H.P)) for r in bases[:3]]
+    t = emul.build_table(bases, 7, 4, mode=1)
+    for i, p in enumerate(pts):
+        q = pyref.mul(1 << 14, p)
+        row = t[2 * n + i]
+        assert (pyref.from_mont(H.to_int(row[:32]), H.P), pyref.from_mont(H.to_int(row[32:]), H.P)) == q
