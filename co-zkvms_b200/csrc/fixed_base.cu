@@ -115,20 +115,20 @@ extern "C" int cozk_fixed_base_batch_mul(cozk_ctx* ctx, const void* base72, cons
             FB_CUDA(cudaGetLastError());
             FB_CUDA(cudaStreamSynchronize(D.stream));
         }
-        if (out_points72 || out_srs) {
-            host_out.resize(n * 72);
-            FB_CUDA(cudaMemcpyAsync(host_out.data(), d_out, n * 72, cudaMemcpyDeviceToHost, D.stream));
-            FB_CUDA(cudaStreamSynchronize(D.stream));
-        }
+        // straight into the caller's buffer when there is one (a staging vector would cost a second 72 n byte copy and its page faults)
+        if (!out_points72) host_out.resize(n * 72);
+        uint8_t* host_dst = out_points72 ? reinterpret_cast<uint8_t*>(out_points72) : host_out.data();
+        FB_CUDA(cudaMemcpyAsync(host_dst, d_out, n * 72, cudaMemcpyDeviceToHost, D.stream));
+        FB_CUDA(cudaStreamSynchronize(D.stream));
     }
     cleanup();
 #undef FB_CUDA
-    if (out_points72) memcpy(out_points72, host_out.data(), n * 72);
     if (out_srs) {
         // register the points as an SRS (stride 72 with per-point infinity flags, exactly ark_ec's Affine image)
+        const uint8_t* pts = out_points72 ? reinterpret_cast<const uint8_t*>(out_points72) : host_out.data();
         std::vector<uint8_t> inf(n);
-        for (size_t i = 0; i < n; ++i) inf[i] = host_out[72 * i + 64];
-        return cozk_srs_register(ctx, host_out.data(), n, 72, inf.data(), out_srs);
+        for (size_t i = 0; i < n; ++i) inf[i] = pts[72 * i + 64];
+        return cozk_srs_register(ctx, pts, n, 72, inf.data(), out_srs);
     }
     return COZK_OK;
 }
