@@ -1181,16 +1181,17 @@ static int srs_register_core(cozk_ctx* ctx, const SrsSource& src, size_t n, cons
                 // 0.277 / 1.06 / 4.14 s row by row, 0.057 / 0.22 / 1.03 s this way
                 const size_t slab = std::min<size_t>(n, (size_t)1 << 20);
                 xyzz* tmp = nullptr;
-                if (S.table_W <= TABLE_MAX_ROWS && !ctx->opt_table_rowwise && n >= 8192 &&  // (tiny tables: the scratch allocation costs more than it saves)
-                    cudaMalloc(&tmp, (size_t)(S.table_W - 1) * slab * sizeof(xyzz)) == cudaSuccess) {
+                // (scratch from the device's stream-ordered pool: registrations in a row reuse it, nothing synchronises the device)
+                if (S.table_W <= TABLE_MAX_ROWS && !ctx->opt_table_rowwise && n >= 8192 &&  // (tiny tables: not worth the scratch)
+                    cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)(S.table_W - 1) * slab * sizeof(xyzz), D.stream) == cudaSuccess) {
                     for (size_t first = 0; first < n; first += slab) {
                         TableSlabArgs A{d, tmp, n, first, slab, S.table_c, S.table_W};
                         k_table_chain<<<grid_for(slab, 128), 128, 0, D.stream>>>(A);
                         k_table_norm<<<grid_for(slab, 128), 128, 0, D.stream>>>(A);
                     }
                     cudaError_t e = cudaGetLastError();
+                    cudaFreeAsync(tmp, D.stream);
                     if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
-                    cudaFree(tmp);
                     if (e != cudaSuccess) {
                         set_error(std::string("SRS table build failed: ") + cudaGetErrorString(e));
                         return COZK_ERR_CUDA;
