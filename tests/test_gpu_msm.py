@@ -135,6 +135,16 @@ def test_edge_cases_and_errors(cozk, ctx, orc):
     pm = np.tile(H.le32(H.R - 1), (n, 1))
     pm[0::2] = H.le32(1)
     assert ctx.msm_batch(srs, pm, form=1)[0][64] == 1
+    # a batch of more than four vectors is finished on the device and normalised on the host with ONE inversion: identity
+    # results (first, in the middle, last) must not disturb their neighbours
+    u = [orc.gen_scalars("uniform", 90 + j, n) for j in range(4)]
+    canon = lambda v: np.stack([H.le32(pyref.from_mont(H.to_int(r), H.R)) for r in v])  # noqa: E731
+    zero = np.zeros((n, 32), np.uint8)
+    batch = [pm, canon(u[0]), canon(u[1]), zero, canon(u[2]), pm, canon(u[3]), zero]
+    got = ctx.msm_batch(srs, batch, n=n, form=1)
+    for j, v in enumerate(batch):
+        assert (got[j] == orc.msm(dup, v, form=1)).all(), j
+    assert got[0][64] == 1 and got[3][64] == 1 and got[5][64] == 1 and got[7][64] == 1 and got[1][64] == 0
     ctx.srs_release(srs)
 
 
