@@ -758,6 +758,9 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                     COZK_CUDA(cudaMemcpyAsync(D.scalars[slot].as<uint8_t>() + v * vstride, src, (pn - 1) * stride + 32,
                                               cudaMemcpyHostToDevice, D.copy_stream));
                 }
+            } else if (g == 1) {
+                // one device-resident vector: its pointer travels in the kernel arguments, nothing to stage (no pointer-table copy,
+                // no host synchronisation in front of the call)
             } else {
                 int rc = D.vec_ptrs.ensure(2 * 4096 * sizeof(void*));
                 if (rc) return rc;
@@ -783,8 +786,10 @@ static int run_on_device(cozk_ctx* ctx, int dev_index, const SrsEntry& S, size_t
                 // the other staging slot was last read by group gi-1, which has been synchronised below
                 if ((rc = stage(gi + 1))) return rc;
             }
-            const uint8_t* g_scalars = host_scalars ? D.scalars[slot].as<uint8_t>() : nullptr;
-            const uint8_t* const* g_ptrs = host_scalars ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096;
+            const bool one_resident = !host_scalars && g == 1;
+            const uint8_t* g_scalars = host_scalars ? D.scalars[slot].as<uint8_t>()
+                                       : one_resident ? reinterpret_cast<const uint8_t*>(dev_scalars[v0]) + lo * stride : nullptr;
+            const uint8_t* const* g_ptrs = (host_scalars || one_resident) ? nullptr : D.vec_ptrs.as<const uint8_t*>() + slot * 4096;
             DecomposeArgs dom = {};
             bool use_dom = false;
             // the whole SRS or a power-of-two prefix of it: the sums of those point ranges were computed at registration
